@@ -1,0 +1,341 @@
+// raster_math.h -- integer rasterisers behind draw_area (Project.py:144-170), shared by the CUDA
+// raster kernel (lane_raster.cuh) and the CPU-only fuzz harness under tests/hostsim.
+//
+// The reference draws with  cv2.polylines(canvas, pts, False, (200,0,0), thickness=30)  and
+// cv2.fillPoly(canvas, pts, (0,255,0))  (Project.py:160-164).  OpenCV is not in /root/reference;
+// what follows restates the published behaviour of its non-antialiased 8-connected primitives
+// (imgproc drawing: thick line = filled convex quad in 16.16 fixed point + filled end discs;
+// polygon fill = 1-px outline + even-odd scanline spans) and is pinned by fuzzing against the
+// cv2 build in this image (tests/test_raster_hostsim.py).
+//
+// Everything writes through a Plotter:  void span(int y, int x1, int x2)  -- inclusive, the
+// callee clips to the image -- so the same code sets bits with atomicOr on the device and
+// plain stores on the host.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifndef LD_HD
+#if defined(__CUDACC__)
+#define LD_HD __host__ __device__ __forceinline__
+#else
+#define LD_HD static inline
+#endif
+#endif
+
+namespace laneraster {
+
+enum { XY_SHIFT = 16, XY_ONE = 1 << XY_SHIFT };
+
+struct Pt { int64_t x, y; };
+
+LD_HD int64_t round_half_even(double v) {       // cvRound: lrint in the default rounding mode
+#if defined(__CUDA_ARCH__)
+    return (int64_t)__double2ll_rn(v);
+#else
+    return (int64_t)nearbyint(v);
+#endif
+}
+
+// cv::clipLine on 64-bit points (Cohen-Sutherland with the double-precision slope OpenCV uses).
+// Returns false when the segment lies completely outside [0,w-1]x[0,h-1].
+LD_HD bool clip_line(int64_t w, int64_t h, Pt& p1, Pt& p2) {
+    if (w <= 0 || h <= 0) return false;
+    int64_t right = w - 1, bottom = h - 1;
+    int64_t &x1 = p1.x, &y1 = p1.y, &x2 = p2.x, &y2 = p2.y;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        int64_t a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (int64_t)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (int64_t)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (int64_t)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (int64_t)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// 1-px 8-connected line between integer points (the outline fillPoly draws for every edge).
+template <class Plotter>
+LD_HD void line8(Plotter& P, int w, int h, Pt a, Pt b) {
+    if ((uint64_t)a.x >= (uint64_t)w || (uint64_t)b.x >= (uint64_t)w ||
+        (uint64_t)a.y >= (uint64_t)h || (uint64_t)b.y >= (uint64_t)h) {
+        if (!clip_line(w, h, a, b)) return;
+    }
+    int dx = (int)(b.x - a.x), dy = (int)(b.y - a.y);
+    int sx = 1, sy = 1;
+    int x = (int)a.x, y = (int)a.y;
+    if (dx < 0) { dx = -dx; dy = -dy; x = (int)b.x; y = (int)b.y; }     // always walk left to right
+    if (dy < 0) { dy = -dy; sy = -1; }
+    bool vert = dy > dx;
+    int major = vert ? dy : dx, minor = vert ? dx : dy;
+    int err = major - 2 * minor;
+    for (int i = 0; i <= major; ++i) {
+        P.span(y, x, x);
+        bool step = err < 0;
+        err += -2 * minor + (step ? 2 * major : 0);
+        if (vert) { y += sy; if (step) x += sx; }
+        else      { x += sx; if (step) y += sy; }
+    }
+}
+
+// 1-px line between 16.16 fixed-point points (the outline of a thick-line quad).
+template <class Plotter>
+LD_HD void line_fx(Plotter& P, int w, int h, Pt p1, Pt p2) {
+    if (!clip_line((int64_t)w << XY_SHIFT, (int64_t)h << XY_SHIFT, p1, p2)) return;
+    int64_t dx = p2.x - p1.x, dy = p2.y - p1.y;
+    int64_t ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+    int64_t x_step, y_step;
+    int ecount;
+    bool xmajor = ax > ay;
+    if (xmajor) {
+        if (dx < 0) { Pt t = p1; p1 = p2; p2 = t; dy = -dy; }
+        x_step = XY_ONE;
+        y_step = dy * (int64_t)XY_ONE / (ax | 1);
+        ecount = (int)((p2.x - p1.x) >> XY_SHIFT);
+    } else {
+        if (dy < 0) { Pt t = p1; p1 = p2; p2 = t; dx = -dx; }
+        x_step = dx * (int64_t)XY_ONE / (ay | 1);
+        y_step = XY_ONE;
+        ecount = (int)((p2.y - p1.y) >> XY_SHIFT);
+    }
+    p1.x += XY_ONE >> 1;
+    p1.y += XY_ONE >> 1;
+    {
+        int ex = (int)((p2.x + (XY_ONE >> 1)) >> XY_SHIFT), ey = (int)((p2.y + (XY_ONE >> 1)) >> XY_SHIFT);
+        if (ex >= 0 && ex < w && ey >= 0 && ey < h) P.span(ey, ex, ex);
+    }
+    if (xmajor) {
+        p1.x >>= XY_SHIFT;
+        while (ecount-- >= 0) {
+            int px = (int)p1.x, py = (int)(p1.y >> XY_SHIFT);
+            if (px >= 0 && px < w && py >= 0 && py < h) P.span(py, px, px);
+            p1.x++;
+            p1.y += y_step;
+        }
+    } else {
+        p1.y >>= XY_SHIFT;
+        while (ecount-- >= 0) {
+            int px = (int)(p1.x >> XY_SHIFT), py = (int)p1.y;
+            if (px >= 0 && px < w && py >= 0 && py < h) P.span(py, px, px);
+            p1.x += x_step;
+            p1.y++;
+        }
+    }
+}
+
+// Filled convex polygon with 16.16 vertices: outline + scanline spans between the two chains.
+template <class Plotter>
+LD_HD void fill_convex_fx(Plotter& P, int w, int h, const Pt* v, int npts) {
+    struct Edge { int idx, di; int64_t x, dx; int ye; } edge[2];
+    const int delta = XY_ONE >> 1;
+    int imin = 0;
+    int64_t xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
+    Pt p0 = v[npts - 1];
+    for (int i = 0; i < npts; ++i) {
+        Pt p = v[i];
+        if (p.y < ymin) { ymin = p.y; imin = i; }
+        if (p.y > ymax) ymax = p.y;
+        if (p.x > xmax) xmax = p.x;
+        if (p.x < xmin) xmin = p.x;
+        line_fx(P, w, h, p0, p);
+        p0 = p;
+    }
+    xmin = (xmin + delta) >> XY_SHIFT;
+    xmax = (xmax + delta) >> XY_SHIFT;
+    ymin = (ymin + delta) >> XY_SHIFT;
+    ymax = (ymax + delta) >> XY_SHIFT;
+    if (npts < 3 || (int)xmax < 0 || (int)ymax < 0 || (int)xmin >= w || (int)ymin >= h) return;
+    if (ymax > h - 1) ymax = h - 1;
+    int edges = npts;
+    int y = (int)ymin;
+    edge[0].idx = edge[1].idx = imin;
+    edge[0].ye = edge[1].ye = y;
+    edge[0].di = 1;
+    edge[1].di = npts - 1;
+    edge[0].x = edge[1].x = -(int64_t)XY_ONE;
+    edge[0].dx = edge[1].dx = 0;
+    do {
+        for (int i = 0; i < 2; ++i) {
+            if (y >= edge[i].ye) {
+                int idx0 = edge[i].idx, di = edge[i].di;
+                int idx = idx0 + di;
+                if (idx >= npts) idx -= npts;
+                int ty = 0;
+                for (; edges-- > 0;) {
+                    ty = (int)((v[idx].y + delta) >> XY_SHIFT);
+                    if (ty > y) {
+                        int64_t xs = v[idx0].x, xe = v[idx].x;
+                        edge[i].ye = ty;
+                        edge[i].dx = ((xe - xs) * 2 + ((int64_t)ty - y)) / (2 * ((int64_t)ty - y));
+                        edge[i].x = xs;
+                        edge[i].idx = idx;
+                        break;
+                    }
+                    idx0 = idx;
+                    idx += di;
+                    if (idx >= npts) idx -= npts;
+                }
+            }
+        }
+        if (edges < 0) break;
+        if (y >= 0) {
+            int left = 0, right = 1;
+            if (edge[0].x > edge[1].x) { left = 1; right = 0; }
+            int xx1 = (int)((edge[left].x + delta) >> XY_SHIFT);
+            int xx2 = (int)((edge[right].x + delta) >> XY_SHIFT);
+            if (xx2 >= 0 && xx1 < w) {
+                if (xx1 < 0) xx1 = 0;
+                if (xx2 >= w) xx2 = w - 1;
+                P.span(y, xx1, xx2);
+            }
+        }
+        edge[0].x += edge[0].dx;
+        edge[1].x += edge[1].dx;
+    } while (++y <= (int)ymax);
+}
+
+// half-widths of cv2.circle(filled) per row offset |dy| <= r, by running its midpoint loop
+LD_HD void circle_half_widths(int radius, int* hw /* [radius+1] */) {
+    for (int i = 0; i <= radius; ++i) hw[i] = -1;
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        if (dx > hw[dy]) hw[dy] = dx;
+        if (dy > hw[dx]) hw[dx] = dy;
+        dy++;
+        err += plus;
+        plus += 2;
+        int mask = (err <= 0) - 1;
+        err -= minus & mask;
+        dx += mask;
+        minus -= mask & 2;
+    }
+}
+
+template <class Plotter>
+LD_HD void disc(Plotter& P, int w, int h, int cx, int cy, int radius, const int* hw) {
+    for (int d = -radius; d <= radius; ++d) {
+        int y = cy + d;
+        if (y < 0 || y >= h) continue;
+        int half = hw[d < 0 ? -d : d];
+        if (half < 0) continue;
+        int x1 = cx - half, x2 = cx + half;
+        if (x1 >= w || x2 < 0) continue;
+        P.span(y, x1 < 0 ? 0 : x1, x2 >= w ? w - 1 : x2);
+    }
+}
+
+// the quad part of one thick segment (integer end points, even thickness)
+template <class Plotter>
+LD_HD void thick_segment_quad(Plotter& P, int w, int h, int x0, int y0, int x1, int y1, int thickness) {
+    Pt p0, p1;
+    p0.x = (int64_t)x0 << XY_SHIFT; p0.y = (int64_t)y0 << XY_SHIFT;
+    p1.x = (int64_t)x1 << XY_SHIFT; p1.y = (int64_t)y1 << XY_SHIFT;
+    const double inv = 1.0 / XY_ONE;
+    double dx = (double)(p0.x - p1.x) * inv, dy = (double)(p1.y - p0.y) * inv;
+    double r = dx * dx + dy * dy;
+    int odd = thickness & 1;
+    int64_t th = (int64_t)thickness << (XY_SHIFT - 1);
+    if (fabs(r) > 2.220446049250313e-16) {
+        r = ((double)th + odd * XY_ONE * 0.5) / sqrt(r);
+        Pt dp;
+        dp.x = round_half_even(dy * r);
+        dp.y = round_half_even(dx * r);
+        Pt q[4];
+        q[0].x = p0.x + dp.x; q[0].y = p0.y + dp.y;
+        q[1].x = p0.x - dp.x; q[1].y = p0.y - dp.y;
+        q[2].x = p1.x - dp.x; q[2].y = p1.y - dp.y;
+        q[3].x = p1.x + dp.x; q[3].y = p1.y + dp.y;
+        fill_convex_fx(P, w, h, q, 4);
+    }
+}
+
+// One segment of cv2.polylines(thickness >= 2, even): both end points are first clipped to the
+// image rectangle inflated by `thickness` on every side (a segment entirely outside it draws
+// nothing), then the quad and the end disc(s) are drawn -- the start disc only for the first
+// segment of the polyline, the end disc always.
+template <class Plotter>
+LD_HD void thick_segment(Plotter& P, int w, int h, int x0, int y0, int x1, int y1, int thickness,
+                         const int* hw, bool first) {
+    Pt a, b;
+    a.x = x0 + thickness; a.y = y0 + thickness;
+    b.x = x1 + thickness; b.y = y1 + thickness;
+    if (!clip_line((int64_t)w + 2 * thickness, (int64_t)h + 2 * thickness, a, b)) return;
+    x0 = (int)a.x - thickness; y0 = (int)a.y - thickness;
+    x1 = (int)b.x - thickness; y1 = (int)b.y - thickness;
+    thick_segment_quad(P, w, h, x0, y0, x1, y1, thickness);
+    if (first) disc(P, w, h, x0, y0, thickness / 2, hw);
+    disc(P, w, h, x1, y1, thickness / 2, hw);
+}
+
+// one polygon edge as fillPoly's scanline stage sees it: x(y) = x + (y - y0) * dx for y0 <= y < y1
+struct PolyEdge { int y0, y1; int64_t x, dx; int valid; };
+
+// Builds the scan edge for vertices a -> b and draws its 1-px outline.
+template <class Plotter>
+LD_HD PolyEdge poly_edge(Plotter& P, int w, int h, int ax, int ay, int bx, int by) {
+    PolyEdge e;
+    e.valid = 0;
+    Pt pt0, pt1;
+    pt0.x = (int64_t)ax << XY_SHIFT; pt0.y = ay;
+    pt1.x = (int64_t)bx << XY_SHIFT; pt1.y = by;
+    Pt t0, t1;
+    t0.x = ax; t0.y = ay; t1.x = bx; t1.y = by;
+    line8(P, w, h, t0, t1);
+    Pt pt0c = pt0, pt1c = pt1;
+    if ((uint64_t)t0.x >= (uint64_t)w || (uint64_t)t1.x >= (uint64_t)w ||
+        (uint64_t)t0.y >= (uint64_t)h || (uint64_t)t1.y >= (uint64_t)h) {
+        clip_line(w, h, t0, t1);
+        if (t0.y != t1.y) {
+            pt0c.y = t0.y; pt1c.y = t1.y;
+            pt0c.x = t0.x << XY_SHIFT; pt1c.x = t1.x << XY_SHIFT;
+        }
+    }
+    if (pt0.y == pt1.y) return e;
+    e.dx = (pt1c.x - pt0c.x) / (pt1c.y - pt0c.y);
+    if (pt0.y < pt1.y) {
+        e.y0 = (int)pt0.y; e.y1 = (int)pt1.y;
+        e.x = pt0c.x + (pt0.y - pt0c.y) * e.dx;
+    } else {
+        e.y0 = (int)pt1.y; e.y1 = (int)pt0.y;
+        e.x = pt1c.x + (pt1.y - pt1c.y) * e.dx;
+    }
+    e.valid = 1;
+    return e;
+}
+
+// span between two sorted crossings xa <= xb (16.16) on one scanline
+template <class Plotter>
+LD_HD void poly_span(Plotter& P, int w, int y, int64_t xa, int64_t xb) {
+    int x1 = (int)((xa + XY_ONE - 1) >> XY_SHIFT);       // ceil
+    int x2 = (int)(xb >> XY_SHIFT);                      // floor
+    if (x1 < w && x2 >= 0) {
+        if (x1 < 0) x1 = 0;
+        if (x2 >= w) x2 = w - 1;
+        if (x1 <= x2) P.span(y, x1, x2);
+    }
+}
+
+}  // namespace laneraster

@@ -1,0 +1,82 @@
+"""numpy emulation of what the kernels do with the plan tables.  TEST INFRASTRUCTURE: lets the
+CPU-only suite prove the plan tables (not the kernels) against the oracle; never imported by the package."""
+import numpy as np
+
+
+def emu_undistort(plan, frame):
+    W, H = plan.size
+    m = plan.und_map
+    fi = (m & 1023).astype(np.int64)
+    sx = ((m >> 10) & 2047).astype(np.int64) - 1024 + np.arange(W)[None, :]
+    sy = ((m >> 21) & 2047).astype(np.int64) - 1024 + np.arange(H)[:, None]
+    pad = np.zeros((H + 2, W + 2, 3), np.int64)
+    pad[1:-1, 1:-1] = frame
+    w = plan.wtab.astype(np.int64) & 0xFFFF
+    acc = np.zeros((H, W, 3), np.int64)
+    for k, (oy, ox) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        acc += pad[sy + oy + 1, sx + ox + 1] * w[fi, k][..., None]
+    return np.clip((acc + 16384) >> 15, 0, 255).astype(np.uint8)
+
+
+def emu_colour(plan, rgb):
+    r, g, b = (rgb[..., i].astype(np.int64) for i in range(3))
+    e = plan.ctab[(r << 8) | g].astype(np.int64)
+    lo1, hi1, lo2, hi2 = e & 255, (e >> 8) & 255, (e >> 16) & 255, (e >> 24) & 255
+    on = ((b >= lo1) & (b <= hi1)) | ((b >= lo2) & (b <= hi2))
+    exc = e == 0x00010001
+    idx = (r << 16) | (g << 8) | b
+    raw = (plan.cbits[idx >> 5] >> (idx & 31).astype(np.uint32)) & 1
+    return np.where(exc, raw.astype(bool), on)
+
+
+def emu_mask(plan, frame):
+    """two-phase fused mask: phase A bits over each tile's box, phase B bmap pick."""
+    W, H = plan.size
+    und = emu_undistort(plan, frame)
+    on = emu_colour(plan, und)
+    mask = np.zeros((H, W), np.uint8)
+    for (y0, y1, u0, v0, rw, rows, _, _) in plan.tiles:
+        if rows == 0:
+            continue
+        box = np.zeros((rows, rw * 32), bool)
+        u1 = min(u0 + rw * 32, W)
+        box[:, :u1 - u0] = on[v0:v0 + rows, u0:u1]
+        flat = np.concatenate([box.reshape(-1), np.zeros(1, bool)])
+        idx = plan.bmap[y0:y1].astype(np.int64)
+        idx[idx == 0xFFFF] = flat.size - 1
+        mask[y0:y1] = flat[idx]
+    return mask
+
+
+def emu_warp_nearest(plan, img):
+    W, H = plan.size
+    flat = np.concatenate([img.reshape(H * W, -1), np.zeros((1, img.reshape(H * W, -1).shape[1]), img.dtype)])
+    return flat[plan.near.reshape(-1)].reshape(img.shape)
+
+
+def emu_inverse_warp(plan, canvas):
+    W, H = plan.size
+    out = np.zeros((H, W, 3), np.uint8)
+    idx = plan.inv_idx.astype(np.int64)
+    ok = idx != 0xFFFFFFFF
+    sy = (idx >> 16) - 1
+    sx = (idx & 0xFFFF) - 1
+    sy[~ok] = -1
+    sx[~ok] = -1
+    fi = plan.inv_fi.astype(np.int64)
+    pad = np.zeros((H + 2, W + 2, 3), np.int64)
+    pad[1:-1, 1:-1] = canvas
+    w = plan.wtab.astype(np.int64) & 0xFFFF
+    acc = np.zeros(idx.shape + (3,), np.int64)
+    for k, (oy, ox) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        acc += pad[sy + oy + 1, sx + ox + 1] * w[fi, k][..., None]
+    res = np.clip((acc + 16384) >> 15, 0, 255).astype(np.uint8)
+    res[~ok] = 0
+    out[plan.inv_y0:plan.inv_y1] = res
+    return out
+
+
+def emu_blend(undist, warp):
+    """cv2.addWeighted(undist, 1, warp, 0.3, 0): float32 multiply-add, round half to even, saturate."""
+    f = undist.astype(np.float32) + warp.astype(np.float32) * np.float32(0.3)
+    return np.clip(np.rint(f), 0, 255).astype(np.uint8)

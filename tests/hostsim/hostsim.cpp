@@ -1,0 +1,86 @@
+// CPU build of the host/device arithmetic headers, for fuzzing against numpy / cv2 in a container
+// without a GPU.  TEST INFRASTRUCTURE ONLY: built by tests/hostsim/build.py, loaded only by tests.
+#include <cstring>
+#include "../../advanced-lane-detection_b200/csrc/fit_math.h"
+
+extern "C" {
+
+// moments: {n,Sy,Sy2,Sy3,Sy4,Sx,Sxy,Sxy2}; levels: up to n_levels rows of (y, count, xsum)
+int hs_polyfit(const uint64_t* moments, const double* levels, int n_levels, double eps, double* out3) {
+    lanefit::PowerSums ps = lanefit::sums_from_moments(moments);
+    for (int i = 0; i < n_levels; ++i)
+        lanefit::sums_add_level(ps, levels[3 * i], levels[3 * i + 1], lanefit::dd_make(levels[3 * i + 2]));
+    lanefit::FitResult r = lanefit::polyfit2(ps, eps);
+    memcpy(out3, r.c, sizeof(r.c));
+    return r.rank;
+}
+}
+
+#include <vector>
+#include <algorithm>
+#include "../../advanced-lane-detection_b200/csrc/raster_math.h"
+
+namespace {
+struct HostPlotter {
+    uint8_t* img; int w, h;
+    void span(int y, int x1, int x2) {
+        if (y < 0 || y >= h) return;
+        if (x1 < 0) x1 = 0;
+        if (x2 >= w) x2 = w - 1;
+        for (int x = x1; x <= x2; ++x) img[(size_t)y * w + x] = 1;
+    }
+};
+}
+
+extern "C" {
+
+// cv2.polylines(img, [pts], False, 1, thickness) for even thickness >= 2
+void hs_polyline(uint8_t* img, int w, int h, const int32_t* pts, int n, int thickness) {
+    using namespace laneraster;
+    HostPlotter P{img, w, h};
+    int radius = thickness / 2;
+    std::vector<int> hw(radius + 1);
+    circle_half_widths(radius, hw.data());
+    for (int i = 0; i + 1 < n; ++i)
+        thick_segment(P, w, h, pts[2 * i], pts[2 * i + 1], pts[2 * i + 2], pts[2 * i + 3], thickness, hw.data(), i == 0);
+}
+
+// cv2.fillPoly(img, [pts], 1)
+void hs_fillpoly(uint8_t* img, int w, int h, const int32_t* pts, int n) {
+    using namespace laneraster;
+    HostPlotter P{img, w, h};
+    std::vector<PolyEdge> edges;
+    for (int i = 0; i < n; ++i) {
+        int j = (i + n - 1) % n;
+        PolyEdge e = poly_edge(P, w, h, pts[2 * j], pts[2 * j + 1], pts[2 * i], pts[2 * i + 1]);
+        if (e.valid) edges.push_back(e);
+    }
+    for (int y = 0; y < h; ++y) {
+        std::vector<int64_t> xs;
+        for (auto& e : edges)
+            if (e.y0 <= y && y < e.y1) xs.push_back(e.x + (int64_t)(y - e.y0) * e.dx);
+        std::sort(xs.begin(), xs.end());
+        for (size_t k = 0; k + 1 < xs.size(); k += 2) poly_span(P, w, y, xs[k], xs[k + 1]);
+    }
+}
+}
+
+extern "C" int hs_clip_line(int64_t w, int64_t h, int64_t* p /* x1,y1,x2,y2 */) {
+    laneraster::Pt a{p[0], p[1]}, b{p[2], p[3]};
+    bool r = laneraster::clip_line(w, h, a, b);
+    p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+    return r;
+}
+
+extern "C" void hs_line_fx(uint8_t* img, int w, int h, const int64_t* p) {
+    HostPlotter P{img, w, h};
+    laneraster::Pt a{p[0], p[1]}, b{p[2], p[3]};
+    laneraster::line_fx(P, w, h, a, b);
+}
+
+extern "C" void hs_fill_convex_fx(uint8_t* img, int w, int h, const int64_t* p, int n) {
+    HostPlotter P{img, w, h};
+    laneraster::Pt v[16];
+    for (int i = 0; i < n; ++i) { v[i].x = p[2 * i]; v[i].y = p[2 * i + 1]; }
+    laneraster::fill_convex_fx(P, w, h, v, n);
+}
