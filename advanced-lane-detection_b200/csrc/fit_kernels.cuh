@@ -1,0 +1,302 @@
+// fit_kernels.cuh -- K3b: Line.get_fit / car_pos / curvature for a whole batch of frames.
+//
+// Replaces Line.get_fit (Project.py:113-141, harder:154-182), car_pos (Project.py:192-219,
+// harder:240-254), curvature (Project.py:173-189, harder:221-237) and the text formatting of
+// process_image (Project.py:320-332).
+//
+// The reference runs these strictly frame by frame, but the only cross-frame coupling is the
+// deque(maxlen=frame_num) medians: the output of frame k needs the first fits of frames
+// k-(F-1)..k and the second fits of the same range.  So the batch is processed as three
+// frame-parallel passes (fit1 -> medians+fit2 -> medians+position) with the previous batch's
+// deques carried in the context.  The one true recursion -- an empty lane re-uses the previous
+// frame's points INCLUDING its appended anchors (Project.py:98-100) -- is resolved by a short
+// serial walk that only does work for frames whose search failed.
+#pragma once
+#include "common.cuh"
+#include "fit_math.h"
+
+namespace lanedet {
+
+// Points one get_fit call starts from: integer pixels + anchors inherited through fallbacks.
+struct FitInput {
+    unsigned long long mom[8];
+    double c720, s720, c0, s0;      // inherited anchors (count, sum of x) at y=720 and y=0, float32-rounded
+    int valid;                      // 0: no points at all (TypeError in the reference)
+    int n_points;                   // len(self.x) going into get_fit
+};
+
+// One Line object (Project.py:11-37) between calls.
+struct TrackLane {
+    int n_hist;                     // entries in every deque (all are appended once per frame)
+    int has_points;                 // self.x is not None
+    int detected;
+    int n_points;                   // len(self.x) after the last get_fit (with anchors)
+    double bottom[LD_MAX_DEPTH], top[LD_MAX_DEPTH], A[LD_MAX_DEPTH], B[LD_MAX_DEPTH], C[LD_MAX_DEPTH];
+    FitInput pts;                   // points of the last frame BEFORE its anchors were appended
+    double last_bottom, last_top;   // the anchors appended in the last frame (float64, not yet rounded)
+    uint32_t rowmap[LD_ROWMAP_WORDS];
+};
+struct TrackState { TrackLane lane[2]; };
+
+struct FitWork {                    // per (frame, lane) scratch
+    FitInput in;
+    double fit1[3], fit2[3];
+    double bi, ti;                  // intercepts of fit1 (deque entries)
+    double mb, mt;                  // medians = anchors of this frame
+    int rank1, rank2;
+};
+
+__device__ __forceinline__ lanefit::PowerSums sums_of(const FitInput& in) {
+    lanefit::PowerSums ps = lanefit::sums_from_moments(reinterpret_cast<const uint64_t*>(in.mom));
+    if (in.c720 > 0) lanefit::sums_add_level(ps, 720.0, in.c720, lanefit::dd_make(in.s720));
+    if (in.c0 > 0) lanefit::sums_add_level(ps, 0.0, in.c0, lanefit::dd_make(in.s0));
+    return ps;
+}
+
+__device__ __forceinline__ void do_fit1(FitWork& w) {
+    // self.fit = np.polyfit(self.y, self.x, 2) on float32 arrays: rcond = len(x) * eps(float32)
+    const lanefit::FitResult r = lanefit::polyfit2(sums_of(w.in), 1.1920928955078125e-07);
+    w.fit1[0] = r.c[0]; w.fit1[1] = r.c[1]; w.fit1[2] = r.c[2];
+    w.rank1 = r.rank;
+    // get_intercepts (Project.py:43-46): fit[0]*720**2 + fit[1]*720 + fit[2]
+    w.bi = LD_ADD(LD_ADD(LD_MUL(r.c[0], 518400.0), LD_MUL(r.c[1], 720.0)), r.c[2]);
+    w.ti = r.c[2];
+}
+
+// value j of a deque-like series at batch position k-back (back = 0 is frame k itself): the batch
+// entries come from `work`, older ones from the carried state.  Returns false if out of history.
+template <class GetBatch>
+__device__ __forceinline__ int gather_window(int k, int depth, int n_hist, const double* carried, GetBatch get,
+                                             double* out) {
+    int m = 0;
+    for (int back = depth - 1; back >= 0; --back) {
+        const int j = k - back;
+        if (j >= 0) out[m++] = get(j);
+        else if (n_hist + j >= 0) out[m++] = carried[n_hist + j];
+    }
+    return m;
+}
+
+// ---- pass 1: first fit of every frame whose search succeeded (frame-parallel) --------------------
+__global__ void k_fit1(const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work, int n, int* __restrict__ any_fail) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (frame, lane)
+    if (i >= 2 * n) return;
+    FitWork& w = work[i];
+    const ld_lane_record& r = rec[i];
+    w.in.valid = 0;
+    if (!r.ok) { atomicOr(any_fail, 1); return; }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) w.in.mom[m] = r.mom[m];
+    w.in.c720 = w.in.s720 = w.in.c0 = w.in.s0 = 0.0;
+    w.in.valid = 1;
+    w.in.n_points = (int)r.mom[0];
+    do_fit1(w);
+}
+
+// ---- pass 1b: serial walk over the frames whose search failed (one thread per lane) ---------------
+__global__ void k_fit_fallback(const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work,
+                               ld_frame_fit* __restrict__ fit, const TrackState* __restrict__ st, int n, int depth,
+                               int top_anchor, const int* __restrict__ any_fail, int* __restrict__ first_bad) {
+    const int L = threadIdx.x;
+    if (L >= 2 || !*any_fail) return;
+    const TrackLane& T = st->lane[L];
+    for (int k = 0; k < n; ++k) {
+        if (rec[2 * k + L].ok) continue;
+        FitWork& w = work[2 * k + L];
+        // x_inds = self.x, y_inds = self.y (Project.py:98-100): last frame's arrays with its anchors,
+        // then .astype(np.float32) (Project.py:308-311)
+        FitInput prev; double pb, pt; int prev_n;
+        if (k == 0) { prev = T.pts; pb = T.last_bottom; pt = T.last_top; prev_n = T.n_points; if (!T.has_points) prev.valid = 0; }
+        else {
+            const FitWork& p = work[2 * (k - 1) + L];
+            prev = p.in;
+            if (prev.valid) {                                   // anchors of frame k-1 = medians at k-1
+                double tmp[LD_MAX_DEPTH];
+                int m = gather_window(k - 1, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp);
+                pb = lanefit::median_small(tmp, m);
+                m = gather_window(k - 1, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp);
+                pt = lanefit::median_small(tmp, m);
+            }
+            prev_n = prev.n_points + 1 + (top_anchor ? 1 : 0);
+        }
+        if (!prev.valid) {                                      // np.polyfit(array(None)) -> TypeError
+            w.in.valid = 0;
+            atomicMin(first_bad, k);
+            return;
+        }
+        w.in = prev;
+        w.in.c720 += 1.0; w.in.s720 = LD_ADD(w.in.s720, (double)(float)pb);
+        if (top_anchor) { w.in.c0 += 1.0; w.in.s0 = LD_ADD(w.in.s0, (double)(float)pt); }
+        w.in.n_points = prev_n;
+        do_fit1(w);
+        // Line.fity of a fallback frame = the previous frame's fity (its anchors included)
+        for (int i = 0; i < LD_ROWMAP_WORDS; ++i) {
+            uint32_t v;
+            if (k == 0) v = T.rowmap[i];
+            else if (rec[2 * (k - 1) + L].ok) {
+                v = rec[2 * (k - 1) + L].rowmap[i];
+                if (i == (720 >> 5)) v |= 1u << (720 & 31);
+                if (i == 0 && top_anchor) v |= 1u;
+            } else v = fit[k - 1].rowmap[L][i];
+            fit[k].rowmap[L][i] = v;
+        }
+    }
+}
+
+// ---- pass 2: anchors (deque medians) + second fit (frame-parallel) --------------------------------
+__global__ void k_fit2(FitWork* __restrict__ work, const TrackState* __restrict__ st, int n, int depth, int top_anchor,
+                       const int* __restrict__ first_bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const int k = i >> 1, L = i & 1;
+    if (k >= *first_bad) return;
+    const TrackLane& T = st->lane[L];
+    FitWork& w = work[i];
+    double tmp[LD_MAX_DEPTH];
+    int m = gather_window(k, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp);
+    w.mb = lanefit::median_small(tmp, m);                       // np.median(self.bottom_x)
+    m = gather_window(k, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp);
+    w.mt = lanefit::median_small(tmp, m);
+    lanefit::PowerSums ps = sums_of(w.in);
+    lanefit::sums_add_level(ps, 720.0, 1.0, lanefit::dd_make(w.mb));          // np.append(self.x, bottom); (self.y, 720)
+    if (top_anchor) lanefit::sums_add_level(ps, 0.0, 1.0, lanefit::dd_make(w.mt));
+    // arrays are float64 after np.append: rcond = len(x) * eps(float64)
+    const lanefit::FitResult r = lanefit::polyfit2(ps, 2.220446049250313e-16);
+    w.fit2[0] = r.c[0]; w.fit2[1] = r.c[1]; w.fit2[2] = r.c[2];
+    w.rank2 = r.rank;
+}
+
+// '%d' / '%.2f' formatting of the two putText strings into glyph indices (plan.GLYPH_CHARS order:
+// '0'..'9' = 0..9, '-' = 10, '.' = 11, 'R' prefix = 12, 'O' prefix = 13, '(m)' = 14, 'Inf (m)' = 15)
+__device__ __forceinline__ int put_uint(uint8_t* dst, int pos, unsigned long long v) {
+    char tmp[24]; int m = 0;
+    do { tmp[m++] = (char)(v % 10); v /= 10; } while (v && m < 20);
+    while (m && pos < LD_TEXT_MAX_GLYPHS) dst[pos++] = tmp[--m];
+    return pos;
+}
+// round-half-even of |v|*100 from the exact binary value, as glibc's printf("%.2f") does
+__device__ __forceinline__ unsigned long long centi_round(double av) {
+    if (!(av < 1e15)) return 99999999999999999ull;
+    if (av == 0.0) return 0;
+    int e; const double mant = frexp(av, &e);                   // av = mant * 2^e, mant in [0.5,1)
+    const unsigned long long mi = (unsigned long long)ldexp(mant, 53);  // 53-bit integer mantissa
+    const int sh = 53 - e;                                      // av = mi / 2^sh ; sh >= 3 because av < 2^50
+    const unsigned long long prod = mi * 100ull;                // < 2^60, exact
+    if (sh >= 62) return 0;                                     // av*100 < 2^-2
+    unsigned long long q = prod >> sh;
+    const unsigned long long rem = prod & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+    if (rem > half || (rem == half && (q & 1))) ++q;
+    return q;
+}
+
+// ---- pass 3: deque medians of A,B,C, car_pos, curvature, text (frame-parallel, one thread per frame)
+__global__ void k_fit3(const ld_lane_record* __restrict__ rec, const FitWork* __restrict__ work,
+                       const TrackState* __restrict__ st, ld_frame_fit* __restrict__ fit, int n, const PlanDev P,
+                       const int* __restrict__ first_bad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ld_frame_fit& o = fit[k];
+    if (k >= *first_bad) { o.status = (k == *first_bad) ? LD_ERR_EMPTY_LANE : LD_ERR_ARG; return; }
+    o.status = LD_OK;
+    const int depth = P.depth;
+    for (int L = 0; L < 2; ++L) {
+        const TrackLane& T = st->lane[L];
+        const FitWork& w = work[2 * k + L];
+        double tmp[LD_MAX_DEPTH];
+        int m = gather_window(k, depth, T.n_hist, T.A, [&](int j) { return work[2 * j + L].fit2[0]; }, tmp);
+        o.fit[L][0] = lanefit::median_small(tmp, m);
+        m = gather_window(k, depth, T.n_hist, T.B, [&](int j) { return work[2 * j + L].fit2[1]; }, tmp);
+        o.fit[L][1] = lanefit::median_small(tmp, m);
+        m = gather_window(k, depth, T.n_hist, T.C, [&](int j) { return work[2 * j + L].fit2[2]; }, tmp);
+        o.fit[L][2] = lanefit::median_small(tmp, m);
+        for (int c = 0; c < 3; ++c) { o.fit1[L][c] = w.fit1[c]; o.fit2[L][c] = w.fit2[c]; }
+        o.bottom[L] = w.mb; o.top[L] = w.mt;
+        o.rank1[L] = w.rank1; o.rank2[L] = w.rank2;
+        o.detected[L] = rec[2 * k + L].ok;
+        o.n_points[L] = w.in.n_points + 1 + (P.top_anchor ? 1 : 0);
+        if (rec[2 * k + L].ok)
+            for (int i = 0; i < LD_ROWMAP_WORDS; ++i) o.rowmap[L][i] = rec[2 * k + L].rowmap[i];
+        o.rowmap[L][720 >> 5] |= 1u << (720 & 31);              // (median bottom, 720)
+        if (P.top_anchor) o.rowmap[L][0] |= 1u;                 // (median top, 0)
+    }
+    // car_pos (Project.py:192-219 / harder:240-254); np.max(ploty) = H-1
+    const double ymax = (double)(P.H - 1);
+    const double xl = lanefit::eval_fit(o.fit[0], ymax), xr = lanefit::eval_fit(o.fit[1], ymax);
+    const double xm_dyn = LD_DIV(3.7, fabs(LD_SUB(xl, xr)));
+    const double xmean = LD_MUL(LD_ADD(xl, xr), 0.5);
+    o.offset = LD_MUL(LD_SUB((double)P.W * 0.5, xmean), xm_dyn);
+    // curvature: refitting x(y)*xm against y*ym reproduces the same parabola: A*xm/ym^2, B*xm/ym
+    const double ym = P.ym_per_pix, xm = P.curv_fixed_xm ? 3.7 / 700.0 : xm_dyn;
+    for (int L = 0; L < 2; ++L) {
+        const double a = o.fit[L][0] * xm / (ym * ym), b = o.fit[L][1] * xm / ym;
+        const double s = 2.0 * a * ymax * ym + b;
+        o.curv[L] = pow(1.0 + s * s, 1.5) / fabs(2.0 * a);
+    }
+    o.mean_curv = LD_MUL(LD_ADD(o.curv[0], o.curv[1]), 0.5);
+    // text (Project.py:320-332)
+    int p = 0;
+    o.text[0][p++] = 12;
+    if (o.mean_curv < 3000.0) { p = put_uint(o.text[0], p, (unsigned long long)o.mean_curv); o.text[0][p++] = 14; }
+    else o.text[0][p++] = 15;
+    o.n_text[0] = p;
+    p = 0;
+    o.text[1][p++] = 13;
+    const double v = -o.offset;
+    if (v != v) { o.n_text[1] = p; }                            // 'nan' has no glyphs in the atlas; never reached with finite fits
+    else {
+        const unsigned long long q = centi_round(fabs(v));
+        if (signbit(v)) o.text[1][p++] = 10;
+        p = put_uint(o.text[1], p, q / 100);
+        if (p < LD_TEXT_MAX_GLYPHS) o.text[1][p++] = 11;
+        if (p < LD_TEXT_MAX_GLYPHS) o.text[1][p++] = (uint8_t)((q / 10) % 10);
+        if (p < LD_TEXT_MAX_GLYPHS) o.text[1][p++] = (uint8_t)(q % 10);
+        if (p < LD_TEXT_MAX_GLYPHS) o.text[1][p++] = 14;
+        o.n_text[1] = p;
+    }
+    o.pad = 0;
+}
+
+// ---- pass 4: roll the trackers forward to the end of the valid part of the batch (one thread per lane)
+__global__ void k_state_update(const ld_lane_record* __restrict__ rec, const FitWork* __restrict__ work,
+                               const ld_frame_fit* __restrict__ fit, TrackState* __restrict__ st, int n, int depth,
+                               const int* __restrict__ first_bad, int* __restrict__ last_bad_out, int frame_offset) {
+    const int L = threadIdx.x;
+    if (L == 0 && *first_bad < n && *last_bad_out < 0) *last_bad_out = frame_offset + *first_bad;   // sticky until ld_check reports it
+    if (L >= 2) return;
+    const int nv = min(n, *first_bad);
+    if (nv <= 0) return;
+    TrackLane& T = st->lane[L];
+    double nb[LD_MAX_DEPTH], nt[LD_MAX_DEPTH], nA[LD_MAX_DEPTH], nB[LD_MAX_DEPTH], nC[LD_MAX_DEPTH];
+    const int k = nv - 1;
+    const int m = gather_window(k, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, nb);
+    gather_window(k, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, nt);
+    gather_window(k, depth, T.n_hist, T.A, [&](int j) { return work[2 * j + L].fit2[0]; }, nA);
+    gather_window(k, depth, T.n_hist, T.B, [&](int j) { return work[2 * j + L].fit2[1]; }, nB);
+    gather_window(k, depth, T.n_hist, T.C, [&](int j) { return work[2 * j + L].fit2[2]; }, nC);
+    for (int i = 0; i < m; ++i) { T.bottom[i] = nb[i]; T.top[i] = nt[i]; T.A[i] = nA[i]; T.B[i] = nB[i]; T.C[i] = nC[i]; }
+    T.n_hist = m;
+    T.has_points = 1;
+    T.detected = rec[2 * k + L].ok;
+    T.pts = work[2 * k + L].in;
+    T.last_bottom = work[2 * k + L].mb;
+    T.last_top = work[2 * k + L].mt;
+    T.n_points = fit[k].n_points[L];
+    for (int i = 0; i < LD_ROWMAP_WORDS; ++i) T.rowmap[i] = fit[k].rowmap[L][i];
+}
+
+__global__ void k_state_reset(TrackState* st) {
+    uint32_t* p = reinterpret_cast<uint32_t*>(st);
+    for (int i = threadIdx.x; i < (int)(sizeof(TrackState) / 4); i += blockDim.x) p[i] = 0;
+}
+
+// np.polyfit(y, x, 2) of plain pixel sets with float64 rcond (helper.py:309-310, 362-363)
+__global__ void k_polyfit(const ld_lane_record* __restrict__ rec, int n, double* __restrict__ coef, int* __restrict__ rank) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const lanefit::PowerSums ps = lanefit::sums_from_moments(reinterpret_cast<const uint64_t*>(rec[i].mom));
+    const lanefit::FitResult r = lanefit::polyfit2(ps, 2.220446049250313e-16);
+    coef[3 * i] = r.c[0]; coef[3 * i + 1] = r.c[1]; coef[3 * i + 2] = r.c[2];
+    rank[i] = rec[i].mom[0] ? r.rank : 0;
+}
+
+}  // namespace lanedet

@@ -1,0 +1,439 @@
+// lanedet.cu -- the C ABI of liblanedet.so (include/lanedet.h): plan / context management and the
+// launch sequence of the sm_100a kernels.  No CPU fallback anywhere: every entry point either
+// launches kernels on the plan's device or returns an error code.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/lanedet.h"
+#include "common.cuh"
+#include "mask_kernels.cuh"
+#include "search_kernels.cuh"
+#include "fit_kernels.cuh"
+#include "overlay_kernels.cuh"
+
+using namespace lanedet;
+
+static thread_local char g_cuda_err[256] = "";
+
+#define LD_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                     cudaGetErrorString(_e));                                                  \
+            return LD_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+struct ld_plan {
+    int device;
+    PlanDev d;
+    void* allocs[16];
+    int n_allocs;
+    size_t search_smem, raster_smem, mask_smem;
+};
+
+enum { HOST_CHUNK = 32 };
+
+struct ld_ctx {
+    ld_plan* plan;
+    int max_frames;
+    uint32_t* mask;            // [max][H][WW]
+    ld_lane_record* rec;       // [max][2]
+    FitWork* work;             // [max][2]
+    ld_frame_fit* fit;         // [max]
+    uint32_t* planes;          // [max][2][H][WW]
+    uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
+    TrackState* state;
+    int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error
+    int* flags_host;           // pinned mirror
+    // host pipeline
+    cudaStream_t s_in, s_comp, s_out;
+    cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
+    uint8_t* stage_in[2];
+    uint8_t* stage_out[2];
+    int chunk;
+};
+
+extern "C" int ld_abi_version(void) { return LD_ABI_VERSION; }
+
+extern "C" const char* ld_error_string(int status) {
+    switch (status) {
+        case LD_OK: return "ok";
+        case LD_ERR_ARG: return "bad argument";
+        case LD_ERR_CUDA: return "CUDA runtime error";
+        case LD_ERR_NO_DEVICE: return "no usable CUDA device (sm_100a required)";
+        case LD_ERR_EMPTY_LANE: return "expected 1D vector for x";   // the reference's TypeError text
+        case LD_ERR_POLYGON: return "polygon too complex for the scanline fill";
+        default: return "unknown status";
+    }
+}
+extern "C" const char* ld_last_cuda_error(void) { return g_cuda_err; }
+
+template <class T>
+static int upload(ld_plan* p, const T* host, size_t count, const T** dev) {
+    void* d = nullptr;
+    LD_CUDA(cudaMalloc(&d, count * sizeof(T) + 16));
+    LD_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    p->allocs[p->n_allocs++] = d;
+    *dev = static_cast<const T*>(d);
+    return LD_OK;
+}
+
+extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** out) {
+    if (!desc || !out) return LD_ERR_ARG;
+    *out = nullptr;
+    const int W = desc->width, H = desc->height;
+    if (W <= 0 || H <= 0 || (W % 32) || (H % 2) || desc->n_tiles <= 0 || desc->frame_num < 1 ||
+        desc->frame_num > LD_MAX_DEPTH || !desc->und_map || !desc->wtab || !desc->near_map || !desc->tiles ||
+        !desc->bmap || !desc->ctab || !desc->cbits || !desc->inv_idx || !desc->inv_fi || !desc->glyph_bits ||
+        !desc->glyph_adv)
+        return LD_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LD_ERR_NO_DEVICE;
+    LD_CUDA(cudaSetDevice(device));
+    ld_plan* p = new (std::nothrow) ld_plan();
+    if (!p) return LD_ERR_ARG;
+    memset(p, 0, sizeof(*p));
+    p->device = device;
+    PlanDev& d = p->d;
+    d.W = W; d.H = H; d.WW = W / 32;
+    d.search_mode = desc->search_mode; d.margin = desc->margin; d.minpix = desc->minpix;
+    d.depth = desc->frame_num; d.top_anchor = desc->top_anchor; d.clip_polygon = desc->clip_polygon;
+    d.curv_fixed_xm = desc->curv_fixed_xm; d.n_tiles = desc->n_tiles; d.ym_per_pix = desc->ym_per_pix;
+    d.inv_y0 = desc->inv_y0; d.inv_y1 = desc->inv_y1; d.n_glyphs = desc->n_glyphs;
+    int mb = 0;
+    for (int t = 0; t < desc->n_tiles; ++t) {
+        const int words = desc->tiles[8 * t + 4] * desc->tiles[8 * t + 5];
+        if (words > mb) mb = words;
+    }
+    d.max_box_words = mb;
+    const size_t npix = (size_t)W * H, ninv = (size_t)(desc->inv_y1 - desc->inv_y0) * W;
+    int rc;
+    const int16_t* wt = nullptr; const int32_t* tl = nullptr;
+    if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
+        (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
+        (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
+        (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
+        (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) ||
+        (rc = upload(p, desc->glyph_bits, (size_t)desc->n_glyphs * LD_GLYPH_ROWS * LD_GLYPH_WORDS, &d.glyph_bits)) ||
+        (rc = upload(p, desc->glyph_adv, (size_t)desc->n_glyphs, &d.glyph_adv))) {
+        ld_plan_destroy(p);
+        return rc;
+    }
+    d.wtab = reinterpret_cast<const uint2*>(wt);
+    d.tiles = reinterpret_cast<const int4*>(tl);
+    p->mask_smem = (2048 + mb + 1) * sizeof(uint32_t);
+    p->search_smem = (size_t)H * d.WW * 4 + (size_t)9 * W * 2;
+    p->raster_smem = (size_t)H * (d.WW + 1 + LD_MAX_CROSSINGS) * 4 + sizeof(RasterShared);
+    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->mask_smem));
+    LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
+    LD_CUDA(cudaFuncSetAttribute(k_margin_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
+    LD_CUDA(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->raster_smem));
+    *out = p;
+    return LD_OK;
+}
+
+extern "C" int ld_plan_destroy(ld_plan* p) {
+    if (!p) return LD_ERR_ARG;
+    cudaSetDevice(p->device);
+    for (int i = 0; i < p->n_allocs; ++i) cudaFree(p->allocs[i]);
+    delete p;
+    return LD_OK;
+}
+
+extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
+    if (!plan || !out || max_frames < 1) return LD_ERR_ARG;
+    *out = nullptr;
+    LD_CUDA(cudaSetDevice(plan->device));
+    ld_ctx* c = new (std::nothrow) ld_ctx();
+    if (!c) return LD_ERR_ARG;
+    memset(c, 0, sizeof(*c));
+    c->plan = plan;
+    c->max_frames = max_frames;
+    const PlanDev& d = plan->d;
+    const size_t mw = (size_t)d.H * d.WW, fb = (size_t)d.W * d.H * 3;
+    c->chunk = max_frames < HOST_CHUNK ? max_frames : HOST_CHUNK;
+#define CTX_ALLOC(ptr, bytes)                                   \
+    do {                                                        \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));   \
+        if (_e != cudaSuccess) {                                \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(_e)); \
+            ld_ctx_destroy(c);                                  \
+            return LD_ERR_CUDA;                                 \
+        }                                                       \
+    } while (0)
+    CTX_ALLOC(c->mask, mw * 4 * max_frames);
+    CTX_ALLOC(c->rec, sizeof(ld_lane_record) * 2 * max_frames);
+    CTX_ALLOC(c->work, sizeof(FitWork) * 2 * max_frames);
+    CTX_ALLOC(c->fit, sizeof(ld_frame_fit) * max_frames);
+    CTX_ALLOC(c->planes, mw * 4 * 2 * max_frames);
+    CTX_ALLOC(c->text, (size_t)LD_TEXT_ROWS * LD_TEXT_WORDS * 4 * max_frames);
+    CTX_ALLOC(c->state, sizeof(TrackState));
+    CTX_ALLOC(c->flags, 16 * sizeof(int));
+    for (int b = 0; b < 2; ++b) {
+        CTX_ALLOC(c->stage_in[b], fb * c->chunk);
+        CTX_ALLOC(c->stage_out[b], fb * c->chunk);
+    }
+#undef CTX_ALLOC
+    LD_CUDA(cudaMallocHost((void**)&c->flags_host, 16 * sizeof(int)));
+    LD_CUDA(cudaMemset(c->state, 0, sizeof(TrackState)));
+    LD_CUDA(cudaMemset(c->flags, 0, 16 * sizeof(int)));
+    LD_CUDA(cudaMemset(c->flags + 2, 0xFF, sizeof(int)));       // last_bad = -1
+    LD_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    LD_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    LD_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        LD_CUDA(cudaEventCreateWithFlags(&c->ev_in[b], cudaEventDisableTiming));
+        LD_CUDA(cudaEventCreateWithFlags(&c->ev_comp[b], cudaEventDisableTiming));
+        LD_CUDA(cudaEventCreateWithFlags(&c->ev_out[b], cudaEventDisableTiming));
+    }
+    *out = c;
+    return LD_OK;
+}
+
+extern "C" int ld_ctx_destroy(ld_ctx* c) {
+    if (!c) return LD_ERR_ARG;
+    cudaSetDevice(c->plan->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->mask); cudaFree(c->rec); cudaFree(c->work); cudaFree(c->fit); cudaFree(c->planes);
+    cudaFree(c->text); cudaFree(c->state); cudaFree(c->flags);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(c->stage_in[b]); cudaFree(c->stage_out[b]);
+        if (c->ev_in[b]) cudaEventDestroy(c->ev_in[b]);
+        if (c->ev_comp[b]) cudaEventDestroy(c->ev_comp[b]);
+        if (c->ev_out[b]) cudaEventDestroy(c->ev_out[b]);
+    }
+    if (c->flags_host) cudaFreeHost(c->flags_host);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    delete c;
+    return LD_OK;
+}
+
+static inline int check_launch() {
+    LD_CUDA(cudaGetLastError());
+    return LD_OK;
+}
+#define ARGS_OK(c, a, b, n) ((c) && (a) && (b) && (n) >= 0)
+
+// ------------------------------------------------------------------------------------- stages
+extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, void* stream) {
+    if (!ARGS_OK(c, frames, mask, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    k_mask<<<dim3(d.n_tiles, n), MASK_THREADS, c->plan->mask_smem, (cudaStream_t)stream>>>(frames, mask, d);
+    return check_launch();
+}
+
+extern "C" int ld_hist(ld_ctx* c, const uint32_t* mask, int n, uint16_t* hist, void* stream) {
+    if (!ARGS_OK(c, mask, hist, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    const int band_h = d.H / 8;                                 // 90 rows at H = 720 (Project.py:78-79)
+    k_hist<<<dim3(8, n), HIST_THREADS, 0, (cudaStream_t)stream>>>(mask, hist, d.W, d.H, d.WW, band_h, 8);
+    return check_launch();
+}
+
+extern "C" int ld_search(ld_ctx* c, const uint32_t* mask, int n, ld_lane_record* rec, void* stream) {
+    if (!ARGS_OK(c, mask, rec, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    if (d.H != 720 || d.W != 1280) return LD_ERR_ARG;           // window geometry of the reference is hard-wired to 1280x720
+    k_search<<<n, SEARCH_THREADS, c->plan->search_smem, (cudaStream_t)stream>>>(mask, rec, d, nullptr);
+    return check_launch();
+}
+
+extern "C" int ld_margin_search(ld_ctx* c, const uint32_t* mask, const double* fits, int n, ld_lane_record* rec,
+                                void* stream) {
+    if (!ARGS_OK(c, mask, rec, n) || !fits) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    k_margin_search<<<n, SEARCH_THREADS, (size_t)d.H * d.WW * 4, (cudaStream_t)stream>>>(mask, fits, rec, d);
+    return check_launch();
+}
+
+extern "C" int ld_polyfit(ld_ctx* c, const ld_lane_record* rec, int n, double* coef, int32_t* rank, void* stream) {
+    if (!ARGS_OK(c, rec, coef, n) || !rank) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    k_polyfit<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(rec, n, coef, rank);
+    return check_launch();
+}
+
+static int fit_impl(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, cudaStream_t s, int frame_offset) {
+    if (!ARGS_OK(c, rec, fit, n) || n > c->max_frames) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    LD_CUDA(cudaMemsetAsync(c->flags, 0, sizeof(int), s));              // any_fail = 0
+    LD_CUDA(cudaMemsetAsync(c->flags + 1, 0x7F, sizeof(int), s));       // first_bad = 0x7f7f7f7f
+    const int t = 64, g2 = (2 * n + t - 1) / t, g1 = (n + t - 1) / t;
+    k_fit1<<<g2, t, 0, s>>>(rec, c->work, n, c->flags);
+    k_fit_fallback<<<1, 32, 0, s>>>(rec, c->work, fit, c->state, n, d.depth, d.top_anchor, c->flags, c->flags + 1);
+    k_fit2<<<g2, t, 0, s>>>(c->work, c->state, n, d.depth, d.top_anchor, c->flags + 1);
+    k_fit3<<<g1, t, 0, s>>>(rec, c->work, c->state, fit, n, d, c->flags + 1);
+    k_state_update<<<1, 32, 0, s>>>(rec, c->work, fit, c->state, n, d.depth, c->flags + 1, c->flags + 2, frame_offset);
+    return check_launch();
+}
+extern "C" int ld_fit(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, void* stream) {
+    return fit_impl(c, rec, n, fit, (cudaStream_t)stream, 0);
+}
+
+static int launch_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* fit, const int32_t* verts,
+                          const int32_t* counts, int max_verts, int thickness, int n, uint8_t* out, cudaStream_t s,
+                          int already_undistorted, int with_text) {
+    const PlanDev& d = c->plan->d;
+    if (d.H != 720 || d.W != 1280) return LD_ERR_ARG;
+    for (int done = 0; done < n; done += c->max_frames) {
+        const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
+        k_raster<<<m, RASTER_THREADS, c->plan->raster_smem, s>>>(fit ? fit + done : nullptr,
+                                                                 verts ? verts + (size_t)done * max_verts * 2 : nullptr,
+                                                                 counts ? counts + done : nullptr, max_verts, thickness,
+                                                                 c->planes, c->text, d, c->flags + 3);
+        const int quads = d.W * d.H / 4;
+        k_overlay<<<dim3((quads + 255) / 256, m), 256, 0, s>>>(frames + (size_t)done * d.W * d.H * 3, c->planes, c->text,
+                                                              out + (size_t)done * d.W * d.H * 3, d, already_undistorted,
+                                                              with_text);
+    }
+    return check_launch();
+}
+
+extern "C" int ld_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* fit, int n, uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, frames, out, n) || !fit) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    return launch_overlay(c, frames, fit, nullptr, nullptr, 0, 30, n, out, (cudaStream_t)stream, 0, 1);
+}
+
+extern "C" int ld_draw(ld_ctx* c, const uint8_t* undist, const int32_t* verts, const int32_t* counts, int max_verts,
+                       int thickness, int n, uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, undist, out, n) || !verts || !counts || max_verts < 0 || thickness < 0 || thickness > 30 || (thickness & 1))
+        return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    return launch_overlay(c, undist, nullptr, verts, counts, max_verts, thickness, n, out, (cudaStream_t)stream, 1, 0);
+}
+
+static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, cudaStream_t s,
+                        int frame_offset) {
+    if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
+    const PlanDev& d = c->plan->d;
+    const size_t fb = (size_t)d.W * d.H * 3;
+    for (int done = 0; done < n; done += c->max_frames) {
+        const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
+        int rc;
+        if ((rc = ld_mask(c, frames + done * fb, m, c->mask, s))) return rc;
+        if ((rc = ld_search(c, c->mask, m, c->rec, s))) return rc;
+        if ((rc = fit_impl(c, c->rec, m, c->fit, s, frame_offset + done))) return rc;
+        if ((rc = ld_overlay(c, frames + done * fb, c->fit, m, out + done * fb, s))) return rc;
+        if (fit_out) LD_CUDA(cudaMemcpyAsync(fit_out + done, c->fit, sizeof(ld_frame_fit) * m, cudaMemcpyDeviceToDevice, s));
+    }
+    return LD_OK;
+}
+extern "C" int ld_process_batch(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, void* stream) {
+    return process_impl(c, frames, n, out, fit_out, (cudaStream_t)stream, 0);
+}
+
+extern "C" int ld_check(ld_ctx* c, void* stream, int* first_bad_frame) {
+    if (!c) return LD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    LD_CUDA(cudaMemcpyAsync(c->flags_host, c->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    LD_CUDA(cudaStreamSynchronize(s));
+    const int last_bad = c->flags_host[2], poly = c->flags_host[3];
+    if (first_bad_frame) *first_bad_frame = last_bad;
+    if (last_bad >= 0) {                                        // report once, then clear (the reference raised and moved on)
+        cudaMemsetAsync(c->flags + 2, 0xFF, sizeof(int), s);
+        return LD_ERR_EMPTY_LANE;
+    }
+    if (poly) { cudaMemsetAsync(c->flags + 3, 0, sizeof(int), s); return LD_ERR_POLYGON; }
+    return LD_OK;
+}
+
+extern "C" int ld_process_batch_host(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fits) {
+    if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
+    LD_CUDA(cudaSetDevice(c->plan->device));
+    const PlanDev& d = c->plan->d;
+    const size_t fb = (size_t)d.W * d.H * 3;
+    int chunk_i = 0, rc = LD_OK;
+    for (int done = 0; done < n; done += c->chunk, ++chunk_i) {
+        const int m = (n - done) < c->chunk ? (n - done) : c->chunk;
+        const int b = chunk_i & 1;
+        if (chunk_i >= 2) {
+            LD_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_comp[b], 0));        // stage_in[b] consumed by chunk i-2
+            LD_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_out[b], 0));       // stage_out[b] drained by chunk i-2
+        }
+        LD_CUDA(cudaMemcpyAsync(c->stage_in[b], frames + done * fb, m * fb, cudaMemcpyHostToDevice, c->s_in));
+        LD_CUDA(cudaEventRecord(c->ev_in[b], c->s_in));
+        LD_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_in[b], 0));
+        if ((rc = process_impl(c, c->stage_in[b], m, c->stage_out[b], nullptr, c->s_comp, done))) break;
+        if (fits) LD_CUDA(cudaMemcpyAsync(fits + done, c->fit, sizeof(ld_frame_fit) * m, cudaMemcpyDeviceToHost, c->s_comp));
+        LD_CUDA(cudaEventRecord(c->ev_comp[b], c->s_comp));
+        LD_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_comp[b], 0));
+        LD_CUDA(cudaMemcpyAsync(out + done * fb, c->stage_out[b], m * fb, cudaMemcpyDeviceToHost, c->s_out));
+        LD_CUDA(cudaEventRecord(c->ev_out[b], c->s_out));
+    }
+    LD_CUDA(cudaStreamSynchronize(c->s_in));
+    const int st = ld_check(c, c->s_comp, &c->flags_host[8]);   // flags_host[8] = index of the offending frame
+    LD_CUDA(cudaStreamSynchronize(c->s_out));
+    if (rc) return rc;
+    return st;
+}
+
+// ------------------------------------------------------------------------------------- tracker state
+extern "C" int ld_state_reset(ld_ctx* c, void* stream) {
+    if (!c) return LD_ERR_ARG;
+    k_state_reset<<<1, 128, 0, (cudaStream_t)stream>>>(c->state);
+    LD_CUDA(cudaMemsetAsync(c->flags + 2, 0xFF, sizeof(int), (cudaStream_t)stream));
+    return check_launch();
+}
+extern "C" size_t ld_state_size(void) { return sizeof(TrackState); }
+extern "C" int ld_state_export(ld_ctx* c, void* blob, void* stream) {
+    if (!c || !blob) return LD_ERR_ARG;
+    LD_CUDA(cudaMemcpyAsync(blob, c->state, sizeof(TrackState), cudaMemcpyDefault, (cudaStream_t)stream));
+    LD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return LD_OK;
+}
+extern "C" int ld_state_import(ld_ctx* c, const void* blob, void* stream) {
+    if (!c || !blob) return LD_ERR_ARG;
+    LD_CUDA(cudaMemcpyAsync(c->state, blob, sizeof(TrackState), cudaMemcpyDefault, (cudaStream_t)stream));
+    LD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return LD_OK;
+}
+
+// ------------------------------------------------------------------------------------- helper.py surface
+extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    const int quads = d.W * d.H / 4;
+    k_undistort<<<dim3((quads + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(frames, out, d);
+    return check_launch();
+}
+extern "C" int ld_warp(ld_ctx* c, const uint8_t* img, int n, int channels, uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, img, out, n) || (channels != 1 && channels != 3)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    k_warp<<<dim3((d.W * d.H + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, out, d, channels);
+    return check_launch();
+}
+extern "C" int ld_colour_mask(ld_ctx* c, const uint8_t* img, int n, uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, img, out, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    k_colour_mask<<<dim3((d.W * d.H + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, out, d);
+    return check_launch();
+}
+extern "C" int ld_pack_mask(ld_ctx* c, const uint8_t* bin, int n, uint32_t* mask, void* stream) {
+    if (!ARGS_OK(c, bin, mask, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const size_t np = (size_t)c->plan->d.W * c->plan->d.H * n;
+    k_pack_mask<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bin, mask, np);
+    return check_launch();
+}
+extern "C" int ld_unpack_mask(ld_ctx* c, const uint32_t* mask, int n, uint8_t* bin, void* stream) {
+    if (!ARGS_OK(c, mask, bin, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const size_t np = (size_t)c->plan->d.W * c->plan->d.H * n;
+    k_unpack_mask<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, bin, np);
+    return check_launch();
+}

@@ -1,0 +1,270 @@
+"""LaneEngine: one plan + one context (= one video stream on one GPU) behind a small Python API.
+
+torch is used for what it is good at here -- device/pinned memory and streams; every computation
+goes through the C ABI of csrc/liblanedet.so (include/lanedet.h).  All *_dev methods take and
+return CUDA tensors and are asynchronous on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from .plan import LanePlan, Variant, VARIANTS, build_plan
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class LaneEngine:
+    def __init__(self, variant="project", mtx=None, dist=None, size=(1280, 720), device: Optional[int] = None,
+                 max_frames: int = 64, l_thresh=None, b_thresh=None, plan: Optional[LanePlan] = None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("advanced-lane-detection_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.torch = torch
+        self.lib = _abi.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        if plan is None:
+            v = VARIANTS[variant] if isinstance(variant, str) else variant
+            plan = build_plan(v, mtx, dist, size, l_thresh, b_thresh)
+        self.plan = plan
+        self.variant: Variant = plan.variant
+        self.W, self.H = plan.size
+        self.WW = self.W // 32
+        self.max_frames = int(max_frames)
+        self._keep = []                     # host arrays referenced by the descriptor
+        self._plan_h = C.c_void_p()
+        self._ctx_h = C.c_void_p()
+        _abi.check(self.lib, self.lib.ld_plan_create(C.byref(self._descriptor(plan)), self.device, C.byref(self._plan_h)))
+        _abi.check(self.lib, self.lib.ld_ctx_create(self._plan_h, self.max_frames, C.byref(self._ctx_h)))
+        self._pin_in = self._pin_out = self._pin_fit = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _descriptor(self, p: LanePlan) -> _abi.PlanDesc:
+        v = p.variant
+
+        def host(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            self._keep.append(a)
+            return a.ctypes.data
+
+        d = _abi.PlanDesc()
+        d.width, d.height = p.size
+        d.search_mode, d.margin, d.minpix, d.frame_num = v.search, v.margin, v.minpix, v.frame_num
+        d.top_anchor, d.clip_polygon, d.curv_fixed_xm = int(v.top_anchor), int(v.clip_polygon), int(v.curv_fixed_xm)
+        d.n_tiles = len(p.tiles)
+        d.ym_per_pix = v.ym_per_pix
+        d.und_map, d.wtab = host(p.und_map, np.uint32), host(p.wtab, np.int16)
+        d.near_map, d.tiles, d.bmap = host(p.near, np.int32), host(p.tiles, np.int32), host(p.bmap, np.uint16)
+        d.ctab, d.cbits = host(p.ctab, np.uint32), host(p.cbits, np.uint32)
+        d.inv_y0, d.inv_y1 = p.inv_y0, p.inv_y1
+        d.inv_idx, d.inv_fi = host(p.inv_idx, np.uint32), host(p.inv_fi, np.uint16)
+        d.glyph_bits, d.glyph_adv = host(p.glyph_bits, np.uint32), host(p.glyph_adv, np.int32)
+        d.n_glyphs = len(p.glyph_adv)
+        return d
+
+    def close(self):
+        if getattr(self, "_ctx_h", None) and self._ctx_h.value:
+            self.lib.ld_ctx_destroy(self._ctx_h)
+            self._ctx_h = C.c_void_p()
+        if getattr(self, "_plan_h", None) and self._plan_h.value:
+            self.lib.ld_plan_destroy(self._plan_h)
+            self._plan_h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, shape, dtype):
+        return self.torch.empty(shape, dtype=dtype, device="cuda:%d" % self.device)
+
+    def _frames(self, t, channels=3):
+        torch = self.torch
+        if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError("expected a contiguous CUDA uint8 tensor")
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        want = (self.H, self.W, channels) if channels > 1 else (self.H, self.W)
+        if tuple(t.shape[1:]) != want:
+            raise ValueError("expected frames of shape %s, got %s" % (want, tuple(t.shape[1:])))
+        return t
+
+    def to_device(self, a):
+        return self.torch.as_tensor(np.ascontiguousarray(a)).to("cuda:%d" % self.device)
+
+    def check(self):
+        """Wait for the current stream; raise TypeError like the reference if a tracker had no points."""
+        bad = C.c_int(-1)
+        _abi.check(self.lib, self.lib.ld_check(self._ctx_h, self._stream(), C.byref(bad)))
+
+    # ------------------------------------------------------------------ hot path, stage by stage
+    def mask_dev(self, frames):
+        """undistort + warp + luv_lab_filter -> packed mask int32[n,H,W/32] (bit i of word k = pixel 32k+i)."""
+        frames = self._frames(frames)
+        out = self._dev((frames.shape[0], self.H, self.WW), self.torch.int32)
+        _abi.check(self.lib, self.lib.ld_mask(self._ctx_h, _ptr(frames), frames.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def hist_dev(self, mask):
+        out = self._dev((mask.shape[0], 8, self.W), self.torch.int16)
+        _abi.check(self.lib, self.lib.ld_hist(self._ctx_h, _ptr(mask), mask.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def search_dev(self, mask):
+        out = self._dev((mask.shape[0], 2, _abi.RECORD_DTYPE.itemsize), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_search(self._ctx_h, _ptr(mask), mask.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def fit_dev(self, records):
+        n = records.shape[0]
+        out = self._dev((n, _abi.FIT_DTYPE.itemsize), self.torch.uint8)
+        for a in range(0, n, self.max_frames):
+            b = min(n, a + self.max_frames)
+            _abi.check(self.lib, self.lib.ld_fit(self._ctx_h, _ptr(records[a:b]), b - a, _ptr(out[a:b]), self._stream()))
+        return out
+
+    def overlay_dev(self, frames, fits):
+        frames = self._frames(frames)
+        out = self.torch.empty_like(frames)
+        _abi.check(self.lib, self.lib.ld_overlay(self._ctx_h, _ptr(frames), _ptr(fits), frames.shape[0], _ptr(out),
+                                                 self._stream()))
+        return out
+
+    def process_dev(self, frames, out=None, fits=None):
+        """process_image for a batch of device-resident frames, in frame order."""
+        frames = self._frames(frames)
+        n = frames.shape[0]
+        if out is None:
+            out = self.torch.empty_like(frames)
+        if fits is None:
+            fits = self._dev((n, _abi.FIT_DTYPE.itemsize), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_process_batch(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits), self._stream()))
+        return out, fits
+
+    def process_host(self, frames: np.ndarray, want_fits: bool = True):
+        """process_image for a batch of host frames (uint8 [n,H,W,3]); copies in/out are pipelined inside."""
+        torch = self.torch
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        n = frames.shape[0]
+        if frames.shape[1:] != (self.H, self.W, 3):
+            raise ValueError("expected frames of shape (n, %d, %d, 3)" % (self.H, self.W))
+        if self._pin_in is None or self._pin_in.shape[0] < n:
+            self._pin_in = torch.empty((n, self.H, self.W, 3), dtype=torch.uint8, pin_memory=True)
+            self._pin_out = torch.empty((n, self.H, self.W, 3), dtype=torch.uint8, pin_memory=True)
+            self._pin_fit = torch.empty((n, _abi.FIT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+        self._pin_in[:n].numpy()[...] = frames
+        self.process_pinned(self._pin_in[:n], self._pin_out[:n], self._pin_fit[:n] if want_fits else None)
+        out = self._pin_out[:n].numpy().copy()
+        fits = self._pin_fit[:n].numpy().copy().view(_abi.FIT_DTYPE).reshape(n) if want_fits else None
+        return out, fits
+
+    def process_pinned(self, pin_in, pin_out, pin_fit=None):
+        """The timed end-to-end call of bench.py: pinned host in -> pinned host out, synchronous."""
+        n = pin_in.shape[0]
+        st = self.lib.ld_process_batch_host(self._ctx_h, _ptr(pin_in), n, _ptr(pin_out),
+                                            _ptr(pin_fit) if pin_fit is not None else None)
+        _abi.check(self.lib, st)
+
+    # ------------------------------------------------------------------ tracker state
+    def reset(self):
+        _abi.check(self.lib, self.lib.ld_state_reset(self._ctx_h, self._stream()))
+
+    def export_state(self) -> bytes:
+        buf = C.create_string_buffer(self.lib.ld_state_size())
+        _abi.check(self.lib, self.lib.ld_state_export(self._ctx_h, buf, self._stream()))
+        return buf.raw
+
+    def import_state(self, blob: bytes):
+        if len(blob) != self.lib.ld_state_size():
+            raise ValueError("tracker state blob has the wrong size")
+        _abi.check(self.lib, self.lib.ld_state_import(self._ctx_h, C.create_string_buffer(blob, len(blob)), self._stream()))
+
+    def export_state_dev(self, blob_dev):
+        """tracker blob into a CUDA uint8 tensor (what ranks exchange over NVLink)"""
+        _abi.check(self.lib, self.lib.ld_state_export(self._ctx_h, _ptr(blob_dev), self._stream()))
+        return blob_dev
+
+    def import_state_dev(self, blob_dev):
+        _abi.check(self.lib, self.lib.ld_state_import(self._ctx_h, _ptr(blob_dev), self._stream()))
+
+    def overlay_into(self, frames, fits, out):
+        frames = self._frames(frames)
+        _abi.check(self.lib, self.lib.ld_overlay(self._ctx_h, _ptr(frames), _ptr(fits), frames.shape[0], _ptr(out),
+                                                 self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ helper.py surface
+    def undistort_dev(self, frames):
+        frames = self._frames(frames)
+        out = self.torch.empty_like(frames)
+        _abi.check(self.lib, self.lib.ld_undistort(self._ctx_h, _ptr(frames), frames.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def warp_dev(self, img):
+        channels = 3 if (img.dim() == 4 or (img.dim() == 3 and img.shape[-1] == 3)) else 1
+        img = self._frames(img, channels)
+        out = self.torch.empty_like(img)
+        _abi.check(self.lib, self.lib.ld_warp(self._ctx_h, _ptr(img), img.shape[0], channels, _ptr(out), self._stream()))
+        return out
+
+    def colour_mask_dev(self, img):
+        img = self._frames(img)
+        out = self._dev((img.shape[0], self.H, self.W), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_colour_mask(self._ctx_h, _ptr(img), img.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def pack_dev(self, binary):
+        binary = self._frames(binary, 1)
+        out = self._dev((binary.shape[0], self.H, self.WW), self.torch.int32)
+        _abi.check(self.lib, self.lib.ld_pack_mask(self._ctx_h, _ptr(binary), binary.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def unpack_dev(self, mask):
+        out = self._dev((mask.shape[0], self.H, self.W), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_unpack_mask(self._ctx_h, _ptr(mask), mask.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def margin_search_dev(self, mask, fits):
+        """helper.skip_sliding_window: fits = float64[n,2,3] (left, right)."""
+        out = self._dev((mask.shape[0], 2, _abi.RECORD_DTYPE.itemsize), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_margin_search(self._ctx_h, _ptr(mask), _ptr(fits), mask.shape[0], _ptr(out),
+                                                       self._stream()))
+        return out
+
+    def polyfit_dev(self, records):
+        n = records.numel() // _abi.RECORD_DTYPE.itemsize
+        coef = self._dev((n, 3), self.torch.float64)
+        rank = self._dev((n,), self.torch.int32)
+        _abi.check(self.lib, self.lib.ld_polyfit(self._ctx_h, _ptr(records), n, _ptr(coef), _ptr(rank), self._stream()))
+        return coef, rank
+
+    def draw_dev(self, undist, verts, counts, thickness=30):
+        """draw_area on already-undistorted frames with explicit integer polygon vertices
+        (verts int32[n,max_verts,2], counts int32[n])."""
+        undist = self._frames(undist)
+        out = self.torch.empty_like(undist)
+        _abi.check(self.lib, self.lib.ld_draw(self._ctx_h, _ptr(undist), _ptr(verts), _ptr(counts), verts.shape[1],
+                                              thickness, undist.shape[0], _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ host views
+    @staticmethod
+    def records_to_numpy(t):
+        a = t.cpu().numpy()
+        return a.view(_abi.RECORD_DTYPE).reshape(a.shape[:-1])
+
+    @staticmethod
+    def fits_to_numpy(t):
+        a = t.cpu().numpy()
+        return a.view(_abi.FIT_DTYPE).reshape(a.shape[:-1])

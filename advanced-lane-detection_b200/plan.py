@@ -266,7 +266,7 @@ def mask_tiles(nx, ny, size, max_bits=61440, target_tiles=24):
 
 
 # ----------------------------------------------------------------------------- text
-TEXT_X0, TEXT_Y0, TEXT_WORDS, TEXT_ROWS = 32, 72, 24, 70     # the window of the frame putText can touch
+TEXT_X0, TEXT_Y0, TEXT_WORDS, TEXT_ROWS = 32, 70, 24, 70     # the window of the frame putText can touch (lanedet.h LD_TEXT_*)
 GLYPH_CHARS = "0123456789-.RO(I"   # R = 'Radius of Curvature: ', O = 'Offset from center: ', ( = '(m)', I = 'Inf (m)'
 GLYPH_STRINGS = {"R": "Radius of Curvature: ", "O": "Offset from center: ", "(": "(m)", "I": "Inf (m)"}
 GLYPH_ROWS, GLYPH_WORDS = 40, 12   # bitmap cell: 40 rows x 384 px, row 0 = baseline-30, col 0 = pen-2

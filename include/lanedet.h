@@ -1,0 +1,179 @@
+/* lanedet.h -- C ABI of liblanedet.so, the sm_100a implementation of the per-frame lane-finding
+ * hot path of uranus4ever/Advanced-Lane-Detection.
+ *
+ * The reference has no FFI: its boundary is the Python module surface that moviepy's
+ * fl_image calls (Project.py:360 -> process_image, Project.py:289-334).  Each entry point below
+ * names the reference function(s) whose arithmetic it replaces; INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions: every function returns an int status (LD_OK == 0), never throws, never prints.
+ * "dev" pointers are CUDA device pointers on the plan's device; "host" pointers are ordinary (ideally
+ * pinned) host memory.  `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ * stream); all *_dev calls are asynchronous on that stream.  Frames are uint8 RGB, HWC,
+ * contiguous, `width x height` of the plan.  Nothing here falls back to the CPU.
+ */
+#ifndef LANEDET_H
+#define LANEDET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LD_ABI_VERSION 1
+
+enum {
+    LD_OK = 0,
+    LD_ERR_ARG = 1,          /* bad argument (null pointer, size mismatch, n > max_frames ...) */
+    LD_ERR_CUDA = 2,         /* a CUDA runtime call failed; see ld_last_cuda_error() */
+    LD_ERR_NO_DEVICE = 3,    /* no CUDA device / wrong architecture */
+    LD_ERR_EMPTY_LANE = 4,   /* a lane had no pixels and the tracker had no previous points:
+                                the reference raises TypeError("expected 1D vector for x")
+                                (Project.py:98-100 -> :308-311 -> :118) */
+    LD_ERR_POLYGON = 5       /* draw: more than LD_MAX_CROSSINGS polygon edges cross one scanline */
+};
+
+enum { LD_SEARCH_PROJECT = 0, LD_SEARCH_HARDER = 1, LD_SEARCH_HELPER = 2 };
+enum { LD_MAX_DEPTH = 16, LD_MAX_WINDOWS = 9, LD_ROWMAP_WORDS = 24, LD_MAX_CROSSINGS = 8 };
+enum { LD_TEXT_X0 = 32, LD_TEXT_Y0 = 70, LD_TEXT_WORDS = 24, LD_TEXT_ROWS = 70,
+       LD_GLYPH_ROWS = 40, LD_GLYPH_WORDS = 12, LD_TEXT_MAX_GLYPHS = 24 };
+
+/* Host-side description of a plan: the constant tables advanced-lane-detection_b200/plan.py builds
+ * (all pointers are HOST pointers, copied to the device by ld_plan_create). */
+typedef struct ld_plan_desc {
+    int32_t width, height;
+    int32_t search_mode;             /* LD_SEARCH_* : Project.py:73-101 / harder:73-142 / helper.py:224-328 */
+    int32_t margin, minpix;          /* Project.py:88 (50) / harder:79-80 (45, 50) / helper.py:246-248 (50, 40) */
+    int32_t frame_num;               /* deque depth, Project.py:350 (15) / harder:426 (5) */
+    int32_t top_anchor;              /* Project.py:128,130 appends (top_x, 0); harder:169,171 does not */
+    int32_t clip_polygon;            /* harder:192-197 */
+    int32_t curv_fixed_xm;           /* harder:227-228 (3.7/700) vs Project.py:202 (3.7/|xl-xr|) */
+    int32_t n_tiles;
+    double ym_per_pix;               /* Project.py:179,201 (18/720) / harder:227 (30/720) */
+    const uint32_t* und_map;         /* [H*W]   cv2.undistort tap origin + 10-bit fraction */
+    const int16_t* wtab;             /* [1024*4] OpenCV 8U bilinear weights */
+    const int32_t* near_map;         /* [H*W]   INTER_NEAREST source index of warp(), -1 = border */
+    const int32_t* tiles;            /* [n_tiles*8] mask-kernel bands */
+    const uint16_t* bmap;            /* [H*W]   bird's-eye pixel -> bit of its band's box */
+    const uint32_t* ctab;            /* [65536] colour decision, <=2 B-intervals per (R,G) */
+    const uint32_t* cbits;           /* [1<<19] colour decision, raw bit per colour */
+    int32_t inv_y0, inv_y1;          /* output rows the inverse warp can touch */
+    const uint32_t* inv_idx;         /* [(inv_y1-inv_y0)*W] */
+    const uint16_t* inv_fi;          /* [(inv_y1-inv_y0)*W] */
+    const uint32_t* glyph_bits;      /* [n_glyphs*40*12] */
+    const int32_t* glyph_adv;        /* [n_glyphs] */
+    int32_t n_glyphs;
+    int32_t reserved;
+} ld_plan_desc;
+
+/* One lane of one frame as the window search leaves it (Line.blind_search, Project.py:73-101):
+ * exact integer power sums of the selected pixels instead of the pixel lists. */
+typedef struct ld_lane_record {
+    uint64_t mom[8];                 /* n, Sy, Sy2, Sy3, Sy4, Sx, Sxy, Sxy2 */
+    uint32_t rowmap[LD_ROWMAP_WORDS];/* bit y: row y holds >=1 selected pixel */
+    int32_t ok;                      /* np.sum(x_inds) > 0  (Project.py:96) */
+    int32_t n_windows;
+    int32_t win_base[LD_MAX_WINDOWS];
+    int32_t win_n[LD_MAX_WINDOWS];
+    int32_t win_kept[LD_MAX_WINDOWS];
+    int32_t pad;
+} ld_lane_record;
+
+/* Everything process_image derives from the two lanes of one frame (Project.py:313-332). */
+typedef struct ld_frame_fit {
+    double fit[2][3];                /* Line.fit: medians of the A/B/C deques (Project.py:138) */
+    double fit1[2][3];               /* first np.polyfit (Project.py:118) */
+    double fit2[2][3];               /* second np.polyfit with the anchors (Project.py:133) */
+    double bottom[2], top[2];        /* median intercepts used as anchors (Project.py:124-125) */
+    double curv[2];
+    double offset, mean_curv;        /* car_pos (Project.py:192-219) */
+    int32_t rank1[2], rank2[2];      /* <3 => numpy would emit RankWarning */
+    int32_t detected[2];
+    int32_t n_points[2];             /* len(Line.fity) */
+    int32_t status;                  /* LD_OK or LD_ERR_EMPTY_LANE */
+    int32_t n_text[2];               /* glyphs of the two putText lines */
+    uint8_t text[2][LD_TEXT_MAX_GLYPHS];
+    uint32_t rowmap[2][LD_ROWMAP_WORDS]; /* distinct values of Line.fity (bit 720 = bottom anchor) */
+    int32_t pad;
+} ld_frame_fit;
+
+typedef struct ld_plan ld_plan;
+typedef struct ld_ctx ld_ctx;
+
+int ld_abi_version(void);
+const char* ld_error_string(int status);
+const char* ld_last_cuda_error(void);
+
+/* plan / context ------------------------------------------------------------------------- */
+int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** out);
+int ld_plan_destroy(ld_plan* plan);
+/* A context owns the workspace for up to max_frames frames per call and the two Line trackers
+ * (`left`, `right`, Project.py:351-352).  One context per stream / video. */
+int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out);
+int ld_ctx_destroy(ld_ctx* ctx);
+
+/* the hot path, stage by stage (device buffers) ------------------------------------------ */
+/* cv2.undistort + warp + luv_lab_filter (Project.py:294-295, 222-248) -> packed mask
+ * u32[n][H][W/32], bit i of word k = pixel 32k+i. */
+int ld_mask(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint32_t* mask_dev, void* stream);
+/* np.sum(image[top:bottom,:], axis=0) for the eight 90-row bands (Project.py:83) ->
+ * u16[n][8][W], band k = rows [H-90(k+1), H-90k). */
+int ld_hist(ld_ctx* ctx, const uint32_t* mask_dev, int n, uint16_t* hist_dev, void* stream);
+/* Line.blind_search for both lanes (Project.py:73-101 / harder:73-142 / helper.py:224-328)
+ * -> ld_lane_record[n][2]. */
+int ld_search(ld_ctx* ctx, const uint32_t* mask_dev, int n, ld_lane_record* rec_dev, void* stream);
+/* Line.get_fit x2 + car_pos + curvature (Project.py:113-141, 173-219), in frame order, updating the
+ * context's trackers -> ld_frame_fit[n]. */
+int ld_fit(ld_ctx* ctx, const ld_lane_record* rec_dev, int n, ld_frame_fit* fit_dev, void* stream);
+/* draw_area + putText (Project.py:144-170, 320-332) on the undistorted frame -> u8[n][H][W][3]. */
+int ld_overlay(ld_ctx* ctx, const uint8_t* frames_dev, const ld_frame_fit* fit_dev, int n,
+               uint8_t* out_dev, void* stream);
+/* process_image for n consecutive frames (Project.py:289-334).  fit_dev may be NULL. */
+int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev,
+                     ld_frame_fit* fit_dev, void* stream);
+/* Same with host buffers: chunks are copied in, processed and copied out on three streams.
+ * Synchronous; returns LD_ERR_EMPTY_LANE like the reference raises.  fits_host may be NULL. */
+int ld_process_batch_host(ld_ctx* ctx, const uint8_t* frames_host, int n, uint8_t* out_host,
+                          ld_frame_fit* fits_host);
+/* Waits for `stream` and reports the first per-frame error of the calls issued so far
+ * (*first_bad_frame = index inside the last ld_fit / ld_process_batch call, or -1). */
+int ld_check(ld_ctx* ctx, void* stream, int* first_bad_frame);
+
+/* tracker state (class Line, Project.py:11-37): reset, and an opaque blob for hand-off between
+ * GPUs / checkpointing ------------------------------------------------------------------- */
+int ld_state_reset(ld_ctx* ctx, void* stream);
+size_t ld_state_size(void);
+/* `blob` may be host or device memory (UVA); device blobs are what ranks exchange over NVLink. */
+int ld_state_export(ld_ctx* ctx, void* blob, void* stream);
+int ld_state_import(ld_ctx* ctx, const void* blob, void* stream);
+
+/* helper.py surface (device buffers) ------------------------------------------------------ */
+/* cv2.undistort(img, mtx, dist, None, mtx) (helper.py:35-47, Project.py:294) */
+int ld_undistort(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
+/* warp(): cv2.warpPerspective(img, M, (W,H), INTER_NEAREST) (helper.py:11-21); channels = 1 or 3 */
+int ld_warp(ld_ctx* ctx, const uint8_t* img_dev, int n, int channels, uint8_t* out_dev, void* stream);
+/* helper.luv_lab_filter (helper.py:125-147, no warp): u8 RGB -> u8 {0,1}[n][H][W] */
+int ld_colour_mask(ld_ctx* ctx, const uint8_t* img_dev, int n, uint8_t* out_dev, void* stream);
+/* u8 {0,!=0}[n][H][W] <-> packed u32[n][H][W/32] */
+int ld_pack_mask(ld_ctx* ctx, const uint8_t* bin_dev, int n, uint32_t* mask_dev, void* stream);
+int ld_unpack_mask(ld_ctx* ctx, const uint32_t* mask_dev, int n, uint8_t* bin_dev, void* stream);
+/* helper.skip_sliding_window (helper.py:331-378): pixels with |x - fit(y)| < 100 for each of the two
+ * previous fits (fits_dev = double[n][2][3]) -> ld_lane_record[n][2] (ok = at least 10 pixels). */
+int ld_margin_search(ld_ctx* ctx, const uint32_t* mask_dev, const double* fits_dev, int n,
+                     ld_lane_record* rec_dev, void* stream);
+/* np.polyfit(y, x, 2) of each record's pixel set with rcond = n*2^-52 (helper.py:309-310,362-363)
+ * -> double[n_records][3], int32 rank[n_records] */
+int ld_polyfit(ld_ctx* ctx, const ld_lane_record* rec_dev, int n_records, double* coef_dev,
+               int32_t* rank_dev, void* stream);
+/* draw_area with explicit polygon vertices (Project.py:144-170; helper.py:758-779 when
+ * thickness == 0): verts_dev = int32[n][max_verts][2] (x,y after np.int_), counts_dev = int32[n].
+ * `undist_dev` is ALREADY undistorted. */
+int ld_draw(ld_ctx* ctx, const uint8_t* undist_dev, const int32_t* verts_dev, const int32_t* counts_dev,
+            int max_verts, int thickness, int n, uint8_t* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANEDET_H */

@@ -1,0 +1,156 @@
+"""CPU-only: the C-ABI library builds/loads/exports what include/lanedet.h declares, the plan tables
+reproduce cv2 (through the numpy emulation of what the kernels do with them), host logic of the package."""
+import ctypes
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_pkg
+from oracle import lane_port as O
+import emu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+    g.build()
+    return load_pkg()
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    abi = pkg._abi
+    declared = abi.declared_symbols()
+    assert len(declared) >= 25 and "ld_process_batch" in declared
+    lib = ctypes.CDLL(abi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(declared) == sorted(abi._SIGNATURES)
+    assert lib.ld_abi_version() == 1
+    # the dynamic symbol table agrees (no stray C++ mangled exports of the entry points)
+    out = subprocess.run(["nm", "-D", "--defined-only", abi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(declared) <= exported
+
+
+def test_struct_layouts_match_header(pkg):
+    abi = pkg._abi
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "lanedet.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(ld_plan_desc), sizeof(ld_lane_record), sizeof(ld_frame_fit),
+             offsetof(ld_plan_desc, ym_per_pix), offsetof(ld_plan_desc, inv_idx), offsetof(ld_frame_fit, rowmap),
+             offsetof(ld_lane_record, win_base));
+      return 0; }'''
+    exe = os.path.join(ROOT, "tests", "hostsim", "_layout")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True, check=True)
+    got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    os.remove(exe)
+    want = [ctypes.sizeof(abi.PlanDesc), ctypes.sizeof(abi.LaneRecord), ctypes.sizeof(abi.FrameFit),
+            abi.PlanDesc.ym_per_pix.offset, abi.PlanDesc.inv_idx.offset, abi.FrameFit.rowmap.offset,
+            abi.LaneRecord.win_base.offset]
+    assert got == want
+
+
+def test_no_gpu_means_loud_failure(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pkg.LaneEngine("project")
+    desc = pkg._abi.PlanDesc()
+    h = ctypes.c_void_p()
+    assert pkg._lib.ld_plan_create(ctypes.byref(desc), 0, ctypes.byref(h)) == pkg._abi.LD_ERR_ARG
+
+
+def test_product_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "advanced-lane-detection_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "lane_port" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+@pytest.mark.parametrize("variant", ["project", "harder"])
+def test_plan_tables_reproduce_cv2(pkg, variant, stills):
+    import cv2
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    plan = P.build_plan(P.VARIANTS[variant])
+    orc = O.LaneOracle(variant)
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    for img in (stills("test2"), stills("test_ch12"), noise):
+        und = O.undistort(img, orc.mtx, orc.dist)
+        assert (emu.emu_undistort(plan, img) == und).all()
+        assert (emu.emu_mask(plan, img) == O.binary_birdseye(und, orc.v)).all()
+    assert (emu.emu_warp_nearest(plan, noise) == O.birdseye(noise, orc.v)).all()
+    minv = cv2.getPerspectiveTransform(np.float32(orc.v.dst), np.float32(orc.v.src))
+    back = cv2.warpPerspective(noise, minv, (1280, 720))
+    assert (emu.emu_inverse_warp(plan, noise) == back).all()
+    und = O.undistort(noise, orc.mtx, orc.dist)
+    assert (emu.emu_blend(und, back) == cv2.addWeighted(und, 1, back, 0.3, 0)).all()
+    assert plan.mask_algorithmic_bytes == {"project": 1006080, "harder": 825600}[variant]
+    t = plan.tiles
+    assert t[0, 0] == 0 and t[-1, 1] == 720 and (t[1:, 0] == t[:-1, 1]).all()
+    assert (t[:, 4] * 32 * t[:, 5] < 0xFFFF).all()
+
+
+def test_colour_tables_all_colours(pkg):
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    for l, b in (((215, 255), (145, 200)), ((210, 255), (143, 200)), ((100, 180), (120, 150))):
+        ctab, cbits = P.colour_tables(l, b)
+        L, Bc = P._all_colour_channels()
+        on = ((L >= l[0]) & (L <= l[1])) | ((Bc >= b[0]) & (Bc <= b[1]))
+        bits = np.unpackbits(cbits.view(np.uint8), bitorder="little").reshape(256, 256, 256).astype(bool)
+        assert (bits == on).all()
+        bv = np.arange(256)[None, :]
+        e = ctab.astype(np.int64)[:, None]
+        dec = ((bv >= (e & 255)) & (bv <= ((e >> 8) & 255))) | ((bv >= ((e >> 16) & 255)) & (bv <= (e >> 24)))
+        exc = (ctab == P.CTAB_EXCEPTION)
+        assert (dec[~exc] == on.reshape(65536, 256)[~exc]).all()
+        assert exc.sum() < 64
+
+
+def test_text_atlas_composes_like_puttext(pkg):
+    import cv2
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    bits, adv = P.glyph_atlas()
+    font = cv2.FONT_HERSHEY_SIMPLEX
+
+    def compose(glyphs, baseline, canvas):
+        pen = 60
+        for g in glyphs:
+            bm = np.unpackbits(bits[g].view(np.uint8), axis=1, bitorder="little").astype(bool)
+            ys, xs = np.nonzero(bm)
+            canvas[baseline - 30 + ys, pen - 2 + xs] = 255
+            pen += adv[g]
+
+    idx = {c: i for i, c in enumerate(P.GLYPH_CHARS)}
+    for curv, off in ((1266, "-0.33"), (2999, "0.00"), (7, "-12.50"), (None, "1.07")):
+        want = np.zeros((200, 900), np.uint8)
+        t1 = "Radius of Curvature: %d(m)" % curv if curv is not None else "Radius of Curvature: Inf (m)"
+        cv2.putText(want, t1, (60, 100), font, 1.0, 255, thickness=2)
+        cv2.putText(want, "Offset from center: %s(m)" % off, (60, 130), font, 1.0, 255, thickness=2)
+        got = np.zeros_like(want)
+        g1 = [idx["R"]] + ([idx[c] for c in str(curv)] + [idx["("]] if curv is not None else [idx["I"]])
+        compose(g1, 100, got)
+        compose([idx["O"]] + [idx[c] for c in off] + [idx["("]], 130, got)
+        assert (got == want).all()
+        ys, xs = np.nonzero(want)
+        assert ys.min() >= P.TEXT_Y0 and ys.max() < P.TEXT_Y0 + P.TEXT_ROWS
+        assert xs.min() >= P.TEXT_X0 and xs.max() < P.TEXT_X0 + 32 * P.TEXT_WORDS
+
+
+def test_partition():
+    S = importlib.import_module("advanced-lane-detection_b200.sharding")
+    assert S.partition(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert S.partition(1260, 8)[-1] == (1260 - 157, 1260)
+    assert sum(b - a for a, b in S.partition(1261, 8)) == 1261
+    with pytest.raises(ValueError):
+        S.partition(5, 0)

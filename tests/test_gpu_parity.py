@@ -1,0 +1,227 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden vectors produced by the
+unmodified reference.  Bars (BASELINE.json north_star): masks / histograms / moments bit-exact, fit
+coefficients <= 1e-9 relative, curvature / offset <= 1e-6 relative, overlay within +-1 LSB."""
+import hashlib
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import unhex, load_pkg
+from oracle import lane_port as O
+
+pytestmark = pytest.mark.gpu
+
+PROJECT_STILLS = ["straight_lines1", "straight_lines2"] + ["test%d" % i for i in range(1, 7)]
+ALL = PROJECT_STILLS + ["test_ch%d" % i for i in range(15)]
+FIT_RTOL = 1e-9
+POS_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def engines():
+    pkg = load_pkg()
+    made = {}
+
+    def get(variant):
+        if variant not in made:
+            made[variant] = pkg.LaneEngine(variant, max_frames=48)
+        return made[variant]
+    yield get
+    for e in made.values():
+        e.close()
+
+
+def unpack(mask_t):
+    a = mask_t.cpu().numpy().view(np.uint32)
+    return np.unpackbits(a.view(np.uint8), axis=-1, bitorder="little").reshape(a.shape[0], a.shape[1], -1)
+
+
+def assert_fit_close(got, want, what):
+    got, want = np.asarray(got, float), np.asarray(want, float)
+    err = np.abs(got - want) / np.abs(want)
+    assert (err <= FIT_RTOL).all(), "%s: rel err %s (got %s want %s)" % (what, err, got, want)
+
+
+@pytest.mark.parametrize("variant", ["project", "harder"])
+def test_mask_hist_search_stills(variant, engines, stills, golden):
+    eng = engines(variant)
+    orc = O.LaneOracle(variant)
+    frames = np.stack([stills(n) for n in ALL])
+    dev = eng.to_device(frames)
+    mask_t = eng.mask_dev(dev)
+    masks = unpack(mask_t)
+    hist = eng.hist_dev(mask_t).cpu().numpy().astype(np.int64)
+    rec = eng.records_to_numpy(eng.search_dev(mask_t))
+    for i, name in enumerate(ALL):
+        g = golden["stills"][name][variant]
+        want = O.binary_birdseye(O.undistort(frames[i], orc.mtx, orc.dist), orc.v)
+        assert (masks[i] == want).all(), "%s mask differs in %d px" % (name, (masks[i] != want).sum())
+        assert int(masks[i].sum()) == g["mask_popcount"]
+        assert hashlib.sha1(np.packbits(masks[i].astype(bool), axis=1, bitorder="little").tobytes()).hexdigest() == g["mask_sha1"]
+        assert (hist[i] == O.band_histograms(want)).all(), name
+        for lane in (0, 1):
+            x, y, wins = O.window_search(want, bool(lane), orc.v)
+            r = rec[i, lane]
+            assert [int(b) for b in r["win_base"][:8]] == [w[1] for w in wins], (name, lane)
+            assert [int(b) for b in r["win_n"][:8]] == [w[2] for w in wins], (name, lane)
+            assert [bool(b) for b in r["win_kept"][:8]] == [w[3] for w in wins], (name, lane)
+            if g["lanes"][lane] is None:
+                assert not r["ok"]
+            else:
+                assert r["ok"]
+                assert [str(int(m)) for m in r["mom"]] == g["lanes"][lane]["moments"], (name, lane)
+                rows = np.unique(y)
+                got_rows = np.nonzero(np.unpackbits(r["rowmap"].view(np.uint8), bitorder="little"))[0]
+                assert (rows == got_rows).all()
+
+
+def test_mask_noise_and_extremes(engines):
+    """uniform noise exercises all 1024 bilinear fractions and the whole colour table; flat frames the borders"""
+    eng = engines("project")
+    orc = O.LaneOracle("project")
+    rng = np.random.default_rng(7)
+    frames = [rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8) for _ in range(3)]
+    frames += [np.zeros((720, 1280, 3), np.uint8), np.full((720, 1280, 3), 255, np.uint8)]
+    yellow = np.zeros((720, 1280, 3), np.uint8)
+    yellow[..., 0], yellow[..., 1] = 255, 220
+    frames.append(yellow)
+    frames = np.stack(frames)
+    masks = unpack(eng.mask_dev(eng.to_device(frames)))
+    for i in range(len(frames)):
+        want = O.binary_birdseye(O.undistort(frames[i], orc.mtx, orc.dist), orc.v)
+        assert (masks[i] == want).all(), "frame %d differs in %d px" % (i, (masks[i] != want).sum())
+
+
+def test_colour_decision_all_colours(engines):
+    """all 2^24 colours through the stand-alone colour stage (helper.luv_lab_filter, no warp)"""
+    import cv2
+    eng = engines("project")
+    r, g, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8),
+                          indexing="ij")
+    img = np.stack([r, g, b], -1).reshape(4096, 4096, 3)
+    want = O.colour_mask(img, O.PROJECT.l_thresh, O.PROJECT.b_thresh).reshape(-1)
+    flat = img.reshape(-1, 3)
+    per = 720 * 1280
+    n = (flat.shape[0] + per - 1) // per
+    padded = np.zeros((n * per, 3), np.uint8)
+    padded[:flat.shape[0]] = flat
+    got = []
+    for a in range(0, n, 6):
+        chunk = padded[a * per:(a + 6) * per].reshape(-1, 720, 1280, 3)
+        got.append(eng.colour_mask_dev(eng.to_device(chunk)).cpu().numpy().reshape(-1))
+    got = np.concatenate(got)[:flat.shape[0]]
+    assert (got == want).all(), "%d colours differ" % (got != want).sum()
+    assert int(got.sum()) == 7267295
+
+
+@pytest.mark.parametrize("variant", ["project", "harder"])
+def test_stills_fit_position_overlay(variant, engines, stills, golden):
+    eng = engines(variant)
+    orc = O.LaneOracle(variant)
+    for name in ALL:
+        g = golden["stills"][name][variant]
+        eng.reset()
+        orc.reset()
+        frame = stills(name)
+        dev = eng.to_device(frame[None])
+        if g["status"] != "ok":
+            eng.process_dev(dev)
+            with pytest.raises(TypeError, match="expected 1D vector for x"):
+                eng.check()
+            continue
+        out_t, fit_t = eng.process_dev(dev)
+        eng.check()
+        fit = eng.fits_to_numpy(fit_t)[0]
+        assert_fit_close(fit["fit"][0], [unhex(c) for c in g["left_fit"]], name + " left")
+        assert_fit_close(fit["fit"][1], [unhex(c) for c in g["right_fit"]], name + " right")
+        assert abs(fit["offset"] - unhex(g["offset"])) <= POS_RTOL * abs(unhex(g["offset"]))
+        assert abs(fit["mean_curv"] - unhex(g["mean_curv"])) <= POS_RTOL * abs(unhex(g["mean_curv"]))
+        assert [int(v) for v in fit["n_points"]] == g["n_fit_points"]
+        assert int((np.asarray(fit["rank1"]) < 3).sum() + (np.asarray(fit["rank2"]) < 3).sum()) == g["rank_warnings"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = orc.process(frame).out
+        got = out_t[0].cpu().numpy()
+        diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        assert diff.max() <= 1, "%s: overlay differs by up to %d in %d px" % (name, diff.max(), (diff > 1).any(-1).sum())
+
+
+@pytest.mark.parametrize("key,variant", [("project_seed0_40", "project"), ("harder_seed3_32", "harder"),
+                                         ("project_on_ch_seed3_32", "project")])
+def test_sequences_tracking(key, variant, engines, stills, golden):
+    """Line tracking across frames (deque medians, empty-lane fallback) in ONE batched call, against the
+    reference's frame-by-frame results; then the same sequence split into uneven chunks must give identical bits."""
+    g = golden["sequences"][key]
+    n = len(g["records"])
+    frames = np.stack(list(O.synth_sequence([stills(s) for s in g["stills"]], n, seed=g["seed"])))
+    eng = engines(variant)
+    eng.reset()
+    dev = eng.to_device(frames)
+    out_t, fit_t = eng.process_dev(dev)
+    eng.check()
+    fits = eng.fits_to_numpy(fit_t)
+    orc = O.LaneOracle(variant)
+    out = out_t.cpu().numpy()
+    for i, rec in enumerate(g["records"]):
+        assert_fit_close(fits[i]["fit"][0], [unhex(c) for c in rec["left_fit"]], "%s[%d] left" % (key, i))
+        assert_fit_close(fits[i]["fit"][1], [unhex(c) for c in rec["right_fit"]], "%s[%d] right" % (key, i))
+        assert [bool(v) for v in fits[i]["detected"]] == rec["detected"], i
+        assert [int(v) for v in fits[i]["n_points"]] == rec["n_fit_points"], i
+        assert abs(fits[i]["offset"] - unhex(rec["offset"])) <= POS_RTOL * abs(unhex(rec["offset"]))
+        assert abs(fits[i]["mean_curv"] - unhex(rec["mean_curv"])) <= POS_RTOL * abs(unhex(rec["mean_curv"]))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = orc.process(frames[i]).out
+        diff = np.abs(out[i].astype(np.int16) - want.astype(np.int16))
+        assert diff.max() <= 1, "%s[%d]: overlay differs by up to %d in %d px" % (key, i, diff.max(), (diff > 1).any(-1).sum())
+    # chunked: 1 + 7 + rest, state carried in the context
+    eng.reset()
+    parts = [eng.process_dev(dev[a:b]) for a, b in ((0, 1), (1, 8), (8, n))]
+    eng.check()
+    fits2 = np.concatenate([eng.fits_to_numpy(p[1]) for p in parts])
+    out2 = np.concatenate([p[0].cpu().numpy() for p in parts])
+    assert fits2.tobytes() == fits.tobytes()
+    assert (out2 == out).all()
+    # host entry (pinned, pipelined copies) gives the same bytes as the device entry
+    eng.reset()
+    out3, fits3 = eng.process_host(frames)
+    assert (out3 == out).all() and fits3.tobytes() == fits.tobytes()
+
+
+def test_state_export_import_handoff(engines, stills, golden):
+    """the tracker blob handed between GPUs at chunk boundaries reproduces the single-context run"""
+    g = golden["sequences"]["project_seed0_40"]
+    frames = np.stack(list(O.synth_sequence([stills(s) for s in g["stills"]], 40, seed=g["seed"])))
+    eng = engines("project")
+    dev = eng.to_device(frames)
+    eng.reset()
+    _, fit_all = eng.process_dev(dev)
+    eng.check()
+    want = eng.fits_to_numpy(fit_all)
+    eng.reset()
+    _, fa = eng.process_dev(dev[:17])
+    blob = eng.export_state()
+    eng.reset()
+    eng.import_state(blob)
+    _, fb = eng.process_dev(dev[17:])
+    eng.check()
+    got = np.concatenate([eng.fits_to_numpy(fa), eng.fits_to_numpy(fb)])
+    assert got.tobytes() == want.tobytes()
+
+
+def test_helper_surface_stages(engines, stills):
+    import cv2
+    eng = engines("project")
+    orc = O.LaneOracle("project")
+    frame = stills("test3")
+    dev = eng.to_device(frame[None])
+    und = O.undistort(frame, orc.mtx, orc.dist)
+    assert (eng.undistort_dev(dev)[0].cpu().numpy() == und).all()
+    assert (eng.warp_dev(eng.to_device(und[None]))[0].cpu().numpy() == O.birdseye(und, orc.v)).all()
+    want = O.colour_mask(und, orc.v.l_thresh, orc.v.b_thresh)
+    assert (eng.colour_mask_dev(eng.to_device(und[None]))[0].cpu().numpy() == want).all()
+    m = O.binary_birdseye(und, orc.v)
+    packed = eng.pack_dev(eng.to_device(m[None]))
+    assert (eng.unpack_dev(packed)[0].cpu().numpy() == m).all()
+    assert (packed.cpu().numpy().view(np.uint32)[0] == O.pack_mask(m)).all()
