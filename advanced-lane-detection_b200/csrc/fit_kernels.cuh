@@ -234,6 +234,7 @@ __global__ void k_fit3(const ld_lane_record* __restrict__ rec, const FitWork* __
     }
     o.mean_curv = LD_MUL(LD_ADD(o.curv[0], o.curv[1]), 0.5);
     // text (Project.py:320-332)
+    for (int i = 0; i < LD_TEXT_MAX_GLYPHS; ++i) o.text[0][i] = o.text[1][i] = 0;
     int p = 0;
     o.text[0][p++] = 12;
     if (o.mean_curv < 3000.0) { p = put_uint(o.text[0], p, (unsigned long long)o.mean_curv); o.text[0][p++] = 14; }

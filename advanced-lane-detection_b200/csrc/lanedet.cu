@@ -128,10 +128,15 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     p->mask_smem = (2048 + mb + 1) * sizeof(uint32_t);
     p->search_smem = (size_t)H * d.WW * 4 + (size_t)9 * W * 2;
     p->raster_smem = (size_t)H * (d.WW + 1 + LD_MAX_CROSSINGS) * 4 + sizeof(RasterShared);
-    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->mask_smem));
-    LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
-    LD_CUDA(cudaFuncSetAttribute(k_margin_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
-    LD_CUDA(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->raster_smem));
+    // The opt-in limit is a per-function, per-device attribute shared by every plan: always raise it to
+    // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
+    if (mb > 2048) { ld_plan_destroy(p); return LD_ERR_ARG; }
+    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 2048 + 1) * sizeof(uint32_t))));
+    if (W == 1280 && H == 720) {        // search / raster stage the whole 115,200-byte mask plane per CTA
+        LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
+        LD_CUDA(cudaFuncSetAttribute(k_margin_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
+        LD_CUDA(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->raster_smem));
+    }
     *out = p;
     return LD_OK;
 }
@@ -252,6 +257,7 @@ extern "C" int ld_margin_search(ld_ctx* c, const uint32_t* mask, const double* f
     if (!ARGS_OK(c, mask, rec, n) || !fits) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
+    if (d.H != 720 || d.W != 1280) return LD_ERR_ARG;
     k_margin_search<<<n, SEARCH_THREADS, (size_t)d.H * d.WW * 4, (cudaStream_t)stream>>>(mask, fits, rec, d);
     return check_launch();
 }

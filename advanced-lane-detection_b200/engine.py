@@ -91,7 +91,7 @@ class LaneEngine:
         torch = self.torch
         if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous():
             raise ValueError("expected a contiguous CUDA uint8 tensor")
-        if t.dim() == 3:
+        if t.dim() == (3 if channels > 1 else 2):
             t = t.unsqueeze(0)
         want = (self.H, self.W, channels) if channels > 1 else (self.H, self.W)
         if tuple(t.shape[1:]) != want:
