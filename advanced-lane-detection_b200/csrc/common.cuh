@@ -24,6 +24,13 @@ struct PlanDev {
     const uint32_t* glyph_bits;
     const int32_t* glyph_adv;
     int n_glyphs;
+    const int4* frame_tiles;         // 2 x int4 per tile (plan.gather_tiles)
+    int n_frame_tiles;
+    const int4* mask_chunks;
+    const int32_t* mask_chunk_start;
+    int n_mask_chunks;
+    const uint4* bdesc;              // per output mask word: (first source bit | BORDER | FALLBACK, step1, step2, valid)
+    int max_out_words;
 };
 
 // ---- cv2.undistort / cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) for one output pixel -----------

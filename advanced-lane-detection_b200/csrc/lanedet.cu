@@ -32,7 +32,7 @@ struct ld_plan {
     PlanDev d;
     void* allocs[16];
     int n_allocs;
-    size_t search_smem, raster_smem, mask_smem;
+    size_t search_smem, raster_smem, mask_smem, frame_smem;
 };
 
 enum { HOST_CHUNK = 32 };
@@ -89,7 +89,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     if (W <= 0 || H <= 0 || (W % 32) || (H % 2) || desc->n_tiles <= 0 || desc->frame_num < 1 ||
         desc->frame_num > LD_MAX_DEPTH || !desc->und_map || !desc->wtab || !desc->near_map || !desc->tiles ||
         !desc->bmap || !desc->ctab || !desc->cbits || !desc->inv_idx || !desc->inv_fi || !desc->glyph_bits ||
-        !desc->glyph_adv)
+        !desc->glyph_adv || !desc->frame_tiles || !desc->mask_chunks || !desc->mask_chunk_start || !desc->bdesc || desc->n_frame_tiles <= 0)
         return LD_ERR_ARG;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LD_ERR_NO_DEVICE;
@@ -112,26 +112,54 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     d.max_box_words = mb;
     const size_t npix = (size_t)W * H, ninv = (size_t)(desc->inv_y1 - desc->inv_y0) * W;
     int rc;
-    const int16_t* wt = nullptr; const int32_t* tl = nullptr;
+    const int16_t* wt = nullptr; const int32_t* tl = nullptr; const int32_t* ft = nullptr; const int32_t* mc = nullptr; const uint32_t* bd = nullptr;
+    d.n_frame_tiles = desc->n_frame_tiles; d.n_mask_chunks = desc->n_mask_chunks;
+    size_t fs = 0, ms = 0;
+    for (int t = 0; t < desc->n_frame_tiles; ++t) {
+        const size_t b = (size_t)(desc->frame_tiles[8 * t + 6] & 0xFFFF) * (size_t)(desc->frame_tiles[8 * t + 7] & 0x7FFFFFFF);
+        if (b > fs) fs = b;
+    }
+    for (int t = 0; t < desc->n_mask_chunks; ++t) {
+        const size_t b = (size_t)(desc->mask_chunks[8 * t + 6] & 0xFFFF) * (size_t)(desc->mask_chunks[8 * t + 7] & 0x7FFFFFFF);
+        if (b > ms) ms = b;
+    }
+    if (fs > 160 * 1024 || ms > 160 * 1024) return LD_ERR_ARG;
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
         (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
         (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) ||
         (rc = upload(p, desc->glyph_bits, (size_t)desc->n_glyphs * LD_GLYPH_ROWS * LD_GLYPH_WORDS, &d.glyph_bits)) ||
-        (rc = upload(p, desc->glyph_adv, (size_t)desc->n_glyphs, &d.glyph_adv))) {
+        (rc = upload(p, desc->glyph_adv, (size_t)desc->n_glyphs, &d.glyph_adv)) ||
+        (rc = upload(p, desc->frame_tiles, (size_t)desc->n_frame_tiles * 8, &ft)) ||
+        (rc = upload(p, desc->mask_chunks, (size_t)(desc->n_mask_chunks ? desc->n_mask_chunks : 1) * 8, &mc)) ||
+        (rc = upload(p, desc->mask_chunk_start, (size_t)desc->n_tiles + 1, &d.mask_chunk_start)) ||
+        (rc = upload(p, desc->bdesc, (size_t)H * (W / 32) * 4, &bd))) {
         ld_plan_destroy(p);
         return rc;
     }
     d.wtab = reinterpret_cast<const uint2*>(wt);
     d.tiles = reinterpret_cast<const int4*>(tl);
-    p->mask_smem = (2048 + mb + 1) * sizeof(uint32_t);
+    d.frame_tiles = reinterpret_cast<const int4*>(ft);
+    d.mask_chunks = reinterpret_cast<const int4*>(mc);
+    d.bdesc = reinterpret_cast<const uint4*>(bd);
+    p->frame_smem = fs + 16;
+    int mow = 0;
+    for (int t = 0; t < desc->n_tiles; ++t) {
+        const int words = (desc->tiles[8 * t + 1] - desc->tiles[8 * t]) * (W / 32);
+        if (words > mow) mow = words;
+    }
+    d.max_out_words = mow;
+    // k_mask shared memory: box bits (+4 zero words) | job list (u16 per output word) | staged source box
+    p->mask_smem = (((size_t)mb + 4) * 4 + (size_t)mow * 2 + 15) / 16 * 16 + ms + 32;
     p->search_smem = (size_t)H * d.WW * 4 + (size_t)9 * W * 2;
-    p->raster_smem = (size_t)H * (d.WW + 1 + LD_MAX_CROSSINGS) * 4 + sizeof(RasterShared);
+    p->raster_smem = ((size_t)2 * RASTER_BAND * d.WW + LD_TEXT_ROWS * LD_TEXT_WORDS) * 4 + sizeof(RasterShared);
     // The opt-in limit is a per-function, per-device attribute shared by every plan: always raise it to
     // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
-    if (mb > 2048) { ld_plan_destroy(p); return LD_ERR_ARG; }
-    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 2048 + 1) * sizeof(uint32_t))));
+    if (p->mask_smem > 200 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }
+    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
     if (W == 1280 && H == 720) {        // search / raster stage the whole 115,200-byte mask plane per CTA
         LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
         LD_CUDA(cudaFuncSetAttribute(k_margin_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
@@ -289,19 +317,21 @@ extern "C" int ld_fit(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit*
 
 static int launch_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* fit, const int32_t* verts,
                           const int32_t* counts, int max_verts, int thickness, int n, uint8_t* out, cudaStream_t s,
-                          int already_undistorted, int with_text) {
+                          int already_undistorted) {
     const PlanDev& d = c->plan->d;
     if (d.H != 720 || d.W != 1280) return LD_ERR_ARG;
     for (int done = 0; done < n; done += c->max_frames) {
         const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
-        k_raster<<<m, RASTER_THREADS, c->plan->raster_smem, s>>>(fit ? fit + done : nullptr,
+        k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(fit ? fit + done : nullptr,
                                                                  verts ? verts + (size_t)done * max_verts * 2 : nullptr,
                                                                  counts ? counts + done : nullptr, max_verts, thickness,
                                                                  c->planes, c->text, d, c->flags + 3);
-        const int quads = d.W * d.H / 4;
-        k_overlay<<<dim3((quads + 255) / 256, m), 256, 0, s>>>(frames + (size_t)done * d.W * d.H * 3, c->planes, c->text,
-                                                              out + (size_t)done * d.W * d.H * 3, d, already_undistorted,
-                                                              with_text);
+        const uint8_t* fin = frames + (size_t)done * d.W * d.H * 3;
+        uint8_t* fout = out + (size_t)done * d.W * d.H * 3;
+        if (already_undistorted)
+            k_frame_pass<2><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, c->planes, c->text, fout, d);
+        else
+            k_frame_pass<1><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, c->plan->frame_smem, s>>>(fin, c->planes, c->text, fout, d);
     }
     return check_launch();
 }
@@ -309,7 +339,7 @@ static int launch_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* 
 extern "C" int ld_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* fit, int n, uint8_t* out, void* stream) {
     if (!ARGS_OK(c, frames, out, n) || !fit) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
-    return launch_overlay(c, frames, fit, nullptr, nullptr, 0, 30, n, out, (cudaStream_t)stream, 0, 1);
+    return launch_overlay(c, frames, fit, nullptr, nullptr, 0, 30, n, out, (cudaStream_t)stream, 0);
 }
 
 extern "C" int ld_draw(ld_ctx* c, const uint8_t* undist, const int32_t* verts, const int32_t* counts, int max_verts,
@@ -317,7 +347,7 @@ extern "C" int ld_draw(ld_ctx* c, const uint8_t* undist, const int32_t* verts, c
     if (!ARGS_OK(c, undist, out, n) || !verts || !counts || max_verts < 0 || thickness < 0 || thickness > 30 || (thickness & 1))
         return LD_ERR_ARG;
     if (n == 0) return LD_OK;
-    return launch_overlay(c, undist, nullptr, verts, counts, max_verts, thickness, n, out, (cudaStream_t)stream, 1, 0);
+    return launch_overlay(c, undist, nullptr, verts, counts, max_verts, thickness, n, out, (cudaStream_t)stream, 1);
 }
 
 static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, cudaStream_t s,
@@ -411,8 +441,7 @@ extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* ou
     if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    const int quads = d.W * d.H / 4;
-    k_undistort<<<dim3((quads + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(frames, out, d);
+    k_frame_pass<0><<<dim3(d.n_frame_tiles, n), FRAME_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(frames, nullptr, nullptr, out, d);
     return check_launch();
 }
 extern "C" int ld_warp(ld_ctx* c, const uint8_t* img, int n, int channels, uint8_t* out, void* stream) {

@@ -1,6 +1,7 @@
 // mask_kernels.cuh -- K1 fused mask, K2 band histogram, and the stand-alone per-pixel stages.
 #pragma once
 #include "common.cuh"
+#include "gather.cuh"
 
 namespace lanedet {
 
@@ -11,56 +12,122 @@ namespace lanedet {
 // One CTA = one band of bird's-eye rows of one frame (plan.tiles).  The bird's-eye warp is
 // INTER_NEAREST, so every output pixel is a copy of ONE undistorted pixel and its mask bit is a
 // function of that pixel alone; the band's rows sample a small box of the undistorted image
-// (~5.5x fewer distinct pixels than outputs).  Phase A evaluates the box once -- bilinear
-// undistort gather + colour decision -> one bit per box pixel in shared memory (warp ballot).
-// Phase B builds the packed output rows: each lane picks its pixel's bit through the u16 `bmap`,
-// a ballot packs 32 of them, 32 ballots are transposed across the warp and stored as one 128-byte line.
+// (~4.4x fewer distinct pixels than outputs).
+//   Phase A evaluates the box once, in column chunks: the source bytes a chunk's taps read are staged in
+//   shared memory by TMA bulk copies (gather.cuh), then bilinear (dp2a) + colour decision -> one bit per
+//   box pixel (warp ballot) in shared memory.
+//   Phase B builds the packed output per OUTPUT WORD: a perspective warp keeps a word's 32 pixels on one
+//   source row, stepping 0/1/2 source pixels per output pixel (plan.bdesc), so a thread cuts a 64-bit
+//   window out of the bit array and expands it with one funnel shift per bit.  Windows that are all
+//   zero / all one (most of a road scene) are finished in pass 1; the rest are compacted into a job
+//   list so the bit-serial loop runs with full warps.
 constexpr int MASK_THREADS = 256;
+constexpr uint32_t BDESC_BORDER = 0xFFFFFFFFu, BDESC_FALLBACK = 0xFFFFFFFEu;
 
 __global__ void __launch_bounds__(MASK_THREADS)
 k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const PlanDev P) {
-    extern __shared__ uint32_t smem[];
-    uint2* s_wt = reinterpret_cast<uint2*>(smem);                 // 1024 x 8 B
-    uint32_t* s_bits = smem + 2048;                               // box bits (+1 zero word for the border)
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int n_jobs;
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);                       // box bits + 4 zero words
+    uint16_t* s_job = reinterpret_cast<uint16_t*>(s_bits + P.max_box_words + 4);
+    uint8_t* s_box = smem_raw + (((size_t)(P.max_box_words + 4) * 4 + (size_t)P.max_out_words * 2 + 15) / 16) * 16;
 
     const int tile = blockIdx.x, f = blockIdx.y;
     const int4 t0 = P.tiles[2 * tile], t1 = P.tiles[2 * tile + 1];
-    const int y0 = t0.x, y1 = t0.y, u0 = t0.z, v0 = t0.w, rw = t1.x, rows = t1.y;
+    const int y0 = t0.x, y1 = t0.y, u0 = t0.z, rw = t1.x, rows = t1.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = MASK_THREADS / 32;
     const uint8_t* frame = frames + (size_t)f * P.W * P.H * 3;
-
-    for (int i = threadIdx.x; i < 1024; i += MASK_THREADS) s_wt[i] = P.wtab[i];
-    __syncthreads();
-
-    // ---- phase A: one bit per undistorted pixel of the box
     const int box_words = rw * rows;
-    for (int wi = warp; wi < box_words; wi += nwarp) {
-        const int v = v0 + wi / rw;
-        const int u = u0 + (wi % rw) * 32 + lane;
-        bool on = false;
-        if (u < P.W) {
-            const uint32_t e = __ldg(P.und_map + (size_t)v * P.W + u);
-            on = colour_on(bilinear_rgb(frame, P.W, P.H, u, v, e, s_wt), P.ctab, P.cbits);
+
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); n_jobs = 0; }
+    if (threadIdx.x < 4) s_bits[box_words + threadIdx.x] = 0;
+
+    // ---- phase A: one bit per undistorted pixel of the box, chunk by chunk
+    int staged = 0;
+    for (int c = P.mask_chunk_start[tile]; c < P.mask_chunk_start[tile + 1]; ++c) {
+        const GTile g = load_gtile(P.mask_chunks, c);
+        __syncthreads();                                   // barrier initialised / previous chunk's box no longer read
+        stage_box(s_box, frame, P.W, g, &bar);
+        if (!g.slow) { mbar_wait(&bar, staged & 1); ++staged; }
+        const int nwc = (g.w + 31) >> 5, wc0 = (g.x0 - u0) >> 5;
+        for (int wi = warp; wi < nwc * g.h; wi += nwarp) {
+            const int r = wi / nwc, wc = wi - r * nwc;
+            const int u = g.x0 + wc * 32 + lane, v = g.y0 + r;
+            bool on = false;
+            if (u < g.x0 + g.w) {
+                const uint32_t e = __ldg(P.und_map + (size_t)v * P.W + u);
+                const uint32_t rgb = g.slow ? bilinear_rgb(frame, P.W, P.H, u, v, e, P.wtab) : bilinear_rgb_box(s_box, g, u, v, e, P.wtab);
+                on = colour_on(rgb, P.ctab, P.cbits);
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) s_bits[r * rw + wc0 + wc] = word;
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, on);
-        if (lane == 0) s_bits[wi] = word;
     }
     __syncthreads();
 
-    // ---- phase B: packed bird's-eye rows of the band (contiguous in the output)
+    // ---- phase B, pass 1: one thread per output word
     const int out_words = (y1 - y0) * P.WW;
     uint32_t* out = mask + ((size_t)f * P.H + y0) * P.WW;
-    const uint16_t* bm = P.bmap + (size_t)y0 * P.W;
-    for (int base = warp * 32; base < out_words; base += nwarp * 32) {
-        uint32_t mine = 0;
-        const int cnt = min(32, out_words - base);
-        for (int j = 0; j < cnt; ++j) {
-            const uint32_t idx = __ldg(bm + (size_t)(base + j) * 32 + lane);
-            const bool bit = idx != 0xFFFFu && ((s_bits[idx >> 5] >> (idx & 31)) & 1u);
-            const uint32_t word = __ballot_sync(0xffffffffu, bit);
-            if (lane == j) mine = word;
+    const uint4* bd = P.bdesc + (size_t)y0 * P.WW;
+    for (int wi = threadIdx.x; wi < out_words; wi += MASK_THREADS) {
+        const uint4 d = __ldg(bd + wi);
+        uint32_t o = 0;
+        bool job = false;
+        if (d.x == BDESC_FALLBACK) job = true;
+        else if (d.x != BDESC_BORDER) {
+            const uint32_t* p = s_bits + (d.x >> 5);
+            const uint32_t sh = d.x & 31;
+            uint32_t lo = __funnelshift_r(p[0], p[1], sh), hi = __funnelshift_r(p[1], p[2], sh);
+            const int span = __popc(d.y) + __popc(d.z) + 1;                          // source bits the word reads (<= 63)
+            const uint32_t mlo = span >= 32 ? 0xFFFFFFFFu : (1u << span) - 1u;
+            const uint32_t mhi = span <= 32 ? 0u : (1u << (span - 32)) - 1u;
+            lo &= mlo; hi &= mhi;
+            if ((lo | hi) == 0u) o = 0u;
+            else if (lo == mlo && hi == mhi) o = d.w;
+            else job = true;
         }
-        if (lane < cnt) out[base + lane] = mine;
+        if (job) s_job[atomicAdd(&n_jobs, 1)] = (uint16_t)wi;
+        else out[wi] = o;
+    }
+    __syncthreads();
+
+    // ---- phase B, pass 2: bit-serial expansion of the mixed words
+    const int nj = n_jobs;
+    for (int k = threadIdx.x; k < nj; k += MASK_THREADS) {
+        const int wi = s_job[k];
+        const uint4 d = __ldg(bd + wi);
+        uint32_t o = 0;
+        if (d.x == BDESC_FALLBACK) {                       // general homography: per-pixel index map
+            const uint16_t* bm = P.bmap + (size_t)y0 * P.W + (size_t)wi * 32;
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t idx = __ldg(bm + i);
+                if (idx != 0xFFFFu) o |= ((s_bits[idx >> 5] >> (idx & 31)) & 1u) << i;
+            }
+        } else {
+            const uint32_t* p = s_bits + (d.x >> 5);
+            const uint32_t sh = d.x & 31;
+            uint32_t lo = __funnelshift_r(p[0], p[1], sh), hi = __funnelshift_r(p[1], p[2], sh);
+            if (d.z == 0u) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    o = __funnelshift_r(o, lo, 1);         // append source bit 0 at the top; after 32 steps bit i = pixel i
+                    const uint32_t st = (d.y >> i) & 1u;
+                    lo = __funnelshift_r(lo, hi, st);
+                    hi >>= st;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    o = __funnelshift_r(o, lo, 1);
+                    const uint32_t st = ((d.y >> i) & 1u) + ((d.z >> i) & 1u);
+                    lo = __funnelshift_r(lo, hi, st);
+                    hi >>= st;
+                }
+            }
+            o &= d.w;
+        }
+        out[wi] = o;
     }
 }
 
@@ -92,29 +159,6 @@ k_hist(const uint32_t* __restrict__ mask, uint16_t* __restrict__ hist, int W, in
 }
 
 // ============================ stand-alone stages of the helper.py surface ===========================
-// cv2.undistort (helper.py:35-47): 4 pixels per thread, 12 output bytes as three u32 stores.
-__global__ void __launch_bounds__(256)
-k_undistort(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, const PlanDev P) {
-    __shared__ uint2 s_wt[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_wt[i] = P.wtab[i];
-    __syncthreads();
-    const int f = blockIdx.y;
-    const int quad = blockIdx.x * blockDim.x + threadIdx.x;      // index of a 4-pixel group
-    const int npix = P.W * P.H;
-    if (quad * 4 >= npix) return;
-    const uint8_t* frame = frames + (size_t)f * npix * 3;
-    const uint4 e = __ldg(reinterpret_cast<const uint4*>(P.und_map) + quad);
-    const int p0 = quad * 4, y = p0 / P.W, x = p0 - y * P.W;     // W % 4 == 0: the group stays in one row
-    const uint32_t c0 = bilinear_rgb(frame, P.W, P.H, x, y, e.x, s_wt);
-    const uint32_t c1 = bilinear_rgb(frame, P.W, P.H, x + 1, y, e.y, s_wt);
-    const uint32_t c2 = bilinear_rgb(frame, P.W, P.H, x + 2, y, e.z, s_wt);
-    const uint32_t c3 = bilinear_rgb(frame, P.W, P.H, x + 3, y, e.w, s_wt);
-    uint32_t* o = reinterpret_cast<uint32_t*>(out + (size_t)f * npix * 3) + (size_t)quad * 3;
-    o[0] = c0 | (c1 << 24);
-    o[1] = (c1 >> 8) | (c2 << 16);
-    o[2] = (c2 >> 16) | (c3 << 8);
-}
-
 // warp(): INTER_NEAREST gather through near_map (helper.py:11-21), 1 or 3 channels
 __global__ void __launch_bounds__(256)
 k_warp(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, const PlanDev P, int channels) {

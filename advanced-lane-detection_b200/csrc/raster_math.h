@@ -128,13 +128,20 @@ LD_HD void line_fx(Plotter& P, int w, int h, Pt p1, Pt p2) {
         if (ex >= 0 && ex < w && ey >= 0 && ey < h) P.span(ey, ex, ex);
     }
     if (xmajor) {
+        // consecutive pixels of an x-major line share rows: emit one span per run instead of one per pixel
         p1.x >>= XY_SHIFT;
+        int run_y = 0x7fffffff, run_x0 = 0, run_x1 = -1;
         while (ecount-- >= 0) {
             int px = (int)p1.x, py = (int)(p1.y >> XY_SHIFT);
-            if (px >= 0 && px < w && py >= 0 && py < h) P.span(py, px, px);
+            if (py != run_y) {
+                if (run_x1 >= run_x0) P.span(run_y, run_x0, run_x1);
+                run_y = py; run_x0 = px;
+            }
+            run_x1 = px;
             p1.x++;
             p1.y += y_step;
         }
+        if (run_x1 >= run_x0) P.span(run_y, run_x0, run_x1);     // span() clips to the image like the per-pixel test did
     } else {
         p1.y >>= XY_SHIFT;
         while (ecount-- >= 0) {
@@ -288,6 +295,38 @@ LD_HD void thick_segment(Plotter& P, int w, int h, int x0, int y0, int x1, int y
     thick_segment_quad(P, w, h, x0, y0, x1, y1, thickness);
     if (first) disc(P, w, h, x0, y0, thickness / 2, hw);
     disc(P, w, h, x1, y1, thickness / 2, hw);
+}
+
+// A unit vertical step between two vertices with the same x (the common case along a lane: x = trunc(fit(y))
+// changes every few rows only) draws a quad that is exactly the two rows [x-r, x+r]; and the end disc of a vertex
+// in the middle of such a run is covered by the run's rows and its two end discs (half-widths do not grow with |dy|).
+LD_HD bool trivial_step(int ax, int ay, int bx, int by, int w, int h, int t) {
+    return ax == bx && (by - ay == 1 || ay - by == 1) && ax >= -t && ax <= w + t - 1 && ay >= -t && ay <= h + t - 1 &&
+           by >= -t && by <= h + t - 1;
+}
+
+// Classification of segment (a -> b) of cv2.polylines with the shortcuts above; (c) is the vertex after b if has_next.
+enum { SEG_TRIVIAL = 1, SEG_END_DISC = 2, SEG_START_DISC = 4 };
+LD_HD int classify_segment(int w, int h, int ax, int ay, int bx, int by, bool has_next, int cx, int cy, int thickness, bool first) {
+    if (!trivial_step(ax, ay, bx, by, w, h, thickness)) return 0;
+    const bool covered = has_next && trivial_step(bx, by, cx, cy, w, h, thickness) && (cy - by) == (by - ay);
+    return SEG_TRIVIAL | (covered ? 0 : SEG_END_DISC) | (first ? SEG_START_DISC : 0);
+}
+
+// The whole segment, shortcuts included (the CUDA kernel defers the expensive parts to a compacted job list instead).
+template <class Plotter>
+LD_HD void polyline_segment(Plotter& P, int w, int h, int ax, int ay, int bx, int by, bool has_next, int cx, int cy,
+                            int thickness, const int* hw, bool first) {
+    const int cls = classify_segment(w, h, ax, ay, bx, by, has_next, cx, cy, thickness, first);
+    if (!(cls & SEG_TRIVIAL)) {
+        thick_segment(P, w, h, ax, ay, bx, by, thickness, hw, first);
+        return;
+    }
+    const int r = thickness / 2;
+    P.span(ay, ax - r, ax + r);
+    P.span(by, ax - r, ax + r);
+    if (cls & SEG_START_DISC) disc(P, w, h, ax, ay, r, hw);
+    if (cls & SEG_END_DISC) disc(P, w, h, bx, by, r, hw);
 }
 
 // one polygon edge as fillPoly's scanline stage sees it: x(y) = x + (y - y0) * dx for y0 <= y < y1

@@ -65,6 +65,10 @@ class LaneEngine:
         d.inv_idx, d.inv_fi = host(p.inv_idx, np.uint32), host(p.inv_fi, np.uint16)
         d.glyph_bits, d.glyph_adv = host(p.glyph_bits, np.uint32), host(p.glyph_adv, np.int32)
         d.n_glyphs = len(p.glyph_adv)
+        d.n_frame_tiles, d.frame_tiles = len(p.frame_tiles), host(p.frame_tiles, np.int32)
+        d.n_mask_chunks, d.mask_chunks = len(p.mask_chunks), host(p.mask_chunks, np.int32)
+        d.mask_chunk_start = host(p.mask_chunk_start, np.int32)
+        d.bdesc = host(p.bdesc, np.uint32)
         return d
 
     def close(self):

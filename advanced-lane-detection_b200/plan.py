@@ -265,6 +265,66 @@ def mask_tiles(nx, ny, size, max_bits=61440, target_tiles=24):
     return tiles, bmap
 
 
+def gather_tiles(sx, sy, size, regions, tw=128):
+    """Source boxes of the bilinear undistort gather.  `regions` lists output rectangles
+    (x0, y0, w, h); each is cut into column chunks of `tw` pixels and, per chunk, the box of source bytes its
+    taps read is recorded so a CTA can stage it in shared memory with row-wise bulk copies:
+    int32[T,8] = (x0, y0, w, h, first_source_byte_in_row (16-aligned), first_source_row, rows | copy_bytes << 16,
+                  smem_row_stride | slow << 31).  slow = some tap falls outside the frame (global-memory path)."""
+    W, H = size
+    out = []
+    for (rx, ry, rw, rh) in regions:
+        for x0 in range(rx, rx + rw, tw):
+            w = min(tw, rx + rw - x0)
+            bx, by = sx[ry:ry + rh, x0:x0 + w], sy[ry:ry + rh, x0:x0 + w]
+            slow = bool(bx.min() < 0 or bx.max() + 1 > W - 1 or by.min() < 0 or by.max() + 1 > H - 1)
+            if slow:
+                out.append((x0, ry, w, rh, 0, 0, 0, 1 << 31))
+                continue
+            b0 = (3 * int(bx.min())) // 16 * 16
+            copy = min((3 * (int(bx.max()) + 2) - b0 + 15) // 16 * 16, W * 3 - b0)
+            rows = int(by.max()) + 2 - int(by.min())
+            out.append((x0, ry, w, rh, b0, int(by.min()), rows | (copy << 16), copy + 16))
+    return np.array(out, np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8)
+
+
+BDESC_BORDER, BDESC_FALLBACK = 0xFFFFFFFF, 0xFFFFFFFE
+
+
+def mask_word_descriptors(nx, ny, tiles, size):
+    """Phase B of the mask kernel per OUTPUT WORD instead of per pixel.  A perspective warp keeps the 32 pixels of
+    an output word on one source row, marching right by 0, 1 or 2 source pixels per output pixel, so the word is
+    fully described by (first source bit, 32 one-steps, 32 extra-steps, valid pixels) -- u32[H, W/32, 4].
+    Words that do not fit the pattern (general homographies, holes) are flagged and use `bmap`."""
+    W, H = size
+    WW = W // 32
+    desc = np.zeros((H, WW, 4), np.uint32)
+    for (y0, y1, u0, v0, rw, rows, _, _) in tiles:
+        sl = slice(y0, y1)
+        valid = (nx[sl] >= 0).reshape(-1, WW, 32)
+        idx = ((ny[sl] - v0).astype(np.int64) * (rw * 32) + (nx[sl] - u0)).reshape(-1, WW, 32)
+        any_valid = valid.any(-1)
+        first = np.argmax(valid, -1)
+        last = 31 - np.argmax(valid[..., ::-1], -1)
+        pos = np.arange(32)[None, None, :]
+        contiguous = (valid == ((pos >= first[..., None]) & (pos <= last[..., None]))).all(-1)
+        base = np.take_along_axis(idx, first[..., None], -1)[..., 0]
+        step = np.diff(idx, axis=-1)                                  # step i: pixel i -> i+1
+        both = valid[..., :-1] & valid[..., 1:]
+        step = np.where(both, step, 0)
+        ok = any_valid & contiguous & (step >= 0).all(-1) & (step <= 2).all(-1)
+        weights = (1 << np.arange(31, dtype=np.int64))[None, None, :]
+        inc1 = ((step >= 1) * weights).sum(-1)
+        inc2 = ((step >= 2) * weights).sum(-1)
+        vmask = (valid * (1 << np.arange(32, dtype=np.int64))[None, None, :]).sum(-1)
+        d = desc[sl]
+        d[..., 0] = np.where(~any_valid, BDESC_BORDER, np.where(ok, base, BDESC_FALLBACK)).astype(np.uint32)
+        d[..., 1] = inc1.astype(np.uint32)
+        d[..., 2] = inc2.astype(np.uint32)
+        d[..., 3] = vmask.astype(np.uint32)
+    return desc
+
+
 # ----------------------------------------------------------------------------- text
 TEXT_X0, TEXT_Y0, TEXT_WORDS, TEXT_ROWS = 32, 70, 24, 70     # the window of the frame putText can touch (lanedet.h LD_TEXT_*)
 GLYPH_CHARS = "0123456789-.RO(I"   # R = 'Radius of Curvature: ', O = 'Offset from center: ', ( = '(m)', I = 'Inf (m)'
@@ -303,6 +363,7 @@ class LanePlan:
     near: np.ndarray           # i32[H,W]   ny*W+nx, -1 = border   (stand-alone warp())
     tiles: np.ndarray          # i32[T,8]
     bmap: np.ndarray           # u16[H,W]
+    bdesc: np.ndarray          # u32[H,W/32,4]
     ctab: np.ndarray           # u32[65536]
     cbits: np.ndarray          # u32[2^19]
     inv_y0: int                # first output row the inverse warp can touch
@@ -313,6 +374,9 @@ class LanePlan:
     src_row1: int
     glyph_bits: np.ndarray
     glyph_adv: np.ndarray
+    frame_tiles: np.ndarray    # i32[T,8]   gather_tiles over the whole frame, 128 x 16 px (undistort / overlay)
+    mask_chunks: np.ndarray    # i32[C,8]   gather_tiles over each mask band's box of undistorted pixels
+    mask_chunk_start: np.ndarray  # i32[n_tiles+1]  first chunk of each band
 
     @property
     def mask_algorithmic_bytes(self) -> int:
@@ -346,6 +410,14 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     inv_idx = np.where(touch, ((iy + 1) << 16) | (ix + 1), 0xFFFFFFFF).astype(np.uint32)[inv_y0:inv_y1]
     inv_fi = ifi.astype(np.uint16)[inv_y0:inv_y1]
     gb, ga = glyph_atlas()
-    return LanePlan(variant, (W, H), mtx, dist, und_map, bilinear_weight_table(), near, tiles, bmap, ctab, cbits,
+    frame_tiles = gather_tiles(sx, sy, size, [(0, y, W, 16) for y in range(0, H, 16)], 128)
+    chunks, starts = [], [0]
+    for (y0, y1, u0, v0, rw, rows, _, _) in tiles:
+        c = gather_tiles(sx, sy, size, [(int(u0), int(v0), min(int(rw) * 32, W - int(u0)), int(rows))], 256) if rows else np.zeros((0, 8), np.int32)
+        chunks.append(c)
+        starts.append(starts[-1] + len(c))
+    mask_chunks = np.concatenate(chunks) if chunks else np.zeros((0, 8), np.int32)
+    bdesc = mask_word_descriptors(nx, ny, tiles, size)
+    return LanePlan(variant, (W, H), mtx, dist, und_map, bilinear_weight_table(), near, tiles, bmap, bdesc, ctab, cbits,
                     inv_y0, inv_y1, np.ascontiguousarray(inv_idx), np.ascontiguousarray(inv_fi),
-                    src_row0, src_row1, gb, ga)
+                    src_row0, src_row1, gb, ga, frame_tiles, mask_chunks, np.array(starts, np.int32))

@@ -65,6 +65,12 @@ typedef struct ld_plan_desc {
     const uint32_t* glyph_bits;      /* [n_glyphs*40*12] */
     const int32_t* glyph_adv;        /* [n_glyphs] */
     int32_t n_glyphs;
+    int32_t n_frame_tiles;
+    const int32_t* frame_tiles;      /* [n_frame_tiles*8] 128x16 output tiles + the source box each one gathers from */
+    const int32_t* mask_chunks;      /* [n_mask_chunks*8] column chunks of each mask band's box of undistorted pixels */
+    const int32_t* mask_chunk_start; /* [n_tiles+1] */
+    const uint32_t* bdesc;           /* [H*(W/32)*4] per output word of the mask: first source bit, step masks, valid pixels */
+    int32_t n_mask_chunks;
     int32_t reserved;
 } ld_plan_desc;
 

@@ -80,3 +80,28 @@ def emu_blend(undist, warp):
     """cv2.addWeighted(undist, 1, warp, 0.3, 0): float32 multiply-add, round half to even, saturate."""
     f = undist.astype(np.float32) + warp.astype(np.float32) * np.float32(0.3)
     return np.clip(np.rint(f), 0, 255).astype(np.uint8)
+
+
+def emu_mask_words(plan, frame):
+    """phase B through the per-word descriptors (what k_mask does), bit-serial like the kernel's loop"""
+    W, H = plan.size
+    und = emu_undistort(plan, frame)
+    on = emu_colour(plan, und)
+    out = np.zeros((H, W // 32), np.uint32)
+    for (y0, y1, u0, v0, rw, rows, _, _) in plan.tiles:
+        box = np.zeros((rows, rw * 32), bool)
+        u1 = min(u0 + rw * 32, W)
+        box[:, :u1 - u0] = on[v0:v0 + rows, u0:u1]
+        flat = np.concatenate([box.reshape(-1), np.zeros(128, bool)])
+        for y in range(y0, y1):
+            for w in range(W // 32):
+                s, inc1, inc2, valid = (int(v) for v in plan.bdesc[y, w])
+                if s == 0xFFFFFFFF:
+                    continue
+                assert s != 0xFFFFFFFE
+                word, off = 0, 0
+                for i in range(32):
+                    word |= int(flat[s + off]) << i
+                    off += ((inc1 >> i) & 1) + ((inc2 >> i) & 1)
+                out[y, w] = word & valid
+    return np.unpackbits(out.view(np.uint8), axis=1, bitorder="little").reshape(H, W)

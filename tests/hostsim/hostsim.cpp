@@ -42,7 +42,8 @@ void hs_polyline(uint8_t* img, int w, int h, const int32_t* pts, int n, int thic
     std::vector<int> hw(radius + 1);
     circle_half_widths(radius, hw.data());
     for (int i = 0; i + 1 < n; ++i)
-        thick_segment(P, w, h, pts[2 * i], pts[2 * i + 1], pts[2 * i + 2], pts[2 * i + 3], thickness, hw.data(), i == 0);
+        polyline_segment(P, w, h, pts[2 * i], pts[2 * i + 1], pts[2 * i + 2], pts[2 * i + 3], i + 2 < n,
+                         i + 2 < n ? pts[2 * i + 4] : 0, i + 2 < n ? pts[2 * i + 5] : 0, thickness, hw.data(), i == 0);
 }
 
 // cv2.fillPoly(img, [pts], 1)
