@@ -29,6 +29,8 @@ struct PlanDev {
     const int4* mask_chunks;
     const int32_t* mask_chunk_start;
     int n_mask_chunks;
+    const uint32_t* frame_amap; const int32_t* frame_amap_start;
+    const uint32_t* mask_amap; const int32_t* mask_amap_start;
     const uint4* bdesc;              // per output mask word: (first source bit | BORDER | FALLBACK, step1, step2, valid)
     int max_out_words;
 };

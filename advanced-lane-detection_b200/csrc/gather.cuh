@@ -65,6 +65,41 @@ __device__ __forceinline__ void stage_box(uint8_t* s_box, const uint8_t* __restr
         bulk_g2s(s_box + r * t.stride, frame + (size_t)(t.sy0 + r) * W * 3 + t.b0, (uint32_t)t.copy, bar);
 }
 
+// Wait for the staged box with ONE warp polling the mbarrier; everybody else parks at the CTA barrier
+// (a spinning try_wait in all warps burns the issue slots the other resident CTAs need).
+__device__ __forceinline__ void wait_box(uint64_t* bar, uint32_t parity, bool staged) {
+    if (staged && threadIdx.x < 32) mbar_wait(bar, parity);
+    __syncthreads();
+}
+
+// Same from a precomputed (box byte offset << 10 | fraction) entry (plan.gather_offsets): no coordinate arithmetic.
+__device__ __forceinline__ uint32_t bilinear_rgb_off(const uint8_t* s_box, int stride, uint32_t e2, const uint2* __restrict__ wtab) {
+    // OpenCV's weight table in closed form: with 5-bit fractions the four float32 products are exact integers,
+    // w00 = 32(32-fy)(32-fx), w01 = 32(32-fy)fx, w10 = 32 fy (32-fx), w11 = 32 fy fx  (tested against the table)
+    const uint32_t fx = e2 & 31u, fy = (e2 >> 5) & 31u;
+    const uint32_t t = (32u - fx) | (fx << 16);
+    uint2 w;
+    w.x = t * (1024u - 32u * fy);
+    w.y = t * (32u * fy);
+    const uint32_t o = e2 >> 10;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(s_box) + (o >> 2);
+    const uint32_t* q = p + (stride >> 2);
+    const uint32_t sh = (o & 3) * 8;
+    const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], q0 = q[0], q1 = q[1], q2 = q[2];
+    const uint32_t lt = __funnelshift_r(p0, p1, sh), ht = __funnelshift_r(p1, p2, sh);   // r0 g0 b0 r1 | g1 b1 . .
+    const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
+    const uint32_t R = __byte_perm(lt, lb, 0x7430);
+    const uint32_t Gt = __byte_perm(lt, ht, 0x0041), Gb = __byte_perm(lb, hb, 0x0041);
+    const uint32_t Bt = __byte_perm(lt, ht, 0x0052), Bb = __byte_perm(lb, hb, 0x0052);
+    uint32_t r = __dp2a_lo(w.x, R, 16384u);
+    r = __dp2a_hi(w.y, R, r);
+    uint32_t g = __dp2a_lo(w.x, Gt, 16384u);
+    g = __dp2a_lo(w.y, Gb, g);
+    uint32_t b = __dp2a_lo(w.x, Bt, 16384u);
+    b = __dp2a_lo(w.y, Bb, b);
+    return (r >> 15) | ((g >> 15) << 8) | ((b >> 15) << 16);
+}
+
 // r | g<<8 | b<<16 of undistorted pixel (x, y) from the staged box
 __device__ __forceinline__ uint32_t bilinear_rgb_box(const uint8_t* s_box, const GTile& t, int x, int y, uint32_t e,
                                                      const uint2* __restrict__ wtab) {

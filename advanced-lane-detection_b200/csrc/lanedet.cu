@@ -30,7 +30,7 @@ static thread_local char g_cuda_err[256] = "";
 struct ld_plan {
     int device;
     PlanDev d;
-    void* allocs[16];
+    void* allocs[32];
     int n_allocs;
     size_t search_smem, raster_smem, mask_smem, frame_smem;
 };
@@ -75,7 +75,8 @@ extern "C" const char* ld_last_cuda_error(void) { return g_cuda_err; }
 template <class T>
 static int upload(ld_plan* p, const T* host, size_t count, const T** dev) {
     void* d = nullptr;
-    LD_CUDA(cudaMalloc(&d, count * sizeof(T) + 16));
+    if (p->n_allocs >= 32) return LD_ERR_ARG;
+    LD_CUDA(cudaMalloc(&d, count * sizeof(T) + 64));
     LD_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
     p->allocs[p->n_allocs++] = d;
     *dev = static_cast<const T*>(d);
@@ -89,7 +90,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     if (W <= 0 || H <= 0 || (W % 32) || (H % 2) || desc->n_tiles <= 0 || desc->frame_num < 1 ||
         desc->frame_num > LD_MAX_DEPTH || !desc->und_map || !desc->wtab || !desc->near_map || !desc->tiles ||
         !desc->bmap || !desc->ctab || !desc->cbits || !desc->inv_idx || !desc->inv_fi || !desc->glyph_bits ||
-        !desc->glyph_adv || !desc->frame_tiles || !desc->mask_chunks || !desc->mask_chunk_start || !desc->bdesc || desc->n_frame_tiles <= 0)
+        !desc->glyph_adv || !desc->frame_tiles || !desc->mask_chunks || !desc->mask_chunk_start || !desc->bdesc || !desc->frame_amap || !desc->frame_amap_start || !desc->mask_amap || !desc->mask_amap_start || desc->n_frame_tiles <= 0)
         return LD_ERR_ARG;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LD_ERR_NO_DEVICE;
@@ -134,7 +135,11 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         (rc = upload(p, desc->frame_tiles, (size_t)desc->n_frame_tiles * 8, &ft)) ||
         (rc = upload(p, desc->mask_chunks, (size_t)(desc->n_mask_chunks ? desc->n_mask_chunks : 1) * 8, &mc)) ||
         (rc = upload(p, desc->mask_chunk_start, (size_t)desc->n_tiles + 1, &d.mask_chunk_start)) ||
-        (rc = upload(p, desc->bdesc, (size_t)H * (W / 32) * 4, &bd))) {
+        (rc = upload(p, desc->bdesc, (size_t)H * (W / 32) * 4, &bd)) ||
+        (rc = upload(p, desc->frame_amap_start, (size_t)desc->n_frame_tiles + 1, &d.frame_amap_start)) ||
+        (rc = upload(p, desc->frame_amap, (size_t)desc->frame_amap_start[desc->n_frame_tiles], &d.frame_amap)) ||
+        (rc = upload(p, desc->mask_amap_start, (size_t)desc->n_mask_chunks + 1, &d.mask_amap_start)) ||
+        (rc = upload(p, desc->mask_amap, (size_t)(desc->mask_amap_start[desc->n_mask_chunks] ? desc->mask_amap_start[desc->n_mask_chunks] : 1), &d.mask_amap))) {
         ld_plan_destroy(p);
         return rc;
     }

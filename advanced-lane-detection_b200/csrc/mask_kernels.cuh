@@ -49,19 +49,24 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
         const GTile g = load_gtile(P.mask_chunks, c);
         __syncthreads();                                   // barrier initialised / previous chunk's box no longer read
         stage_box(s_box, frame, P.W, g, &bar);
-        if (!g.slow) { mbar_wait(&bar, staged & 1); ++staged; }
+        wait_box(&bar, staged & 1, !g.slow);
+        if (!g.slow) ++staged;
         const int nwc = (g.w + 31) >> 5, wc0 = (g.x0 - u0) >> 5;
-        for (int wi = warp; wi < nwc * g.h; wi += nwarp) {
-            const int r = wi / nwc, wc = wi - r * nwc;
-            const int u = g.x0 + wc * 32 + lane, v = g.y0 + r;
-            bool on = false;
-            if (u < g.x0 + g.w) {
-                const uint32_t e = __ldg(P.und_map + (size_t)v * P.W + u);
-                const uint32_t rgb = g.slow ? bilinear_rgb(frame, P.W, P.H, u, v, e, P.wtab) : bilinear_rgb_box(s_box, g, u, v, e, P.wtab);
-                on = colour_on(rgb, P.ctab, P.cbits);
+        const uint32_t* am = P.mask_amap + P.mask_amap_start[c];
+        for (int r = warp; r < g.h; r += nwarp) {
+            const int v = g.y0 + r;
+            for (int wc = 0; wc < nwc; ++wc) {
+                const int col = wc * 32 + lane;
+                bool on = false;
+                if (col < g.w) {
+                    uint32_t rgb;
+                    if (!g.slow) rgb = bilinear_rgb_off(s_box, g.stride, __ldg(am + r * g.w + col), P.wtab);
+                    else rgb = bilinear_rgb(frame, P.W, P.H, g.x0 + col, v, __ldg(P.und_map + (size_t)v * P.W + g.x0 + col), P.wtab);
+                    on = colour_on(rgb, P.ctab, P.cbits);
+                }
+                const uint32_t word = __ballot_sync(0xffffffffu, on);
+                if (lane == 0) s_bits[r * rw + wc0 + wc] = word;
             }
-            const uint32_t word = __ballot_sync(0xffffffffu, on);
-            if (lane == 0) s_bits[r * rw + wc0 + wc] = word;
         }
     }
     __syncthreads();

@@ -35,7 +35,7 @@ struct BandPlotter {                // sets bits [x1,x2] of canvas row y if the 
 };
 
 struct RasterShared {
-    int n_verts, overflow, cut, n_jobs;
+    int n_verts, overflow, cut, n_jobs, n_big, n_bigedge;
     int count[2];
     int hw[16];
     uint32_t rowmask[2][LD_ROWMAP_WORDS];
@@ -43,8 +43,17 @@ struct RasterShared {
     int vx[MAX_VERTS], vy[MAX_VERTS];
     int cnt[RASTER_BAND];
     int cross[RASTER_BAND * LD_MAX_CROSSINGS];
-    int job[2 * MAX_VERTS];
+    unsigned short job[2 * MAX_VERTS];       // segment index | type << 14
+    unsigned short big[MAX_VERTS], bigedge[MAX_VERTS];
 };
+
+__device__ __forceinline__ void add_crossing(RasterShared& R, const laneraster::PolyEdge& e, int y, int y_lo) {
+    long long x = e.x + (long long)(y - e.y0) * e.dx;
+    x = x < -(1ll << 30) ? -(1ll << 30) : x > (1ll << 30) ? (1ll << 30) : x;   // order-preserving clamp far outside the image
+    const int slot = atomicAdd(&R.cnt[y - y_lo], 1);
+    if (slot < LD_MAX_CROSSINGS) R.cross[(y - y_lo) * LD_MAX_CROSSINGS + slot] = (int)x;
+    else R.overflow = 1;
+}
 
 // np.int_() of fit[0]*y**2 + fit[1]*y + fit[2]  (Project.py:139, :160)
 __device__ __forceinline__ int vertex_x(const double* c, int y) {
@@ -58,7 +67,7 @@ __device__ __forceinline__ int vertex_x(const double* c, int y) {
 // text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  Vertices come from the frame's fit + row maps
 // (verts == nullptr) or are given explicitly (ld_draw).  Every CTA lists all vertices (cheap, parallel) and
 // draws only the primitives whose rows can touch its band, one primitive per thread.
-__global__ void __launch_bounds__(RASTER_THREADS)
+__global__ void __launch_bounds__(RASTER_THREADS, 4)
 k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts, const int32_t* __restrict__ counts,
          int max_verts, int thickness, uint32_t* __restrict__ planes, uint32_t* __restrict__ text, const PlanDev P,
          int* __restrict__ poly_error) {
@@ -83,6 +92,8 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         R.overflow = 0;
         R.n_verts = 0;
         R.n_jobs = 0;
+        R.n_big = 0;
+        R.n_bigedge = 0;
         laneraster::circle_half_widths(radius, R.hw);
         int cut = -1;                                                   // harder:192-197 drops y <= max(min lefty, min righty)
         if (fit && !bad && P.clip_polygon) {
@@ -150,18 +161,28 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
             const bool nx = i + 2 < nv;
             const int cls = laneraster::classify_segment(W, H, R.vx[i], ya, R.vx[i + 1], yb, nx, nx ? R.vx[i + 2] : 0,
                                                          nx ? R.vy[i + 2] : 0, thickness, i == 0);
-            if (!(cls & laneraster::SEG_TRIVIAL)) { R.job[atomicAdd(&R.n_jobs, 1)] = i; continue; }
+            if (!(cls & laneraster::SEG_TRIVIAL)) {
+                // long segments (lane gaps, the connector between the lanes) are drawn by the whole CTA in pass 3
+                if (max(abs(R.vx[i + 1] - R.vx[i]), abs(yb - ya)) > 24) R.big[atomicAdd(&R.n_big, 1)] = (unsigned short)i;
+                else R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)i;
+                continue;
+            }
             red.span(ya, R.vx[i] - radius, R.vx[i] + radius);
             red.span(yb, R.vx[i] - radius, R.vx[i] + radius);
-            if (cls & laneraster::SEG_END_DISC) R.job[atomicAdd(&R.n_jobs, 1)] = i | (1 << 16);
-            if (cls & laneraster::SEG_START_DISC) R.job[atomicAdd(&R.n_jobs, 1)] = i | (2 << 16);
+            if (cls & laneraster::SEG_END_DISC) R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (1 << 14));
+            if (cls & laneraster::SEG_START_DISC) R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (2 << 14));
         }
     __syncthreads();
     for (int k = tid; k < R.n_jobs; k += RASTER_THREADS) {
-        const int i = R.job[k] & 0xFFFF, type = R.job[k] >> 16;
+        const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
         if (type == 0) laneraster::thick_segment(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0);
         else if (type == 1) laneraster::disc(red, W, H, R.vx[i + 1], R.vy[i + 1], radius, R.hw);
         else laneraster::disc(red, W, H, R.vx[i], R.vy[i], radius, R.hw);
+    }
+    for (int k = 0; k < R.n_big; ++k) {
+        const int i = R.big[k];
+        laneraster::thick_segment_part(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, tid,
+                                       RASTER_THREADS, y_lo, y_hi);
     }
 
     // ---- green: cv2.fillPoly(canvas, pts, (0,255,0)) (Project.py:164): outline + scanline crossings of this band
@@ -169,15 +190,20 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         const int j = i == 0 ? nv - 1 : i - 1;
         const int ya = R.vy[j], yb = R.vy[i];
         if (max(ya, yb) < y_lo || min(ya, yb) >= y_hi) continue;
+        if (max(abs(R.vx[i] - R.vx[j]), abs(yb - ya)) > 32) { R.bigedge[atomicAdd(&R.n_bigedge, 1)] = (unsigned short)i; continue; }
         const laneraster::PolyEdge e = laneraster::poly_edge(green, W, H, R.vx[j], ya, R.vx[i], yb);
         if (!e.valid) continue;
-        for (int y = max(e.y0, y_lo); y < min(e.y1, y_hi); ++y) {
-            long long x = e.x + (long long)(y - e.y0) * e.dx;
-            x = x < -(1ll << 30) ? -(1ll << 30) : x > (1ll << 30) ? (1ll << 30) : x;   // order-preserving clamp far outside the image
-            const int slot = atomicAdd(&R.cnt[y - y_lo], 1);
-            if (slot < LD_MAX_CROSSINGS) R.cross[(y - y_lo) * LD_MAX_CROSSINGS + slot] = (int)x;
-            else R.overflow = 1;
-        }
+        for (int y = max(e.y0, y_lo); y < min(e.y1, y_hi); ++y) add_crossing(R, e, y, y_lo);
+    }
+    __syncthreads();
+    for (int k = 0; k < R.n_bigedge; ++k) {
+        const int i = R.bigedge[k], j = i == 0 ? nv - 1 : i - 1;
+        laneraster::Pt a, b;
+        a.x = R.vx[j]; a.y = R.vy[j]; b.x = R.vx[i]; b.y = R.vy[i];
+        laneraster::line8_part(green, W, H, a, b, tid, RASTER_THREADS);
+        const laneraster::PolyEdge e = laneraster::poly_edge_scan(W, H, R.vx[j], R.vy[j], R.vx[i], R.vy[i]);
+        if (!e.valid) continue;
+        for (int y = max(e.y0, y_lo) + tid; y < min(e.y1, y_hi); y += RASTER_THREADS) add_crossing(R, e, y, y_lo);
     }
     __syncthreads();
     for (int r = tid; r < y_hi - y_lo; r += RASTER_THREADS) {
@@ -207,10 +233,11 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
             for (int gi = 0; gi < F.n_text[line]; ++gi) {
                 const int g = F.text[line][gi];
                 const uint32_t* gb = P.glyph_bits + (size_t)g * LD_GLYPH_ROWS * LD_GLYPH_WORDS;
-                for (int i = tid; i < LD_GLYPH_ROWS * LD_GLYPH_WORDS; i += RASTER_THREADS) {
-                    const uint32_t v = __ldg(gb + i);
+                const int gwords = min((int)LD_GLYPH_WORDS, (__ldg(P.glyph_adv + g) + 4 + 31) / 32 + 1);   // ink stays within advance + thickness
+                for (int i = tid; i < LD_GLYPH_ROWS * gwords; i += RASTER_THREADS) {
+                    const int gr = i / gwords, gw = i % gwords;
+                    const uint32_t v = __ldg(gb + gr * LD_GLYPH_WORDS + gw);
                     if (!v) continue;
-                    const int gr = i / LD_GLYPH_WORDS, gw = i % LD_GLYPH_WORDS;
                     const int y = baseline - 30 + gr - LD_TEXT_Y0;
                     const int xbit = pen - 2 + gw * 32 - LD_TEXT_X0;    // plane bit of glyph word bit 0
                     if (y < 0 || y >= LD_TEXT_ROWS || xbit < 0) continue;
@@ -234,7 +261,9 @@ __device__ __forceinline__ uint32_t canvas_tap(const uint32_t* __restrict__ red,
     return ((__ldg(red + i) >> b) & 1u) | (((__ldg(green + i) >> b) & 1u) << 1);
 }
 
-// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170) for 4 consecutive pixels of row y starting at x0
+// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170) for 4 consecutive pixels of row y starting at x0.
+// Most pixels of the trapezoid see four equal taps (all background or all green), so those two cases are
+// decided from the plane words directly: 0 -> nothing to add; all green -> the warped pixel is exactly (0,255,0).
 __device__ __forceinline__ void blend_canvas4(uint32_t* c, const uint32_t* __restrict__ red, const uint32_t* __restrict__ green,
                                               const PlanDev& P, int x0, int y) {
     if (y < P.inv_y0 || y >= P.inv_y1) return;
@@ -242,18 +271,32 @@ __device__ __forceinline__ void blend_canvas4(uint32_t* c, const uint32_t* __res
     const size_t mi = (size_t)(y - P.inv_y0) * W + x0;
     const uint4 idx4 = __ldg(reinterpret_cast<const uint4*>(P.inv_idx + mi));
     if ((idx4.x & idx4.y & idx4.z & idx4.w) == 0xFFFFFFFFu) return;
-    const uint2 fi4 = __ldg(reinterpret_cast<const uint2*>(P.inv_fi + mi));
     const uint32_t idx[4] = {idx4.x, idx4.y, idx4.z, idx4.w};
-    const uint32_t fis[4] = {fi4.x & 0xFFFFu, fi4.x >> 16, fi4.y & 0xFFFFu, fi4.y >> 16};
+    uint2 fi4 = make_uint2(0u, 0u);
+    bool have_fi = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (idx[k] == 0xFFFFFFFFu) continue;
         const int sx = (int)(idx[k] & 0xFFFFu) - 1, sy = (int)(idx[k] >> 16) - 1;
-        const uint32_t t00 = canvas_tap(red, green, W, H, WW, sx, sy), t01 = canvas_tap(red, green, W, H, WW, sx + 1, sy);
-        const uint32_t t10 = canvas_tap(red, green, W, H, WW, sx, sy + 1), t11 = canvas_tap(red, green, W, H, WW, sx + 1, sy + 1);
-        if (!(t00 | t01 | t10 | t11)) continue;
-        const uint2 w = __ldg(P.wtab + fis[k]);
-        const int w00 = w.x & 0xFFFF, w01 = w.x >> 16, w10 = w.y & 0xFFFF, w11 = w.y >> 16;
+        uint32_t t00, t01, t10, t11;
+        const int b = sx & 31;
+        if (sx >= 0 && b != 31 && sy >= 0 && sy < H - 1) {           // both columns in one word, both rows inside
+            const int i = sy * WW + (sx >> 5);
+            const uint32_t r0 = (__ldg(red + i) >> b) & 3u, g0 = (__ldg(green + i) >> b) & 3u;
+            const uint32_t r1 = (__ldg(red + i + WW) >> b) & 3u, g1 = (__ldg(green + i + WW) >> b) & 3u;
+            if (!(r0 | g0 | r1 | g1)) continue;
+            if ((g0 & g1) == 3u) { c[k] = (c[k] & 0xFF00FFu) | (blend_u8((c[k] >> 8) & 255u, 255u) << 8); continue; }
+            t00 = (r0 & 1u) | ((g0 & 1u) << 1); t01 = (r0 >> 1) | ((g0 >> 1) << 1);
+            t10 = (r1 & 1u) | ((g1 & 1u) << 1); t11 = (r1 >> 1) | ((g1 >> 1) << 1);
+        } else {
+            t00 = canvas_tap(red, green, W, H, WW, sx, sy); t01 = canvas_tap(red, green, W, H, WW, sx + 1, sy);
+            t10 = canvas_tap(red, green, W, H, WW, sx, sy + 1); t11 = canvas_tap(red, green, W, H, WW, sx + 1, sy + 1);
+            if (!(t00 | t01 | t10 | t11)) continue;
+        }
+        if (!have_fi) { fi4 = __ldg(reinterpret_cast<const uint2*>(P.inv_fi + mi)); have_fi = true; }
+        const uint32_t fi = (k == 0 ? fi4.x : k == 1 ? fi4.x >> 16 : k == 2 ? fi4.y : fi4.y >> 16) & 0xFFFFu;
+        const int fx = fi & 31, fy = fi >> 5;
+        const int w00 = 32 * (32 - fy) * (32 - fx), w01 = 32 * (32 - fy) * fx, w10 = 32 * fy * (32 - fx), w11 = 32 * fy * fx;
         const int wr = (t00 & 1) * w00 + (t01 & 1) * w01 + (t10 & 1) * w10 + (t11 & 1) * w11;
         const int wg = (t00 >> 1) * w00 + (t01 >> 1) * w01 + (t10 >> 1) * w10 + (t11 >> 1) * w11;
         const uint32_t cr = (uint32_t)(wr * 200 + 16384) >> 15, cg = (uint32_t)(wg * 255 + 16384) >> 15;
@@ -302,9 +345,10 @@ k_frame_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
         stage_box(s_box, frame, W, t, &bar);
     }
     const int gx = (threadIdx.x & 31) * 4, r0 = threadIdx.x >> 5;
-    if (MODE != 2 && !t.slow) mbar_wait(&bar, 0);
+    if (MODE != 2) wait_box(&bar, 0, !t.slow);
     if (gx >= t.w) return;
     const int x0 = t.x0 + gx;
+    const uint32_t* am = P.frame_amap + P.frame_amap_start[blockIdx.x];
     for (int r = r0; r < t.h; r += FRAME_THREADS / 32) {
         const int y = t.y0 + r;
         uint32_t c[4];
@@ -312,19 +356,18 @@ k_frame_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
             const uint32_t* s = reinterpret_cast<const uint32_t*>(frame + ((size_t)y * W + x0) * 3);
             const uint32_t a = __ldg(s), b = __ldg(s + 1), d = __ldg(s + 2);
             c[0] = a & 0xFFFFFFu; c[1] = (a >> 24) | ((b & 0xFFFFu) << 8); c[2] = (b >> 16) | ((d & 0xFFu) << 16); c[3] = d >> 8;
+        } else if (!t.slow) {
+            const uint4 e = __ldg(reinterpret_cast<const uint4*>(am + r * t.w + gx));      // t.w % 4 == 0, tile starts 16-byte aligned
+            c[0] = bilinear_rgb_off(s_box, t.stride, e.x, P.wtab);
+            c[1] = bilinear_rgb_off(s_box, t.stride, e.y, P.wtab);
+            c[2] = bilinear_rgb_off(s_box, t.stride, e.z, P.wtab);
+            c[3] = bilinear_rgb_off(s_box, t.stride, e.w, P.wtab);
         } else {
             const uint4 e = __ldg(reinterpret_cast<const uint4*>(P.und_map + (size_t)y * W + x0));
-            if (!t.slow) {
-                c[0] = bilinear_rgb_box(s_box, t, x0, y, e.x, P.wtab);
-                c[1] = bilinear_rgb_box(s_box, t, x0 + 1, y, e.y, P.wtab);
-                c[2] = bilinear_rgb_box(s_box, t, x0 + 2, y, e.z, P.wtab);
-                c[3] = bilinear_rgb_box(s_box, t, x0 + 3, y, e.w, P.wtab);
-            } else {
-                c[0] = bilinear_rgb(frame, W, H, x0, y, e.x, P.wtab);
-                c[1] = bilinear_rgb(frame, W, H, x0 + 1, y, e.y, P.wtab);
-                c[2] = bilinear_rgb(frame, W, H, x0 + 2, y, e.z, P.wtab);
-                c[3] = bilinear_rgb(frame, W, H, x0 + 3, y, e.w, P.wtab);
-            }
+            c[0] = bilinear_rgb(frame, W, H, x0, y, e.x, P.wtab);
+            c[1] = bilinear_rgb(frame, W, H, x0 + 1, y, e.y, P.wtab);
+            c[2] = bilinear_rgb(frame, W, H, x0 + 2, y, e.z, P.wtab);
+            c[3] = bilinear_rgb(frame, W, H, x0 + 3, y, e.w, P.wtab);
         }
         if (MODE != 0) blend_canvas4(c, red, green, P, x0, y);
         if (MODE == 1) text4(c, text, f, x0, y);

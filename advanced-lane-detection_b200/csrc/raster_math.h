@@ -329,12 +329,225 @@ LD_HD void polyline_segment(Plotter& P, int w, int h, int ax, int ay, int bx, in
     if (cls & SEG_END_DISC) disc(P, w, h, bx, by, r, hw);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Cooperative forms of the same primitives.  Long segments (lane gaps, the connector between the two lanes) would
+// otherwise be drawn by one thread while the rest of the CTA waits; here `nt` workers each take every nt-th pixel /
+// row.  All of them rebuild the (cheap) setup themselves, so no synchronisation is needed.  Every closed form below
+// reproduces the sequential loop above exactly (the DDA state after i steps is start + i*step).
+struct LineFx { int valid, xmajor, ecount, ex, ey; int64_t x, y, step; };
+
+LD_HD LineFx line_fx_setup(int w, int h, Pt p1, Pt p2) {
+    LineFx L;
+    L.valid = 0;
+    if (!clip_line((int64_t)w << XY_SHIFT, (int64_t)h << XY_SHIFT, p1, p2)) return L;
+    int64_t dx = p2.x - p1.x, dy = p2.y - p1.y;
+    int64_t ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+    L.xmajor = ax > ay;
+    if (L.xmajor) {
+        if (dx < 0) { Pt t = p1; p1 = p2; p2 = t; dy = -dy; }
+        L.step = dy * (int64_t)XY_ONE / (ax | 1);
+        L.ecount = (int)((p2.x - p1.x) >> XY_SHIFT);
+    } else {
+        if (dy < 0) { Pt t = p1; p1 = p2; p2 = t; dx = -dx; }
+        L.step = dx * (int64_t)XY_ONE / (ay | 1);
+        L.ecount = (int)((p2.y - p1.y) >> XY_SHIFT);
+    }
+    L.x = p1.x + (XY_ONE >> 1);
+    L.y = p1.y + (XY_ONE >> 1);
+    L.ex = (int)((p2.x + (XY_ONE >> 1)) >> XY_SHIFT);
+    L.ey = (int)((p2.y + (XY_ONE >> 1)) >> XY_SHIFT);
+    L.valid = 1;
+    return L;
+}
+
+template <class Plotter>
+LD_HD void line_fx_part(Plotter& P, int w, int h, const LineFx& L, int tid, int nt) {
+    if (!L.valid) return;
+    if (tid == 0 && L.ex >= 0 && L.ex < w && L.ey >= 0 && L.ey < h) P.span(L.ey, L.ex, L.ex);
+    for (int i = tid; i <= L.ecount; i += nt) {
+        int px, py;
+        if (L.xmajor) { px = (int)(L.x >> XY_SHIFT) + i; py = (int)((L.y + (int64_t)i * L.step) >> XY_SHIFT); }
+        else          { px = (int)((L.x + (int64_t)i * L.step) >> XY_SHIFT); py = (int)(L.y >> XY_SHIFT) + i; }
+        if (px >= 0 && px < w && py >= 0 && py < h) P.span(py, px, px);
+    }
+}
+
+struct QuadRec { int y0, y1; int64_t xa, dxa, xb, dxb; };       // rows [y0, y1): both scan edges are linear
+struct QuadScan { int n; QuadRec r[8]; };
+
+// fill_convex_fx's edge walk, advanced from event to event instead of row by row
+LD_HD QuadScan fill_convex_setup(int w, int h, const Pt* v, int npts) {
+    QuadScan S;
+    S.n = 0;
+    struct Edge { int idx, di; int64_t x, dx; int ye; } edge[2];
+    const int delta = XY_ONE >> 1;
+    int imin = 0;
+    int64_t xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
+    for (int i = 0; i < npts; ++i) {
+        Pt p = v[i];
+        if (p.y < ymin) { ymin = p.y; imin = i; }
+        if (p.y > ymax) ymax = p.y;
+        if (p.x > xmax) xmax = p.x;
+        if (p.x < xmin) xmin = p.x;
+    }
+    xmin = (xmin + delta) >> XY_SHIFT;
+    xmax = (xmax + delta) >> XY_SHIFT;
+    ymin = (ymin + delta) >> XY_SHIFT;
+    ymax = (ymax + delta) >> XY_SHIFT;
+    if (npts < 3 || (int)xmax < 0 || (int)ymax < 0 || (int)xmin >= w || (int)ymin >= h) return S;
+    if (ymax > h - 1) ymax = h - 1;
+    int edges = npts;
+    int y = (int)ymin;
+    edge[0].idx = edge[1].idx = imin;
+    edge[0].ye = edge[1].ye = y;
+    edge[0].di = 1;
+    edge[1].di = npts - 1;
+    edge[0].x = edge[1].x = -(int64_t)XY_ONE;
+    edge[0].dx = edge[1].dx = 0;
+    while (S.n < 8) {
+        for (int i = 0; i < 2; ++i) {
+            if (y >= edge[i].ye) {
+                int idx0 = edge[i].idx, di = edge[i].di;
+                int idx = idx0 + di;
+                if (idx >= npts) idx -= npts;
+                int ty = 0;
+                for (; edges-- > 0;) {
+                    ty = (int)((v[idx].y + delta) >> XY_SHIFT);
+                    if (ty > y) {
+                        int64_t xs = v[idx0].x, xe = v[idx].x;
+                        edge[i].ye = ty;
+                        edge[i].dx = ((xe - xs) * 2 + ((int64_t)ty - y)) / (2 * ((int64_t)ty - y));
+                        edge[i].x = xs;
+                        edge[i].idx = idx;
+                        break;
+                    }
+                    idx0 = idx;
+                    idx += di;
+                    if (idx >= npts) idx -= npts;
+                }
+            }
+        }
+        if (edges < 0) break;
+        int yn = edge[0].ye < edge[1].ye ? edge[0].ye : edge[1].ye;
+        if (yn > (int)ymax + 1) yn = (int)ymax + 1;
+        if (yn <= y) yn = y + 1;                       // an exhausted chain keeps its old ye: advance row by row like the original
+        QuadRec& q = S.r[S.n++];
+        q.y0 = y; q.y1 = yn;
+        q.xa = edge[0].x; q.dxa = edge[0].dx; q.xb = edge[1].x; q.dxb = edge[1].dx;
+        edge[0].x += (int64_t)(yn - y) * edge[0].dx;
+        edge[1].x += (int64_t)(yn - y) * edge[1].dx;
+        y = yn;
+        if (y > (int)ymax) break;
+    }
+    return S;
+}
+
+template <class Plotter>
+LD_HD void fill_convex_rows_part(Plotter& P, int w, const QuadScan& S, int tid, int nt, int ylo, int yhi) {
+    const int delta = XY_ONE >> 1;
+    for (int k = 0; k < S.n; ++k) {
+        const QuadRec& q = S.r[k];
+        int a = q.y0 > ylo ? q.y0 : ylo, b = q.y1 < yhi ? q.y1 : yhi;
+        if (a < 0) a = 0;
+        for (int y = a + tid; y < b; y += nt) {
+            int64_t xa = q.xa + (int64_t)(y - q.y0) * q.dxa, xb = q.xb + (int64_t)(y - q.y0) * q.dxb;
+            if (xa > xb) { int64_t t = xa; xa = xb; xb = t; }
+            int xx1 = (int)((xa + delta) >> XY_SHIFT), xx2 = (int)((xb + delta) >> XY_SHIFT);
+            if (xx2 >= 0 && xx1 < w) {
+                if (xx1 < 0) xx1 = 0;
+                if (xx2 >= w) xx2 = w - 1;
+                P.span(y, xx1, xx2);
+            }
+        }
+    }
+}
+
+template <class Plotter>
+LD_HD void disc_part(Plotter& P, int w, int h, int cx, int cy, int radius, const int* hw, int tid, int nt) {
+    for (int d = -radius + tid; d <= radius; d += nt) {
+        int y = cy + d;
+        if (y < 0 || y >= h) continue;
+        int half = hw[d < 0 ? -d : d];
+        if (half < 0) continue;
+        int x1 = cx - half, x2 = cx + half;
+        if (x1 >= w || x2 < 0) continue;
+        P.span(y, x1 < 0 ? 0 : x1, x2 >= w ? w - 1 : x2);
+    }
+}
+
+// thick_segment() shared among nt workers; rows outside [ylo, yhi) are skipped (the caller's band)
+template <class Plotter>
+LD_HD void thick_segment_part(Plotter& P, int w, int h, int x0, int y0, int x1, int y1, int thickness, const int* hw,
+                              bool first, int tid, int nt, int ylo, int yhi) {
+    Pt a, b;
+    a.x = x0 + thickness; a.y = y0 + thickness;
+    b.x = x1 + thickness; b.y = y1 + thickness;
+    if (!clip_line((int64_t)w + 2 * thickness, (int64_t)h + 2 * thickness, a, b)) return;
+    x0 = (int)a.x - thickness; y0 = (int)a.y - thickness;
+    x1 = (int)b.x - thickness; y1 = (int)b.y - thickness;
+    Pt p0, p1;
+    p0.x = (int64_t)x0 << XY_SHIFT; p0.y = (int64_t)y0 << XY_SHIFT;
+    p1.x = (int64_t)x1 << XY_SHIFT; p1.y = (int64_t)y1 << XY_SHIFT;
+    const double inv = 1.0 / XY_ONE;
+    double dx = (double)(p0.x - p1.x) * inv, dy = (double)(p1.y - p0.y) * inv;
+    double r = dx * dx + dy * dy;
+    int64_t th = (int64_t)thickness << (XY_SHIFT - 1);
+    if (fabs(r) > 2.220446049250313e-16) {
+        r = ((double)th + (thickness & 1) * XY_ONE * 0.5) / sqrt(r);
+        Pt dp;
+        dp.x = round_half_even(dy * r);
+        dp.y = round_half_even(dx * r);
+        Pt q[4];
+        q[0].x = p0.x + dp.x; q[0].y = p0.y + dp.y;
+        q[1].x = p0.x - dp.x; q[1].y = p0.y - dp.y;
+        q[2].x = p1.x - dp.x; q[2].y = p1.y - dp.y;
+        q[3].x = p1.x + dp.x; q[3].y = p1.y + dp.y;
+        for (int e = 0; e < 4; ++e) line_fx_part(P, w, h, line_fx_setup(w, h, q[(e + 3) & 3], q[e]), tid, nt);
+        const QuadScan S = fill_convex_setup(w, h, q, 4);
+        fill_convex_rows_part(P, w, S, tid, nt, ylo, yhi);
+    }
+    if (first) disc_part(P, w, h, x0, y0, thickness / 2, hw, tid, nt);
+    disc_part(P, w, h, x1, y1, thickness / 2, hw, tid, nt);
+}
+
+// line8() shared among nt workers: after i iterations the minor coordinate has advanced by
+// S(i) = (2*minor*i + major - 1) / (2*major)
+template <class Plotter>
+LD_HD void line8_part(Plotter& P, int w, int h, Pt a, Pt b, int tid, int nt) {
+    if ((uint64_t)a.x >= (uint64_t)w || (uint64_t)b.x >= (uint64_t)w ||
+        (uint64_t)a.y >= (uint64_t)h || (uint64_t)b.y >= (uint64_t)h) {
+        if (!clip_line(w, h, a, b)) return;
+    }
+    int dx = (int)(b.x - a.x), dy = (int)(b.y - a.y);
+    int sy = 1;
+    int x = (int)a.x, y = (int)a.y;
+    if (dx < 0) { dx = -dx; dy = -dy; x = (int)b.x; y = (int)b.y; }
+    if (dy < 0) { dy = -dy; sy = -1; }
+    const bool vert = dy > dx;
+    const int major = vert ? dy : dx, minor = vert ? dx : dy;
+    for (int i = tid; i <= major; i += nt) {
+        const int s = major ? (int)(((int64_t)2 * minor * i + major - 1) / (2 * (int64_t)major)) : 0;
+        if (vert) P.span(y + sy * i, x + s, x + s);
+        else      P.span(y + sy * s, x + i, x + i);
+    }
+}
+
 // one polygon edge as fillPoly's scanline stage sees it: x(y) = x + (y - y0) * dx for y0 <= y < y1
 struct PolyEdge { int y0, y1; int64_t x, dx; int valid; };
 
 // Builds the scan edge for vertices a -> b and draws its 1-px outline.
+LD_HD PolyEdge poly_edge_scan(int w, int h, int ax, int ay, int bx, int by);
+
 template <class Plotter>
 LD_HD PolyEdge poly_edge(Plotter& P, int w, int h, int ax, int ay, int bx, int by) {
+    Pt t0, t1;
+    t0.x = ax; t0.y = ay; t1.x = bx; t1.y = by;
+    line8(P, w, h, t0, t1);
+    return poly_edge_scan(w, h, ax, ay, bx, by);
+}
+
+// the scan edge alone (no outline)
+LD_HD PolyEdge poly_edge_scan(int w, int h, int ax, int ay, int bx, int by) {
     PolyEdge e;
     e.valid = 0;
     Pt pt0, pt1;
@@ -342,7 +555,6 @@ LD_HD PolyEdge poly_edge(Plotter& P, int w, int h, int ax, int ay, int bx, int b
     pt1.x = (int64_t)bx << XY_SHIFT; pt1.y = by;
     Pt t0, t1;
     t0.x = ax; t0.y = ay; t1.x = bx; t1.y = by;
-    line8(P, w, h, t0, t1);
     Pt pt0c = pt0, pt1c = pt1;
     if ((uint64_t)t0.x >= (uint64_t)w || (uint64_t)t1.x >= (uint64_t)w ||
         (uint64_t)t0.y >= (uint64_t)h || (uint64_t)t1.y >= (uint64_t)h) {

@@ -69,6 +69,8 @@ class LaneEngine:
         d.n_mask_chunks, d.mask_chunks = len(p.mask_chunks), host(p.mask_chunks, np.int32)
         d.mask_chunk_start = host(p.mask_chunk_start, np.int32)
         d.bdesc = host(p.bdesc, np.uint32)
+        d.frame_amap, d.frame_amap_start = host(p.frame_amap, np.uint32), host(p.frame_amap_start, np.int32)
+        d.mask_amap, d.mask_amap_start = host(p.mask_amap, np.uint32), host(p.mask_amap_start, np.int32)
         return d
 
     def close(self):

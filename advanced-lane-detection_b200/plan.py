@@ -284,8 +284,29 @@ def gather_tiles(sx, sy, size, regions, tw=128):
             b0 = (3 * int(bx.min())) // 16 * 16
             copy = min((3 * (int(bx.max()) + 2) - b0 + 15) // 16 * 16, W * 3 - b0)
             rows = int(by.max()) + 2 - int(by.min())
-            out.append((x0, ry, w, rh, b0, int(by.min()), rows | (copy << 16), copy + 16))
+            # row stride = multiple of 128 B: the bank of a tap then depends on its column only, so lanes of a warp that
+            # sit on different source rows never collide in shared memory
+            out.append((x0, ry, w, rh, b0, int(by.min()), rows | (copy << 16), (copy + 16 + 127) // 128 * 128))
     return np.array(out, np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8)
+
+
+def gather_offsets(sx, sy, fi, gt, size):
+    """Per output pixel of every gather tile: (byte offset of its first tap inside the tile's staged box) << 10 | fraction.
+    Returns (amap u32[sum of tile pixels], start int32[T+1]); pixels of a tile are stored row-major, w*h entries.
+    Slow tiles get zeros (the kernels use und_map there)."""
+    g = gt.view(np.uint32).astype(np.int64)
+    start = np.zeros(len(g) + 1, np.int64)
+    start[1:] = np.cumsum(g[:, 2] * g[:, 3])
+    amap = np.zeros(int(start[-1]), np.uint32)
+    for i, (x0, y0, w, h, b0, sy0, rc, st) in enumerate(g):
+        if st >> 31:
+            continue
+        stride = st & 0x7FFFFFFF
+        bx, by, bf = sx[y0:y0 + h, x0:x0 + w], sy[y0:y0 + h, x0:x0 + w], fi[y0:y0 + h, x0:x0 + w]
+        off = (by - sy0).astype(np.int64) * stride + bx.astype(np.int64) * 3 - b0
+        assert off.min() >= 0 and off.max() < (1 << 22)
+        amap[start[i]:start[i + 1]] = ((off << 10) | bf).astype(np.uint32).reshape(-1)
+    return amap, start.astype(np.int32)
 
 
 BDESC_BORDER, BDESC_FALLBACK = 0xFFFFFFFF, 0xFFFFFFFE
@@ -377,6 +398,10 @@ class LanePlan:
     frame_tiles: np.ndarray    # i32[T,8]   gather_tiles over the whole frame, 128 x 16 px (undistort / overlay)
     mask_chunks: np.ndarray    # i32[C,8]   gather_tiles over each mask band's box of undistorted pixels
     mask_chunk_start: np.ndarray  # i32[n_tiles+1]  first chunk of each band
+    frame_amap: np.ndarray     # u32[sum tile px]  gather_offsets of frame_tiles (tile-major)
+    frame_amap_start: np.ndarray
+    mask_amap: np.ndarray      # u32[sum chunk px] gather_offsets of mask_chunks
+    mask_amap_start: np.ndarray
 
     @property
     def mask_algorithmic_bytes(self) -> int:
@@ -418,6 +443,9 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
         starts.append(starts[-1] + len(c))
     mask_chunks = np.concatenate(chunks) if chunks else np.zeros((0, 8), np.int32)
     bdesc = mask_word_descriptors(nx, ny, tiles, size)
+    frame_amap, frame_amap_start = gather_offsets(sx, sy, fi, frame_tiles, size)
+    mask_amap, mask_amap_start = gather_offsets(sx, sy, fi, mask_chunks, size)
     return LanePlan(variant, (W, H), mtx, dist, und_map, bilinear_weight_table(), near, tiles, bmap, bdesc, ctab, cbits,
                     inv_y0, inv_y1, np.ascontiguousarray(inv_idx), np.ascontiguousarray(inv_fi),
-                    src_row0, src_row1, gb, ga, frame_tiles, mask_chunks, np.array(starts, np.int32))
+                    src_row0, src_row1, gb, ga, frame_tiles, mask_chunks, np.array(starts, np.int32),
+                    frame_amap, frame_amap_start, mask_amap, mask_amap_start)

@@ -69,6 +69,10 @@ typedef struct ld_plan_desc {
     const int32_t* frame_tiles;      /* [n_frame_tiles*8] 128x16 output tiles + the source box each one gathers from */
     const int32_t* mask_chunks;      /* [n_mask_chunks*8] column chunks of each mask band's box of undistorted pixels */
     const int32_t* mask_chunk_start; /* [n_tiles+1] */
+    const uint32_t* frame_amap;      /* per pixel of every frame tile: staged-box byte offset << 10 | fraction */
+    const int32_t* frame_amap_start; /* [n_frame_tiles+1] */
+    const uint32_t* mask_amap;       /* same for the mask chunks */
+    const int32_t* mask_amap_start;  /* [n_mask_chunks+1] */
     const uint32_t* bdesc;           /* [H*(W/32)*4] per output word of the mask: first source bit, step masks, valid pixels */
     int32_t n_mask_chunks;
     int32_t reserved;

@@ -85,3 +85,35 @@ extern "C" void hs_fill_convex_fx(uint8_t* img, int w, int h, const int64_t* p, 
     for (int i = 0; i < n; ++i) { v[i].x = p[2 * i]; v[i].y = p[2 * i + 1]; }
     laneraster::fill_convex_fx(P, w, h, v, n);
 }
+
+// the cooperative forms, executed by `nt` simulated workers one after the other
+extern "C" void hs_polyline_coop(uint8_t* img, int w, int h, const int32_t* pts, int n, int thickness, int nt) {
+    using namespace laneraster;
+    HostPlotter P{img, w, h};
+    int radius = thickness / 2;
+    std::vector<int> hw(radius + 1);
+    circle_half_widths(radius, hw.data());
+    for (int i = 0; i + 1 < n; ++i)
+        for (int t = 0; t < nt; ++t)
+            thick_segment_part(P, w, h, pts[2 * i], pts[2 * i + 1], pts[2 * i + 2], pts[2 * i + 3], thickness, hw.data(), i == 0, t, nt,
+                               0, h);
+}
+extern "C" void hs_fillpoly_coop(uint8_t* img, int w, int h, const int32_t* pts, int n, int nt) {
+    using namespace laneraster;
+    HostPlotter P{img, w, h};
+    std::vector<PolyEdge> edges;
+    for (int i = 0; i < n; ++i) {
+        int j = (i + n - 1) % n;
+        Pt a{pts[2 * j], pts[2 * j + 1]}, b{pts[2 * i], pts[2 * i + 1]};
+        for (int t = 0; t < nt; ++t) line8_part(P, w, h, a, b, t, nt);
+        PolyEdge e = poly_edge_scan(w, h, pts[2 * j], pts[2 * j + 1], pts[2 * i], pts[2 * i + 1]);
+        if (e.valid) edges.push_back(e);
+    }
+    for (int y = 0; y < h; ++y) {
+        std::vector<int64_t> xs;
+        for (auto& e : edges)
+            if (e.y0 <= y && y < e.y1) xs.push_back(e.x + (int64_t)(y - e.y0) * e.dx);
+        std::sort(xs.begin(), xs.end());
+        for (size_t k = 0; k + 1 < xs.size(); k += 2) poly_span(P, w, y, xs[k], xs[k + 1]);
+    }
+}
