@@ -213,7 +213,7 @@ k_search(const uint32_t* __restrict__ mask, ld_lane_record* __restrict__ rec, co
                 base = a > 0 ? a : warp_argmax_first(s_ext, 0, half);
             }
         } else {                                                          // helper.py:239-240, :863-864
-            base = L ? warp_argmax_first(s_ext, 800, W - 200) + 800 : warp_argmax_first(s_ext, 200, 640);
+            base = L ? warp_argmax_first(s_ext, 800, W - 200) + 800 : warp_argmax_first(s_ext, 200, 640) + 200;
         }
         for (int k = 0; k < n_win; ++k) {
             const int top = H - win_h * (k + 1), bot = top + win_h;
