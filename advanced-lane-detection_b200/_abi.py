@@ -85,6 +85,9 @@ _SIGNATURES = {
     "ld_overlay": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "ld_process_batch": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "ld_process_batch_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "ld_prepass": (C.c_int, [_P, _P, C.c_int, _P]),
+    "ld_postpass": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
+    "ld_wait_state": (C.c_int, [_P, _P]),
     "ld_check": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "ld_state_reset": (C.c_int, [_P, _P]),
     "ld_state_size": (C.c_size_t, []),

@@ -31,6 +31,7 @@ struct PlanDev {
     int n_mask_chunks;
     const uint32_t* frame_amap; const int32_t* frame_amap_start;
     const uint32_t* mask_amap; const int32_t* mask_amap_start;
+    const void* stamps;              // laneraster::Stamp[STAMP_N] for thickness 30 (raster_math.h)
     const uint4* bdesc;              // per output mask word: (first source bit | BORDER | FALLBACK, step1, step2, valid)
     int max_out_words;
 };

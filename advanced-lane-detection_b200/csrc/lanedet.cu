@@ -35,7 +35,7 @@ struct ld_plan {
     size_t search_smem, raster_smem, mask_smem, frame_smem;
 };
 
-enum { HOST_CHUNK = 32 };
+enum { HOST_CHUNK = 32, PIPE_SUB = 8 };
 
 struct ld_ctx {
     ld_plan* plan;
@@ -52,6 +52,9 @@ struct ld_ctx {
     // host pipeline
     cudaStream_t s_in, s_comp, s_out;
     cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
+    // intra-batch pipeline: pixel-heavy kernels on s_pix, the latency-bound search/fit/raster chain on s_lat
+    cudaStream_t s_pix, s_lat;
+    cudaEvent_t ev_fork, ev_state, ev_join[2], ev_mask[PIPE_SUB], ev_rast[PIPE_SUB];
     uint8_t* stage_in[2];
     uint8_t* stage_out[2];
     int chunk;
@@ -148,6 +151,18 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     d.frame_tiles = reinterpret_cast<const int4*>(ft);
     d.mask_chunks = reinterpret_cast<const int4*>(mc);
     d.bdesc = reinterpret_cast<const uint4*>(bd);
+    {   // stamps of the short thick-line steps (translation invariant away from the border), built with the same host/device code
+        static laneraster::Stamp stamps[laneraster::STAMP_N];
+        int hw[16];
+        laneraster::circle_half_widths(15, hw);
+        laneraster::StampCanvas cv;
+        for (int dy = -laneraster::STAMP_K; dy <= laneraster::STAMP_K; ++dy)
+            for (int dx = -laneraster::STAMP_K; dx <= laneraster::STAMP_K; ++dx)
+                laneraster::build_stamp(dx, dy, 30, hw, stamps[laneraster::stamp_index(dx, dy)], cv);
+        const laneraster::Stamp* sd = nullptr;
+        if ((rc = upload(p, stamps, (size_t)laneraster::STAMP_N, &sd))) { ld_plan_destroy(p); return rc; }
+        d.stamps = sd;
+    }
     p->frame_smem = fs + 16;
     int mow = 0;
     for (int t = 0; t < desc->n_tiles; ++t) {
@@ -165,6 +180,15 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LD_CUDA(cudaFuncSetAttribute(k_frame_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
     LD_CUDA(cudaFuncSetAttribute(k_frame_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
+    // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
+    // carveout, otherwise an SM has to drain before a kernel with a different carveout can start on it.
+    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA(cudaFuncSetAttribute(k_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA(cudaFuncSetAttribute(k_fit1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA(cudaFuncSetAttribute(k_fit2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA(cudaFuncSetAttribute(k_fit3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (W == 1280 && H == 720) {        // search / raster stage the whole 115,200-byte mask plane per CTA
         LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
         LD_CUDA(cudaFuncSetAttribute(k_margin_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
@@ -223,6 +247,20 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     LD_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     LD_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
     LD_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    LD_CUDA(cudaStreamCreateWithFlags(&c->s_pix, cudaStreamNonBlocking));
+    {   // the latency-bound chain gets the highest priority: its few CTAs take SM slots as soon as they free up and run
+        // concurrently with the bandwidth-bound kernel instead of queueing behind its whole grid
+        int lo = 0, hi = 0;
+        LD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        LD_CUDA(cudaStreamCreateWithPriority(&c->s_lat, cudaStreamNonBlocking, hi));
+    }
+    LD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    LD_CUDA(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) LD_CUDA(cudaEventCreateWithFlags(&c->ev_join[b], cudaEventDisableTiming));
+    for (int b = 0; b < PIPE_SUB; ++b) {
+        LD_CUDA(cudaEventCreateWithFlags(&c->ev_mask[b], cudaEventDisableTiming));
+        LD_CUDA(cudaEventCreateWithFlags(&c->ev_rast[b], cudaEventDisableTiming));
+    }
     for (int b = 0; b < 2; ++b) {
         LD_CUDA(cudaEventCreateWithFlags(&c->ev_in[b], cudaEventDisableTiming));
         LD_CUDA(cudaEventCreateWithFlags(&c->ev_comp[b], cudaEventDisableTiming));
@@ -248,6 +286,12 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_pix) cudaStreamDestroy(c->s_pix);
+    if (c->s_lat) cudaStreamDestroy(c->s_lat);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_state) cudaEventDestroy(c->ev_state);
+    for (int b = 0; b < 2; ++b) if (c->ev_join[b]) cudaEventDestroy(c->ev_join[b]);
+    for (int b = 0; b < PIPE_SUB; ++b) { if (c->ev_mask[b]) cudaEventDestroy(c->ev_mask[b]); if (c->ev_rast[b]) cudaEventDestroy(c->ev_rast[b]); }
     delete c;
     return LD_OK;
 }
@@ -320,25 +364,39 @@ extern "C" int ld_fit(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit*
     return fit_impl(c, rec, n, fit, (cudaStream_t)stream, 0);
 }
 
+// raster + frame pass for m frames whose workspace slots start at `slot` (frame index inside the context buffers)
+static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* verts, const int32_t* counts, int max_verts,
+                         int thickness, int m, cudaStream_t s, int slot) {
+    const PlanDev& d = c->plan->d;
+    k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(
+        fit, verts, counts, max_verts, thickness, c->planes + (size_t)slot * 2 * d.H * d.WW,
+        c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);
+    return check_launch();
+}
+static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted) {
+    const PlanDev& d = c->plan->d;
+    const uint32_t* planes = c->planes + (size_t)slot * 2 * d.H * d.WW;
+    const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
+    if (already_undistorted)
+        k_frame_pass<2><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, planes, text, fout, d);
+    else
+        k_frame_pass<1><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, c->plan->frame_smem, s>>>(fin, planes, text, fout, d);
+    return check_launch();
+}
 static int launch_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* fit, const int32_t* verts,
                           const int32_t* counts, int max_verts, int thickness, int n, uint8_t* out, cudaStream_t s,
                           int already_undistorted) {
     const PlanDev& d = c->plan->d;
     if (d.H != 720 || d.W != 1280) return LD_ERR_ARG;
+    const size_t fb = (size_t)d.W * d.H * 3;
     for (int done = 0; done < n; done += c->max_frames) {
         const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
-        k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(fit ? fit + done : nullptr,
-                                                                 verts ? verts + (size_t)done * max_verts * 2 : nullptr,
-                                                                 counts ? counts + done : nullptr, max_verts, thickness,
-                                                                 c->planes, c->text, d, c->flags + 3);
-        const uint8_t* fin = frames + (size_t)done * d.W * d.H * 3;
-        uint8_t* fout = out + (size_t)done * d.W * d.H * 3;
-        if (already_undistorted)
-            k_frame_pass<2><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, c->planes, c->text, fout, d);
-        else
-            k_frame_pass<1><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, c->plan->frame_smem, s>>>(fin, c->planes, c->text, fout, d);
+        int rc;
+        if ((rc = launch_raster(c, fit ? fit + done : nullptr, verts ? verts + (size_t)done * max_verts * 2 : nullptr,
+                                counts ? counts + done : nullptr, max_verts, thickness, m, s, 0))) return rc;
+        if ((rc = launch_frame_pass(c, frames + done * fb, m, out + done * fb, s, 0, already_undistorted))) return rc;
     }
-    return check_launch();
+    return LD_OK;
 }
 
 extern "C" int ld_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* fit, int n, uint8_t* out, void* stream) {
@@ -355,20 +413,111 @@ extern "C" int ld_draw(ld_ctx* c, const uint8_t* undist, const int32_t* verts, c
     return launch_overlay(c, undist, nullptr, verts, counts, max_verts, thickness, n, out, (cudaStream_t)stream, 1);
 }
 
+// process_image over n <= max_frames frames in two passes, each software-pipelined over two internal streams in up to
+// PIPE_SUB sub-batches: the bandwidth-bound kernels (mask, frame pass) keep s_pix busy while the latency-bound ones
+// (search, raster: few resident CTAs) run on s_lat one sub-batch behind / ahead.  The fit stage sits between the
+// passes; it is the only place the tracker state is read or written, so a multi-GPU caller imports its predecessor's
+// state between ld_prepass and ld_postpass and may ship its own as soon as ev_state fires.
+static int sub_batches(int M) {
+    int nsub = M / 48;
+    return nsub > PIPE_SUB ? PIPE_SUB : (nsub < 1 ? 1 : nsub);
+}
+static int fork_streams(ld_ctx* c, cudaStream_t s) {
+    LD_CUDA(cudaEventRecord(c->ev_fork, s));
+    LD_CUDA(cudaStreamWaitEvent(c->s_pix, c->ev_fork, 0));
+    LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
+    return LD_OK;
+}
+static int join_streams(ld_ctx* c, cudaStream_t s) {
+    LD_CUDA(cudaEventRecord(c->ev_join[0], c->s_pix));
+    LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));
+    LD_CUDA(cudaStreamWaitEvent(s, c->ev_join[0], 0));
+    LD_CUDA(cudaStreamWaitEvent(s, c->ev_join[1], 0));
+    return LD_OK;
+}
+
+static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
+    const PlanDev& d = c->plan->d;
+    const size_t fb = (size_t)d.W * d.H * 3, mw = (size_t)d.H * d.WW;
+    const int nsub = sub_batches(M);
+    int rc;
+    if (nsub < 2) {
+        if ((rc = ld_mask(c, fin, M, c->mask, s))) return rc;
+        return ld_search(c, c->mask, M, c->rec, s);
+    }
+    const int S = (M + nsub - 1) / nsub;
+    if ((rc = fork_streams(c, s))) return rc;
+    for (int i = 0; i < nsub; ++i) {
+        const int off = i * S, m = (M - off) < S ? (M - off) : S;
+        if (m <= 0) break;
+        if ((rc = ld_mask(c, fin + off * fb, m, c->mask + off * mw, c->s_pix))) return rc;
+        LD_CUDA(cudaEventRecord(c->ev_mask[i], c->s_pix));
+        LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_mask[i], 0));
+        if ((rc = ld_search(c, c->mask + off * mw, m, c->rec + 2 * off, c->s_lat))) return rc;
+    }
+    return join_streams(c, s);
+}
+
+static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld_frame_fit* fit_out, void* state_out,
+                         cudaStream_t s, int frame_offset) {
+    const PlanDev& d = c->plan->d;
+    const size_t fb = (size_t)d.W * d.H * 3;
+    const int nsub = sub_batches(M);
+    int rc;
+    if (nsub < 2) {
+        if ((rc = fit_impl(c, c->rec, M, c->fit, s, frame_offset))) return rc;
+        if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, s));
+        LD_CUDA(cudaEventRecord(c->ev_state, s));
+        if ((rc = launch_raster(c, c->fit, nullptr, nullptr, 0, 30, M, s, 0))) return rc;
+        if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0))) return rc;
+    } else {
+        const int S = (M + nsub - 1) / nsub;
+        if ((rc = fork_streams(c, s))) return rc;
+        if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset))) return rc;
+        if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
+        LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
+        for (int i = 0; i < nsub; ++i) {
+            const int off = i * S, m = (M - off) < S ? (M - off) : S;
+            if (m <= 0) break;
+            if ((rc = launch_raster(c, c->fit + off, nullptr, nullptr, 0, 30, m, c->s_lat, off))) return rc;
+            LD_CUDA(cudaEventRecord(c->ev_rast[i], c->s_lat));
+            LD_CUDA(cudaStreamWaitEvent(c->s_pix, c->ev_rast[i], 0));
+            if ((rc = launch_frame_pass(c, fin + off * fb, m, fout + off * fb, c->s_pix, off, 0))) return rc;
+        }
+        if ((rc = join_streams(c, s))) return rc;
+    }
+    if (fit_out) LD_CUDA(cudaMemcpyAsync(fit_out, c->fit, sizeof(ld_frame_fit) * M, cudaMemcpyDeviceToDevice, s));
+    return LD_OK;
+}
+
 static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, cudaStream_t s,
                         int frame_offset) {
     if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
     const PlanDev& d = c->plan->d;
+    if (d.H != 720 || d.W != 1280) return LD_ERR_ARG;
     const size_t fb = (size_t)d.W * d.H * 3;
-    for (int done = 0; done < n; done += c->max_frames) {
-        const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
-        int rc;
-        if ((rc = ld_mask(c, frames + done * fb, m, c->mask, s))) return rc;
-        if ((rc = ld_search(c, c->mask, m, c->rec, s))) return rc;
-        if ((rc = fit_impl(c, c->rec, m, c->fit, s, frame_offset + done))) return rc;
-        if ((rc = ld_overlay(c, frames + done * fb, c->fit, m, out + done * fb, s))) return rc;
-        if (fit_out) LD_CUDA(cudaMemcpyAsync(fit_out + done, c->fit, sizeof(ld_frame_fit) * m, cudaMemcpyDeviceToDevice, s));
+    int rc;
+    for (int base = 0; base < n; base += c->max_frames) {
+        const int M = (n - base) < c->max_frames ? (n - base) : c->max_frames;
+        if ((rc = prepass_impl(c, frames + base * fb, M, s))) return rc;
+        if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
+                                frame_offset + base))) return rc;
     }
+    return LD_OK;
+}
+extern "C" int ld_prepass(ld_ctx* c, const uint8_t* frames, int n, void* stream) {
+    if (!c || !frames || n < 0 || n > c->max_frames) return LD_ERR_ARG;
+    if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
+    return n ? prepass_impl(c, frames, n, (cudaStream_t)stream) : LD_OK;
+}
+extern "C" int ld_postpass(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, void* state_out,
+                           void* stream) {
+    if (!ARGS_OK(c, frames, out, n) || n > c->max_frames) return LD_ERR_ARG;
+    return n ? postpass_impl(c, frames, n, out, fit_out, state_out, (cudaStream_t)stream, 0) : LD_OK;
+}
+extern "C" int ld_wait_state(ld_ctx* c, void* stream) {
+    if (!c) return LD_ERR_ARG;
+    LD_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_state, 0));
     return LD_OK;
 }
 extern "C" int ld_process_batch(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, void* stream) {
@@ -431,13 +580,21 @@ extern "C" size_t ld_state_size(void) { return sizeof(TrackState); }
 extern "C" int ld_state_export(ld_ctx* c, void* blob, void* stream) {
     if (!c || !blob) return LD_ERR_ARG;
     LD_CUDA(cudaMemcpyAsync(blob, c->state, sizeof(TrackState), cudaMemcpyDefault, (cudaStream_t)stream));
-    LD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, blob) != cudaSuccess || at.type != cudaMemoryTypeDevice) {   // host blob: make it readable now
+        cudaGetLastError();
+        LD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
     return LD_OK;
 }
 extern "C" int ld_state_import(ld_ctx* c, const void* blob, void* stream) {
     if (!c || !blob) return LD_ERR_ARG;
     LD_CUDA(cudaMemcpyAsync(c->state, blob, sizeof(TrackState), cudaMemcpyDefault, (cudaStream_t)stream));
-    LD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, blob) != cudaSuccess || at.type != cudaMemoryTypeDevice) {   // host blob may be freed by the caller
+        cudaGetLastError();
+        LD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
     return LD_OK;
 }
 

@@ -83,6 +83,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     uint32_t* out_green = out_red + (size_t)H * WW;
     BandPlotter red{s_red, WW, W, y_lo, y_hi}, green{s_green, WW, W, y_lo, y_hi};
     const int tid = threadIdx.x;
+    const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
 
     for (int i = tid; i < 2 * RASTER_BAND * WW; i += RASTER_THREADS) s_red[i] = 0;
     for (int i = tid; i < RASTER_BAND; i += RASTER_THREADS) R.cnt[i] = 0;
@@ -163,7 +164,11 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
                                                          nx ? R.vy[i + 2] : 0, thickness, i == 0);
             if (!(cls & laneraster::SEG_TRIVIAL)) {
                 // long segments (lane gaps, the connector between the lanes) are drawn by the whole CTA in pass 3
-                if (max(abs(R.vx[i + 1] - R.vx[i]), abs(yb - ya)) > 24) R.big[atomicAdd(&R.n_big, 1)] = (unsigned short)i;
+                if (thickness == 30 && laneraster::stamp_applies(R.vx[i], ya, R.vx[i + 1], yb, W, H) &&
+                    stamps[laneraster::stamp_index(R.vx[i + 1] - R.vx[i], yb - ya)].ok) {
+                    R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (3 << 14));      // precomputed quad + end disc
+                    if (i == 0) R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (2 << 14));
+                } else if (max(abs(R.vx[i + 1] - R.vx[i]), abs(yb - ya)) > 24) R.big[atomicAdd(&R.n_big, 1)] = (unsigned short)i;
                 else R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)i;
                 continue;
             }
@@ -176,6 +181,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     for (int k = tid; k < R.n_jobs; k += RASTER_THREADS) {
         const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
         if (type == 0) laneraster::thick_segment(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0);
+        else if (type == 3) laneraster::draw_stamp(red, stamps[laneraster::stamp_index(R.vx[i + 1] - R.vx[i], R.vy[i + 1] - R.vy[i])], R.vx[i], R.vy[i]);
         else if (type == 1) laneraster::disc(red, W, H, R.vx[i + 1], R.vy[i + 1], radius, R.hw);
         else laneraster::disc(red, W, H, R.vx[i], R.vy[i], radius, R.hw);
     }

@@ -22,6 +22,11 @@
 #define LD_HD static inline
 #endif
 #endif
+#if defined(__CUDACC__)
+#define LD_HDM __host__ __device__ __forceinline__     // member functions
+#else
+#define LD_HDM inline
+#endif
 
 namespace laneraster {
 
@@ -305,6 +310,62 @@ LD_HD bool trivial_step(int ax, int ay, int bx, int by, int w, int h, int t) {
            by >= -t && by <= h + t - 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stamps.  Away from the frame border the rasterisation of one thick segment depends only on (dx, dy): every step of
+// the quad / disc arithmetic is translation invariant for integer pixel offsets.  For the short steps that make up
+// a lane (|dx|, |dy| <= STAMP_K) the pixels of  quad(a->b) U disc(b)  are therefore precomputed once, per row
+// offset from a, as one inclusive x-interval (a convexity check at build time rejects a stamp that is not a single
+// interval per row; such steps keep using the general code).
+enum { STAMP_K = 3, STAMP_N = (2 * STAMP_K + 1) * (2 * STAMP_K + 1), STAMP_ROWS = 40, STAMP_HALF = 16 + STAMP_K };
+struct Stamp { short x1[STAMP_ROWS], x2[STAMP_ROWS]; short ok, pad; };      // row r <-> y = a.y - STAMP_HALF + r
+
+struct StampCanvas {                 // 96 x 96 host/device scratch raster
+    unsigned long long lo[96], hi[96];
+    LD_HDM void clear() { for (int i = 0; i < 96; ++i) lo[i] = hi[i] = 0; }
+    LD_HDM void span(int y, int x1, int x2) {
+        if (y < 0 || y >= 96) return;
+        if (x1 < 0) x1 = 0;
+        if (x2 > 95) x2 = 95;
+        for (int x = x1; x <= x2; ++x) { if (x < 64) lo[y] |= 1ull << x; else hi[y] |= 1ull << (x - 64); }
+    }
+    LD_HDM bool get(int y, int x) const { return x < 64 ? (lo[y] >> x) & 1ull : (hi[y] >> (x - 64)) & 1ull; }
+};
+
+LD_HD int stamp_index(int dx, int dy) { return (dy + STAMP_K) * (2 * STAMP_K + 1) + (dx + STAMP_K); }
+
+LD_HD void build_stamp(int dx, int dy, int thickness, const int* hw, Stamp& st, StampCanvas& cv) {
+    const int c = 48;
+    cv.clear();
+    st.ok = 0; st.pad = 0;
+    for (int r = 0; r < STAMP_ROWS; ++r) { st.x1[r] = 1; st.x2[r] = 0; }
+    if (dx == 0 && dy == 0) return;
+    thick_segment_quad(cv, 96, 96, c, c, c + dx, c + dy, thickness);
+    disc(cv, 96, 96, c + dx, c + dy, thickness / 2, hw);
+    for (int y = 0; y < 96; ++y) {
+        int a = -1, b = -1, n = 0;
+        for (int x = 0; x < 96; ++x)
+            if (cv.get(y, x)) { if (a < 0) a = x; b = x; ++n; }
+        if (n == 0) continue;
+        const int r = y - c + STAMP_HALF;
+        if (r < 0 || r >= STAMP_ROWS || n != b - a + 1) return;          // outside the table or not one interval: no stamp
+        st.x1[r] = (short)(a - c); st.x2[r] = (short)(b - c);
+    }
+    st.ok = 1;
+}
+
+// a stamp may replace the general code when nothing of the segment's footprint is clipped anywhere
+LD_HD bool stamp_applies(int ax, int ay, int bx, int by, int w, int h) {
+    const int dx = bx - ax, dy = by - ay, m = STAMP_HALF + 1;
+    return dx >= -STAMP_K && dx <= STAMP_K && dy >= -STAMP_K && dy <= STAMP_K && (dx | dy) != 0 &&
+           ax >= m && ax < w - m && ay >= m && ay < h - m && bx >= m && bx < w - m && by >= m && by < h - m;
+}
+
+template <class Plotter>
+LD_HD void draw_stamp(Plotter& P, const Stamp& st, int ax, int ay) {
+    for (int r = 0; r < STAMP_ROWS; ++r)
+        if (st.x1[r] <= st.x2[r]) P.span(ay - STAMP_HALF + r, ax + st.x1[r], ax + st.x2[r]);
+}
+
 // Classification of segment (a -> b) of cv2.polylines with the shortcuts above; (c) is the vertex after b if has_next.
 enum { SEG_TRIVIAL = 1, SEG_END_DISC = 2, SEG_START_DISC = 4 };
 LD_HD int classify_segment(int w, int h, int ax, int ay, int bx, int by, bool has_next, int cx, int cy, int thickness, bool first) {
@@ -316,9 +377,14 @@ LD_HD int classify_segment(int w, int h, int ax, int ay, int bx, int by, bool ha
 // The whole segment, shortcuts included (the CUDA kernel defers the expensive parts to a compacted job list instead).
 template <class Plotter>
 LD_HD void polyline_segment(Plotter& P, int w, int h, int ax, int ay, int bx, int by, bool has_next, int cx, int cy,
-                            int thickness, const int* hw, bool first) {
+                            int thickness, const int* hw, bool first, const Stamp* stamps = 0) {
     const int cls = classify_segment(w, h, ax, ay, bx, by, has_next, cx, cy, thickness, first);
     if (!(cls & SEG_TRIVIAL)) {
+        if (stamps && stamp_applies(ax, ay, bx, by, w, h) && stamps[stamp_index(bx - ax, by - ay)].ok) {
+            draw_stamp(P, stamps[stamp_index(bx - ax, by - ay)], ax, ay);
+            if (first) disc(P, w, h, ax, ay, thickness / 2, hw);
+            return;
+        }
         thick_segment(P, w, h, ax, ay, bx, by, thickness, hw, first);
         return;
     }

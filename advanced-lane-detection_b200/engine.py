@@ -156,6 +156,26 @@ class LaneEngine:
         _abi.check(self.lib, self.lib.ld_process_batch(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits), self._stream()))
         return out, fits
 
+    def prepass_dev(self, frames):
+        """mask + search of a frame range into the context workspace (no tracker access)"""
+        frames = self._frames(frames)
+        _abi.check(self.lib, self.lib.ld_prepass(self._ctx_h, _ptr(frames), frames.shape[0], self._stream()))
+
+    def postpass_dev(self, frames, out=None, fits=None, state_out=None):
+        """fit (tracker order!) + overlay of the range given to prepass_dev; state_out = CUDA uint8 blob or None"""
+        frames = self._frames(frames)
+        n = frames.shape[0]
+        if out is None:
+            out = self.torch.empty_like(frames)
+        if fits is None:
+            fits = self._dev((n, _abi.FIT_DTYPE.itemsize), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_postpass(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits),
+                                                  _ptr(state_out) if state_out is not None else None, self._stream()))
+        return out, fits
+
+    def wait_state(self, stream):
+        _abi.check(self.lib, self.lib.ld_wait_state(self._ctx_h, C.c_void_p(stream.cuda_stream)))
+
     def process_host(self, frames: np.ndarray, want_fits: bool = True):
         """process_image for a batch of host frames (uint8 [n,H,W,3]); copies in/out are pipelined inside."""
         torch = self.torch

@@ -36,37 +36,34 @@ def handoff_chain(rank: int, world: int, recv_fn, send_fn, run_ordered):
     return new_state
 
 
-def process_sharded(engine, frames_dev, rank: int, world: int, group=None, out=None):
+def process_sharded(engine, frames_dev, rank: int, world: int, group=None, out=None, fits=None):
     """Run this rank's frame range of a video whose ranges are laid out rank after rank.
-    frames_dev: this rank's frames (CUDA uint8 [n,H,W,3]).  Returns (out, fits) like LaneEngine.process_dev."""
+    frames_dev: this rank's frames (CUDA uint8 [n,H,W,3], n <= engine.max_frames).
+    Returns (out, fits) like LaneEngine.process_dev."""
     import torch
     import torch.distributed as dist
-    mask = engine.mask_dev(frames_dev)
-    rec = engine.search_dev(mask)
+    engine.prepass_dev(frames_dev)                              # mask + search: no tracker access, runs on every rank at once
     nbytes = engine.lib.ld_state_size()
-    blob = torch.empty(nbytes, dtype=torch.uint8, device=frames_dev.device)
+    blob_in = torch.empty(nbytes, dtype=torch.uint8, device=frames_dev.device)
+    blob_out = torch.empty(nbytes, dtype=torch.uint8, device=frames_dev.device) if rank + 1 < world else None
+    result = {}
 
     def recv():
-        dist.recv(blob, src=rank - 1, group=group)
-        return blob
+        dist.recv(blob_in, src=rank - 1, group=group)
+        return blob_in
 
     def run(state):
         if state is not None:
             engine.import_state_dev(state)
-        fits = engine.fit_dev(rec)
-        engine.export_state_dev(blob)
-        return fits
-
-    holder = {}
-
-    def run_and_keep(state):
-        holder["fits"] = run(state)
-        return blob
+        result["v"] = engine.postpass_dev(frames_dev, out=out, fits=fits, state_out=blob_out)
+        return blob_out
 
     def send(state):
-        dist.send(state, dst=rank + 1, group=group)
+        side = torch.cuda.Stream(device=frames_dev.device)      # ship the blob as soon as the fit stage is done,
+        engine.wait_state(side)                                 # while this rank's overlay is still running
+        with torch.cuda.stream(side):
+            dist.send(state, dst=rank + 1, group=group)
+        torch.cuda.current_stream(frames_dev.device).wait_stream(side)
 
-    handoff_chain(rank, world, recv, send, run_and_keep)
-    fits = holder["fits"]
-    res = engine.overlay_dev(frames_dev, fits) if out is None else engine.overlay_into(frames_dev, fits, out)
-    return res, fits
+    handoff_chain(rank, world, recv, send, run)
+    return result["v"]

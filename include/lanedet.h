@@ -143,6 +143,15 @@ int ld_overlay(ld_ctx* ctx, const uint8_t* frames_dev, const ld_frame_fit* fit_d
 /* process_image for n consecutive frames (Project.py:289-334).  fit_dev may be NULL. */
 int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev,
                      ld_frame_fit* fit_dev, void* stream);
+/* The same work split around the only order-dependent stage, for frame-range sharding over several GPUs
+ * (n <= max_frames): ld_prepass = mask + search of the range (no tracker access); ld_postpass = fit (reads and
+ * updates the trackers) + overlay.  Between the two a rank imports its predecessor's tracker blob
+ * (ld_state_import).  If state_out_dev is not NULL the updated blob is copied there right after the fit stage and
+ * ld_wait_state makes `stream` wait for exactly that copy, so it can be sent on while the overlay still runs. */
+int ld_prepass(ld_ctx* ctx, const uint8_t* frames_dev, int n, void* stream);
+int ld_postpass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, ld_frame_fit* fit_dev,
+                void* state_out_dev, void* stream);
+int ld_wait_state(ld_ctx* ctx, void* stream);
 /* Same with host buffers: chunks are copied in, processed and copied out on three streams.
  * Synchronous; returns LD_ERR_EMPTY_LANE like the reference raises.  fits_host may be NULL. */
 int ld_process_batch_host(ld_ctx* ctx, const uint8_t* frames_host, int n, uint8_t* out_host,

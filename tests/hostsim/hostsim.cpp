@@ -41,9 +41,19 @@ void hs_polyline(uint8_t* img, int w, int h, const int32_t* pts, int n, int thic
     int radius = thickness / 2;
     std::vector<int> hw(radius + 1);
     circle_half_widths(radius, hw.data());
+    static std::vector<Stamp> stamps;                  // built once per thickness, like ld_plan_create does
+    static int stamps_for = -1;
+    if (stamps_for != thickness) {
+        stamps.assign(STAMP_N, Stamp());
+        StampCanvas cv;
+        for (int dy = -STAMP_K; dy <= STAMP_K; ++dy)
+            for (int dx = -STAMP_K; dx <= STAMP_K; ++dx) build_stamp(dx, dy, thickness, hw.data(), stamps[stamp_index(dx, dy)], cv);
+        stamps_for = thickness;
+    }
     for (int i = 0; i + 1 < n; ++i)
         polyline_segment(P, w, h, pts[2 * i], pts[2 * i + 1], pts[2 * i + 2], pts[2 * i + 3], i + 2 < n,
-                         i + 2 < n ? pts[2 * i + 4] : 0, i + 2 < n ? pts[2 * i + 5] : 0, thickness, hw.data(), i == 0);
+                         i + 2 < n ? pts[2 * i + 4] : 0, i + 2 < n ? pts[2 * i + 5] : 0, thickness, hw.data(), i == 0,
+                         thickness == 30 ? stamps.data() : nullptr);
 }
 
 // cv2.fillPoly(img, [pts], 1)
@@ -66,6 +76,15 @@ void hs_fillpoly(uint8_t* img, int w, int h, const int32_t* pts, int n) {
 }
 }
 
+extern "C" int hs_stamps_ok(int thickness) {        // how many of the (2K+1)^2-1 stamps are single-interval
+    using namespace laneraster;
+    std::vector<int> hw(thickness / 2 + 1);
+    circle_half_widths(thickness / 2, hw.data());
+    StampCanvas cv; Stamp st; int n = 0;
+    for (int dy = -STAMP_K; dy <= STAMP_K; ++dy)
+        for (int dx = -STAMP_K; dx <= STAMP_K; ++dx) { build_stamp(dx, dy, thickness, hw.data(), st, cv); n += st.ok; }
+    return n;
+}
 extern "C" int hs_clip_line(int64_t w, int64_t h, int64_t* p /* x1,y1,x2,y2 */) {
     laneraster::Pt a{p[0], p[1]}, b{p[2], p[3]};
     bool r = laneraster::clip_line(w, h, a, b);
@@ -116,4 +135,12 @@ extern "C" void hs_fillpoly_coop(uint8_t* img, int w, int h, const int32_t* pts,
         std::sort(xs.begin(), xs.end());
         for (size_t k = 0; k + 1 < xs.size(); k += 2) poly_span(P, w, y, xs[k], xs[k + 1]);
     }
+}
+extern "C" int hs_stamp_ok(int dx, int dy, int thickness) {
+    using namespace laneraster;
+    std::vector<int> hw(thickness / 2 + 1);
+    circle_half_widths(thickness / 2, hw.data());
+    StampCanvas cv; Stamp st;
+    build_stamp(dx, dy, thickness, hw.data(), st, cv);
+    return st.ok;
 }

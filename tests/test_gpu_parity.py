@@ -225,3 +225,23 @@ def test_helper_surface_stages(engines, stills):
     packed = eng.pack_dev(eng.to_device(m[None]))
     assert (eng.unpack_dev(packed)[0].cpu().numpy() == m).all()
     assert (packed.cpu().numpy().view(np.uint32)[0] == O.pack_mask(m)).all()
+
+
+def test_prepass_postpass_equals_process(engines, stills, golden):
+    """the split the multi-GPU path uses (mask+search | fit+overlay, state blob copied out after the fit stage)"""
+    import torch
+    g = golden["sequences"]["project_seed0_40"]
+    frames = np.stack(list(O.synth_sequence([stills(s) for s in g["stills"]], 40, seed=g["seed"])))
+    eng = engines("project")
+    dev = eng.to_device(frames)
+    eng.reset()
+    out_a, fit_a = eng.process_dev(dev)
+    eng.check()
+    want_state = eng.export_state()
+    eng.reset()
+    blob = torch.zeros(eng.lib.ld_state_size(), dtype=torch.uint8, device=dev.device)
+    eng.prepass_dev(dev)
+    out_b, fit_b = eng.postpass_dev(dev, state_out=blob)
+    eng.check()
+    assert (out_a == out_b).all() and (fit_a == fit_b).all()
+    assert bytes(blob.cpu().numpy().tobytes()) == want_state
