@@ -245,3 +245,58 @@ def test_prepass_postpass_equals_process(engines, stills, golden):
     eng.check()
     assert (out_a == out_b).all() and (fit_a == fit_b).all()
     assert bytes(blob.cpu().numpy().tobytes()) == want_state
+
+
+def test_config4_4k_mask_and_histogram():
+    """BASELINE.json configs[3]: 3840x2160 frames through the fused mask + histogram kernels (maps from the
+    calibration scaled x3), against cv2 run directly at that size."""
+    import cv2
+    import importlib
+    pkg = load_pkg()
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    k, W, H = 3, 3840, 2160
+    v = P.scaled_variant(P.PROJECT, k)
+    mtx = P.scaled_calibration(P.CAL_MTX, k)
+    plan = P.build_plan(v, mtx, P.CAL_DIST, size=(W, H))
+    eng = pkg.LaneEngine(plan=plan, max_frames=2)
+    rng = np.random.default_rng(1)
+    noise = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    from conftest import read_still
+    up = np.repeat(np.repeat(read_still("test1"), k, axis=0), k, axis=1)          # nearest-upscaled still
+    frames = np.stack([noise, up])
+    mask_t = eng.mask_dev(eng.to_device(frames))
+    masks = unpack(mask_t)
+    hist = eng.hist_dev(mask_t).cpu().numpy().astype(np.int64)
+    M = cv2.getPerspectiveTransform(np.float32(v.src), np.float32(v.dst))
+    for i in range(2):
+        und = cv2.undistort(frames[i], mtx, P.CAL_DIST, None, mtx)
+        warped = cv2.warpPerspective(und, M, (W, H), flags=cv2.INTER_NEAREST)
+        want = O.colour_mask(warped, v.l_thresh, v.b_thresh)
+        assert (masks[i] == want).all(), "4K frame %d differs in %d px" % (i, (masks[i] != want).sum())
+        bh = H // 8
+        for b in range(8):
+            top = H - bh * (b + 1)
+            assert (hist[i, b] == want[top:top + bh].sum(axis=0)).all()
+    assert masks[1].sum() > 100000
+    eng.close()
+
+
+def test_config5_independent_streams(engines, stills, golden):
+    """BASELINE.json configs[4]: independent video streams = independent contexts; interleaving their calls on one
+    GPU must not mix tracker state (one context per stream is what maps one stream per GPU)."""
+    pkg = load_pkg()
+    g = golden["sequences"]["project_seed0_40"]
+    a = np.stack(list(O.synth_sequence([stills(s) for s in g["stills"]], 20, seed=0)))
+    b = np.stack(list(O.synth_sequence([stills(s) for s in g["stills"][::-1]], 20, seed=1)))
+    e1, e2 = pkg.LaneEngine("project", max_frames=32), pkg.LaneEngine("project", max_frames=32)
+    da, db = e1.to_device(a), e2.to_device(b)
+    ref_a = e1.fits_to_numpy(e1.process_dev(da)[1]).copy()
+    e1.reset()
+    parts_a, parts_b = [], []
+    for lo in range(0, 20, 5):
+        parts_a.append(e1.fits_to_numpy(e1.process_dev(da[lo:lo + 5])[1]))
+        parts_b.append(e2.fits_to_numpy(e2.process_dev(db[lo:lo + 5])[1]))
+    e1.check(); e2.check()
+    assert np.concatenate(parts_a).tobytes() == ref_a.tobytes()
+    assert np.concatenate(parts_b).tobytes() != ref_a.tobytes()
+    e1.close(); e2.close()
