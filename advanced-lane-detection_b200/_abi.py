@@ -42,7 +42,7 @@ class PlanDesc(C.Structure):
                 ("und_map", C.c_void_p), ("wtab", C.c_void_p), ("near_map", C.c_void_p), ("tiles", C.c_void_p),
                 ("bmap", C.c_void_p), ("ctab", C.c_void_p), ("cbits", C.c_void_p),
                 ("inv_y0", C.c_int32), ("inv_y1", C.c_int32),
-                ("inv_idx", C.c_void_p), ("inv_fi", C.c_void_p), ("glyph_bits", C.c_void_p), ("glyph_adv", C.c_void_p),
+                ("inv_idx", C.c_void_p), ("inv_fi", C.c_void_p), ("inv_pack", C.c_void_p), ("glyph_bits", C.c_void_p), ("glyph_adv", C.c_void_p),
                 ("n_glyphs", C.c_int32), ("n_frame_tiles", C.c_int32),
                 ("frame_tiles", C.c_void_p), ("mask_chunks", C.c_void_p), ("mask_chunk_start", C.c_void_p), ("frame_amap", C.c_void_p), ("frame_amap_start", C.c_void_p),
                 ("mask_amap", C.c_void_p), ("mask_amap_start", C.c_void_p), ("bdesc", C.c_void_p),

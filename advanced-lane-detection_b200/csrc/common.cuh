@@ -21,6 +21,7 @@ struct PlanDev {
     int inv_y0, inv_y1;
     const uint32_t* inv_idx;
     const uint16_t* inv_fi;
+    const uint32_t* inv_pack;
     const uint32_t* glyph_bits;
     const int32_t* glyph_adv;
     int n_glyphs;

@@ -44,7 +44,7 @@ struct ld_ctx {
     ld_lane_record* rec;       // [max][2]
     FitWork* work;             // [max][2]
     ld_frame_fit* fit;         // [max]
-    uint32_t* planes;          // [max][2][H][WW]
+    uint32_t* planes;          // [max][H][WW][2]  (red without green, green) interleaved per word
     uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
     TrackState* state;
     int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error
@@ -92,7 +92,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     const int W = desc->width, H = desc->height;
     if (W <= 0 || H <= 0 || (W % 32) || (H % 2) || desc->n_tiles <= 0 || desc->frame_num < 1 ||
         desc->frame_num > LD_MAX_DEPTH || !desc->und_map || !desc->wtab || !desc->near_map || !desc->tiles ||
-        !desc->bmap || !desc->ctab || !desc->cbits || !desc->inv_idx || !desc->inv_fi || !desc->glyph_bits ||
+        !desc->bmap || !desc->ctab || !desc->cbits || !desc->inv_idx || !desc->inv_fi || !desc->inv_pack || !desc->glyph_bits ||
         !desc->glyph_adv || !desc->frame_tiles || !desc->mask_chunks || !desc->mask_chunk_start || !desc->bdesc || !desc->frame_amap || !desc->frame_amap_start || !desc->mask_amap || !desc->mask_amap_start || desc->n_frame_tiles <= 0)
         return LD_ERR_ARG;
     int count = 0;
@@ -132,7 +132,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
         (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
-        (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) ||
+        (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) || (rc = upload(p, desc->inv_pack, ninv ? ninv : 1, &d.inv_pack)) ||
         (rc = upload(p, desc->glyph_bits, (size_t)desc->n_glyphs * LD_GLYPH_ROWS * LD_GLYPH_WORDS, &d.glyph_bits)) ||
         (rc = upload(p, desc->glyph_adv, (size_t)desc->n_glyphs, &d.glyph_adv)) ||
         (rc = upload(p, desc->frame_tiles, (size_t)desc->n_frame_tiles * 8, &ft)) ||

@@ -63,7 +63,7 @@ __device__ __forceinline__ int vertex_x(const double* c, int y) {
     return (int)v;                                              // truncation toward zero
 }
 
-// One CTA = one 90-row band of one frame's canvas.  planes: u32[n][2][H][WW] (red without green, green);
+// One CTA = one 90-row band of one frame's canvas.  planes: u32[n][H][WW][2] (red without green, green) per word;
 // text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  Vertices come from the frame's fit + row maps
 // (verts == nullptr) or are given explicitly (ld_draw).  Every CTA lists all vertices (cheap, parallel) and
 // draws only the primitives whose rows can touch its band, one primitive per thread.
@@ -79,8 +79,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     RasterShared& R = *reinterpret_cast<RasterShared*>(s_text + LD_TEXT_ROWS * LD_TEXT_WORDS);
     const int f = blockIdx.y, band = blockIdx.x;
     const int y_lo = band * RASTER_BAND, y_hi = min(H, y_lo + RASTER_BAND);
-    uint32_t* out_red = planes + ((size_t)f * 2 * H + y_lo) * WW;
-    uint32_t* out_green = out_red + (size_t)H * WW;
+    uint2* out_planes = reinterpret_cast<uint2*>(planes) + ((size_t)f * H + y_lo) * WW;
     BandPlotter red{s_red, WW, W, y_lo, y_hi}, green{s_green, WW, W, y_lo, y_hi};
     const int tid = threadIdx.x;
     const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
@@ -221,8 +220,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     __syncthreads();
     for (int i = tid; i < (y_hi - y_lo) * WW; i += RASTER_THREADS) {    // green overwrites red
         const uint32_t g = s_green[i];
-        out_green[i] = g;
-        out_red[i] = s_red[i] & ~g;
+        out_planes[i] = make_uint2(s_red[i] & ~g, g);
     }
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
 
@@ -260,48 +258,50 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
 }
 
 // canvas colour code at (cx, cy): bit0 = red, bit1 = green, 0 outside (BORDER_CONSTANT)
-__device__ __forceinline__ uint32_t canvas_tap(const uint32_t* __restrict__ red, const uint32_t* __restrict__ green,
-                                               int W, int H, int WW, int cx, int cy) {
+__device__ __forceinline__ uint32_t canvas_tap(const uint2* __restrict__ cv, int W, int H, int WW, int cx, int cy) {
     if ((unsigned)cx >= (unsigned)W || (unsigned)cy >= (unsigned)H) return 0u;
-    const int i = cy * WW + (cx >> 5), b = cx & 31;
-    return ((__ldg(red + i) >> b) & 1u) | (((__ldg(green + i) >> b) & 1u) << 1);
+    const uint2 w = __ldg(cv + cy * WW + (cx >> 5));
+    const int b = cx & 31;
+    return ((w.x >> b) & 1u) | (((w.y >> b) & 1u) << 1);
 }
 
 // + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170) for 4 consecutive pixels of row y starting at x0.
-// Most pixels of the trapezoid see four equal taps (all background or all green), so those two cases are
-// decided from the plane words directly: 0 -> nothing to add; all green -> the warped pixel is exactly (0,255,0).
-__device__ __forceinline__ void blend_canvas4(uint32_t* c, const uint32_t* __restrict__ red, const uint32_t* __restrict__ green,
-                                              const PlanDev& P, int x0, int y) {
+// cv = this frame's canvas, one (red, green) word pair per 32 pixels.  Most pixels of the trapezoid see four equal
+// taps (all background or all green), so those two cases are decided from the plane words directly: 0 -> nothing
+// to add; all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to even) to g + 76 + (g & 1).
+__device__ __forceinline__ void blend_canvas4(uint32_t* c, const uint2* __restrict__ cv, const PlanDev& P, int x0, int y) {
     if (y < P.inv_y0 || y >= P.inv_y1) return;
     const int W = P.W, H = P.H, WW = P.WW;
     const size_t mi = (size_t)(y - P.inv_y0) * W + x0;
-    const uint4 idx4 = __ldg(reinterpret_cast<const uint4*>(P.inv_idx + mi));
-    if ((idx4.x & idx4.y & idx4.z & idx4.w) == 0xFFFFFFFFu) return;
-    const uint32_t idx[4] = {idx4.x, idx4.y, idx4.z, idx4.w};
-    uint2 fi4 = make_uint2(0u, 0u);
-    bool have_fi = false;
+    const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(P.inv_pack + mi));
+    if ((e4.x & e4.y & e4.z & e4.w) == 0xFFFFFFFFu) return;
+    const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (idx[k] == 0xFFFFFFFFu) continue;
-        const int sx = (int)(idx[k] & 0xFFFFu) - 1, sy = (int)(idx[k] >> 16) - 1;
+        const uint32_t e = es[k];
+        if (e == 0xFFFFFFFFu) continue;
         uint32_t t00, t01, t10, t11;
-        const int b = sx & 31;
-        if (sx >= 0 && b != 31 && sy >= 0 && sy < H - 1) {           // both columns in one word, both rows inside
-            const int i = sy * WW + (sx >> 5);
-            const uint32_t r0 = (__ldg(red + i) >> b) & 3u, g0 = (__ldg(green + i) >> b) & 3u;
-            const uint32_t r1 = (__ldg(red + i + WW) >> b) & 3u, g1 = (__ldg(green + i + WW) >> b) & 3u;
+        if (e & 0x800u) {                                                // both columns in one word, both rows inside
+            const uint2* p = cv + (e >> 17);
+            const uint32_t b = (e >> 12) & 31u;
+            const uint2 a0 = __ldg(p), a1 = __ldg(p + WW);
+            const uint32_t r0 = (a0.x >> b) & 3u, g0 = (a0.y >> b) & 3u, r1 = (a1.x >> b) & 3u, g1 = (a1.y >> b) & 3u;
             if (!(r0 | g0 | r1 | g1)) continue;
-            if ((g0 & g1) == 3u) { c[k] = (c[k] & 0xFF00FFu) | (blend_u8((c[k] >> 8) & 255u, 255u) << 8); continue; }
+            if ((g0 & g1) == 3u) {
+                const uint32_t g = (c[k] >> 8) & 255u;
+                c[k] = (c[k] & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
+                continue;
+            }
             t00 = (r0 & 1u) | ((g0 & 1u) << 1); t01 = (r0 >> 1) | ((g0 >> 1) << 1);
             t10 = (r1 & 1u) | ((g1 & 1u) << 1); t11 = (r1 >> 1) | ((g1 >> 1) << 1);
         } else {
-            t00 = canvas_tap(red, green, W, H, WW, sx, sy); t01 = canvas_tap(red, green, W, H, WW, sx + 1, sy);
-            t10 = canvas_tap(red, green, W, H, WW, sx, sy + 1); t11 = canvas_tap(red, green, W, H, WW, sx + 1, sy + 1);
+            const uint32_t idx = __ldg(P.inv_idx + mi + k);
+            const int sx = (int)(idx & 0xFFFFu) - 1, sy = (int)(idx >> 16) - 1;
+            t00 = canvas_tap(cv, W, H, WW, sx, sy); t01 = canvas_tap(cv, W, H, WW, sx + 1, sy);
+            t10 = canvas_tap(cv, W, H, WW, sx, sy + 1); t11 = canvas_tap(cv, W, H, WW, sx + 1, sy + 1);
             if (!(t00 | t01 | t10 | t11)) continue;
         }
-        if (!have_fi) { fi4 = __ldg(reinterpret_cast<const uint2*>(P.inv_fi + mi)); have_fi = true; }
-        const uint32_t fi = (k == 0 ? fi4.x : k == 1 ? fi4.x >> 16 : k == 2 ? fi4.y : fi4.y >> 16) & 0xFFFFu;
-        const int fx = fi & 31, fy = fi >> 5;
+        const int fx = e & 31, fy = (e >> 5) & 31;
         const int w00 = 32 * (32 - fy) * (32 - fx), w01 = 32 * (32 - fy) * fx, w10 = 32 * fy * (32 - fx), w11 = 32 * fy * fx;
         const int wr = (t00 & 1) * w00 + (t01 & 1) * w01 + (t10 & 1) * w10 + (t11 & 1) * w11;
         const int wg = (t00 >> 1) * w00 + (t01 >> 1) * w01 + (t10 >> 1) * w10 + (t11 >> 1) * w11;
@@ -342,8 +342,7 @@ k_frame_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
     const int f = blockIdx.y;
     const uint8_t* frame = frames + (size_t)f * fbytes;
     uint8_t* out_frame = out + (size_t)f * fbytes;
-    const uint32_t* red = planes + (size_t)f * 2 * H * WW;
-    const uint32_t* green = red + (size_t)H * WW;
+    const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * H * WW;
     const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
     if (MODE != 2) {
         if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -375,7 +374,7 @@ k_frame_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
             c[2] = bilinear_rgb(frame, W, H, x0 + 2, y, e.z, P.wtab);
             c[3] = bilinear_rgb(frame, W, H, x0 + 3, y, e.w, P.wtab);
         }
-        if (MODE != 0) blend_canvas4(c, red, green, P, x0, y);
+        if (MODE != 0) blend_canvas4(c, cv, P, x0, y);
         if (MODE == 1) text4(c, text, f, x0, y);
         store4(out_frame, W, x0, y, c);
     }

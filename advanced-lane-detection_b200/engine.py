@@ -63,6 +63,7 @@ class LaneEngine:
         d.ctab, d.cbits = host(p.ctab, np.uint32), host(p.cbits, np.uint32)
         d.inv_y0, d.inv_y1 = p.inv_y0, p.inv_y1
         d.inv_idx, d.inv_fi = host(p.inv_idx, np.uint32), host(p.inv_fi, np.uint16)
+        d.inv_pack = host(p.inv_pack, np.uint32)
         d.glyph_bits, d.glyph_adv = host(p.glyph_bits, np.uint32), host(p.glyph_adv, np.int32)
         d.n_glyphs = len(p.glyph_adv)
         d.n_frame_tiles, d.frame_tiles = len(p.frame_tiles), host(p.frame_tiles, np.int32)

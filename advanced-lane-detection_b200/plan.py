@@ -391,6 +391,7 @@ class LanePlan:
     inv_y1: int
     inv_idx: np.ndarray        # u32[inv_y1-inv_y0, W]  (sy+1)<<16 | (sx+1) of the tap origin, ~0 = fully outside
     inv_fi: np.ndarray         # u16[inv_y1-inv_y0, W]
+    inv_pack: np.ndarray       # u32[inv_y1-inv_y0, W]  one-word form of (inv_idx, inv_fi), see build_plan
     src_row0: int              # first/last source row the mask kernel reads (algorithmic-bytes accounting)
     src_row1: int
     glyph_bits: np.ndarray
@@ -434,6 +435,14 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     inv_y0, inv_y1 = (int(trows.min()), int(trows.max()) + 1) if trows.size else (0, 0)
     inv_idx = np.where(touch, ((iy + 1) << 16) | (ix + 1), 0xFFFFFFFF).astype(np.uint32)[inv_y0:inv_y1]
     inv_fi = ifi.astype(np.uint16)[inv_y0:inv_y1]
+    # one-word form for the common case (both tap columns inside one canvas word, both rows inside the canvas):
+    # canvas word index << 17 | bit << 12 | 1 << 11 | fraction;  0xFFFFFFFF = no tap inside;  bit 11 clear = use inv_idx
+    fast = touch & (ix >= 0) & ((ix & 31) != 31) & (iy >= 0) & (iy < H - 1)
+    if H * (W // 32) >= (1 << 15):
+        fast = np.zeros_like(fast)                                   # word index would not fit 15 bits (4K): slow form only
+    word = np.where(fast, iy * (W // 32) + (ix >> 5), 0).astype(np.int64)
+    inv_pack = np.where(~touch, 0xFFFFFFFF,
+                        np.where(fast, (word << 17) | ((ix & 31).astype(np.int64) << 12) | (1 << 11) | ifi, ifi)).astype(np.uint32)[inv_y0:inv_y1]
     gb, ga = glyph_atlas()
     frame_tiles = gather_tiles(sx, sy, size, [(0, y, W, 16) for y in range(0, H, 16)], 128)
     chunks, starts = [], [0]
@@ -446,6 +455,6 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     frame_amap, frame_amap_start = gather_offsets(sx, sy, fi, frame_tiles, size)
     mask_amap, mask_amap_start = gather_offsets(sx, sy, fi, mask_chunks, size)
     return LanePlan(variant, (W, H), mtx, dist, und_map, bilinear_weight_table(), near, tiles, bmap, bdesc, ctab, cbits,
-                    inv_y0, inv_y1, np.ascontiguousarray(inv_idx), np.ascontiguousarray(inv_fi),
+                    inv_y0, inv_y1, np.ascontiguousarray(inv_idx), np.ascontiguousarray(inv_fi), np.ascontiguousarray(inv_pack),
                     src_row0, src_row1, gb, ga, frame_tiles, mask_chunks, np.array(starts, np.int32),
                     frame_amap, frame_amap_start, mask_amap, mask_amap_start)
