@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "liblanedet.so")
+LIB_PATH = os.environ.get("LANEDET_LIB") or os.path.join(CSRC, "liblanedet.so")   # LANEDET_LIB: instrumented debug builds only
 HEADER = os.path.join(os.path.dirname(HERE), "include", "lanedet.h")
 
 LD_OK, LD_ERR_ARG, LD_ERR_CUDA, LD_ERR_NO_DEVICE, LD_ERR_EMPTY_LANE, LD_ERR_POLYGON = range(6)
@@ -83,6 +83,8 @@ _SIGNATURES = {
     "ld_search": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_fit": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_overlay": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
+    "ld_raster": (C.c_int, [_P, _P, C.c_int, _P]),
+    "ld_frame_pass": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_process_batch": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "ld_process_batch_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_prepass": (C.c_int, [_P, _P, C.c_int, _P]),

@@ -127,7 +127,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         const size_t b = (size_t)(desc->mask_chunks[8 * t + 6] & 0xFFFF) * (size_t)(desc->mask_chunks[8 * t + 7] & 0x7FFFFFFF);
         if (b > ms) ms = b;
     }
-    if (fs > 160 * 1024 || ms > 160 * 1024) return LD_ERR_ARG;
+    if (fs > 96 * 1024 || ms > 160 * 1024) return LD_ERR_ARG;           // the frame pass double-buffers its box
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
@@ -163,7 +163,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if ((rc = upload(p, stamps, (size_t)laneraster::STAMP_N, &sd))) { ld_plan_destroy(p); return rc; }
         d.stamps = sd;
     }
-    p->frame_smem = fs + 16;
+    p->frame_smem = 2 * ((fs + 127) / 128 * 128) + 128;                  // two boxes (double buffered)
     int mow = 0;
     for (int t = 0; t < desc->n_tiles; ++t) {
         const int words = (desc->tiles[8 * t + 1] - desc->tiles[8 * t]) * (W / 32);
@@ -178,14 +178,14 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
     if (p->mask_smem > 200 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }
     LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
     // carveout, otherwise an SM has to drain before a kernel with a different carveout can start on it.
     LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LD_CUDA(cudaFuncSetAttribute(k_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LD_CUDA(cudaFuncSetAttribute(k_fit1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LD_CUDA(cudaFuncSetAttribute(k_fit2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LD_CUDA(cudaFuncSetAttribute(k_fit3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -373,14 +373,24 @@ static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* vert
         c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);
     return check_launch();
 }
+// frames one CTA of the multi-frame pass walks through: long enough to amortise its per-tile set-up, short enough
+// that a small batch still fills the machine with several waves of CTAs
+static int frames_per_cta(int m) {
+    const int f = m / 8;
+    return f < 1 ? 1 : (f > FRAME_FPC ? FRAME_FPC : f);
+}
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted) {
     const PlanDev& d = c->plan->d;
     const uint32_t* planes = c->planes + (size_t)slot * 2 * d.H * d.WW;
     const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
     if (already_undistorted)
-        k_frame_pass<2><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, planes, text, fout, d);
+        k_blend_pass<<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, planes, fout, d);
     else
-        k_frame_pass<1><<<dim3(d.n_frame_tiles, m), FRAME_THREADS, c->plan->frame_smem, s>>>(fin, planes, text, fout, d);
+    {
+        const int fpc = frames_per_cta(m);
+        k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, (m + fpc - 1) / fpc), FRAME_THREADS, c->plan->frame_smem, s>>>(
+            fin, planes, text, fout, d, m, fpc);
+    }
     return check_launch();
 }
 static int launch_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* fit, const int32_t* verts,
@@ -403,6 +413,17 @@ extern "C" int ld_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* 
     if (!ARGS_OK(c, frames, out, n) || !fit) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     return launch_overlay(c, frames, fit, nullptr, nullptr, 0, 30, n, out, (cudaStream_t)stream, 0);
+}
+
+extern "C" int ld_raster(ld_ctx* c, const ld_frame_fit* fit, int n, void* stream) {
+    if (!c || !fit || n < 0 || n > c->max_frames) return LD_ERR_ARG;
+    if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
+    return n ? launch_raster(c, fit, nullptr, nullptr, 0, 30, n, (cudaStream_t)stream, 0) : LD_OK;
+}
+extern "C" int ld_frame_pass(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, frames, out, n) || n > c->max_frames) return LD_ERR_ARG;
+    if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
+    return n ? launch_frame_pass(c, frames, n, out, (cudaStream_t)stream, 0, 0) : LD_OK;
 }
 
 extern "C" int ld_draw(ld_ctx* c, const uint8_t* undist, const int32_t* verts, const int32_t* counts, int max_verts,
@@ -603,7 +624,9 @@ extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* ou
     if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    k_frame_pass<0><<<dim3(d.n_frame_tiles, n), FRAME_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(frames, nullptr, nullptr, out, d);
+    const int fpc = frames_per_cta(n);
+    k_frame_pass_mf<0><<<dim3(d.n_frame_tiles, (n + fpc - 1) / fpc), FRAME_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(
+        frames, nullptr, nullptr, out, d, n, fpc);
     return check_launch();
 }
 extern "C" int ld_warp(ld_ctx* c, const uint8_t* img, int n, int channels, uint8_t* out, void* stream) {
@@ -634,3 +657,10 @@ extern "C" int ld_unpack_mask(ld_ctx* c, const uint32_t* mask, int n, uint8_t* b
     k_unpack_mask<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, bin, np);
     return check_launch();
 }
+
+#ifdef LD_RASTER_PROF
+extern "C" int ld_debug_raster_prof(long long* out) {
+    LD_CUDA(cudaMemcpyFromSymbol(out, g_raster_prof, sizeof(long long) * 64 * 16));
+    return LD_OK;
+}
+#endif

@@ -19,6 +19,13 @@ constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_BAND = 90;                 // canvas rows per CTA (8 bands of a 720-row frame)
 constexpr int MAX_VERTS = 2 * 724;
 
+#ifdef LD_RASTER_PROF
+__device__ long long g_raster_prof[64][16];
+#define RPROF(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.y < 8) g_raster_prof[blockIdx.y * 8 + blockIdx.x][i] = clock64(); } while (0)
+#else
+#define RPROF(i) do {} while (0)
+#endif
+
 struct BandPlotter {                // sets bits [x1,x2] of canvas row y if the row belongs to this CTA's band
     uint32_t* plane; int WW, W, y_lo, y_hi;
     __device__ __forceinline__ void span(int y, int x1, int x2) {
@@ -84,6 +91,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     const int tid = threadIdx.x;
     const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
 
+    RPROF(0);
     for (int i = tid; i < 2 * RASTER_BAND * WW; i += RASTER_THREADS) s_red[i] = 0;
     for (int i = tid; i < RASTER_BAND; i += RASTER_THREADS) R.cnt[i] = 0;
     const bool bad = fit && fit[f].status != LD_OK;
@@ -149,6 +157,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     }
     __syncthreads();
     const int nv = R.n_verts;
+    RPROF(1);
 
     // ---- red: cv2.polylines(canvas, pts, False, (200,0,0), thickness) (Project.py:160-161)
     // pass 1: every segment that can touch the band is classified; unit vertical steps (most of a lane) cost two row
@@ -177,6 +186,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
             if (cls & laneraster::SEG_START_DISC) R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (2 << 14));
         }
     __syncthreads();
+    RPROF(2);
     for (int k = tid; k < R.n_jobs; k += RASTER_THREADS) {
         const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
         if (type == 0) laneraster::thick_segment(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0);
@@ -184,12 +194,14 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         else if (type == 1) laneraster::disc(red, W, H, R.vx[i + 1], R.vy[i + 1], radius, R.hw);
         else laneraster::disc(red, W, H, R.vx[i], R.vy[i], radius, R.hw);
     }
+    RPROF(3);
     for (int k = 0; k < R.n_big; ++k) {
         const int i = R.big[k];
         laneraster::thick_segment_part(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, tid,
                                        RASTER_THREADS, y_lo, y_hi);
     }
 
+    RPROF(4);
     // ---- green: cv2.fillPoly(canvas, pts, (0,255,0)) (Project.py:164): outline + scanline crossings of this band
     for (int i = tid; i < nv && nv >= 2; i += RASTER_THREADS) {
         const int j = i == 0 ? nv - 1 : i - 1;
@@ -201,6 +213,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         for (int y = max(e.y0, y_lo); y < min(e.y1, y_hi); ++y) add_crossing(R, e, y, y_lo);
     }
     __syncthreads();
+    RPROF(5);
     for (int k = 0; k < R.n_bigedge; ++k) {
         const int i = R.bigedge[k], j = i == 0 ? nv - 1 : i - 1;
         laneraster::Pt a, b;
@@ -211,6 +224,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         for (int y = max(e.y0, y_lo) + tid; y < min(e.y1, y_hi); y += RASTER_THREADS) add_crossing(R, e, y, y_lo);
     }
     __syncthreads();
+    RPROF(6);
     for (int r = tid; r < y_hi - y_lo; r += RASTER_THREADS) {
         const int m = min(R.cnt[r], (int)LD_MAX_CROSSINGS);
         int* c = R.cross + r * LD_MAX_CROSSINGS;
@@ -218,11 +232,17 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         for (int i = 0; i + 1 < m; i += 2) laneraster::poly_span(green, W, y_lo + r, (int64_t)c[i], (int64_t)c[i + 1]);
     }
     __syncthreads();
+    RPROF(7);
     for (int i = tid; i < (y_hi - y_lo) * WW; i += RASTER_THREADS) {    // green overwrites red
         const uint32_t g = s_green[i];
         out_planes[i] = make_uint2(s_red[i] & ~g, g);
     }
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
+    RPROF(8);
+#ifdef LD_RASTER_PROF
+    if (tid == 0 && blockIdx.y < 8) { g_raster_prof[blockIdx.y * 8 + blockIdx.x][10] = R.n_jobs; g_raster_prof[blockIdx.y * 8 + blockIdx.x][11] = R.n_big;
+        g_raster_prof[blockIdx.y * 8 + blockIdx.x][12] = R.n_bigedge; g_raster_prof[blockIdx.y * 8 + blockIdx.x][13] = nv; }
+#endif
 
     // ---- text plane: glyph bitmaps OR-ed at integer pen positions (Project.py:326-332); band 0 only
     if (band != 0) return;
@@ -265,78 +285,200 @@ __device__ __forceinline__ uint32_t canvas_tap(const uint2* __restrict__ cv, int
     return ((w.x >> b) & 1u) | (((w.y >> b) & 1u) << 1);
 }
 
-// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170) for 4 consecutive pixels of row y starting at x0.
-// cv = this frame's canvas, one (red, green) word pair per 32 pixels.  Most pixels of the trapezoid see four equal
-// taps (all background or all green), so those two cases are decided from the plane words directly: 0 -> nothing
-// to add; all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to even) to g + 76 + (g & 1).
-__device__ __forceinline__ void blend_canvas4(uint32_t* c, const uint2* __restrict__ cv, const PlanDev& P, int x0, int y) {
-    if (y < P.inv_y0 || y >= P.inv_y1) return;
+// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170) for ONE pixel whose inv_pack entry is e (!= ~0) and whose
+// index into the inverse-warp tables is mi.  cv = this frame's canvas, one (red, green) word pair per 32 pixels.
+// Fast form (bit 11 of e): both tap rows and both tap columns lie inside the canvas; the two columns are bits b, b+1
+// of one word pair, or -- when b == 31 -- bit 31 and bit 0 of the next pair.  Most pixels of the trapezoid see four
+// equal taps (all background or all green), so those two cases are decided from the plane words directly:
+// 0 -> nothing to add; all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to even) to
+// g + 76 + (g & 1).
+__device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, size_t mi, const uint2* __restrict__ cv, const PlanDev& P) {
     const int W = P.W, H = P.H, WW = P.WW;
-    const size_t mi = (size_t)(y - P.inv_y0) * W + x0;
-    const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(P.inv_pack + mi));
-    if ((e4.x & e4.y & e4.z & e4.w) == 0xFFFFFFFFu) return;
-    const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
+    uint32_t t00, t01, t10, t11;
+    if (e & 0x800u) {
+        const uint2* p = cv + (e >> 17);
+        const uint32_t b = (e >> 12) & 31u;
+        const uint2 a0 = __ldg(p), a1 = __ldg(p + WW);
+        uint32_t r0 = a0.x >> b, g0 = a0.y >> b, r1 = a1.x >> b, g1 = a1.y >> b;
+        if (b == 31u) {
+            const uint2 n0 = __ldg(p + 1), n1 = __ldg(p + WW + 1);
+            r0 |= n0.x << 1; g0 |= n0.y << 1; r1 |= n1.x << 1; g1 |= n1.y << 1;
+        }
+        r0 &= 3u; g0 &= 3u; r1 &= 3u; g1 &= 3u;
+        if (!(r0 | g0 | r1 | g1)) return c;
+        if ((g0 & g1) == 3u) {
+            const uint32_t g = (c >> 8) & 255u;
+            return (c & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
+        }
+        t00 = (r0 & 1u) | ((g0 & 1u) << 1); t01 = (r0 >> 1) | ((g0 >> 1) << 1);
+        t10 = (r1 & 1u) | ((g1 & 1u) << 1); t11 = (r1 >> 1) | ((g1 >> 1) << 1);
+    } else {
+        const uint32_t idx = __ldg(P.inv_idx + mi);
+        const int sx = (int)(idx & 0xFFFFu) - 1, sy = (int)(idx >> 16) - 1;
+        t00 = canvas_tap(cv, W, H, WW, sx, sy); t01 = canvas_tap(cv, W, H, WW, sx + 1, sy);
+        t10 = canvas_tap(cv, W, H, WW, sx, sy + 1); t11 = canvas_tap(cv, W, H, WW, sx + 1, sy + 1);
+        if (!(t00 | t01 | t10 | t11)) return c;
+    }
+    const int fx = e & 31, fy = (e >> 5) & 31;
+    const int w00 = 32 * (32 - fy) * (32 - fx), w01 = 32 * (32 - fy) * fx, w10 = 32 * fy * (32 - fx), w11 = 32 * fy * fx;
+    const int wr = (t00 & 1) * w00 + (t01 & 1) * w01 + (t10 & 1) * w10 + (t11 & 1) * w11;
+    const int wg = (t00 >> 1) * w00 + (t01 >> 1) * w01 + (t10 >> 1) * w10 + (t11 >> 1) * w11;
+    const uint32_t cr = (uint32_t)(wr * 200 + 16384) >> 15, cg = (uint32_t)(wg * 255 + 16384) >> 15;
+    const uint32_t r = blend_u8(c & 255u, cr), g = blend_u8((c >> 8) & 255u, cg);
+    return (c & 0xFF0000u) | (g << 8) | r;
+}
+
+// The tail of a tile row, shared by the frame-pass kernels: canvas blend, text, and the store.  Lane i holds pixels
+// x0 + i + 32 k (k < ngroups) in c[k].  A 32-pixel group is 96 output bytes = 24 words; lane j < 24 assembles word j
+// from the pixels of lanes floor(4j/3), +1 with two shuffles and stores it (24 x 4 B contiguous, three full sectors).
+template <int MODE>
+__device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], int ngroups, int x0, int y, int lane,
+                                           const uint2* __restrict__ cv, const uint32_t* __restrict__ trow,
+                                           uint8_t* __restrict__ out_frame, const PlanDev& P) {
+    if (MODE != 0 && y >= P.inv_y0 && y < P.inv_y1) {
+        const size_t mi = (size_t)(y - P.inv_y0) * P.W + x0 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (ie[k] != 0xFFFFFFFFu) c[k] = blend_canvas_px(c[k], ie[k], mi + 32 * k, cv, P);
+    }
+    if (MODE == 1 && trow) {                                             // tile columns and LD_TEXT_X0 are multiples of 32
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int tw = (x0 + 32 * k - LD_TEXT_X0) >> 5;
+            if (k < ngroups && tw >= 0 && tw < LD_TEXT_WORDS && ((__ldg(trow + tw) >> lane) & 1u)) c[k] = 0xFFFFFFu;
+        }
+    }
+    const int wp = (4 * lane) / 3, wsh = ((4 * lane) % 3) * 8;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * P.W + x0) * 3) + lane;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t e = es[k];
-        if (e == 0xFFFFFFFFu) continue;
-        uint32_t t00, t01, t10, t11;
-        if (e & 0x800u) {                                                // both columns in one word, both rows inside
-            const uint2* p = cv + (e >> 17);
-            const uint32_t b = (e >> 12) & 31u;
-            const uint2 a0 = __ldg(p), a1 = __ldg(p + WW);
-            const uint32_t r0 = (a0.x >> b) & 3u, g0 = (a0.y >> b) & 3u, r1 = (a1.x >> b) & 3u, g1 = (a1.y >> b) & 3u;
-            if (!(r0 | g0 | r1 | g1)) continue;
-            if ((g0 & g1) == 3u) {
-                const uint32_t g = (c[k] >> 8) & 255u;
-                c[k] = (c[k] & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
-                continue;
-            }
-            t00 = (r0 & 1u) | ((g0 & 1u) << 1); t01 = (r0 >> 1) | ((g0 >> 1) << 1);
-            t10 = (r1 & 1u) | ((g1 & 1u) << 1); t11 = (r1 >> 1) | ((g1 >> 1) << 1);
-        } else {
-            const uint32_t idx = __ldg(P.inv_idx + mi + k);
-            const int sx = (int)(idx & 0xFFFFu) - 1, sy = (int)(idx >> 16) - 1;
-            t00 = canvas_tap(cv, W, H, WW, sx, sy); t01 = canvas_tap(cv, W, H, WW, sx + 1, sy);
-            t10 = canvas_tap(cv, W, H, WW, sx, sy + 1); t11 = canvas_tap(cv, W, H, WW, sx + 1, sy + 1);
-            if (!(t00 | t01 | t10 | t11)) continue;
-        }
-        const int fx = e & 31, fy = (e >> 5) & 31;
-        const int w00 = 32 * (32 - fy) * (32 - fx), w01 = 32 * (32 - fy) * fx, w10 = 32 * fy * (32 - fx), w11 = 32 * fy * fx;
-        const int wr = (t00 & 1) * w00 + (t01 & 1) * w01 + (t10 & 1) * w10 + (t11 & 1) * w11;
-        const int wg = (t00 >> 1) * w00 + (t01 >> 1) * w01 + (t10 >> 1) * w10 + (t11 >> 1) * w11;
-        const uint32_t cr = (uint32_t)(wr * 200 + 16384) >> 15, cg = (uint32_t)(wg * 255 + 16384) >> 15;
-        const uint32_t r = blend_u8(c[k] & 255u, cr), g = blend_u8((c[k] >> 8) & 255u, cg);
-        c[k] = (c[k] & 0xFF0000u) | (g << 8) | r;
+        const uint32_t a = __shfl_sync(0xffffffffu, c[k], wp), b = __shfl_sync(0xffffffffu, c[k], min(wp + 1, 31));
+        const uint32_t word = __funnelshift_r(a | (b << 24), b >> 8, wsh);
+        if (k < ngroups && lane < 24) orow[24 * k] = word;
     }
 }
 
-__device__ __forceinline__ void text4(uint32_t* c, const uint32_t* __restrict__ text, int f, int x0, int y) {
-    if (y < LD_TEXT_Y0 || y >= LD_TEXT_Y0 + LD_TEXT_ROWS || x0 < LD_TEXT_X0 || x0 >= LD_TEXT_X0 + LD_TEXT_WORDS * 32) return;
-    const int xb = x0 - LD_TEXT_X0;
-    const uint32_t tw = __ldg(text + ((size_t)f * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS + (xb >> 5)) >> (xb & 31);
+// inv_pack entries of the four pixels lane i owns in tile row y (~0 = the inverse warp does not touch the pixel)
+__device__ __forceinline__ void load_inv4(uint32_t (&ie)[4], int ngroups, int x0, int y, int lane, const PlanDev& P) {
+    const bool in = y >= P.inv_y0 && y < P.inv_y1;
+    const uint32_t* ip = P.inv_pack + (size_t)(in ? y - P.inv_y0 : 0) * P.W + x0 + lane;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if ((tw >> k) & 1u) c[k] = 0xFFFFFFu;
+    for (int k = 0; k < 4; ++k) ie[k] = (in && k < ngroups) ? __ldg(ip + 32 * k) : 0xFFFFFFFFu;
 }
 
-__device__ __forceinline__ void store4(uint8_t* __restrict__ out_frame, int W, int x0, int y, const uint32_t* c) {
-    uint32_t* o = reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + x0) * 3);
-    o[0] = c[0] | (c[1] << 24);
-    o[1] = (c[1] >> 8) | (c[2] << 16);
-    o[2] = (c[2] >> 16) | (c[3] << 8);
-}
-
-// K4b / stand-alone undistort.  One CTA = one 128x16 output tile (plan.frame_tiles): stage the source box,
-// then each thread produces 4 consecutive pixels of two rows.  MODE 0: cv2.undistort only (helper.py:35-47);
-// MODE 1: undistort + canvas blend + text (process_image); MODE 2: input already undistorted + canvas blend (ld_draw).
 constexpr int FRAME_THREADS = 256;
+constexpr int FRAME_FPC = 8;                    // frames per CTA of the multi-frame pass
 
+// bilinear_rgb_off with everything that does not depend on the frame hoisted out: po = (tap byte offset & ~3) |
+// (offset & 3) << 30, wx / wy = the dp2a weight pairs of the top / bottom tap row.
+__device__ __forceinline__ uint32_t bilinear_rgb_pre(uint32_t box, uint32_t stride, uint32_t po, uint32_t wx, uint32_t wy) {
+    const uint32_t a = box + (po & 0x3FFFFFFFu), sh = po >> 27;
+    uint32_t p0, p1, p2, q0, q1, q2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p0) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(p1) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(p2) : "r"(a));
+    const uint32_t a2 = a + stride;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q0) : "r"(a2));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(q1) : "r"(a2));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(q2) : "r"(a2));
+    const uint32_t lt = __funnelshift_r(p0, p1, sh), ht = __funnelshift_r(p1, p2, sh);   // r0 g0 b0 r1 | g1 b1 . .
+    const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
+    const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11
+    const uint32_t GBt = __byte_perm(lt, ht, 0x5241), GBb = __byte_perm(lb, hb, 0x5241);   // g0 g1 b0 b1
+    uint32_t r = __dp2a_lo(wx, R, 16384u);
+    r = __dp2a_hi(wy, R, r);
+    uint32_t g = __dp2a_lo(wx, GBt, 16384u);
+    g = __dp2a_lo(wy, GBb, g);
+    uint32_t b = __dp2a_hi(wx, GBt, 16384u);
+    b = __dp2a_hi(wy, GBb, b);
+    return (r >> 15) | ((g >> 7) & 0xFF00u) | ((b << 1) & 0xFF0000u);
+}
+
+// K4b / stand-alone undistort, multi-frame form.  One CTA = one 128x16 output tile (plan.frame_tiles) of up to
+// FRAME_FPC consecutive frames.  Warp w produces rows w, w+8 of the tile; within a row lane i owns pixels i, i+32, i+64,
+// i+96, so the lanes of one shared-memory load sit on ADJACENT output pixels (their taps fall into ~22 consecutive
+// words).  Everything that depends only on the tile -- tap offsets, dp2a weight pairs, inverse-warp entries -- is decoded
+// once into registers; per frame the CTA only stages the source box (TMA bulk row copies, double buffered: frame i+1
+// lands while frame i is computed), gathers, blends and stores.
+// MODE 0: cv2.undistort only (helper.py:35-47); MODE 1: undistort + canvas blend + text (process_image).
 template <int MODE>
+__global__ void __launch_bounds__(FRAME_THREADS, 3)
+k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes, const uint32_t* __restrict__ text,
+                uint8_t* __restrict__ out, const PlanDev P, int n, int fpc) {
+    extern __shared__ __align__(128) uint8_t s_boxes[];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int W = P.W, H = P.H, WW = P.WW;
+    const size_t fbytes = (size_t)W * H * 3;
+    const int f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
+    const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ngroups = t.w >> 5;                                        // 32-pixel groups in a tile row (W % 32 == 0)
+    const uint32_t box_bytes = ((uint32_t)(t.rows * t.stride) + 127u) & ~127u;
+    const uint32_t box0 = smem_u32(s_boxes);
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+
+    // ---- per-tile constants of this thread's two rows
+    uint32_t po[2][4], wx[2][4], wy[2][4], ie[2][4];
+    const uint4* am4 = reinterpret_cast<const uint4*>(P.frame_amap + P.frame_amap_start[blockIdx.x]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int r = warp + 8 * j;
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (r < t.h && !t.slow) e = __ldg(am4 + r * 32 + lane);
+        const uint32_t es[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t fx = es[k] & 31u, fy = (es[k] >> 5) & 31u, o = es[k] >> 10;
+            const uint32_t tt = (32u - fx) | (fx << 16);
+            wx[j][k] = tt * (1024u - 32u * fy);
+            wy[j][k] = tt * (32u * fy);
+            po[j][k] = (o & ~3u) | (o << 30);
+        }
+        if (MODE != 0) load_inv4(ie[j], r < t.h ? ngroups : 0, t.x0, t.y0 + r, lane, P);
+        else { ie[j][0] = ie[j][1] = ie[j][2] = ie[j][3] = 0xFFFFFFFFu; }
+    }
+    __syncthreads();                                                     // barriers initialised
+
+    if (!t.slow) stage_box(s_boxes, frames + (size_t)f0 * fbytes, W, t, &bar[0]);
+    for (int i = 0; i < nf; ++i) {
+        const int f = f0 + i;
+        const uint8_t* frame = frames + (size_t)f * fbytes;
+        uint8_t* out_frame = out + (size_t)f * fbytes;
+        const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * H * WW;
+        if (!t.slow) {
+            // the other buffer was last read in iteration i-1, which ended with a CTA barrier: safe to refill
+            if (i + 1 < nf) stage_box(s_boxes + ((i + 1) & 1) * box_bytes, frame + fbytes, W, t, &bar[(i + 1) & 1]);
+            mbar_wait(&bar[i & 1], (i >> 1) & 1);
+        }
+        const uint32_t box = box0 + (i & 1) * box_bytes;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = warp + 8 * j;
+            if (r >= t.h) continue;                                      // warp-uniform
+            const int y = t.y0 + r;
+            uint32_t c[4];
+            if (!t.slow) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_pre(box, (uint32_t)t.stride, po[j][k], wx[j][k], wy[j][k]);
+            } else {
+                const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
+            }
+            const uint32_t* trow = (MODE == 1 && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS)
+                                       ? text + ((size_t)f * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS : nullptr;
+            finish_row<MODE>(c, ie[j], ngroups, t.x0, y, lane, cv, trow, out_frame, P);
+        }
+        if (!t.slow) __syncthreads();                                    // everyone is done with box (i & 1)
+    }
+}
+
+// ld_draw: the input is ALREADY undistorted -> canvas blend only (helper.py:758-779, Project.py:144-170 with explicit
+// vertices).  One CTA per 128x16 tile and frame; pixels are fetched as words by lanes < 24 and dealt to their owners
+// with two shuffles (the mirror image of the store in finish_row).
 __global__ void __launch_bounds__(FRAME_THREADS)
-k_frame_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes, const uint32_t* __restrict__ text,
-             uint8_t* __restrict__ out, const PlanDev P) {
-    extern __shared__ __align__(16) uint8_t s_box[];
-    __shared__ __align__(8) uint64_t bar;
+k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes, uint8_t* __restrict__ out, const PlanDev P) {
     const int W = P.W, H = P.H, WW = P.WW;
     const size_t fbytes = (size_t)W * H * 3;
     const int f = blockIdx.y;
@@ -344,39 +486,21 @@ k_frame_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
     uint8_t* out_frame = out + (size_t)f * fbytes;
     const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * H * WW;
     const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
-    if (MODE != 2) {
-        if (threadIdx.x == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        stage_box(s_box, frame, W, t, &bar);
-    }
-    const int gx = (threadIdx.x & 31) * 4, r0 = threadIdx.x >> 5;
-    if (MODE != 2) wait_box(&bar, 0, !t.slow);
-    if (gx >= t.w) return;
-    const int x0 = t.x0 + gx;
-    const uint32_t* am = P.frame_amap + P.frame_amap_start[blockIdx.x];
-    for (int r = r0; r < t.h; r += FRAME_THREADS / 32) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ngroups = t.w >> 5;
+    const int rq = (3 * lane) >> 2, rsh = ((3 * lane) & 3) * 8;         // pixel `lane` of a group: words rq, rq+1
+    for (int r = warp; r < t.h; r += FRAME_THREADS / 32) {
         const int y = t.y0 + r;
-        uint32_t c[4];
-        if (MODE == 2) {
-            const uint32_t* s = reinterpret_cast<const uint32_t*>(frame + ((size_t)y * W + x0) * 3);
-            const uint32_t a = __ldg(s), b = __ldg(s + 1), d = __ldg(s + 2);
-            c[0] = a & 0xFFFFFFu; c[1] = (a >> 24) | ((b & 0xFFFFu) << 8); c[2] = (b >> 16) | ((d & 0xFFu) << 16); c[3] = d >> 8;
-        } else if (!t.slow) {
-            const uint4 e = __ldg(reinterpret_cast<const uint4*>(am + r * t.w + gx));      // t.w % 4 == 0, tile starts 16-byte aligned
-            c[0] = bilinear_rgb_off(s_box, t.stride, e.x, P.wtab);
-            c[1] = bilinear_rgb_off(s_box, t.stride, e.y, P.wtab);
-            c[2] = bilinear_rgb_off(s_box, t.stride, e.z, P.wtab);
-            c[3] = bilinear_rgb_off(s_box, t.stride, e.w, P.wtab);
-        } else {
-            const uint4 e = __ldg(reinterpret_cast<const uint4*>(P.und_map + (size_t)y * W + x0));
-            c[0] = bilinear_rgb(frame, W, H, x0, y, e.x, P.wtab);
-            c[1] = bilinear_rgb(frame, W, H, x0 + 1, y, e.y, P.wtab);
-            c[2] = bilinear_rgb(frame, W, H, x0 + 2, y, e.z, P.wtab);
-            c[3] = bilinear_rgb(frame, W, H, x0 + 3, y, e.w, P.wtab);
+        uint32_t c[4], ie[4];
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(frame + ((size_t)y * W + t.x0) * 3);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t wd = (k < ngroups && lane < 24) ? __ldg(srow + 24 * k + lane) : 0u;
+            const uint32_t a = __shfl_sync(0xffffffffu, wd, rq), b = __shfl_sync(0xffffffffu, wd, min(rq + 1, 23));
+            c[k] = __funnelshift_r(a, b, rsh) & 0xFFFFFFu;
         }
-        if (MODE != 0) blend_canvas4(c, cv, P, x0, y);
-        if (MODE == 1) text4(c, text, f, x0, y);
-        store4(out_frame, W, x0, y, c);
+        load_inv4(ie, ngroups, t.x0, y, lane, P);
+        finish_row<2>(c, ie, ngroups, t.x0, y, lane, cv, nullptr, out_frame, P);
     }
 }
 

@@ -290,12 +290,30 @@ def gather_tiles(sx, sy, size, regions, tw=128):
     return np.array(out, np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8)
 
 
-def gather_offsets(sx, sy, fi, gt, size):
+def gather_offsets(sx, sy, fi, gt, size, lane_strided=False):
     """Per output pixel of every gather tile: (byte offset of its first tap inside the tile's staged box) << 10 | fraction.
     Returns (amap u32[sum of tile pixels], start int32[T+1]); pixels of a tile are stored row-major, w*h entries.
-    Slow tiles get zeros (the kernels use und_map there)."""
+    Slow tiles get zeros (the kernels use und_map there).
+    lane_strided (the frame pass): every tile row holds 128 entries ordered [lane][k] = column lane + 32 k, so that a
+    warp's lanes sit on ADJACENT pixels (their taps fall into ~22 consecutive shared-memory words: no bank conflicts)
+    and each lane still fetches its four entries with one 16-byte load; columns >= w are zero."""
     g = gt.view(np.uint32).astype(np.int64)
     start = np.zeros(len(g) + 1, np.int64)
+    if lane_strided:
+        assert (g[:, 2] <= 128).all()
+        start[1:] = np.cumsum(128 * g[:, 3])
+        amap = np.zeros(int(start[-1]), np.uint32)
+        for i, (x0, y0, w, h, b0, sy0, rc, st) in enumerate(g):
+            if st >> 31:
+                continue
+            stride = st & 0x7FFFFFFF
+            bx, by, bf = sx[y0:y0 + h, x0:x0 + w], sy[y0:y0 + h, x0:x0 + w], fi[y0:y0 + h, x0:x0 + w]
+            off = (by - sy0).astype(np.int64) * stride + bx.astype(np.int64) * 3 - b0
+            assert off.min() >= 0 and off.max() < (1 << 22)
+            e = np.zeros((h, 128), np.uint32)
+            e[:, :w] = ((off << 10) | bf).astype(np.uint32)
+            amap[start[i]:start[i + 1]] = e.reshape(h, 4, 32).transpose(0, 2, 1).reshape(-1)     # [row][lane][k]
+        return amap, start.astype(np.int32)
     start[1:] = np.cumsum(g[:, 2] * g[:, 3])
     amap = np.zeros(int(start[-1]), np.uint32)
     for i, (x0, y0, w, h, b0, sy0, rc, st) in enumerate(g):
@@ -435,9 +453,10 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     inv_y0, inv_y1 = (int(trows.min()), int(trows.max()) + 1) if trows.size else (0, 0)
     inv_idx = np.where(touch, ((iy + 1) << 16) | (ix + 1), 0xFFFFFFFF).astype(np.uint32)[inv_y0:inv_y1]
     inv_fi = ifi.astype(np.uint16)[inv_y0:inv_y1]
-    # one-word form for the common case (both tap columns inside one canvas word, both rows inside the canvas):
+    # one-word form for the common case (all four taps inside the canvas; tap columns = bits b, b+1 of a word pair, or bit 31
+    # and bit 0 of the next pair):
     # canvas word index << 17 | bit << 12 | 1 << 11 | fraction;  0xFFFFFFFF = no tap inside;  bit 11 clear = use inv_idx
-    fast = touch & (ix >= 0) & ((ix & 31) != 31) & (iy >= 0) & (iy < H - 1)
+    fast = touch & (ix >= 0) & (ix <= W - 2) & (iy >= 0) & (iy < H - 1)
     if H * (W // 32) >= (1 << 15):
         fast = np.zeros_like(fast)                                   # word index would not fit 15 bits (4K): slow form only
     word = np.where(fast, iy * (W // 32) + (ix >> 5), 0).astype(np.int64)
@@ -452,7 +471,7 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
         starts.append(starts[-1] + len(c))
     mask_chunks = np.concatenate(chunks) if chunks else np.zeros((0, 8), np.int32)
     bdesc = mask_word_descriptors(nx, ny, tiles, size)
-    frame_amap, frame_amap_start = gather_offsets(sx, sy, fi, frame_tiles, size)
+    frame_amap, frame_amap_start = gather_offsets(sx, sy, fi, frame_tiles, size, lane_strided=True)
     mask_amap, mask_amap_start = gather_offsets(sx, sy, fi, mask_chunks, size)
     return LanePlan(variant, (W, H), mtx, dist, und_map, bilinear_weight_table(), near, tiles, bmap, bdesc, ctab, cbits,
                     inv_y0, inv_y1, np.ascontiguousarray(inv_idx), np.ascontiguousarray(inv_fi), np.ascontiguousarray(inv_pack),

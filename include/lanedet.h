@@ -141,6 +141,12 @@ int ld_fit(ld_ctx* ctx, const ld_lane_record* rec_dev, int n, ld_frame_fit* fit_
 /* draw_area + putText (Project.py:144-170, 320-332) on the undistorted frame -> u8[n][H][W][3]. */
 int ld_overlay(ld_ctx* ctx, const uint8_t* frames_dev, const ld_frame_fit* fit_dev, int n,
                uint8_t* out_dev, void* stream);
+/* The two halves of ld_overlay as separate stages (n <= max_frames): ld_raster draws the canvas of
+ * draw_area (cv2.polylines + cv2.fillPoly, Project.py:153-164) and the putText glyph plane into the
+ * context; ld_frame_pass undistorts, inverse-warps that canvas, blends and writes the frames
+ * (Project.py:294, 167-170, 320-332). */
+int ld_raster(ld_ctx* ctx, const ld_frame_fit* fit_dev, int n, void* stream);
+int ld_frame_pass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
 /* process_image for n consecutive frames (Project.py:289-334).  fit_dev may be NULL. */
 int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev,
                      ld_frame_fit* fit_dev, void* stream);
