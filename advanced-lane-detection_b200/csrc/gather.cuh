@@ -65,6 +65,15 @@ __device__ __forceinline__ void stage_box(uint8_t* s_box, const uint8_t* __restr
         bulk_g2s(s_box + r * t.stride, frame + (size_t)(t.sy0 + r) * W * 3 + t.b0, (uint32_t)t.copy, bar);
 }
 
+// The same with the row copies dealt round-robin to the warps (row r -> warp r % nwarps, lane r / nwarps): a bulk copy is a
+// warp-serial instruction, so one warp issuing all ~22 rows of a box did 50 % more work than its seven siblings.
+__device__ __forceinline__ void stage_box_spread(uint8_t* s_box, const uint8_t* __restrict__ frame, int W, const GTile& t, uint64_t* bar) {
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (uint32_t)(t.rows * t.copy));
+    const int nw = blockDim.x >> 5, r = (threadIdx.x & 31) * nw + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) * nw < t.rows && r < t.rows)
+        bulk_g2s(s_box + r * t.stride, frame + (size_t)(t.sy0 + r) * W * 3 + t.b0, (uint32_t)t.copy, bar);
+}
+
 // Wait for the staged box with ONE warp polling the mbarrier; everybody else parks at the CTA barrier
 // (a spinning try_wait in all warps burns the issue slots the other resident CTAs need).
 __device__ __forceinline__ void wait_box(uint64_t* bar, uint32_t parity, bool staged) {

@@ -44,7 +44,7 @@ struct ld_ctx {
     ld_lane_record* rec;       // [max][2]
     FitWork* work;             // [max][2]
     ld_frame_fit* fit;         // [max]
-    uint32_t* planes;          // [max][H][WW][2]  (red without green, green) interleaved per word
+    uint32_t* planes;          // [max][H][WW][4]  (red lo, red hi, green lo, green hi): 64-bit windows of (red without green, green)
     uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
     TrackState* state;
     int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error
@@ -173,7 +173,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     // k_mask shared memory: box bits (+4 zero words) | job list (u16 per output word) | staged source box
     p->mask_smem = (((size_t)mb + 4) * 4 + (size_t)mow * 2 + 15) / 16 * 16 + ms + 32;
     p->search_smem = (size_t)H * d.WW * 4 + (size_t)9 * W * 2;
-    p->raster_smem = ((size_t)2 * RASTER_BAND * d.WW + LD_TEXT_ROWS * LD_TEXT_WORDS) * 4 + sizeof(RasterShared);
+    p->raster_smem = (size_t)2 * RASTER_BAND * d.WW * 4 + sizeof(RasterShared);   // text plane (6.7 KB) aliases the red plane
     // The opt-in limit is a per-function, per-device attribute shared by every plan: always raise it to
     // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
     if (p->mask_smem > 200 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }
@@ -231,7 +231,7 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     CTX_ALLOC(c->rec, sizeof(ld_lane_record) * 2 * max_frames);
     CTX_ALLOC(c->work, sizeof(FitWork) * 2 * max_frames);
     CTX_ALLOC(c->fit, sizeof(ld_frame_fit) * max_frames);
-    CTX_ALLOC(c->planes, mw * 4 * 2 * max_frames);
+    CTX_ALLOC(c->planes, mw * 4 * 4 * max_frames);
     CTX_ALLOC(c->text, (size_t)LD_TEXT_ROWS * LD_TEXT_WORDS * 4 * max_frames);
     CTX_ALLOC(c->state, sizeof(TrackState));
     CTX_ALLOC(c->flags, 16 * sizeof(int));
@@ -369,7 +369,7 @@ static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* vert
                          int thickness, int m, cudaStream_t s, int slot) {
     const PlanDev& d = c->plan->d;
     k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(
-        fit, verts, counts, max_verts, thickness, c->planes + (size_t)slot * 2 * d.H * d.WW,
+        fit, verts, counts, max_verts, thickness, c->planes + (size_t)slot * 4 * d.H * d.WW,
         c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);
     return check_launch();
 }
@@ -381,7 +381,7 @@ static int frames_per_cta(int m) {
 }
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted) {
     const PlanDev& d = c->plan->d;
-    const uint32_t* planes = c->planes + (size_t)slot * 2 * d.H * d.WW;
+    const uint32_t* planes = c->planes + (size_t)slot * 4 * d.H * d.WW;
     const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
     if (already_undistorted)
         k_blend_pass<<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, planes, fout, d);

@@ -70,7 +70,7 @@ __device__ __forceinline__ int vertex_x(const double* c, int y) {
     return (int)v;                                              // truncation toward zero
 }
 
-// One CTA = one 90-row band of one frame's canvas.  planes: u32[n][H][WW][2] (red without green, green) per word;
+// One CTA = one 90-row band of one frame's canvas.  planes: u32[n][H][WW][4] = (red lo, red hi, green lo, green hi), red = red without green;
 // text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  Vertices come from the frame's fit + row maps
 // (verts == nullptr) or are given explicitly (ld_draw).  Every CTA lists all vertices (cheap, parallel) and
 // draws only the primitives whose rows can touch its band, one primitive per thread.
@@ -82,11 +82,11 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     const int W = P.W, H = P.H, WW = P.WW;
     uint32_t* s_red = smem;                                             // RASTER_BAND*WW
     uint32_t* s_green = s_red + RASTER_BAND * WW;
-    uint32_t* s_text = s_green + RASTER_BAND * WW;                      // TEXT_ROWS*TEXT_WORDS (band 0 only)
-    RasterShared& R = *reinterpret_cast<RasterShared*>(s_text + LD_TEXT_ROWS * LD_TEXT_WORDS);
+    uint32_t* s_text = s_red;                                           // TEXT_ROWS*TEXT_WORDS: band 0, after the planes are stored
+    RasterShared& R = *reinterpret_cast<RasterShared*>(s_green + RASTER_BAND * WW);
     const int f = blockIdx.y, band = blockIdx.x;
     const int y_lo = band * RASTER_BAND, y_hi = min(H, y_lo + RASTER_BAND);
-    uint2* out_planes = reinterpret_cast<uint2*>(planes) + ((size_t)f * H + y_lo) * WW;
+    uint4* out_planes = reinterpret_cast<uint4*>(planes) + ((size_t)f * H + y_lo) * WW;
     BandPlotter red{s_red, WW, W, y_lo, y_hi}, green{s_green, WW, W, y_lo, y_hi};
     const int tid = threadIdx.x;
     const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
@@ -187,12 +187,21 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         }
     __syncthreads();
     RPROF(2);
-    for (int k = tid; k < R.n_jobs; k += RASTER_THREADS) {
-        const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
-        if (type == 0) laneraster::thick_segment(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0);
-        else if (type == 3) laneraster::draw_stamp(red, stamps[laneraster::stamp_index(R.vx[i + 1] - R.vx[i], R.vy[i + 1] - R.vy[i])], R.vx[i], R.vy[i]);
-        else if (type == 1) laneraster::disc(red, W, H, R.vx[i + 1], R.vy[i + 1], radius, R.hw);
-        else laneraster::disc(red, W, H, R.vx[i], R.vy[i], radius, R.hw);
+    // pass 2: one WARP per job, its lanes sharing the rows of the primitive (a thread per job left the CTA waiting for
+    // the few threads that drew a 40-row stamp or a whole quad on their own)
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int k = warp; k < R.n_jobs; k += RASTER_THREADS / 32) {
+            const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
+            if (type == 0)
+                laneraster::thick_segment_part(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, lane, 32,
+                                               y_lo, y_hi);
+            else if (type == 3)
+                laneraster::draw_stamp_part(red, stamps[laneraster::stamp_index(R.vx[i + 1] - R.vx[i], R.vy[i + 1] - R.vy[i])], R.vx[i],
+                                            R.vy[i], lane, 32);
+            else if (type == 1) laneraster::disc_part(red, W, H, R.vx[i + 1], R.vy[i + 1], radius, R.hw, lane, 32);
+            else laneraster::disc_part(red, W, H, R.vx[i], R.vy[i], radius, R.hw, lane, 32);
+        }
     }
     RPROF(3);
     for (int k = 0; k < R.n_big; ++k) {
@@ -234,8 +243,11 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     __syncthreads();
     RPROF(7);
     for (int i = tid; i < (y_hi - y_lo) * WW; i += RASTER_THREADS) {    // green overwrites red
-        const uint32_t g = s_green[i];
-        out_planes[i] = make_uint2(s_red[i] & ~g, g);
+        // canvas word k = bits [32k, 32k+64) of the row for (red without green, green): two horizontally adjacent taps
+        // always sit in one entry
+        const bool last = (i % WW) == WW - 1;
+        const uint32_t g = s_green[i], g2 = last ? 0u : s_green[i + 1];
+        out_planes[i] = make_uint4(s_red[i] & ~g, last ? 0u : (s_red[i + 1] & ~g2), g, g2);
     }
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
     RPROF(8);
@@ -247,6 +259,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     // ---- text plane: glyph bitmaps OR-ed at integer pen positions (Project.py:326-332); band 0 only
     if (band != 0) return;
     uint32_t* out_text = text + (size_t)f * LD_TEXT_ROWS * LD_TEXT_WORDS;
+    __syncthreads();                                                    // the text plane re-uses the red plane's memory
     for (int i = tid; i < LD_TEXT_ROWS * LD_TEXT_WORDS; i += RASTER_THREADS) s_text[i] = 0;
     __syncthreads();
     if (fit && !bad) {
@@ -278,38 +291,33 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
 }
 
 // canvas colour code at (cx, cy): bit0 = red, bit1 = green, 0 outside (BORDER_CONSTANT)
-__device__ __forceinline__ uint32_t canvas_tap(const uint2* __restrict__ cv, int W, int H, int WW, int cx, int cy) {
+__device__ __forceinline__ uint32_t canvas_tap(const uint4* __restrict__ cv, int W, int H, int WW, int cx, int cy) {
     if ((unsigned)cx >= (unsigned)W || (unsigned)cy >= (unsigned)H) return 0u;
-    const uint2 w = __ldg(cv + cy * WW + (cx >> 5));
+    const uint4 w = __ldg(cv + cy * WW + (cx >> 5));
     const int b = cx & 31;
-    return ((w.x >> b) & 1u) | (((w.y >> b) & 1u) << 1);
+    return ((w.x >> b) & 1u) | (((w.z >> b) & 1u) << 1);
 }
 
 // + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170) for ONE pixel whose inv_pack entry is e (!= ~0) and whose
-// index into the inverse-warp tables is mi.  cv = this frame's canvas, one (red, green) word pair per 32 pixels.
-// Fast form (bit 11 of e): both tap rows and both tap columns lie inside the canvas; the two columns are bits b, b+1
-// of one word pair, or -- when b == 31 -- bit 31 and bit 0 of the next pair.  Most pixels of the trapezoid see four
-// equal taps (all background or all green), so those two cases are decided from the plane words directly:
-// 0 -> nothing to add; all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to even) to
-// g + 76 + (g & 1).
-__device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, size_t mi, const uint2* __restrict__ cv, const PlanDev& P) {
+// index into the inverse-warp tables is mi.  cv = this frame's canvas: per 32 pixels one entry holding the 64-bit window
+// [32k, 32k+64) of the red and of the green plane, so the two tap columns b, b+1 come out of one entry with a funnel shift.
+// Fast form (bit 11 of e): all four taps lie inside the canvas.  Most pixels of the trapezoid see four equal taps (all
+// background or all green); those two cases are decided from the plane words directly: 0 -> nothing to add;
+// all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to even) to g + 76 + (g & 1).
+__device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, size_t mi, const uint4* __restrict__ cv, const PlanDev& P) {
     const int W = P.W, H = P.H, WW = P.WW;
     uint32_t t00, t01, t10, t11;
     if (e & 0x800u) {
-        const uint2* p = cv + (e >> 17);
-        const uint32_t b = (e >> 12) & 31u;
-        const uint2 a0 = __ldg(p), a1 = __ldg(p + WW);
-        uint32_t r0 = a0.x >> b, g0 = a0.y >> b, r1 = a1.x >> b, g1 = a1.y >> b;
-        if (b == 31u) {
-            const uint2 n0 = __ldg(p + 1), n1 = __ldg(p + WW + 1);
-            r0 |= n0.x << 1; g0 |= n0.y << 1; r1 |= n1.x << 1; g1 |= n1.y << 1;
-        }
-        r0 &= 3u; g0 &= 3u; r1 &= 3u; g1 &= 3u;
-        if (!(r0 | g0 | r1 | g1)) return c;
-        if ((g0 & g1) == 3u) {
+        const uint4* p = cv + (e >> 17);
+        const uint32_t b = e >> 12;                                       // the funnel shifts use its low five bits
+        const uint4 a0 = __ldg(p), a1 = __ldg(p + WW);
+        if (!(__funnelshift_r(a0.x | a0.z | a1.x | a1.z, a0.y | a0.w | a1.y | a1.w, b) & 3u)) return c;
+        if ((__funnelshift_r(a0.z & a1.z, a0.w & a1.w, b) & 3u) == 3u) {
             const uint32_t g = (c >> 8) & 255u;
             return (c & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
         }
+        const uint32_t r0 = __funnelshift_r(a0.x, a0.y, b) & 3u, g0 = __funnelshift_r(a0.z, a0.w, b) & 3u;
+        const uint32_t r1 = __funnelshift_r(a1.x, a1.y, b) & 3u, g1 = __funnelshift_r(a1.z, a1.w, b) & 3u;
         t00 = (r0 & 1u) | ((g0 & 1u) << 1); t01 = (r0 >> 1) | ((g0 >> 1) << 1);
         t10 = (r1 & 1u) | ((g1 & 1u) << 1); t11 = (r1 >> 1) | ((g1 >> 1) << 1);
     } else {
@@ -328,15 +336,25 @@ __device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, size
     return (c & 0xFF0000u) | (g << 8) | r;
 }
 
+// Per-lane constants of the row store.  A 32-pixel group is 96 output bytes = 24 words; lane j < 24 builds word j from
+// the pixels of lanes wp = floor(4j/3) and wp + 1 with two shuffles and ONE byte permute (selector by 4j mod 3).
+struct RowStore {
+    int wp, wp1;
+    uint32_t sel;
+    __device__ __forceinline__ RowStore(int lane) {
+        wp = (4 * lane) / 3; wp1 = min(wp + 1, 31);
+        const int m = (4 * lane) % 3;
+        sel = m == 0 ? 0x4210u : (m == 1 ? 0x5421u : 0x6542u);
+    }
+};
+
 // The tail of a tile row, shared by the frame-pass kernels: canvas blend, text, and the store.  Lane i holds pixels
-// x0 + i + 32 k (k < ngroups) in c[k].  A 32-pixel group is 96 output bytes = 24 words; lane j < 24 assembles word j
-// from the pixels of lanes floor(4j/3), +1 with two shuffles and stores it (24 x 4 B contiguous, three full sectors).
+// x0 + i + 32 k (k < ngroups) in c[k] as r | g << 8 | b << 16; orow = this lane's first output word (row start + lane).
 template <int MODE>
-__device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], int ngroups, int x0, int y, int lane,
-                                           const uint2* __restrict__ cv, const uint32_t* __restrict__ trow,
-                                           uint8_t* __restrict__ out_frame, const PlanDev& P) {
-    if (MODE != 0 && y >= P.inv_y0 && y < P.inv_y1) {
-        const size_t mi = (size_t)(y - P.inv_y0) * P.W + x0 + lane;
+__device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], int ngroups, size_t mi, int lane,
+                                           const uint4* __restrict__ cv, const uint32_t* __restrict__ trow, int tw0,
+                                           uint32_t* __restrict__ orow, const RowStore& rs, const PlanDev& P) {
+    if (MODE != 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (ie[k] != 0xFFFFFFFFu) c[k] = blend_canvas_px(c[k], ie[k], mi + 32 * k, cv, P);
@@ -344,17 +362,14 @@ __device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie
     if (MODE == 1 && trow) {                                             // tile columns and LD_TEXT_X0 are multiples of 32
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int tw = (x0 + 32 * k - LD_TEXT_X0) >> 5;
+            const int tw = tw0 + k;
             if (k < ngroups && tw >= 0 && tw < LD_TEXT_WORDS && ((__ldg(trow + tw) >> lane) & 1u)) c[k] = 0xFFFFFFu;
         }
     }
-    const int wp = (4 * lane) / 3, wsh = ((4 * lane) % 3) * 8;
-    uint32_t* orow = reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * P.W + x0) * 3) + lane;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t a = __shfl_sync(0xffffffffu, c[k], wp), b = __shfl_sync(0xffffffffu, c[k], min(wp + 1, 31));
-        const uint32_t word = __funnelshift_r(a | (b << 24), b >> 8, wsh);
-        if (k < ngroups && lane < 24) orow[24 * k] = word;
+        const uint32_t a = __shfl_sync(0xffffffffu, c[k], rs.wp), b = __shfl_sync(0xffffffffu, c[k], rs.wp1);
+        if (k < ngroups && lane < 24) orow[24 * k] = __byte_perm(a, b, rs.sel);
     }
 }
 
@@ -370,7 +385,8 @@ constexpr int FRAME_THREADS = 256;
 constexpr int FRAME_FPC = 8;                    // frames per CTA of the multi-frame pass
 
 // bilinear_rgb_off with everything that does not depend on the frame hoisted out: po = (tap byte offset & ~3) |
-// (offset & 3) << 30, wx / wy = the dp2a weight pairs of the top / bottom tap row.
+// (offset & 3) << 30, wx / wy = the dp2a weight pairs of the top / bottom tap row, DOUBLED (see frame_weights) so that
+// each channel's rounded result is byte 2 of its accumulator and two byte permutes pack the pixel.
 __device__ __forceinline__ uint32_t bilinear_rgb_pre(uint32_t box, uint32_t stride, uint32_t po, uint32_t wx, uint32_t wy) {
     const uint32_t a = box + (po & 0x3FFFFFFFu), sh = po >> 27;
     uint32_t p0, p1, p2, q0, q1, q2;
@@ -385,13 +401,23 @@ __device__ __forceinline__ uint32_t bilinear_rgb_pre(uint32_t box, uint32_t stri
     const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
     const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11
     const uint32_t GBt = __byte_perm(lt, ht, 0x5241), GBb = __byte_perm(lb, hb, 0x5241);   // g0 g1 b0 b1
-    uint32_t r = __dp2a_lo(wx, R, 16384u);
+    uint32_t r = __dp2a_lo(wx, R, 32768u);
     r = __dp2a_hi(wy, R, r);
-    uint32_t g = __dp2a_lo(wx, GBt, 16384u);
+    uint32_t g = __dp2a_lo(wx, GBt, 32768u);
     g = __dp2a_lo(wy, GBb, g);
-    uint32_t b = __dp2a_hi(wx, GBt, 16384u);
+    uint32_t b = __dp2a_hi(wx, GBt, 32768u);
     b = __dp2a_hi(wy, GBb, b);
-    return (r >> 15) | ((g >> 7) & 0xFF00u) | ((b << 1) & 0xFF0000u);
+    return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);           // (r >> 16) | (g >> 16) << 8 | (b >> 16) << 16
+}
+
+// OpenCV's four bilinear weights of fraction (fx, fy) are the exact integers 32(32-fy)(32-fx), 32(32-fy)fx, 32 fy (32-fx),
+// 32 fy fx (sum 2^15); out = (sum w p + 2^14) >> 15.  Doubling them gives out = (sum 2w p + 2^15) >> 16 = byte 2 of
+// the accumulator.  Only w00 = 2^15 (fx = fy = 0, a single tap) does not fit 16 bits doubled; 65535 p + 2^15 >> 16 = p
+// for every p <= 255, so 65535 is exact there.
+__device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t& wx, uint32_t& wy) {
+    const uint32_t tt = (32u - fx) | (fx << 16);
+    wx = (fx | fy) ? tt * (2048u - 64u * fy) : 0xFFFFu;
+    wy = tt * (64u * fy);
 }
 
 // K4b / stand-alone undistort, multi-frame form.  One CTA = one 128x16 output tile (plan.frame_tiles) of up to
@@ -418,7 +444,10 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
 
     // ---- per-tile constants of this thread's two rows
-    uint32_t po[2][4], wx[2][4], wy[2][4], ie[2][4];
+    uint32_t po[2][4], wx[2][4], wy[2][4], ie[2][4], ooff[2];
+    int trow_off[2];                                                      // word offset of the row in a frame's text plane, -1 = none
+    const RowStore rs(lane);
+    const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
     const uint4* am4 = reinterpret_cast<const uint4*>(P.frame_amap + P.frame_amap_start[blockIdx.x]);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -429,25 +458,28 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t fx = es[k] & 31u, fy = (es[k] >> 5) & 31u, o = es[k] >> 10;
-            const uint32_t tt = (32u - fx) | (fx << 16);
-            wx[j][k] = tt * (1024u - 32u * fy);
-            wy[j][k] = tt * (32u * fy);
+            frame_weights(fx, fy, wx[j][k], wy[j][k]);
             po[j][k] = (o & ~3u) | (o << 30);
         }
         if (MODE != 0) load_inv4(ie[j], r < t.h ? ngroups : 0, t.x0, t.y0 + r, lane, P);
         else { ie[j][0] = ie[j][1] = ie[j][2] = ie[j][3] = 0xFFFFFFFFu; }
+        const int y = t.y0 + r;
+        ooff[j] = (uint32_t)(((size_t)y * W + t.x0) * 3) + 4u * lane;
+        trow_off[j] = (MODE == 1 && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS)
+                          ? (y - LD_TEXT_Y0) * LD_TEXT_WORDS : -1;
     }
     __syncthreads();                                                     // barriers initialised
 
-    if (!t.slow) stage_box(s_boxes, frames + (size_t)f0 * fbytes, W, t, &bar[0]);
+    if (!t.slow) stage_box_spread(s_boxes, frames + (size_t)f0 * fbytes, W, t, &bar[0]);
     for (int i = 0; i < nf; ++i) {
         const int f = f0 + i;
         const uint8_t* frame = frames + (size_t)f * fbytes;
         uint8_t* out_frame = out + (size_t)f * fbytes;
-        const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * H * WW;
+        const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f * H * WW;
+        const uint32_t* tplane = text + (size_t)f * LD_TEXT_ROWS * LD_TEXT_WORDS;
         if (!t.slow) {
             // the other buffer was last read in iteration i-1, which ended with a CTA barrier: safe to refill
-            if (i + 1 < nf) stage_box(s_boxes + ((i + 1) & 1) * box_bytes, frame + fbytes, W, t, &bar[(i + 1) & 1]);
+            if (i + 1 < nf) stage_box_spread(s_boxes + ((i + 1) & 1) * box_bytes, frame + fbytes, W, t, &bar[(i + 1) & 1]);
             mbar_wait(&bar[i & 1], (i >> 1) & 1);
         }
         const uint32_t box = box0 + (i & 1) * box_bytes;
@@ -466,9 +498,9 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
                 for (int k = 0; k < 4; ++k)
                     c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
             }
-            const uint32_t* trow = (MODE == 1 && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS)
-                                       ? text + ((size_t)f * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS : nullptr;
-            finish_row<MODE>(c, ie[j], ngroups, t.x0, y, lane, cv, trow, out_frame, P);
+            const uint32_t* trow = (MODE == 1 && trow_off[j] >= 0) ? tplane + trow_off[j] : nullptr;
+            const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;      // only used where ie != ~0, i.e. inside the inverse rows
+            finish_row<MODE>(c, ie[j], ngroups, mi, lane, cv, trow, tw0, reinterpret_cast<uint32_t*>(out_frame + ooff[j]), rs, P);
         }
         if (!t.slow) __syncthreads();                                    // everyone is done with box (i & 1)
     }
@@ -484,10 +516,11 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
     const int f = blockIdx.y;
     const uint8_t* frame = frames + (size_t)f * fbytes;
     uint8_t* out_frame = out + (size_t)f * fbytes;
-    const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * H * WW;
+    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f * H * WW;
     const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ngroups = t.w >> 5;
+    const RowStore rs(lane);
     const int rq = (3 * lane) >> 2, rsh = ((3 * lane) & 3) * 8;         // pixel `lane` of a group: words rq, rq+1
     for (int r = warp; r < t.h; r += FRAME_THREADS / 32) {
         const int y = t.y0 + r;
@@ -500,7 +533,9 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
             c[k] = __funnelshift_r(a, b, rsh) & 0xFFFFFFu;
         }
         load_inv4(ie, ngroups, t.x0, y, lane, P);
-        finish_row<2>(c, ie, ngroups, t.x0, y, lane, cv, nullptr, out_frame, P);
+        const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;
+        finish_row<2>(c, ie, ngroups, mi, lane, cv, nullptr, 0,
+                      reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs, P);
     }
 }
 

@@ -366,6 +366,12 @@ LD_HD void draw_stamp(Plotter& P, const Stamp& st, int ax, int ay) {
         if (st.x1[r] <= st.x2[r]) P.span(ay - STAMP_HALF + r, ax + st.x1[r], ax + st.x2[r]);
 }
 
+template <class Plotter>
+LD_HD void draw_stamp_part(Plotter& P, const Stamp& st, int ax, int ay, int tid, int nt) {
+    for (int r = tid; r < STAMP_ROWS; r += nt)
+        if (st.x1[r] <= st.x2[r]) P.span(ay - STAMP_HALF + r, ax + st.x1[r], ax + st.x2[r]);
+}
+
 // Classification of segment (a -> b) of cv2.polylines with the shortcuts above; (c) is the vertex after b if has_next.
 enum { SEG_TRIVIAL = 1, SEG_END_DISC = 2, SEG_START_DISC = 4 };
 LD_HD int classify_segment(int w, int h, int ax, int ay, int bx, int by, bool has_next, int cx, int cy, int thickness, bool first) {
