@@ -388,7 +388,7 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
     else
     {
         const int fpc = frames_per_cta(m);
-        k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, (m + fpc - 1) / fpc), FRAME_THREADS, c->plan->frame_smem, s>>>(
+        k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, (m + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
             fin, planes, text, fout, d, m, fpc);
     }
     return check_launch();
@@ -625,7 +625,7 @@ extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* ou
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
     const int fpc = frames_per_cta(n);
-    k_frame_pass_mf<0><<<dim3(d.n_frame_tiles, (n + fpc - 1) / fpc), FRAME_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(
+    k_frame_pass_mf<0><<<dim3(d.n_frame_tiles, (n + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(
         frames, nullptr, nullptr, out, d, n, fpc);
     return check_launch();
 }

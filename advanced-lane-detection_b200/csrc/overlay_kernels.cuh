@@ -18,6 +18,7 @@ namespace lanedet {
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_BAND = 90;                 // canvas rows per CTA (8 bands of a 720-row frame)
 constexpr int MAX_VERTS = 2 * 724;
+constexpr int RASTER_BIG_ROUND = 4;             // long segments set up per round (one thread each)
 
 #ifdef LD_RASTER_PROF
 __device__ long long g_raster_prof[64][16];
@@ -49,10 +50,13 @@ struct RasterShared {
     int prefix[2][LD_ROWMAP_WORDS];
     int vx[MAX_VERTS], vy[MAX_VERTS];
     int cnt[RASTER_BAND];
-    int cross[RASTER_BAND * LD_MAX_CROSSINGS];
+    alignas(8) int cross[RASTER_BAND * LD_MAX_CROSSINGS];        // also the ThickSetup records of the long red segments
     unsigned short job[2 * MAX_VERTS];       // segment index | type << 14
     unsigned short big[MAX_VERTS], bigedge[MAX_VERTS];
 };
+
+static_assert(sizeof(laneraster::ThickSetup) * RASTER_BIG_ROUND <= sizeof(int) * RASTER_BAND * LD_MAX_CROSSINGS,
+              "ThickSetup records must fit the crossing lists they alias");
 
 __device__ __forceinline__ void add_crossing(RasterShared& R, const laneraster::PolyEdge& e, int y, int y_lo) {
     long long x = e.x + (long long)(y - e.y0) * e.dx;
@@ -204,12 +208,23 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         }
     }
     RPROF(3);
-    for (int k = 0; k < R.n_big; ++k) {
-        const int i = R.big[k];
-        laneraster::thick_segment_part(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, tid,
-                                       RASTER_THREADS, y_lo, y_hi);
+    // long segments (lane gaps, the connector between the lanes): their set-up (a chain of 64-bit divisions) is done by
+    // ONE thread per segment into shared memory, four segments per round; then the whole CTA draws them
+    {
+        laneraster::ThickSetup* ts = reinterpret_cast<laneraster::ThickSetup*>(R.cross);     // the crossing lists are not in use yet
+        for (int k0 = 0; k0 < R.n_big; k0 += RASTER_BIG_ROUND) {
+            const int nb = min(RASTER_BIG_ROUND, R.n_big - k0);
+            __syncthreads();
+            if ((tid & 31) == 0 && (tid >> 5) < nb) {
+                const int i = R.big[k0 + (tid >> 5)];
+                laneraster::thick_segment_setup(W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, ts[tid >> 5]);
+            }
+            __syncthreads();
+            for (int k = 0; k < nb; ++k)
+                laneraster::thick_segment_draw(red, W, H, ts[k], thickness, R.hw, R.big[k0 + k] == 0, tid, RASTER_THREADS, y_lo, y_hi);
+        }
+        __syncthreads();                                                // ts aliases the crossing lists of the green phase
     }
-
     RPROF(4);
     // ---- green: cv2.fillPoly(canvas, pts, (0,255,0)) (Project.py:164): outline + scanline crossings of this band
     for (int i = tid; i < nv && nv >= 2; i += RASTER_THREADS) {
@@ -421,14 +436,16 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
 }
 
 // K4b / stand-alone undistort, multi-frame form.  One CTA = one 128x16 output tile (plan.frame_tiles) of up to
-// FRAME_FPC consecutive frames.  Warp w produces rows w, w+8 of the tile; within a row lane i owns pixels i, i+32, i+64,
+// FRAME_FPC consecutive frames; warp w produces row w of the tile.  Within the row lane i owns pixels i, i+32, i+64,
 // i+96, so the lanes of one shared-memory load sit on ADJACENT output pixels (their taps fall into ~22 consecutive
-// words).  Everything that depends only on the tile -- tap offsets, dp2a weight pairs, inverse-warp entries -- is decoded
-// once into registers; per frame the CTA only stages the source box (TMA bulk row copies, double buffered: frame i+1
-// lands while frame i is computed), gathers, blends and stores.
+// words).  Everything that depends only on the tile -- tap offsets, dp2a weight pairs, inverse-warp entries, output
+// offsets -- is decoded once into registers; per frame the CTA only stages the source box (TMA bulk row copies, double
+// buffered: frame i+1 lands while frame i is computed), gathers, blends and stores.
 // MODE 0: cv2.undistort only (helper.py:35-47); MODE 1: undistort + canvas blend + text (process_image).
+constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
+
 template <int MODE>
-__global__ void __launch_bounds__(FRAME_THREADS, 3)
+__global__ void __launch_bounds__(FRAME_MF_THREADS, 2)
 k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes, const uint32_t* __restrict__ text,
                 uint8_t* __restrict__ out, const PlanDev P, int n, int fpc) {
     extern __shared__ __align__(128) uint8_t s_boxes[];
@@ -437,71 +454,65 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     const size_t fbytes = (size_t)W * H * 3;
     const int f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
     const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ngroups = t.w >> 5;                                        // 32-pixel groups in a tile row (W % 32 == 0)
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;             // r = this warp's tile row
+    const bool row_on = r < t.h;                                         // warp-uniform
+    const int ngroups = row_on ? (t.w >> 5) : 0;                         // 32-pixel groups in a tile row (W % 32 == 0)
+    const int y = t.y0 + r;
     const uint32_t box_bytes = ((uint32_t)(t.rows * t.stride) + 127u) & ~127u;
     const uint32_t box0 = smem_u32(s_boxes);
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
 
-    // ---- per-tile constants of this thread's two rows
-    uint32_t po[2][4], wx[2][4], wy[2][4], ie[2][4], ooff[2];
-    int trow_off[2];                                                      // word offset of the row in a frame's text plane, -1 = none
-    const RowStore rs(lane);
-    const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
-    const uint4* am4 = reinterpret_cast<const uint4*>(P.frame_amap + P.frame_amap_start[blockIdx.x]);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int r = warp + 8 * j;
+    // ---- per-tile constants of this thread's row
+    uint32_t po[4], wx[4], wy[4], ie[4];
+    {
         uint4 e = make_uint4(0, 0, 0, 0);
-        if (r < t.h && !t.slow) e = __ldg(am4 + r * 32 + lane);
+        if (row_on && !t.slow) e = __ldg(reinterpret_cast<const uint4*>(P.frame_amap + P.frame_amap_start[blockIdx.x]) + r * 32 + lane);
         const uint32_t es[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t fx = es[k] & 31u, fy = (es[k] >> 5) & 31u, o = es[k] >> 10;
-            frame_weights(fx, fy, wx[j][k], wy[j][k]);
-            po[j][k] = (o & ~3u) | (o << 30);
+            const uint32_t o = es[k] >> 10;
+            frame_weights(es[k] & 31u, (es[k] >> 5) & 31u, wx[k], wy[k]);
+            po[k] = (o & ~3u) | (o << 30);
         }
-        if (MODE != 0) load_inv4(ie[j], r < t.h ? ngroups : 0, t.x0, t.y0 + r, lane, P);
-        else { ie[j][0] = ie[j][1] = ie[j][2] = ie[j][3] = 0xFFFFFFFFu; }
-        const int y = t.y0 + r;
-        ooff[j] = (uint32_t)(((size_t)y * W + t.x0) * 3) + 4u * lane;
-        trow_off[j] = (MODE == 1 && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS)
-                          ? (y - LD_TEXT_Y0) * LD_TEXT_WORDS : -1;
     }
+    if (MODE != 0) load_inv4(ie, ngroups, t.x0, y, lane, P);
+    else { ie[0] = ie[1] = ie[2] = ie[3] = 0xFFFFFFFFu; }
+    const RowStore rs(lane);
+    const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
+    const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
+    const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;          // only used where ie != ~0, i.e. inside the inverse rows
+    // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop)
+    const uint8_t* frame = frames + (size_t)f0 * fbytes;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
+    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f0 * H * WW;
+    const uint32_t* trow = text + ((size_t)f0 * LD_TEXT_ROWS + (text_row ? y - LD_TEXT_Y0 : 0)) * LD_TEXT_WORDS;
     __syncthreads();                                                     // barriers initialised
 
-    if (!t.slow) stage_box_spread(s_boxes, frames + (size_t)f0 * fbytes, W, t, &bar[0]);
+    if (!t.slow) stage_box_spread(s_boxes, frame, W, t, &bar[0]);
     for (int i = 0; i < nf; ++i) {
-        const int f = f0 + i;
-        const uint8_t* frame = frames + (size_t)f * fbytes;
-        uint8_t* out_frame = out + (size_t)f * fbytes;
-        const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f * H * WW;
-        const uint32_t* tplane = text + (size_t)f * LD_TEXT_ROWS * LD_TEXT_WORDS;
         if (!t.slow) {
             // the other buffer was last read in iteration i-1, which ended with a CTA barrier: safe to refill
             if (i + 1 < nf) stage_box_spread(s_boxes + ((i + 1) & 1) * box_bytes, frame + fbytes, W, t, &bar[(i + 1) & 1]);
             mbar_wait(&bar[i & 1], (i >> 1) & 1);
         }
-        const uint32_t box = box0 + (i & 1) * box_bytes;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int r = warp + 8 * j;
-            if (r >= t.h) continue;                                      // warp-uniform
-            const int y = t.y0 + r;
+        if (row_on) {
+            const uint32_t box = box0 + (i & 1) * box_bytes;
             uint32_t c[4];
             if (!t.slow) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_pre(box, (uint32_t)t.stride, po[j][k], wx[j][k], wy[j][k]);
+                for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_pre(box, (uint32_t)t.stride, po[k], wx[k], wy[k]);
             } else {
                 const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
             }
-            const uint32_t* trow = (MODE == 1 && trow_off[j] >= 0) ? tplane + trow_off[j] : nullptr;
-            const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;      // only used where ie != ~0, i.e. inside the inverse rows
-            finish_row<MODE>(c, ie[j], ngroups, mi, lane, cv, trow, tw0, reinterpret_cast<uint32_t*>(out_frame + ooff[j]), rs, P);
+            finish_row<MODE>(c, ie, ngroups, mi, lane, cv, text_row ? trow : nullptr, tw0, orow, rs, P);
         }
+        frame += fbytes;
+        orow += fbytes / 4;                                              // W % 32 == 0: a frame is a whole number of words
+        cv += (size_t)H * WW;
+        trow += LD_TEXT_ROWS * LD_TEXT_WORDS;
         if (!t.slow) __syncthreads();                                    // everyone is done with box (i & 1)
     }
 }

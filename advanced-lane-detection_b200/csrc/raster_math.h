@@ -547,16 +547,20 @@ LD_HD void disc_part(Plotter& P, int w, int h, int cx, int cy, int radius, const
     }
 }
 
-// thick_segment() shared among nt workers; rows outside [ylo, yhi) are skipped (the caller's band)
-template <class Plotter>
-LD_HD void thick_segment_part(Plotter& P, int w, int h, int x0, int y0, int x1, int y1, int thickness, const int* hw,
-                              bool first, int tid, int nt, int ylo, int yhi) {
+// thick_segment() shared among nt workers, split into its set-up (clipping, the quad's corners, the four outline DDAs,
+// the scan-edge records: ~10 64-bit divisions, done ONCE, e.g. by one thread into shared memory) and the drawing, which
+// every worker runs from that record.  Rows outside [ylo, yhi) are skipped (the caller's band).
+struct ThickSetup { int valid, quad, x0, y0, x1, y1; LineFx L[4]; QuadScan S; };
+
+LD_HD void thick_segment_setup(int w, int h, int x0, int y0, int x1, int y1, int thickness, ThickSetup& T) {
+    T.valid = 0; T.quad = 0;
     Pt a, b;
     a.x = x0 + thickness; a.y = y0 + thickness;
     b.x = x1 + thickness; b.y = y1 + thickness;
     if (!clip_line((int64_t)w + 2 * thickness, (int64_t)h + 2 * thickness, a, b)) return;
-    x0 = (int)a.x - thickness; y0 = (int)a.y - thickness;
-    x1 = (int)b.x - thickness; y1 = (int)b.y - thickness;
+    T.valid = 1;
+    T.x0 = x0 = (int)a.x - thickness; T.y0 = y0 = (int)a.y - thickness;
+    T.x1 = x1 = (int)b.x - thickness; T.y1 = y1 = (int)b.y - thickness;
     Pt p0, p1;
     p0.x = (int64_t)x0 << XY_SHIFT; p0.y = (int64_t)y0 << XY_SHIFT;
     p1.x = (int64_t)x1 << XY_SHIFT; p1.y = (int64_t)y1 << XY_SHIFT;
@@ -574,12 +578,30 @@ LD_HD void thick_segment_part(Plotter& P, int w, int h, int x0, int y0, int x1, 
         q[1].x = p0.x - dp.x; q[1].y = p0.y - dp.y;
         q[2].x = p1.x - dp.x; q[2].y = p1.y - dp.y;
         q[3].x = p1.x + dp.x; q[3].y = p1.y + dp.y;
-        for (int e = 0; e < 4; ++e) line_fx_part(P, w, h, line_fx_setup(w, h, q[(e + 3) & 3], q[e]), tid, nt);
-        const QuadScan S = fill_convex_setup(w, h, q, 4);
-        fill_convex_rows_part(P, w, S, tid, nt, ylo, yhi);
+        for (int e = 0; e < 4; ++e) T.L[e] = line_fx_setup(w, h, q[(e + 3) & 3], q[e]);
+        T.S = fill_convex_setup(w, h, q, 4);
+        T.quad = 1;
     }
-    if (first) disc_part(P, w, h, x0, y0, thickness / 2, hw, tid, nt);
-    disc_part(P, w, h, x1, y1, thickness / 2, hw, tid, nt);
+}
+
+template <class Plotter>
+LD_HD void thick_segment_draw(Plotter& P, int w, int h, const ThickSetup& T, int thickness, const int* hw, bool first,
+                              int tid, int nt, int ylo, int yhi) {
+    if (!T.valid) return;
+    if (T.quad) {
+        for (int e = 0; e < 4; ++e) line_fx_part(P, w, h, T.L[e], tid, nt);
+        fill_convex_rows_part(P, w, T.S, tid, nt, ylo, yhi);
+    }
+    if (first) disc_part(P, w, h, T.x0, T.y0, thickness / 2, hw, tid, nt);
+    disc_part(P, w, h, T.x1, T.y1, thickness / 2, hw, tid, nt);
+}
+
+template <class Plotter>
+LD_HD void thick_segment_part(Plotter& P, int w, int h, int x0, int y0, int x1, int y1, int thickness, const int* hw,
+                              bool first, int tid, int nt, int ylo, int yhi) {
+    ThickSetup T;
+    thick_segment_setup(w, h, x0, y0, x1, y1, thickness, T);
+    thick_segment_draw(P, w, h, T, thickness, hw, first, tid, nt, ylo, yhi);
 }
 
 // line8() shared among nt workers: after i iterations the minor coordinate has advanced by
