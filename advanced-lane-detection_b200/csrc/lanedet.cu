@@ -127,7 +127,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         const size_t b = (size_t)(desc->mask_chunks[8 * t + 6] & 0xFFFF) * (size_t)(desc->mask_chunks[8 * t + 7] & 0x7FFFFFFF);
         if (b > ms) ms = b;
     }
-    if (fs > 96 * 1024 || ms > 160 * 1024) return LD_ERR_ARG;           // the frame pass double-buffers its box
+    if (fs > 64 * 1024 || ms > 160 * 1024) return LD_ERR_ARG;           // the frame pass keeps FRAME_STAGES boxes in flight
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
@@ -163,7 +163,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if ((rc = upload(p, stamps, (size_t)laneraster::STAMP_N, &sd))) { ld_plan_destroy(p); return rc; }
         d.stamps = sd;
     }
-    p->frame_smem = 2 * ((fs + 127) / 128 * 128) + 128;                  // two boxes (double buffered)
+    p->frame_smem = FRAME_STAGES * ((fs + 127) / 128 * 128) + 128;      // FRAME_STAGES source boxes in flight
     int mow = 0;
     for (int t = 0; t < desc->n_tiles; ++t) {
         const int words = (desc->tiles[8 * t + 1] - desc->tiles[8 * t]) * (W / 32);

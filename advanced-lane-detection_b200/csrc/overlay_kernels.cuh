@@ -313,29 +313,51 @@ __device__ __forceinline__ uint32_t canvas_tap(const uint4* __restrict__ cv, int
     return ((w.x >> b) & 1u) | (((w.z >> b) & 1u) << 1);
 }
 
-// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170) for ONE pixel whose inv_pack entry is e (!= ~0) and whose
-// index into the inverse-warp tables is mi.  cv = this frame's canvas: per 32 pixels one entry holding the 64-bit window
-// [32k, 32k+64) of the red and of the green plane, so the two tap columns b, b+1 come out of one entry with a funnel shift.
-// Fast form (bit 11 of e): all four taps lie inside the canvas.  Most pixels of the trapezoid see four equal taps (all
-// background or all green); those two cases are decided from the plane words directly: 0 -> nothing to add;
-// all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to even) to g + 76 + (g & 1).
-__device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, size_t mi, const uint4* __restrict__ cv, const PlanDev& P) {
-    const int W = P.W, H = P.H, WW = P.WW;
+// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170).  cv = this frame's canvas: per 32 pixels one entry holding
+// the 64-bit window [32k, 32k+64) of the red and of the green plane, so the two tap columns b, b+1 of a pixel come out of
+// one entry with a funnel shift.  An inv_pack entry e is ~0 (pixel not touched), FAST (bit 11: all four taps inside the
+// canvas; entry index e >> 17, bit (e >> 12) & 31) or slow (taps straddle the canvas border: inv_idx + canvas_tap).
+//
+// canvas_codes() fetches the taps of the four pixels a lane owns -- all eight 16-byte loads are issued back to back, and
+// the caller runs it BEFORE its gather so their L2 latency hides behind that -- and squeezes each pixel's taps into one
+// byte: red(x, x+1) | green(x, x+1) << 2 of the top tap row, the same << 4 of the bottom row.
+__device__ __forceinline__ bool inv_fast(uint32_t e) { return e != 0xFFFFFFFFu && (e & 0x800u); }
+
+__device__ __forceinline__ uint32_t canvas_codes(const uint32_t (&ie)[4], const uint4* __restrict__ cv, int WW) {
+    uint4 a0[4], a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a0[k] = a1[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (inv_fast(ie[k])) { const uint4* p = cv + (ie[k] >> 17); a0[k] = __ldg(p); a1[k] = __ldg(p + WW); }
+    }
+    uint32_t codes = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t b = ie[k] >> 12;                                   // the funnel shifts use its low five bits
+        const uint32_t r0 = __funnelshift_r(a0[k].x, a0[k].y, b) & 3u, g0 = __funnelshift_r(a0[k].z, a0[k].w, b) & 3u;
+        const uint32_t r1 = __funnelshift_r(a1[k].x, a1[k].y, b) & 3u, g1 = __funnelshift_r(a1[k].z, a1[k].w, b) & 3u;
+        codes |= (r0 | (g0 << 2) | (r1 << 4) | (g1 << 6)) << (8 * k);
+    }
+    return codes;
+}
+
+// Blend one pixel c (r | g << 8 | b << 16).  Most pixels of the trapezoid see four equal taps (all background or all
+// green): code 0 -> nothing to add; all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to
+// even) to g + 76 + (g & 1).  Everything else takes OpenCV's fixed-point bilinear of the three canvas colours and the
+// float32 blend of cv2.addWeighted.
+__device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, uint32_t code, size_t mi, const uint4* __restrict__ cv,
+                                                    const PlanDev& P) {
     uint32_t t00, t01, t10, t11;
     if (e & 0x800u) {
-        const uint4* p = cv + (e >> 17);
-        const uint32_t b = e >> 12;                                       // the funnel shifts use its low five bits
-        const uint4 a0 = __ldg(p), a1 = __ldg(p + WW);
-        if (!(__funnelshift_r(a0.x | a0.z | a1.x | a1.z, a0.y | a0.w | a1.y | a1.w, b) & 3u)) return c;
-        if ((__funnelshift_r(a0.z & a1.z, a0.w & a1.w, b) & 3u) == 3u) {
+        if (!code) return c;
+        if ((code & 0xCCu) == 0xCCu) {
             const uint32_t g = (c >> 8) & 255u;
             return (c & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
         }
-        const uint32_t r0 = __funnelshift_r(a0.x, a0.y, b) & 3u, g0 = __funnelshift_r(a0.z, a0.w, b) & 3u;
-        const uint32_t r1 = __funnelshift_r(a1.x, a1.y, b) & 3u, g1 = __funnelshift_r(a1.z, a1.w, b) & 3u;
-        t00 = (r0 & 1u) | ((g0 & 1u) << 1); t01 = (r0 >> 1) | ((g0 >> 1) << 1);
-        t10 = (r1 & 1u) | ((g1 & 1u) << 1); t11 = (r1 >> 1) | ((g1 >> 1) << 1);
+        t00 = (code & 1u) | ((code >> 1) & 2u); t01 = ((code >> 1) & 1u) | ((code >> 2) & 2u);
+        t10 = ((code >> 4) & 1u) | ((code >> 5) & 2u); t11 = ((code >> 5) & 1u) | ((code >> 6) & 2u);
     } else {
+        const int W = P.W, H = P.H, WW = P.WW;
         const uint32_t idx = __ldg(P.inv_idx + mi);
         const int sx = (int)(idx & 0xFFFFu) - 1, sy = (int)(idx >> 16) - 1;
         t00 = canvas_tap(cv, W, H, WW, sx, sy); t01 = canvas_tap(cv, W, H, WW, sx + 1, sy);
@@ -364,15 +386,16 @@ struct RowStore {
 };
 
 // The tail of a tile row, shared by the frame-pass kernels: canvas blend, text, and the store.  Lane i holds pixels
-// x0 + i + 32 k (k < ngroups) in c[k] as r | g << 8 | b << 16; orow = this lane's first output word (row start + lane).
+// x0 + i + 32 k (k < ngroups) in c[k] as r | g << 8 | b << 16; codes = canvas_codes() of those pixels (0 where the row is
+// outside the inverse warp); orow = this lane's first output word (row start + lane).
 template <int MODE>
-__device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], int ngroups, size_t mi, int lane,
+__device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], uint32_t codes, int ngroups, size_t mi, int lane,
                                            const uint4* __restrict__ cv, const uint32_t* __restrict__ trow, int tw0,
                                            uint32_t* __restrict__ orow, const RowStore& rs, const PlanDev& P) {
     if (MODE != 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (ie[k] != 0xFFFFFFFFu) c[k] = blend_canvas_px(c[k], ie[k], mi + 32 * k, cv, P);
+            if (ie[k] != 0xFFFFFFFFu) c[k] = blend_canvas_px(c[k], ie[k], (codes >> (8 * k)) & 255u, mi + 32 * k, cv, P);
     }
     if (MODE == 1 && trow) {                                             // tile columns and LD_TEXT_X0 are multiples of 32
 #pragma unroll
@@ -397,7 +420,7 @@ __device__ __forceinline__ void load_inv4(uint32_t (&ie)[4], int ngroups, int x0
 }
 
 constexpr int FRAME_THREADS = 256;
-constexpr int FRAME_FPC = 8;                    // frames per CTA of the multi-frame pass
+constexpr int FRAME_FPC = 16;                   // frames per CTA of the multi-frame pass (upper bound)
 
 // bilinear_rgb_off with everything that does not depend on the frame hoisted out: po = (tap byte offset & ~3) |
 // (offset & 3) << 30, wx / wy = the dp2a weight pairs of the top / bottom tap row, DOUBLED (see frame_weights) so that
@@ -443,13 +466,14 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
 // buffered: frame i+1 lands while frame i is computed), gathers, blends and stores.
 // MODE 0: cv2.undistort only (helper.py:35-47); MODE 1: undistort + canvas blend + text (process_image).
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
+constexpr int FRAME_STAGES = 3;                 // source boxes in flight (two frames ahead of the one being computed)
 
 template <int MODE>
 __global__ void __launch_bounds__(FRAME_MF_THREADS, 2)
 k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes, const uint32_t* __restrict__ text,
                 uint8_t* __restrict__ out, const PlanDev P, int n, int fpc) {
     extern __shared__ __align__(128) uint8_t s_boxes[];
-    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ __align__(8) uint64_t bar[FRAME_STAGES], empty[FRAME_STAGES];     // box landed / box released by all warps
     const int W = P.W, H = P.H, WW = P.WW;
     const size_t fbytes = (size_t)W * H * 3;
     const int f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
@@ -460,7 +484,10 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     const int y = t.y0 + r;
     const uint32_t box_bytes = ((uint32_t)(t.rows * t.stride) + 127u) & ~127u;
     const uint32_t box0 = smem_u32(s_boxes);
-    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < FRAME_STAGES; ++b) { mbar_init(&bar[b], 1); mbar_init(&empty[b], FRAME_MF_THREADS / 32); }
+    }
 
     // ---- per-tile constants of this thread's row
     uint32_t po[4], wx[4], wy[4], ie[4];
@@ -477,10 +504,17 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     }
     if (MODE != 0) load_inv4(ie, ngroups, t.x0, y, lane, P);
     else { ie[0] = ie[1] = ie[2] = ie[3] = 0xFFFFFFFFu; }
+    const bool inv_row = MODE != 0 && __any_sync(0xffffffffu, (ie[0] & ie[1] & ie[2] & ie[3]) != 0xFFFFFFFFu);   // warp-uniform
     const RowStore rs(lane);
     const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
     const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
     const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;          // only used where ie != ~0, i.e. inside the inverse rows
+    // this thread's share of the box copies: the row copies are dealt round-robin to the warps (a bulk copy is a
+    // warp-serial instruction); row cr of the box <- source row t.sy0 + cr
+    const int cr = lane * (FRAME_MF_THREADS / 32) + r;
+    const bool copier = !t.slow && cr < t.rows;
+    const uint32_t copy_src = (uint32_t)((size_t)(t.sy0 + cr) * W * 3 + t.b0), copy_dst = (uint32_t)(cr * t.stride);
+    const uint32_t copy_total = (uint32_t)(t.rows * t.copy);
     // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop)
     const uint8_t* frame = frames + (size_t)f0 * fbytes;
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
@@ -488,32 +522,56 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     const uint32_t* trow = text + ((size_t)f0 * LD_TEXT_ROWS + (text_row ? y - LD_TEXT_Y0 : 0)) * LD_TEXT_WORDS;
     __syncthreads();                                                     // barriers initialised
 
-    if (!t.slow) stage_box_spread(s_boxes, frame, W, t, &bar[0]);
-    for (int i = 0; i < nf; ++i) {
-        if (!t.slow) {
-            // the other buffer was last read in iteration i-1, which ended with a CTA barrier: safe to refill
-            if (i + 1 < nf) stage_box_spread(s_boxes + ((i + 1) & 1) * box_bytes, frame + fbytes, W, t, &bar[(i + 1) & 1]);
-            mbar_wait(&bar[i & 1], (i >> 1) & 1);
+    // Producer side, spread over the CTA: the box of the next frame to stage goes to buffer sb (rotating).  Every copier
+    // waits until all 16 warps have released that buffer (empty[sb]) and issues its own row copy; thread 0 posts the
+    // expected byte count.  There is NO CTA-wide barrier in the frame loop: warps drift up to FRAME_STAGES - 1 frames
+    // apart, so the shared-memory-heavy and the ALU-heavy parts of different warps overlap instead of running in lockstep.
+    const uint8_t* copy_ptr = frame + copy_src;
+    const uint32_t full0 = smem_u32(&bar[0]), empty0 = smem_u32(&empty[0]);
+    int sb = 0, su = 0;                                                  // ring position, and how often the ring has been filled
+    auto stage = [&]() {
+        if (copier || threadIdx.x == 0) {
+            if (su > 0) mbar_wait_addr(empty0 + 8u * sb, (uint32_t)((su - 1) & 1));   // use su of buffer sb needs release su - 1
+            const uint32_t mb = full0 + 8u * sb;
+            if (threadIdx.x == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(copy_total) : "memory");
+            if (copier)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(box0 + sb * box_bytes + copy_dst),
+                             "l"(copy_ptr), "r"((uint32_t)t.copy), "r"(mb) : "memory");
         }
-        if (row_on) {
-            const uint32_t box = box0 + (i & 1) * box_bytes;
-            uint32_t c[4];
-            if (!t.slow) {
+        copy_ptr += fbytes;
+        if (sb == FRAME_STAGES - 1) { sb = 0; ++su; } else ++sb;
+    };
+    if (!t.slow) {
+#pragma unroll
+        for (int i = 0; i < FRAME_STAGES - 1; ++i) if (i < nf) stage();
+    }
+    int b = 0, parity = 0;                                               // buffer / mbarrier phase of the frame being computed
+    for (int i = 0; i < nf; ++i) {
+        if (!t.slow && i + FRAME_STAGES - 1 < nf) stage();
+        const uint32_t codes = (row_on && inv_row) ? canvas_codes(ie, cv, WW) : 0u;  // issued before the wait and the gather
+        uint32_t c[4];
+        if (!t.slow) {
+            mbar_wait_addr(full0 + 8u * b, (uint32_t)parity);
+            const uint32_t box = box0 + b * box_bytes;
+            if (row_on) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_pre(box, (uint32_t)t.stride, po[k], wx[k], wy[k]);
-            } else {
-                const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
             }
-            finish_row<MODE>(c, ie, ngroups, mi, lane, cv, text_row ? trow : nullptr, tw0, orow, rs, P);
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");   // this warp is done with buffer b
+        } else if (row_on) {
+            const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
         }
+        if (row_on) finish_row<MODE>(c, ie, codes, ngroups, mi, lane, cv, text_row ? trow : nullptr, tw0, orow, rs, P);
         frame += fbytes;
         orow += fbytes / 4;                                              // W % 32 == 0: a frame is a whole number of words
         cv += (size_t)H * WW;
         trow += LD_TEXT_ROWS * LD_TEXT_WORDS;
-        if (!t.slow) __syncthreads();                                    // everyone is done with box (i & 1)
+        if (b == FRAME_STAGES - 1) { b = 0; parity ^= 1; } else ++b;
     }
 }
 
@@ -545,7 +603,7 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
         }
         load_inv4(ie, ngroups, t.x0, y, lane, P);
         const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;
-        finish_row<2>(c, ie, ngroups, mi, lane, cv, nullptr, 0,
+        finish_row<2>(c, ie, canvas_codes(ie, cv, WW), ngroups, mi, lane, cv, nullptr, 0,
                       reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs, P);
     }
 }

@@ -1,9 +1,7 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu.log 2>&1
-tail -15 gpurun_out/pytest_gpu.log
-python tools/stage_times.py --frames 1260 > gpurun_out/stages_1260.json 2> gpurun_out/stages_1260.err
-cat gpurun_out/stages_1260.json; tail -3 gpurun_out/stages_1260.err
-python tools/raster_prof.py > gpurun_out/raster_prof.txt 2>&1
-cat gpurun_out/raster_prof.txt
+timeout 120 python tools/stage_times.py --frames 148 --reps 1 --only k_undistort,k_frame_pass > gpurun_out/stages_148.json 2> gpurun_out/stages_148.err &&
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_frame_pass_mf' -c 4 \
+    -o gpurun_out/prof_fp7 -f python tools/stage_times.py --frames 148 --reps 1 --only k_undistort,k_frame_pass > gpurun_out/ncu_fp7.log 2>&1
+tail -3 gpurun_out/ncu_fp7.log

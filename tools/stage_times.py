@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--frames", type=int, default=296)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--variant", default="project")
+    ap.add_argument("--only", default="", help="comma-separated stage names to time (default: all)")
     a = ap.parse_args()
     import torch
     pkg = importlib.import_module(bench.PKG)
@@ -26,7 +27,11 @@ def main():
     out = torch.empty_like(frames)
     stage = {}
 
+    only = set(x for x in a.only.split(",") if x)
+
     def t(name, fn):
+        if only and name not in only:
+            return
         fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
