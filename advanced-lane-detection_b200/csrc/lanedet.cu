@@ -33,6 +33,7 @@ struct ld_plan {
     void* allocs[32];
     int n_allocs;
     size_t search_smem, raster_smem, mask_smem, frame_smem;
+    int frame_box_rows;        // source rows of the largest frame-pass tile box (the TMA box height)
 };
 
 enum { HOST_CHUNK = 32, PIPE_SUB = 8 };
@@ -119,15 +120,21 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     const int16_t* wt = nullptr; const int32_t* tl = nullptr; const int32_t* ft = nullptr; const int32_t* mc = nullptr; const uint32_t* bd = nullptr;
     d.n_frame_tiles = desc->n_frame_tiles; d.n_mask_chunks = desc->n_mask_chunks;
     size_t fs = 0, ms = 0;
+    int box_rows = 1;
     for (int t = 0; t < desc->n_frame_tiles; ++t) {
-        const size_t b = (size_t)(desc->frame_tiles[8 * t + 6] & 0xFFFF) * (size_t)(desc->frame_tiles[8 * t + 7] & 0x7FFFFFFF);
-        if (b > fs) fs = b;
+        const int rows = desc->frame_tiles[8 * t + 6] & 0xFFFF, stride = desc->frame_tiles[8 * t + 7] & 0x7FFFFFFF;
+        if (desc->frame_tiles[8 * t + 7] < 0) continue;                  // slow tile: no staged box
+        // every staged box is one tensor-map TMA copy of FRAME_BOX_PITCH bytes x box_rows rows
+        if (stride != FRAME_BOX_PITCH || desc->frame_tiles[8 * t + 2] > 128 || (desc->frame_tiles[8 * t + 4] & 15)) return LD_ERR_ARG;
+        if (rows > box_rows) box_rows = rows;
     }
+    if (box_rows > 64) return LD_ERR_ARG;
+    fs = (size_t)box_rows * FRAME_BOX_PITCH;
     for (int t = 0; t < desc->n_mask_chunks; ++t) {
         const size_t b = (size_t)(desc->mask_chunks[8 * t + 6] & 0xFFFF) * (size_t)(desc->mask_chunks[8 * t + 7] & 0x7FFFFFFF);
         if (b > ms) ms = b;
     }
-    if (fs > 64 * 1024 || ms > 160 * 1024) return LD_ERR_ARG;           // the frame pass keeps FRAME_STAGES boxes in flight
+    if (ms > 160 * 1024) return LD_ERR_ARG;
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
@@ -163,7 +170,8 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if ((rc = upload(p, stamps, (size_t)laneraster::STAMP_N, &sd))) { ld_plan_destroy(p); return rc; }
         d.stamps = sd;
     }
-    p->frame_smem = FRAME_STAGES * ((fs + 127) / 128 * 128) + 128;      // FRAME_STAGES source boxes in flight
+    p->frame_smem = FRAME_STAGES * fs + 128;                             // FRAME_STAGES source boxes in flight
+    p->frame_box_rows = box_rows;
     int mow = 0;
     for (int t = 0; t < desc->n_tiles; ++t) {
         const int words = (desc->tiles[8 * t + 1] - desc->tiles[8 * t]) * (W / 32);
@@ -373,6 +381,34 @@ static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* vert
         c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);
     return check_launch();
 }
+// Tensor map of m frames at `frames` seen as uint32[m][H][W*3/4], box = 128 words x box_rows rows x 1 frame: the source
+// box of a frame-pass tile is ONE TMA copy (out-of-range words are zero-filled, which is BORDER_CONSTANT 0).
+typedef CUresult (*ld_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int frame_tensor_map(const ld_plan* p, const uint8_t* frames, int m, CUtensorMap* tm) {
+    static ld_encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        LD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled is not available"); return LD_ERR_CUDA; }
+        encode = (ld_encode_tiled_fn)fn;
+    }
+    const PlanDev& d = p->d;
+    if ((uintptr_t)frames & 15) return LD_ERR_ARG;                       // TMA needs a 16-byte aligned base
+    const cuuint64_t row = (cuuint64_t)d.W * 3;
+    const cuuint64_t gdim[3] = {row / 4, (cuuint64_t)d.H, (cuuint64_t)m};
+    const cuuint64_t gstride[2] = {row, row * d.H};
+    const cuuint32_t box[3] = {FRAME_BOX_PITCH / 4, (cuuint32_t)p->frame_box_rows, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed (%d)", (int)r); return LD_ERR_CUDA; }
+    return LD_OK;
+}
+
 // frames one CTA of the multi-frame pass walks through: long enough to amortise its per-tile set-up, short enough
 // that a small batch still fills the machine with several waves of CTAs
 static int frames_per_cta(int m) {
@@ -388,8 +424,11 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
     else
     {
         const int fpc = frames_per_cta(m);
+        CUtensorMap tm;
+        int rc;
+        if ((rc = frame_tensor_map(c->plan, fin, m, &tm))) return rc;
         k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, (m + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-            fin, planes, text, fout, d, m, fpc);
+            tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows);
     }
     return check_launch();
 }
@@ -625,8 +664,11 @@ extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* ou
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
     const int fpc = frames_per_cta(n);
+    CUtensorMap tm;
+    int rc;
+    if ((rc = frame_tensor_map(c->plan, frames, n, &tm))) return rc;
     k_frame_pass_mf<0><<<dim3(d.n_frame_tiles, (n + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(
-        frames, nullptr, nullptr, out, d, n, fpc);
+        tm, frames, nullptr, nullptr, out, d, n, fpc, c->plan->frame_box_rows);
     return check_launch();
 }
 extern "C" int ld_warp(ld_ctx* c, const uint8_t* img, int n, int channels, uint8_t* out, void* stream) {

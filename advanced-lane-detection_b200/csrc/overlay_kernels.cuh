@@ -12,6 +12,7 @@
 #include "fit_math.h"
 #include "gather.cuh"
 #include "raster_math.h"
+#include <cuda.h>                                // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 
 namespace lanedet {
 
@@ -466,12 +467,13 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
 // buffered: frame i+1 lands while frame i is computed), gathers, blends and stores.
 // MODE 0: cv2.undistort only (helper.py:35-47); MODE 1: undistort + canvas blend + text (process_image).
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
-constexpr int FRAME_STAGES = 3;                 // source boxes in flight (two frames ahead of the one being computed)
+constexpr int FRAME_STAGES = 4;                 // source boxes in flight
+constexpr int FRAME_BOX_PITCH = 512;            // bytes per staged source row (plan.FRAME_BOX_PITCH): 128 uint32 = the TMA box width
 
 template <int MODE>
 __global__ void __launch_bounds__(FRAME_MF_THREADS, 2)
-k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes, const uint32_t* __restrict__ text,
-                uint8_t* __restrict__ out, const PlanDev P, int n, int fpc) {
+k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes,
+                const uint32_t* __restrict__ text, uint8_t* __restrict__ out, const PlanDev P, int n, int fpc, int box_rows) {
     extern __shared__ __align__(128) uint8_t s_boxes[];
     __shared__ __align__(8) uint64_t bar[FRAME_STAGES], empty[FRAME_STAGES];     // box landed / box released by all warps
     const int W = P.W, H = P.H, WW = P.WW;
@@ -482,8 +484,8 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     const bool row_on = r < t.h;                                         // warp-uniform
     const int ngroups = row_on ? (t.w >> 5) : 0;                         // 32-pixel groups in a tile row (W % 32 == 0)
     const int y = t.y0 + r;
-    const uint32_t box_bytes = ((uint32_t)(t.rows * t.stride) + 127u) & ~127u;
-    const uint32_t box0 = smem_u32(s_boxes);
+    const uint32_t box_bytes = (uint32_t)(box_rows * FRAME_BOX_PITCH);   // a multiple of 512
+    const uint32_t box0 = (smem_u32(s_boxes) + 127u) & ~127u;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < FRAME_STAGES; ++b) { mbar_init(&bar[b], 1); mbar_init(&empty[b], FRAME_MF_THREADS / 32); }
@@ -509,12 +511,6 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
     const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
     const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;          // only used where ie != ~0, i.e. inside the inverse rows
-    // this thread's share of the box copies: the row copies are dealt round-robin to the warps (a bulk copy is a
-    // warp-serial instruction); row cr of the box <- source row t.sy0 + cr
-    const int cr = lane * (FRAME_MF_THREADS / 32) + r;
-    const bool copier = !t.slow && cr < t.rows;
-    const uint32_t copy_src = (uint32_t)((size_t)(t.sy0 + cr) * W * 3 + t.b0), copy_dst = (uint32_t)(cr * t.stride);
-    const uint32_t copy_total = (uint32_t)(t.rows * t.copy);
     // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop)
     const uint8_t* frame = frames + (size_t)f0 * fbytes;
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
@@ -522,24 +518,20 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
     const uint32_t* trow = text + ((size_t)f0 * LD_TEXT_ROWS + (text_row ? y - LD_TEXT_Y0 : 0)) * LD_TEXT_WORDS;
     __syncthreads();                                                     // barriers initialised
 
-    // Producer side, spread over the CTA: the box of the next frame to stage goes to buffer sb (rotating).  Every copier
-    // waits until all 16 warps have released that buffer (empty[sb]) and issues its own row copy; thread 0 posts the
-    // expected byte count.  There is NO CTA-wide barrier in the frame loop: warps drift up to FRAME_STAGES - 1 frames
-    // apart, so the shared-memory-heavy and the ALU-heavy parts of different warps overlap instead of running in lockstep.
-    const uint8_t* copy_ptr = frame + copy_src;
+    // Producer = thread 0: ONE tensor-map TMA copy stages the whole 512 B x box_rows source box of the next frame into
+    // ring buffer sb, once all 16 warps have released it (empty[sb]).  There is no CTA-wide barrier in the frame loop.
     const uint32_t full0 = smem_u32(&bar[0]), empty0 = smem_u32(&empty[0]);
-    int sb = 0, su = 0;                                                  // ring position, and how often the ring has been filled
+    int sb = 0, su = 0, sf = f0;                                         // ring position, ring passes done, next frame to stage
     auto stage = [&]() {
-        if (copier || threadIdx.x == 0) {
+        if (threadIdx.x == 0) {
             if (su > 0) mbar_wait_addr(empty0 + 8u * sb, (uint32_t)((su - 1) & 1));   // use su of buffer sb needs release su - 1
             const uint32_t mb = full0 + 8u * sb;
-            if (threadIdx.x == 0)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(copy_total) : "memory");
-            if (copier)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(box0 + sb * box_bytes + copy_dst),
-                             "l"(copy_ptr), "r"((uint32_t)t.copy), "r"(mb) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(box_bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(box0 + sb * box_bytes), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(t.b0 >> 2), "r"(t.sy0), "r"(sf), "r"(mb)
+                         : "memory");
         }
-        copy_ptr += fbytes;
+        ++sf;
         if (sb == FRAME_STAGES - 1) { sb = 0; ++su; } else ++sb;
     };
     if (!t.slow) {
@@ -556,7 +548,7 @@ k_frame_pass_mf(const uint8_t* __restrict__ frames, const uint32_t* __restrict__
             const uint32_t box = box0 + b * box_bytes;
             if (row_on) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_pre(box, (uint32_t)t.stride, po[k], wx[k], wy[k]);
+                for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
             }
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");   // this warp is done with buffer b

@@ -40,6 +40,7 @@ CAL_DIST = np.array([[-0.2410179678072197, -0.05307204974677417, -0.001158103177
                       -0.00012831854336287326, 0.02671243019794861]])
 
 SEARCH_PROJECT, SEARCH_HARDER, SEARCH_HELPER = 0, 1, 2
+FRAME_BOX_PITCH = 512          # bytes per staged source row of a frame-pass tile (csrc: FRAME_BOX_PITCH)
 BMAP_BORDER = 0xFFFF
 CTAB_EMPTY = 0x00FF            # (lo=255, hi=0): never true
 CTAB_EXCEPTION = 0x00010001    # both intervals (lo=1, hi=0): consult cbits
@@ -265,12 +266,13 @@ def mask_tiles(nx, ny, size, max_bits=61440, target_tiles=24):
     return tiles, bmap
 
 
-def gather_tiles(sx, sy, size, regions, tw=128):
+def gather_tiles(sx, sy, size, regions, tw=128, fixed_stride=None):
     """Source boxes of the bilinear undistort gather.  `regions` lists output rectangles
     (x0, y0, w, h); each is cut into column chunks of `tw` pixels and, per chunk, the box of source bytes its
     taps read is recorded so a CTA can stage it in shared memory with row-wise bulk copies:
     int32[T,8] = (x0, y0, w, h, first_source_byte_in_row (16-aligned), first_source_row, rows | copy_bytes << 16,
-                  smem_row_stride | slow << 31).  slow = some tap falls outside the frame (global-memory path)."""
+                  smem_row_stride | slow << 31).  slow = some tap falls outside the frame (global-memory path).
+    fixed_stride: use this shared-memory pitch for every tile (frame pass: boxes are staged by a tensor-map TMA copy)."""
     W, H = size
     out = []
     for (rx, ry, rw, rh) in regions:
@@ -286,7 +288,12 @@ def gather_tiles(sx, sy, size, regions, tw=128):
             rows = int(by.max()) + 2 - int(by.min())
             # row stride = multiple of 128 B: the bank of a tap then depends on its column only, so lanes of a warp that
             # sit on different source rows never collide in shared memory
-            out.append((x0, ry, w, rh, b0, int(by.min()), rows | (copy << 16), (copy + 16 + 127) // 128 * 128))
+            stride = (copy + 16 + 127) // 128 * 128
+            if fixed_stride is not None:                 # the frame pass stages every box with ONE tensor-map TMA copy of fixed pitch
+                if stride > fixed_stride:
+                    raise ValueError("a %d-pixel tile needs %d source bytes per row (> %d)" % (w, copy, fixed_stride - 16))
+                stride = fixed_stride
+            out.append((x0, ry, w, rh, b0, int(by.min()), rows | (copy << 16), stride))
     return np.array(out, np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8)
 
 
@@ -463,7 +470,7 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     inv_pack = np.where(~touch, 0xFFFFFFFF,
                         np.where(fast, (word << 17) | ((ix & 31).astype(np.int64) << 12) | (1 << 11) | ifi, ifi)).astype(np.uint32)[inv_y0:inv_y1]
     gb, ga = glyph_atlas()
-    frame_tiles = gather_tiles(sx, sy, size, [(0, y, W, 16) for y in range(0, H, 16)], 128)
+    frame_tiles = gather_tiles(sx, sy, size, [(0, y, W, 16) for y in range(0, H, 16)], 128, fixed_stride=FRAME_BOX_PITCH)
     chunks, starts = [], [0]
     for (y0, y1, u0, v0, rw, rows, _, _) in tiles:
         c = gather_tiles(sx, sy, size, [(int(u0), int(v0), min(int(rw) * 32, W - int(u0)), int(rows))], 256) if rows else np.zeros((0, 8), np.int32)
