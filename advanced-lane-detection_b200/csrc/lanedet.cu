@@ -45,7 +45,7 @@ struct ld_ctx {
     ld_lane_record* rec;       // [max][2]
     FitWork* work;             // [max][2]
     ld_frame_fit* fit;         // [max]
-    uint32_t* planes;          // [max][H][WW][4]  (red lo, red hi, green lo, green hi): 64-bit windows of (red without green, green)
+    uint32_t* planes;          // padded canvas [max][H+2][WW+1][4]  (red lo, red hi, green lo, green hi): 64-bit windows of (red without green, green)
     uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
     TrackState* state;
     int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error
@@ -60,6 +60,9 @@ struct ld_ctx {
     uint8_t* stage_out[2];
     int chunk;
 };
+
+// u32 words of one frame's padded canvas (overlay_kernels.cuh: canvas_codes)
+static inline size_t canvas_words(const PlanDev& d) { return (size_t)(d.H + 2) * (d.WW + 1) * 4; }
 
 extern "C" int ld_abi_version(void) { return LD_ABI_VERSION; }
 
@@ -239,7 +242,7 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     CTX_ALLOC(c->rec, sizeof(ld_lane_record) * 2 * max_frames);
     CTX_ALLOC(c->work, sizeof(FitWork) * 2 * max_frames);
     CTX_ALLOC(c->fit, sizeof(ld_frame_fit) * max_frames);
-    CTX_ALLOC(c->planes, mw * 4 * 4 * max_frames);
+    CTX_ALLOC(c->planes, canvas_words(d) * 4 * max_frames);
     CTX_ALLOC(c->text, (size_t)LD_TEXT_ROWS * LD_TEXT_WORDS * 4 * max_frames);
     CTX_ALLOC(c->state, sizeof(TrackState));
     CTX_ALLOC(c->flags, 16 * sizeof(int));
@@ -249,6 +252,7 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     }
 #undef CTX_ALLOC
     LD_CUDA(cudaMallocHost((void**)&c->flags_host, 16 * sizeof(int)));
+    LD_CUDA(cudaMemset(c->planes, 0, canvas_words(d) * 4 * max_frames));  // the border rows of every canvas stay zero for good
     LD_CUDA(cudaMemset(c->state, 0, sizeof(TrackState)));
     LD_CUDA(cudaMemset(c->flags, 0, 16 * sizeof(int)));
     LD_CUDA(cudaMemset(c->flags + 2, 0xFF, sizeof(int)));       // last_bad = -1
@@ -377,7 +381,7 @@ static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* vert
                          int thickness, int m, cudaStream_t s, int slot) {
     const PlanDev& d = c->plan->d;
     k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(
-        fit, verts, counts, max_verts, thickness, c->planes + (size_t)slot * 4 * d.H * d.WW,
+        fit, verts, counts, max_verts, thickness, c->planes + (size_t)slot * canvas_words(d),
         c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);
     return check_launch();
 }
@@ -417,7 +421,7 @@ static int frames_per_cta(int m) {
 }
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted) {
     const PlanDev& d = c->plan->d;
-    const uint32_t* planes = c->planes + (size_t)slot * 4 * d.H * d.WW;
+    const uint32_t* planes = c->planes + (size_t)slot * canvas_words(d);
     const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
     if (already_undistorted)
         k_blend_pass<<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, planes, fout, d);

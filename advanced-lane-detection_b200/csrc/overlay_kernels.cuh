@@ -75,7 +75,8 @@ __device__ __forceinline__ int vertex_x(const double* c, int y) {
     return (int)v;                                              // truncation toward zero
 }
 
-// One CTA = one 90-row band of one frame's canvas.  planes: u32[n][H][WW][4] = (red lo, red hi, green lo, green hi), red = red without green;
+// One CTA = one 90-row band of one frame's canvas.  planes: padded canvas u32[n][H+2][WW+1][4] = (red lo, red hi, green lo, green hi)
+// per entry (red = red without green; rows 0 and H+1 stay zero);
 // text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  Vertices come from the frame's fit + row maps
 // (verts == nullptr) or are given explicitly (ld_draw).  Every CTA lists all vertices (cheap, parallel) and
 // draws only the primitives whose rows can touch its band, one primitive per thread.
@@ -91,7 +92,8 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     RasterShared& R = *reinterpret_cast<RasterShared*>(s_green + RASTER_BAND * WW);
     const int f = blockIdx.y, band = blockIdx.x;
     const int y_lo = band * RASTER_BAND, y_hi = min(H, y_lo + RASTER_BAND);
-    uint4* out_planes = reinterpret_cast<uint4*>(planes) + ((size_t)f * H + y_lo) * WW;
+    const int CW = WW + 1;                                              // padded canvas: entries per row (see canvas_entries)
+    uint4* out_planes = reinterpret_cast<uint4*>(planes) + ((size_t)f * (H + 2) + y_lo + 1) * CW;
     BandPlotter red{s_red, WW, W, y_lo, y_hi}, green{s_green, WW, W, y_lo, y_hi};
     const int tid = threadIdx.x;
     const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
@@ -258,12 +260,15 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     }
     __syncthreads();
     RPROF(7);
-    for (int i = tid; i < (y_hi - y_lo) * WW; i += RASTER_THREADS) {    // green overwrites red
-        // canvas word k = bits [32k, 32k+64) of the row for (red without green, green): two horizontally adjacent taps
-        // always sit in one entry
-        const bool last = (i % WW) == WW - 1;
-        const uint32_t g = s_green[i], g2 = last ? 0u : s_green[i + 1];
-        out_planes[i] = make_uint4(s_red[i] & ~g, last ? 0u : (s_red[i + 1] & ~g2), g, g2);
+    for (int i = tid; i < (y_hi - y_lo) * CW; i += RASTER_THREADS) {    // green overwrites red
+        // entry e of a row = the 64-bit window of pixels [32e - 32, 32e + 32) of (red without green, green): two
+        // horizontally adjacent taps always sit in one entry, including the pair (-1, 0) and (W - 1, W)
+        const int row = i / CW, e = i - row * CW;
+        const uint32_t* sr = s_red + row * WW;
+        const uint32_t* sg = s_green + row * WW;
+        const uint32_t g0 = e > 0 ? sg[e - 1] : 0u, g1 = e < WW ? sg[e] : 0u;
+        const uint32_t r0 = e > 0 ? (sr[e - 1] & ~g0) : 0u, r1 = e < WW ? (sr[e] & ~g1) : 0u;
+        out_planes[i] = make_uint4(r0, r1, g0, g1);
     }
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
     RPROF(8);
@@ -306,30 +311,21 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     for (int i = tid; i < LD_TEXT_ROWS * LD_TEXT_WORDS; i += RASTER_THREADS) out_text[i] = s_text[i];
 }
 
-// canvas colour code at (cx, cy): bit0 = red, bit1 = green, 0 outside (BORDER_CONSTANT)
-__device__ __forceinline__ uint32_t canvas_tap(const uint4* __restrict__ cv, int W, int H, int WW, int cx, int cy) {
-    if ((unsigned)cx >= (unsigned)W || (unsigned)cy >= (unsigned)H) return 0u;
-    const uint4 w = __ldg(cv + cy * WW + (cx >> 5));
-    const int b = cx & 31;
-    return ((w.x >> b) & 1u) | (((w.z >> b) & 1u) << 1);
-}
-
-// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170).  cv = this frame's canvas: per 32 pixels one entry holding
-// the 64-bit window [32k, 32k+64) of the red and of the green plane, so the two tap columns b, b+1 of a pixel come out of
-// one entry with a funnel shift.  An inv_pack entry e is ~0 (pixel not touched), FAST (bit 11: all four taps inside the
-// canvas; entry index e >> 17, bit (e >> 12) & 31) or slow (taps straddle the canvas border: inv_idx + canvas_tap).
+// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170).  cv = this frame's PADDED canvas (plan.py: inv_pack):
+// (H + 2) x (W/32 + 1) entries, entry (r, e) = the 64-bit windows of pixels [32e - 32, 32e + 32) of canvas row r - 1 in the
+// red and in the green plane, zero outside the frame (BORDER_CONSTANT).  The two tap columns b, b + 1 of a pixel come
+// out of one entry with a funnel shift, the two tap rows are consecutive entries rows; there is no border case.
+// An inv_pack entry e is ~0 (pixel not touched by the warp) or entry index << 17 | b << 12 | fy << 5 | fx.
 //
 // canvas_codes() fetches the taps of the four pixels a lane owns -- all eight 16-byte loads are issued back to back, and
-// the caller runs it BEFORE its gather so their L2 latency hides behind that -- and squeezes each pixel's taps into one
+// the caller runs it BEFORE its gather so their latency hides behind that -- and squeezes each pixel's taps into one
 // byte: red(x, x+1) | green(x, x+1) << 2 of the top tap row, the same << 4 of the bottom row.
-__device__ __forceinline__ bool inv_fast(uint32_t e) { return e != 0xFFFFFFFFu && (e & 0x800u); }
-
-__device__ __forceinline__ uint32_t canvas_codes(const uint32_t (&ie)[4], const uint4* __restrict__ cv, int WW) {
+__device__ __forceinline__ uint32_t canvas_codes(const uint32_t (&ie)[4], const uint4* __restrict__ cv, int CW) {
     uint4 a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         a0[k] = a1[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (inv_fast(ie[k])) { const uint4* p = cv + (ie[k] >> 17); a0[k] = __ldg(p); a1[k] = __ldg(p + WW); }
+        if (ie[k] != 0xFFFFFFFFu) { const uint4* p = cv + (ie[k] >> 17); a0[k] = __ldg(p); a1[k] = __ldg(p + CW); }
     }
     uint32_t codes = 0;
 #pragma unroll
@@ -342,33 +338,31 @@ __device__ __forceinline__ uint32_t canvas_codes(const uint32_t (&ie)[4], const 
     return codes;
 }
 
-// Blend one pixel c (r | g << 8 | b << 16).  Most pixels of the trapezoid see four equal taps (all background or all
-// green): code 0 -> nothing to add; all green -> the warped pixel is exactly (0,255,0) and g + 0.3f*255 rounds (ties to
-// even) to g + 76 + (g & 1).  Everything else takes OpenCV's fixed-point bilinear of the three canvas colours and the
-// float32 blend of cv2.addWeighted.
-__device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, uint32_t code, size_t mi, const uint4* __restrict__ cv,
-                                                    const PlanDev& P) {
-    uint32_t t00, t01, t10, t11;
-    if (e & 0x800u) {
-        if (!code) return c;
-        if ((code & 0xCCu) == 0xCCu) {
-            const uint32_t g = (c >> 8) & 255u;
-            return (c & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
+// pull the entries canvas_codes() will read for the NEXT frame towards the SM (no registers held)
+__device__ __forceinline__ void canvas_prefetch(const uint32_t (&ie)[4], const uint4* __restrict__ cv, int CW) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (ie[k] != 0xFFFFFFFFu) {
+            const uint4* p = cv + (ie[k] >> 17);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + CW));
         }
-        t00 = (code & 1u) | ((code >> 1) & 2u); t01 = ((code >> 1) & 1u) | ((code >> 2) & 2u);
-        t10 = ((code >> 4) & 1u) | ((code >> 5) & 2u); t11 = ((code >> 5) & 1u) | ((code >> 6) & 2u);
-    } else {
-        const int W = P.W, H = P.H, WW = P.WW;
-        const uint32_t idx = __ldg(P.inv_idx + mi);
-        const int sx = (int)(idx & 0xFFFFu) - 1, sy = (int)(idx >> 16) - 1;
-        t00 = canvas_tap(cv, W, H, WW, sx, sy); t01 = canvas_tap(cv, W, H, WW, sx + 1, sy);
-        t10 = canvas_tap(cv, W, H, WW, sx, sy + 1); t11 = canvas_tap(cv, W, H, WW, sx + 1, sy + 1);
-        if (!(t00 | t01 | t10 | t11)) return c;
+}
+
+// Blend one pixel c (r | g << 8 | b << 16) whose taps are `code`.  Most pixels of the trapezoid see four equal taps (all
+// background or all green): code 0 -> nothing to add; all green -> the warped pixel is exactly (0,255,0) and
+// g + 0.3f*255 rounds (ties to even) to g + 76 + (g & 1).  Everything else takes OpenCV's fixed-point bilinear of the
+// three canvas colours and the float32 blend of cv2.addWeighted.
+__device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, uint32_t code) {
+    if (!code) return c;
+    if ((code & 0xCCu) == 0xCCu) {
+        const uint32_t g = (c >> 8) & 255u;
+        return (c & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
     }
     const int fx = e & 31, fy = (e >> 5) & 31;
     const int w00 = 32 * (32 - fy) * (32 - fx), w01 = 32 * (32 - fy) * fx, w10 = 32 * fy * (32 - fx), w11 = 32 * fy * fx;
-    const int wr = (t00 & 1) * w00 + (t01 & 1) * w01 + (t10 & 1) * w10 + (t11 & 1) * w11;
-    const int wg = (t00 >> 1) * w00 + (t01 >> 1) * w01 + (t10 >> 1) * w10 + (t11 >> 1) * w11;
+    const int wr = (code & 1) * w00 + ((code >> 1) & 1) * w01 + ((code >> 4) & 1) * w10 + ((code >> 5) & 1) * w11;
+    const int wg = ((code >> 2) & 1) * w00 + ((code >> 3) & 1) * w01 + ((code >> 6) & 1) * w10 + ((code >> 7) & 1) * w11;
     const uint32_t cr = (uint32_t)(wr * 200 + 16384) >> 15, cg = (uint32_t)(wg * 255 + 16384) >> 15;
     const uint32_t r = blend_u8(c & 255u, cr), g = blend_u8((c >> 8) & 255u, cg);
     return (c & 0xFF0000u) | (g << 8) | r;
@@ -390,13 +384,12 @@ struct RowStore {
 // x0 + i + 32 k (k < ngroups) in c[k] as r | g << 8 | b << 16; codes = canvas_codes() of those pixels (0 where the row is
 // outside the inverse warp); orow = this lane's first output word (row start + lane).
 template <int MODE>
-__device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], uint32_t codes, int ngroups, size_t mi, int lane,
-                                           const uint4* __restrict__ cv, const uint32_t* __restrict__ trow, int tw0,
-                                           uint32_t* __restrict__ orow, const RowStore& rs, const PlanDev& P) {
-    if (MODE != 0) {
+__device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], uint32_t codes, int ngroups, int lane,
+                                           const uint32_t* __restrict__ trow, int tw0, uint32_t* __restrict__ orow, const RowStore& rs) {
+    if (MODE != 0 && codes) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (ie[k] != 0xFFFFFFFFu) c[k] = blend_canvas_px(c[k], ie[k], (codes >> (8 * k)) & 255u, mi + 32 * k, cv, P);
+            c[k] = blend_canvas_px(c[k], ie[k], (codes >> (8 * k)) & 255u);
     }
     if (MODE == 1 && trow) {                                             // tile columns and LD_TEXT_X0 are multiples of 32
 #pragma unroll
@@ -510,11 +503,12 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     const RowStore rs(lane);
     const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
     const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
-    const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;          // only used where ie != ~0, i.e. inside the inverse rows
+    const int CW = WW + 1;                                               // padded canvas geometry (plan.py: inv_pack)
+    const size_t cv_frame = (size_t)(H + 2) * CW;
     // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop)
     const uint8_t* frame = frames + (size_t)f0 * fbytes;
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
-    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f0 * H * WW;
+    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f0 * cv_frame;
     const uint32_t* trow = text + ((size_t)f0 * LD_TEXT_ROWS + (text_row ? y - LD_TEXT_Y0 : 0)) * LD_TEXT_WORDS;
     __syncthreads();                                                     // barriers initialised
 
@@ -541,7 +535,11 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     int b = 0, parity = 0;                                               // buffer / mbarrier phase of the frame being computed
     for (int i = 0; i < nf; ++i) {
         if (!t.slow && i + FRAME_STAGES - 1 < nf) stage();
-        const uint32_t codes = (row_on && inv_row) ? canvas_codes(ie, cv, WW) : 0u;  // issued before the wait and the gather
+        uint32_t codes = 0u;
+        if (row_on && inv_row) {
+            codes = canvas_codes(ie, cv, CW);                            // issued before the wait and the gather
+            if (i + 1 < nf) canvas_prefetch(ie, cv + cv_frame, CW);
+        }
         uint32_t c[4];
         if (!t.slow) {
             mbar_wait_addr(full0 + 8u * b, (uint32_t)parity);
@@ -558,10 +556,10 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             for (int k = 0; k < 4; ++k)
                 c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
         }
-        if (row_on) finish_row<MODE>(c, ie, codes, ngroups, mi, lane, cv, text_row ? trow : nullptr, tw0, orow, rs, P);
+        if (row_on) finish_row<MODE>(c, ie, codes, ngroups, lane, text_row ? trow : nullptr, tw0, orow, rs);
         frame += fbytes;
         orow += fbytes / 4;                                              // W % 32 == 0: a frame is a whole number of words
-        cv += (size_t)H * WW;
+        cv += cv_frame;
         trow += LD_TEXT_ROWS * LD_TEXT_WORDS;
         if (b == FRAME_STAGES - 1) { b = 0; parity ^= 1; } else ++b;
     }
@@ -577,7 +575,8 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
     const int f = blockIdx.y;
     const uint8_t* frame = frames + (size_t)f * fbytes;
     uint8_t* out_frame = out + (size_t)f * fbytes;
-    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f * H * WW;
+    const int CW = WW + 1;
+    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f * (H + 2) * CW;
     const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ngroups = t.w >> 5;
@@ -594,9 +593,8 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
             c[k] = __funnelshift_r(a, b, rsh) & 0xFFFFFFu;
         }
         load_inv4(ie, ngroups, t.x0, y, lane, P);
-        const size_t mi = (size_t)(y - P.inv_y0) * W + t.x0 + lane;
-        finish_row<2>(c, ie, canvas_codes(ie, cv, WW), ngroups, mi, lane, cv, nullptr, 0,
-                      reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs, P);
+        finish_row<2>(c, ie, canvas_codes(ie, cv, CW), ngroups, lane, nullptr, 0,
+                      reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs);
     }
 }
 

@@ -460,15 +460,17 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     inv_y0, inv_y1 = (int(trows.min()), int(trows.max()) + 1) if trows.size else (0, 0)
     inv_idx = np.where(touch, ((iy + 1) << 16) | (ix + 1), 0xFFFFFFFF).astype(np.uint32)[inv_y0:inv_y1]
     inv_fi = ifi.astype(np.uint16)[inv_y0:inv_y1]
-    # one-word form for the common case (all four taps inside the canvas; tap columns = bits b, b+1 of a word pair, or bit 31
-    # and bit 0 of the next pair):
-    # canvas word index << 17 | bit << 12 | 1 << 11 | fraction;  0xFFFFFFFF = no tap inside;  bit 11 clear = use inv_idx
-    fast = touch & (ix >= 0) & (ix <= W - 2) & (iy >= 0) & (iy < H - 1)
-    if H * (W // 32) >= (1 << 15):
-        fast = np.zeros_like(fast)                                   # word index would not fit 15 bits (4K): slow form only
-    word = np.where(fast, iy * (W // 32) + (ix >> 5), 0).astype(np.int64)
-    inv_pack = np.where(~touch, 0xFFFFFFFF,
-                        np.where(fast, (word << 17) | ((ix & 31).astype(np.int64) << 12) | (1 << 11) | ifi, ifi)).astype(np.uint32)[inv_y0:inv_y1]
+    # Packed entry per touched pixel: canvas entry << 17 | first tap's bit << 12 | fraction; 0xFFFFFFFF = no tap inside.
+    # The canvas the kernels keep is PADDED: entry (row r, column e) holds the 64-bit window of pixels [32e - 32, 32e + 32)
+    # of canvas row r - 1, for r in [0, H + 2) and e in [0, W/32 + 1); rows 0 and H + 1 and everything outside the frame
+    # are zero (BORDER_CONSTANT).  Every tap pair (ix, ix + 1) x (iy, iy + 1) of a touched pixel (ix >= -1, iy >= -1) is
+    # then bits b, b + 1 of entries (iy + 1, (ix + 32) >> 5) and (iy + 2, ...), b = (ix + 32) & 31: one code path.
+    CW = W // 32 + 1
+    entry = ((iy + 1).astype(np.int64) * CW + ((ix + 32) >> 5))
+    packed = (entry << 17) | (((ix + 32) & 31).astype(np.int64) << 12) | ifi
+    if (H + 2) * CW >= (1 << 15):
+        packed = np.zeros_like(packed)                                # entry index would not fit 15 bits (4K): the overlay is 720p-only
+    inv_pack = np.where(~touch, 0xFFFFFFFF, packed & 0xFFFFFFFF).astype(np.uint32)[inv_y0:inv_y1]
     gb, ga = glyph_atlas()
     frame_tiles = gather_tiles(sx, sy, size, [(0, y, W, 16) for y in range(0, H, 16)], 128, fixed_stride=FRAME_BOX_PITCH)
     chunks, starts = [], [0]
