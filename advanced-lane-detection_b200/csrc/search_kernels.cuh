@@ -90,21 +90,42 @@ __device__ __forceinline__ void stage_mask(const uint32_t* __restrict__ mask, ui
     for (int i = threadIdx.x; i < words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
-// column histogram of rows [r0, r1) into hist[W] (u16) by ballot transposes; whole CTA participates
-__device__ __forceinline__ void cta_hist_rows(const uint32_t* s_mask, int WW, int r0, int r1, uint16_t* hist) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int wc = warp; wc < WW; wc += nwarp) {
-        uint32_t count = 0;
-        for (int rb = r0; rb < r1; rb += 32) {
-            const int r = rb + lane;
-            const uint32_t word = (r < r1) ? s_mask[r * WW + wc] : 0u;
-#pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                const uint32_t col = __ballot_sync(0xffffffffu, (word >> b) & 1u);
-                if (lane == b) count += __popc(col);
-            }
-        }
-        hist[wc * 32 + lane] = (uint16_t)count;
+// Column histogram of rows [r0, r1), r1 - r0 <= 127, of the 32 columns of word-column wc, by ONE thread: the rows are
+// added bit-parallel into seven bit planes (a ripple-carry counter per column, 32 columns per operation), then each
+// column's 7-bit count is read out of the planes.  np.sum(image[r0:r1, :], axis=0) (Project.py:83) for 32 columns costs
+// ~15 integer operations per row this way; the ballot transpose it replaces took a whole warp ~3 instructions per row
+// and column.  Counts are stored as u16 pairs with a rotation that keeps the 32 threads of a warp on 32 banks.
+__device__ __forceinline__ void thread_hist_rows(const uint32_t* s_mask, int WW, int r0, int r1, int wc, uint16_t* hist) {
+    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0;
+    for (int r = r0; r < r1; ++r) {
+        uint32_t c = s_mask[r * WW + wc], t;
+        t = p0 & c; p0 ^= c; c = t;
+        t = p1 & c; p1 ^= c; c = t;
+        t = p2 & c; p2 ^= c; c = t;
+        t = p3 & c; p3 ^= c; c = t;
+        t = p4 & c; p4 ^= c; c = t;
+        t = p5 & c; p5 ^= c; c = t;
+        p6 ^= c;
+    }
+    uint32_t* out = reinterpret_cast<uint32_t*>(hist) + wc * 16;
+#pragma unroll 4
+    for (int jj = 0; jj < 16; ++jj) {
+        const int j = (jj + (wc >> 1)) & 15, b = 2 * j;                   // columns 32 wc + b, + b + 1
+        const uint32_t q0 = p0 >> b, q1 = p1 >> b, q2 = p2 >> b, q3 = p3 >> b, q4 = p4 >> b, q5 = p5 >> b, q6 = p6 >> b;
+        const uint32_t lo = (q0 & 1u) | ((q1 & 1u) << 1) | ((q2 & 1u) << 2) | ((q3 & 1u) << 3) | ((q4 & 1u) << 4) | ((q5 & 1u) << 5) | ((q6 & 1u) << 6);
+        const uint32_t hi = ((q0 >> 1) & 1u) | (((q1 >> 1) & 1u) << 1) | (((q2 >> 1) & 1u) << 2) | (((q3 >> 1) & 1u) << 3) |
+                            (((q4 >> 1) & 1u) << 4) | (((q5 >> 1) & 1u) << 5) | (((q6 >> 1) & 1u) << 6);
+        out[j] = lo | (hi << 16);
+    }
+}
+
+// histograms of `nb` row ranges (r0[i], r1[i]) into hist + i*W, one thread per (range, word-column); whole CTA participates
+__device__ __forceinline__ void cta_hist_ranges(const uint32_t* s_mask, int WW, int W, int nb, int first_r0, int step, int last_r1,
+                                                uint16_t* hist) {
+    for (int task = threadIdx.x; task < nb * WW; task += blockDim.x) {
+        const int i = task / WW, wc = task - i * WW;
+        const int r0 = first_r0 + i * step, r1 = min(r0 + step, last_r1);
+        thread_hist_rows(s_mask, WW, r0, r1, wc, hist + i * W);
     }
 }
 
@@ -178,10 +199,29 @@ k_search(const uint32_t* __restrict__ mask, ld_lane_record* __restrict__ rec, co
     for (int i = threadIdx.x; i < (int)(sizeof(SearchShared) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&S)[i] = 0;
     __syncthreads();
 
-    if (mode != LD_SEARCH_HELPER)
-        for (int k = 0; k < 8; ++k) cta_hist_rows(s_mask, WW, H - win_h * (k + 1), H - win_h * k, s_hist + k * W);
-    if (mode == LD_SEARCH_HARDER) cta_hist_rows(s_mask, WW, 200, H, s_ext);      // harder:87
-    if (mode == LD_SEARCH_HELPER) cta_hist_rows(s_mask, WW, 100, H, s_ext);      // helper.py:232, :862
+    // band histograms: s_hist[k] = rows [H - win_h (k+1), H - win_h k)  (Project.py:83; harder:103-104)
+    if (mode != LD_SEARCH_HELPER) {
+        for (int task = threadIdx.x; task < 8 * WW; task += blockDim.x) {
+            const int i = task / WW, wc = task - i * WW;
+            thread_hist_rows(s_mask, WW, H - win_h * (i + 1), H - win_h * i, wc, s_hist + i * W);
+        }
+        if (mode == LD_SEARCH_HARDER && (int)threadIdx.x >= 8 * WW && (int)threadIdx.x < 9 * WW)       // rows [200, 270) of harder:87
+            thread_hist_rows(s_mask, WW, 200, H - win_h * 5, threadIdx.x - 8 * WW, s_ext);
+        __syncthreads();
+        if (mode == LD_SEARCH_HARDER)                                     // np.sum(image[200:, :], axis=0) = bands 0..4 + rows [200, 270)
+            for (int i = threadIdx.x; i < W; i += blockDim.x)
+                s_ext[i] += s_hist[i] + s_hist[W + i] + s_hist[2 * W + i] + s_hist[3 * W + i] + s_hist[4 * W + i];
+    } else {
+        // np.sum(binary_warped[100:, :], axis=0) (helper.py:232, :862): eight partial histograms of <= 78 rows, then their sum
+        cta_hist_ranges(s_mask, WW, W, 8, 100, (H - 100 + 7) / 8, H, s_hist);
+        __syncthreads();
+        for (int i = threadIdx.x; i < W; i += blockDim.x) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += s_hist[k * W + i];
+            s_ext[i] = (uint16_t)v;
+        }
+    }
     __syncthreads();
 
     if (mode == LD_SEARCH_PROJECT) {

@@ -241,8 +241,7 @@ def main():
         else:
             sharding.process_sharded(eng, frames, rank, world, out=out)
 
-    nsub = min(8, max(1, n // 48))                       # PIPE_SUB sub-batches inside ld_prepass / ld_postpass
-    launches_per_step = 1 + 4 * nsub + 5                 # state reset; mask, search, raster, frame pass per sub-batch; 5 fit kernels
+    launches_per_step = 1 + 4 + 5                        # state reset; k_mask, k_search, k_raster, k_frame_pass_mf; 5 fit kernels
 
     for _ in range(a.warmup):
         step()
