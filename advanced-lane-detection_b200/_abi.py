@@ -46,7 +46,7 @@ class PlanDesc(C.Structure):
                 ("n_glyphs", C.c_int32), ("n_frame_tiles", C.c_int32),
                 ("frame_tiles", C.c_void_p), ("mask_chunks", C.c_void_p), ("mask_chunk_start", C.c_void_p), ("frame_amap", C.c_void_p), ("frame_amap_start", C.c_void_p),
                 ("mask_amap", C.c_void_p), ("mask_amap_start", C.c_void_p), ("bdesc", C.c_void_p),
-                ("n_mask_chunks", C.c_int32), ("reserved", C.c_int32)]
+                ("n_mask_chunks", C.c_int32), ("reserved", C.c_int32), ("cpre", C.c_void_p)]
 
 
 class LaneRecord(C.Structure):

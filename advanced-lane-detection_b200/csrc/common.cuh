@@ -18,6 +18,7 @@ struct PlanDev {
     const uint16_t* bmap;
     const uint32_t* ctab;
     const uint32_t* cbits;
+    const uint32_t* cpre;            // 2048 words: 2-bit colour pre-decision per 8x8x8 RGB cell (plan.colour_prefilter)
     int inv_y0, inv_y1;
     const uint32_t* inv_idx;
     const uint16_t* inv_fi;
@@ -35,6 +36,7 @@ struct PlanDev {
     const void* stamps;              // laneraster::Stamp[STAMP_N] for thickness 30 (raster_math.h)
     const uint4* bdesc;              // per output mask word: (first source bit | BORDER | FALLBACK, step1, step2, valid)
     int max_out_words;
+    int mask_box_bytes;              // shared-memory bytes of the largest mask chunk box, rounded up to 128
 };
 
 // ---- cv2.undistort / cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) for one output pixel -----------

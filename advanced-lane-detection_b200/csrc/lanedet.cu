@@ -97,7 +97,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     const int W = desc->width, H = desc->height;
     if (W <= 0 || H <= 0 || (W % 32) || (H % 2) || desc->n_tiles <= 0 || desc->frame_num < 1 ||
         desc->frame_num > LD_MAX_DEPTH || !desc->und_map || !desc->wtab || !desc->near_map || !desc->tiles ||
-        !desc->bmap || !desc->ctab || !desc->cbits || !desc->inv_idx || !desc->inv_fi || !desc->inv_pack || !desc->glyph_bits ||
+        !desc->bmap || !desc->ctab || !desc->cbits || !desc->cpre || !desc->inv_idx || !desc->inv_fi || !desc->inv_pack || !desc->glyph_bits ||
         !desc->glyph_adv || !desc->frame_tiles || !desc->mask_chunks || !desc->mask_chunk_start || !desc->bdesc || !desc->frame_amap || !desc->frame_amap_start || !desc->mask_amap || !desc->mask_amap_start || desc->n_frame_tiles <= 0)
         return LD_ERR_ARG;
     int count = 0;
@@ -138,11 +138,11 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         const size_t b = (size_t)(desc->mask_chunks[8 * t + 6] & 0xFFFF) * (size_t)(desc->mask_chunks[8 * t + 7] & 0x7FFFFFFF);
         if (b > ms) ms = b;
     }
-    if (ms > 160 * 1024) return LD_ERR_ARG;
+    if (ms > 96 * 1024) return LD_ERR_ARG;                               // k_mask double-buffers its chunk boxes
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
-        (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
+        (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, desc->cpre, (size_t)MASK_PRE_WORDS, &d.cpre)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
         (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) || (rc = upload(p, desc->inv_pack, ninv ? ninv : 1, &d.inv_pack)) ||
         (rc = upload(p, desc->glyph_bits, (size_t)desc->n_glyphs * LD_GLYPH_ROWS * LD_GLYPH_WORDS, &d.glyph_bits)) ||
         (rc = upload(p, desc->glyph_adv, (size_t)desc->n_glyphs, &d.glyph_adv)) ||
@@ -182,14 +182,15 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if (words > mow) mow = words;
     }
     d.max_out_words = mow;
-    // k_mask shared memory: box bits (+4 zero words) | job list (u16 per output word) | staged source box
-    p->mask_smem = (((size_t)mb + 4) * 4 + (size_t)mow * 2 + 15) / 16 * 16 + ms + 32;
+    // k_mask shared memory: box bits (+4 zero words) | job list (u16 per output word) | colour pre-decision | two chunk boxes
+    d.mask_box_bytes = (int)((ms + 127) / 128 * 128);
+    p->mask_smem = (((size_t)mb + 4) * 4 + (size_t)mow * 2 + 15) / 16 * 16 + MASK_PRE_WORDS * 4 + 2 * (size_t)d.mask_box_bytes + 32;
     p->search_smem = (size_t)H * d.WW * 4 + (size_t)9 * W * 2;
     p->raster_smem = (size_t)2 * RASTER_BAND * d.WW * 4 + sizeof(RasterShared);   // text plane (6.7 KB) aliases the red plane
     // The opt-in limit is a per-function, per-device attribute shared by every plan: always raise it to
     // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
-    if (p->mask_smem > 200 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }
-    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (p->mask_smem > 220 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }
+    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
@@ -320,7 +321,8 @@ extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, 
     if (!ARGS_OK(c, frames, mask, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    k_mask<<<dim3(d.n_tiles, n), MASK_THREADS, c->plan->mask_smem, (cudaStream_t)stream>>>(frames, mask, d);
+    const int fpc = n >= 8 * MASK_FPC ? MASK_FPC : (n >= 16 ? 2 : 1);     // small batches: more, shorter CTAs
+    k_mask<<<dim3(d.n_tiles, (n + fpc - 1) / fpc), MASK_THREADS, c->plan->mask_smem, (cudaStream_t)stream>>>(frames, mask, d, n, fpc);
     return check_launch();
 }
 

@@ -9,130 +9,218 @@ namespace lanedet {
 // Replaces cv2.undistort (Project.py:294) -> warp (Project.py:222-233) -> luv_lab_filter
 // (Project.py:236-248).
 //
-// One CTA = one band of bird's-eye rows of one frame (plan.tiles).  The bird's-eye warp is
-// INTER_NEAREST, so every output pixel is a copy of ONE undistorted pixel and its mask bit is a
-// function of that pixel alone; the band's rows sample a small box of the undistorted image
-// (~4.4x fewer distinct pixels than outputs).
-//   Phase A evaluates the box once, in column chunks: the source bytes a chunk's taps read are staged in
-//   shared memory by TMA bulk copies (gather.cuh), then bilinear (dp2a) + colour decision -> one bit per
-//   box pixel (warp ballot) in shared memory.
+// One CTA = one band of bird's-eye rows (plan.tiles) of up to `fpc` consecutive frames.  The bird's-eye warp is
+// INTER_NEAREST, so every output pixel is a copy of ONE undistorted pixel and its mask bit is a function of that
+// pixel alone; the band's rows sample a small box of the undistorted image (~4.4x fewer distinct pixels than outputs).
+//   Phase A evaluates the box once, in column chunks.  The source bytes a chunk's taps read are staged in shared
+//   memory by TMA bulk row copies, DOUBLE BUFFERED over the sequence (frame, chunk): the next chunk -- of this or of the
+//   next frame -- lands while the current one is evaluated.  A warp item is one box row x 128 columns; lane l owns
+//   columns l, l+32, l+64, l+96 (adjacent lanes = adjacent source pixels: conflict-free shared-memory gathers) and
+//   fetches its four map entries with one 16-byte load, one item ahead.  Bilinear on dp2a, then the colour decision:
+//   a 2-bit pre-decision per 8x8x8 RGB cell in shared memory settles every pixel that is not near a threshold;
+//   only the rest gathers from the exact tables.  One bit per box pixel (warp ballot) into shared memory.
 //   Phase B builds the packed output per OUTPUT WORD: a perspective warp keeps a word's 32 pixels on one
 //   source row, stepping 0/1/2 source pixels per output pixel (plan.bdesc), so a thread cuts a 64-bit
 //   window out of the bit array and expands it with one funnel shift per bit.  Windows that are all
 //   zero / all one (most of a road scene) are finished in pass 1; the rest are compacted into a job
 //   list so the bit-serial loop runs with full warps.
 constexpr int MASK_THREADS = 256;
+constexpr int MASK_FPC = 4;                       // frames per CTA
+constexpr int MASK_PRE_WORDS = 2048;
 constexpr uint32_t BDESC_BORDER = 0xFFFFFFFFu, BDESC_FALLBACK = 0xFFFFFFFEu;
 
-__global__ void __launch_bounds__(MASK_THREADS)
-k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const PlanDev P) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int n_jobs;
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);                       // box bits + 4 zero words
-    uint16_t* s_job = reinterpret_cast<uint16_t*>(s_bits + P.max_box_words + 4);
-    uint8_t* s_box = smem_raw + (((size_t)(P.max_box_words + 4) * 4 + (size_t)P.max_out_words * 2 + 15) / 16) * 16;
+// (LUV-L in l_thresh) | (Lab-b in b_thresh): pre-decision from shared memory, exact tables only for mixed cells
+__device__ __forceinline__ bool colour_on_pre(uint32_t rgb, const uint32_t* s_pre, const uint32_t* __restrict__ ctab,
+                                              const uint32_t* __restrict__ cbits) {
+    const uint32_t idx = ((rgb >> 3) & 0x1Fu) | ((rgb >> 6) & 0x3E0u) | ((rgb >> 9) & 0x7C00u);
+    const uint32_t code = (s_pre[idx >> 4] >> ((idx & 15u) * 2u)) & 3u;
+    if (code != 2u) return code != 0u;
+    return colour_on(rgb, ctab, cbits);
+}
 
-    const int tile = blockIdx.x, f = blockIdx.y;
+// bilinear_rgb_off with the doubled weights / byte-permute pack of the frame pass (overlay_kernels.cuh: frame_weights)
+__device__ __forceinline__ uint32_t bilinear_rgb_smem(uint32_t box, uint32_t stride, uint32_t e2) {
+    const uint32_t fx = e2 & 31u, fy = (e2 >> 5) & 31u, o = e2 >> 10;
+    const uint32_t tt = (32u - fx) | (fx << 16);
+    const uint32_t wx = (fx | fy) ? tt * (2048u - 64u * fy) : 0xFFFFu, wy = tt * (64u * fy);
+    const uint32_t a = box + (o & ~3u), sh = (o & 3u) * 8u;
+    uint32_t p0, p1, p2, q0, q1, q2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p0) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(p1) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(p2) : "r"(a));
+    const uint32_t a2 = a + stride;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q0) : "r"(a2));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(q1) : "r"(a2));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(q2) : "r"(a2));
+    const uint32_t lt = __funnelshift_r(p0, p1, sh), ht = __funnelshift_r(p1, p2, sh);   // r0 g0 b0 r1 | g1 b1 . .
+    const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
+    const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11
+    const uint32_t GBt = __byte_perm(lt, ht, 0x5241), GBb = __byte_perm(lb, hb, 0x5241);   // g0 g1 b0 b1
+    uint32_t r = __dp2a_lo(wx, R, 32768u);
+    r = __dp2a_hi(wy, R, r);
+    uint32_t g = __dp2a_lo(wx, GBt, 32768u);
+    g = __dp2a_lo(wy, GBb, g);
+    uint32_t b = __dp2a_hi(wx, GBt, 32768u);
+    b = __dp2a_hi(wy, GBb, b);
+    return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);
+}
+
+__global__ void __launch_bounds__(MASK_THREADS, 3)
+k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const PlanDev P, int n, int fpc) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int n_jobs;
+    // layout: box bits (+4 zero words) | job list (u16 per output word) | colour pre-decision | two chunk boxes
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);
+    uint16_t* s_job = reinterpret_cast<uint16_t*>(s_bits + P.max_box_words + 4);
+    uint32_t* s_pre = reinterpret_cast<uint32_t*>(smem_raw + (((size_t)(P.max_box_words + 4) * 4 + (size_t)P.max_out_words * 2 + 15) / 16) * 16);
+    uint8_t* s_box = reinterpret_cast<uint8_t*>(s_pre + MASK_PRE_WORDS);
+    const uint32_t box_bytes = (uint32_t)P.mask_box_bytes;              // one chunk box (a multiple of 128)
+    const uint32_t box0 = smem_u32(s_box), bar0 = smem_u32(&bar[0]);
+
+    const int tile = blockIdx.x, f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
     const int4 t0 = P.tiles[2 * tile], t1 = P.tiles[2 * tile + 1];
     const int y0 = t0.x, y1 = t0.y, u0 = t0.z, rw = t1.x, rows = t1.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = MASK_THREADS / 32;
-    const uint8_t* frame = frames + (size_t)f * P.W * P.H * 3;
+    const size_t fbytes = (size_t)P.W * P.H * 3;
     const int box_words = rw * rows;
+    const int c0 = P.mask_chunk_start[tile], nc = P.mask_chunk_start[tile + 1] - c0;
 
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); n_jobs = 0; }
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     if (threadIdx.x < 4) s_bits[box_words + threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += MASK_THREADS) s_pre[i] = __ldg(P.cpre + i);
+    __syncthreads();
 
-    // ---- phase A: one bit per undistorted pixel of the box, chunk by chunk
-    int staged = 0;
-    for (int c = P.mask_chunk_start[tile]; c < P.mask_chunk_start[tile + 1]; ++c) {
+    // the sequence of (frame, chunk) items; item `it` is staged into buffer it & 1
+    const int n_items = nf * nc;
+    auto stage = [&](int it) {
+        const int fi = it / nc, c = c0 + (it - fi * nc);
         const GTile g = load_gtile(P.mask_chunks, c);
-        __syncthreads();                                   // barrier initialised / previous chunk's box no longer read
-        stage_box(s_box, frame, P.W, g, &bar);
-        wait_box(&bar, staged & 1, !g.slow);
-        if (!g.slow) ++staged;
-        const int nwc = (g.w + 31) >> 5, wc0 = (g.x0 - u0) >> 5;
-        const uint32_t* am = P.mask_amap + P.mask_amap_start[c];
-        for (int r = warp; r < g.h; r += nwarp) {
-            const int v = g.y0 + r;
-            for (int wc = 0; wc < nwc; ++wc) {
-                const int col = wc * 32 + lane;
-                bool on = false;
-                if (col < g.w) {
-                    uint32_t rgb;
-                    if (!g.slow) rgb = bilinear_rgb_off(s_box, g.stride, __ldg(am + r * g.w + col), P.wtab);
-                    else rgb = bilinear_rgb(frame, P.W, P.H, g.x0 + col, v, __ldg(P.und_map + (size_t)v * P.W + g.x0 + col), P.wtab);
-                    on = colour_on(rgb, P.ctab, P.cbits);
-                }
-                const uint32_t word = __ballot_sync(0xffffffffu, on);
-                if (lane == 0) s_bits[r * rw + wc0 + wc] = word;
-            }
-        }
-    }
-    __syncthreads();
+        if (g.slow) return;
+        const uint32_t mb = bar0 + 8u * (it & 1);
+        if (threadIdx.x == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(g.rows * g.copy)) : "memory");
+        const int r = lane * nwarp + warp;                               // row copies dealt round-robin to the warps
+        if (r < g.rows)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(box0 + (it & 1) * box_bytes + r * g.stride),
+                         "l"(frames + (size_t)(f0 + fi) * fbytes + (size_t)(g.sy0 + r) * P.W * 3 + g.b0), "r"((uint32_t)g.copy), "r"(mb) : "memory");
+    };
+    if (n_items > 0) stage(0);
+    uint32_t phase0 = 0u, phase1 = 0u;                                   // mbarrier parity per buffer (slow chunks do not use theirs)
 
-    // ---- phase B, pass 1: one thread per output word
-    const int out_words = (y1 - y0) * P.WW;
-    uint32_t* out = mask + ((size_t)f * P.H + y0) * P.WW;
-    const uint4* bd = P.bdesc + (size_t)y0 * P.WW;
-    for (int wi = threadIdx.x; wi < out_words; wi += MASK_THREADS) {
-        const uint4 d = __ldg(bd + wi);
-        uint32_t o = 0;
-        bool job = false;
-        if (d.x == BDESC_FALLBACK) job = true;
-        else if (d.x != BDESC_BORDER) {
-            const uint32_t* p = s_bits + (d.x >> 5);
-            const uint32_t sh = d.x & 31;
-            uint32_t lo = __funnelshift_r(p[0], p[1], sh), hi = __funnelshift_r(p[1], p[2], sh);
-            const int span = __popc(d.y) + __popc(d.z) + 1;                          // source bits the word reads (<= 63)
-            const uint32_t mlo = span >= 32 ? 0xFFFFFFFFu : (1u << span) - 1u;
-            const uint32_t mhi = span <= 32 ? 0u : (1u << (span - 32)) - 1u;
-            lo &= mlo; hi &= mhi;
-            if ((lo | hi) == 0u) o = 0u;
-            else if (lo == mlo && hi == mhi) o = d.w;
-            else job = true;
-        }
-        if (job) s_job[atomicAdd(&n_jobs, 1)] = (uint16_t)wi;
-        else out[wi] = o;
-    }
-    __syncthreads();
-
-    // ---- phase B, pass 2: bit-serial expansion of the mixed words
-    const int nj = n_jobs;
-    for (int k = threadIdx.x; k < nj; k += MASK_THREADS) {
-        const int wi = s_job[k];
-        const uint4 d = __ldg(bd + wi);
-        uint32_t o = 0;
-        if (d.x == BDESC_FALLBACK) {                       // general homography: per-pixel index map
-            const uint16_t* bm = P.bmap + (size_t)y0 * P.W + (size_t)wi * 32;
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t idx = __ldg(bm + i);
-                if (idx != 0xFFFFu) o |= ((s_bits[idx >> 5] >> (idx & 31)) & 1u) << i;
-            }
-        } else {
-            const uint32_t* p = s_bits + (d.x >> 5);
-            const uint32_t sh = d.x & 31;
-            uint32_t lo = __funnelshift_r(p[0], p[1], sh), hi = __funnelshift_r(p[1], p[2], sh);
-            if (d.z == 0u) {
+    int it = 0;
+    for (int fi = 0; fi < nf; ++fi) {
+        if (threadIdx.x == 0) n_jobs = 0;
+        // ---- phase A: one bit per undistorted pixel of the box, chunk by chunk
+        for (int ci = 0; ci < nc; ++ci, ++it) {
+            const GTile g = load_gtile(P.mask_chunks, c0 + ci);
+            __syncthreads();                     // buffer (it+1)&1 is free again; s_bits of the previous frame fully consumed
+            if (it + 1 < n_items) stage(it + 1);
+            const int ncg = (g.w + 127) >> 7, nitems = g.h * ncg, nwc = (g.w + 31) >> 5, wc0 = (g.x0 - u0) >> 5;
+            const uint4* am4 = reinterpret_cast<const uint4*>(P.mask_amap + P.mask_amap_start[c0 + ci]);
+            if (!g.slow) {
+                uint4 e = make_uint4(~0u, ~0u, ~0u, ~0u);
+                if (warp < nitems) e = __ldg(am4 + warp * 32 + lane);                        // first item's entries: before the wait
+                mbar_wait_addr(bar0 + 8u * (it & 1), (it & 1) ? phase1 : phase0);
+                if (it & 1) phase1 ^= 1u; else phase0 ^= 1u;
+                const uint32_t box = box0 + (it & 1) * box_bytes;
+                for (int item = warp; item < nitems; item += nwarp) {
+                    uint4 en = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    if (item + nwarp < nitems) en = __ldg(am4 + (item + nwarp) * 32 + lane);   // one item ahead
+                    const int r = item / ncg, cg = item - r * ncg;
+                    const uint32_t es[4] = {e.x, e.y, e.z, e.w};
+                    uint32_t words[4];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    o = __funnelshift_r(o, lo, 1);         // append source bit 0 at the top; after 32 steps bit i = pixel i
-                    const uint32_t st = (d.y >> i) & 1u;
-                    lo = __funnelshift_r(lo, hi, st);
-                    hi >>= st;
+                    for (int k = 0; k < 4; ++k) {
+                        bool on = false;
+                        if (es[k] != 0xFFFFFFFFu) on = colour_on_pre(bilinear_rgb_smem(box, (uint32_t)g.stride, es[k]), s_pre, P.ctab, P.cbits);
+                        words[k] = __ballot_sync(0xffffffffu, on);
+                    }
+                    if (lane < 4 && cg * 4 + lane < nwc)
+                        s_bits[r * rw + wc0 + cg * 4 + lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
+                    e = en;
                 }
             } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    o = __funnelshift_r(o, lo, 1);
-                    const uint32_t st = ((d.y >> i) & 1u) + ((d.z >> i) & 1u);
-                    lo = __funnelshift_r(lo, hi, st);
-                    hi >>= st;
-                }
+                // some tap leaves the frame: read global memory with border checks (never the case for the shipped calibration)
+                const uint8_t* frame = frames + (size_t)(f0 + fi) * fbytes;
+                for (int r = warp; r < g.h; r += nwarp)
+                    for (int wc = 0; wc < nwc; ++wc) {
+                        const int col = wc * 32 + lane, v = g.y0 + r;
+                        bool on = false;
+                        if (col < g.w)
+                            on = colour_on(bilinear_rgb(frame, P.W, P.H, g.x0 + col, v, __ldg(P.und_map + (size_t)v * P.W + g.x0 + col), P.wtab),
+                                           P.ctab, P.cbits);
+                        const uint32_t word = __ballot_sync(0xffffffffu, on);
+                        if (lane == 0) s_bits[r * rw + wc0 + wc] = word;
+                    }
             }
-            o &= d.w;
         }
-        out[wi] = o;
+        __syncthreads();
+
+        // ---- phase B, pass 1: one thread per output word
+        const int out_words = (y1 - y0) * P.WW;
+        uint32_t* out = mask + ((size_t)(f0 + fi) * P.H + y0) * P.WW;
+        const uint4* bd = P.bdesc + (size_t)y0 * P.WW;
+        for (int wi = threadIdx.x; wi < out_words; wi += MASK_THREADS) {
+            const uint4 d = __ldg(bd + wi);
+            uint32_t o = 0;
+            bool job = false;
+            if (d.x == BDESC_FALLBACK) job = true;
+            else if (d.x != BDESC_BORDER) {
+                const uint32_t* p = s_bits + (d.x >> 5);
+                const uint32_t sh = d.x & 31;
+                uint32_t lo = __funnelshift_r(p[0], p[1], sh), hi = __funnelshift_r(p[1], p[2], sh);
+                const int span = __popc(d.y) + __popc(d.z) + 1;                          // source bits the word reads (<= 63)
+                const uint32_t mlo = span >= 32 ? 0xFFFFFFFFu : (1u << span) - 1u;
+                const uint32_t mhi = span <= 32 ? 0u : (1u << (span - 32)) - 1u;
+                lo &= mlo; hi &= mhi;
+                if ((lo | hi) == 0u) o = 0u;
+                else if (lo == mlo && hi == mhi) o = d.w;
+                else job = true;
+            }
+            if (job) s_job[atomicAdd(&n_jobs, 1)] = (uint16_t)wi;
+            else out[wi] = o;
+        }
+        __syncthreads();
+
+        // ---- phase B, pass 2: bit-serial expansion of the mixed words
+        const int nj = n_jobs;
+        for (int k = threadIdx.x; k < nj; k += MASK_THREADS) {
+            const int wi = s_job[k];
+            const uint4 d = __ldg(bd + wi);
+            uint32_t o = 0;
+            if (d.x == BDESC_FALLBACK) {                       // general homography: per-pixel index map
+                const uint16_t* bm = P.bmap + (size_t)y0 * P.W + (size_t)wi * 32;
+                for (int i = 0; i < 32; ++i) {
+                    const uint32_t idx = __ldg(bm + i);
+                    if (idx != 0xFFFFu) o |= ((s_bits[idx >> 5] >> (idx & 31)) & 1u) << i;
+                }
+            } else {
+                const uint32_t* p = s_bits + (d.x >> 5);
+                const uint32_t sh = d.x & 31;
+                uint32_t lo = __funnelshift_r(p[0], p[1], sh), hi = __funnelshift_r(p[1], p[2], sh);
+                if (d.z == 0u) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        o = __funnelshift_r(o, lo, 1);         // append source bit 0 at the top; after 32 steps bit i = pixel i
+                        const uint32_t st = (d.y >> i) & 1u;
+                        lo = __funnelshift_r(lo, hi, st);
+                        hi >>= st;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        o = __funnelshift_r(o, lo, 1);
+                        const uint32_t st = ((d.y >> i) & 1u) + ((d.z >> i) & 1u);
+                        lo = __funnelshift_r(lo, hi, st);
+                        hi >>= st;
+                    }
+                }
+                o &= d.w;
+            }
+            out[wi] = o;
+        }
+        // the next frame's first phase-A barrier orders these reads of s_bits / s_job before they are overwritten
     }
 }
 

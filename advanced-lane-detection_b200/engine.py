@@ -61,6 +61,7 @@ class LaneEngine:
         d.und_map, d.wtab = host(p.und_map, np.uint32), host(p.wtab, np.int16)
         d.near_map, d.tiles, d.bmap = host(p.near, np.int32), host(p.tiles, np.int32), host(p.bmap, np.uint16)
         d.ctab, d.cbits = host(p.ctab, np.uint32), host(p.cbits, np.uint32)
+        d.cpre = host(p.cpre, np.uint32)
         d.inv_y0, d.inv_y1 = p.inv_y0, p.inv_y1
         d.inv_idx, d.inv_fi = host(p.inv_idx, np.uint32), host(p.inv_fi, np.uint16)
         d.inv_pack = host(p.inv_pack, np.uint32)

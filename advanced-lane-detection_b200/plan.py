@@ -215,6 +215,21 @@ def colour_tables(l_thresh: Tuple[int, int], b_thresh: Tuple[int, int]):
     return ctab, cbits
 
 
+@functools.lru_cache(maxsize=8)
+def colour_prefilter(l_thresh: Tuple[int, int], b_thresh: Tuple[int, int]) -> np.ndarray:
+    """Coarse form of the same decision: RGB space cut into 32^3 cells of 8x8x8 colours, two bits per cell
+    (cell r5 | g5 << 5 | b5 << 10, sixteen cells per u32): 0 = every colour of the cell is OFF, 1 = every colour is ON,
+    2 = mixed (the kernel then asks ctab / cbits).  8 KB: it lives in shared memory, so the common case (road, grass,
+    sky: far from the thresholds) costs no global-memory gather."""
+    L, Bc = _all_colour_channels()
+    on = ((L >= l_thresh[0]) & (L <= l_thresh[1])) | ((Bc >= b_thresh[0]) & (Bc <= b_thresh[1]))
+    cells = on.reshape(32, 8, 32, 8, 32, 8)
+    all_on, any_on = cells.all(axis=(1, 3, 5)), cells.any(axis=(1, 3, 5))        # [r5, g5, b5]
+    code = np.where(all_on, 1, np.where(any_on, 2, 0)).astype(np.uint32)
+    flat = code.transpose(2, 1, 0).reshape(-1)                                   # index = b5 << 10 | g5 << 5 | r5
+    return (flat.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint32))[None, :]).sum(1).astype(np.uint32)
+
+
 # ----------------------------------------------------------------------------- mask-kernel tiling
 def mask_tiles(nx, ny, size, max_bits=61440, target_tiles=24):
     """Cut the bird's-eye rows into bands.  Each band lists the bounding box (u0..u1, v0..v1) of
@@ -295,6 +310,31 @@ def gather_tiles(sx, sy, size, regions, tw=128, fixed_stride=None):
                 stride = fixed_stride
             out.append((x0, ry, w, rh, b0, int(by.min()), rows | (copy << 16), stride))
     return np.array(out, np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8)
+
+
+def gather_offsets_items(sx, sy, fi, gt, size):
+    """gather_offsets for the mask chunks, ordered by WARP ITEM: an item is one row of a chunk x one group of 128 columns;
+    lane l of the warp owns columns 128 cg + l + 32 k (k = 0..3) and fetches its four entries with one 16-byte load:
+    amap[((row * ncg + cg) * 32 + lane) * 4 + k].  Columns beyond the chunk hold 0xFFFFFFFF (skip).  Slow chunks get no
+    entries.  Returns (amap u32, start int32[T+1] in u32 units)."""
+    g = gt.view(np.uint32).astype(np.int64)
+    start = np.zeros(len(g) + 1, np.int64)
+    parts = []
+    for i, (x0, y0, w, h, b0, sy0, rc, st) in enumerate(g):
+        if st >> 31:
+            start[i + 1] = start[i]
+            continue
+        stride = st & 0x7FFFFFFF
+        ncg = (w + 127) // 128
+        bx, by, bf = sx[y0:y0 + h, x0:x0 + w], sy[y0:y0 + h, x0:x0 + w], fi[y0:y0 + h, x0:x0 + w]
+        off = (by - sy0).astype(np.int64) * stride + bx.astype(np.int64) * 3 - b0
+        assert off.min() >= 0 and off.max() < (1 << 22)
+        e = np.full((h, ncg * 128), 0xFFFFFFFF, np.uint32)
+        e[:, :w] = ((off << 10) | bf).astype(np.uint32)
+        parts.append(e.reshape(h, ncg, 4, 32).transpose(0, 1, 3, 2).reshape(-1))    # [row][cg][lane][k]
+        start[i + 1] = start[i] + parts[-1].size
+    amap = np.concatenate(parts) if parts else np.zeros(0, np.uint32)
+    return amap, start.astype(np.int32)
 
 
 def gather_offsets(sx, sy, fi, gt, size, lane_strided=False):
@@ -410,6 +450,7 @@ class LanePlan:
     tiles: np.ndarray          # i32[T,8]
     bmap: np.ndarray           # u16[H,W]
     bdesc: np.ndarray          # u32[H,W/32,4]
+    cpre: np.ndarray           # u32[2048]  colour_prefilter
     ctab: np.ndarray           # u32[65536]
     cbits: np.ndarray          # u32[2^19]
     inv_y0: int                # first output row the inverse warp can touch
@@ -449,6 +490,7 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     near = np.where(nx >= 0, ny * W + nx, -1).astype(np.int32)
     tiles, bmap = mask_tiles(nx, ny, size)
     ctab, cbits = colour_tables(tuple(l_thresh or variant.l_thresh), tuple(b_thresh or variant.b_thresh))
+    cpre = colour_prefilter(tuple(l_thresh or variant.l_thresh), tuple(b_thresh or variant.b_thresh))
     # source rows the mask path touches: taps of every sampled undistorted pixel
     used = np.zeros((H, W), bool)
     used[ny[nx >= 0], nx[nx >= 0]] = True
@@ -481,8 +523,8 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     mask_chunks = np.concatenate(chunks) if chunks else np.zeros((0, 8), np.int32)
     bdesc = mask_word_descriptors(nx, ny, tiles, size)
     frame_amap, frame_amap_start = gather_offsets(sx, sy, fi, frame_tiles, size, lane_strided=True)
-    mask_amap, mask_amap_start = gather_offsets(sx, sy, fi, mask_chunks, size)
-    return LanePlan(variant, (W, H), mtx, dist, und_map, bilinear_weight_table(), near, tiles, bmap, bdesc, ctab, cbits,
+    mask_amap, mask_amap_start = gather_offsets_items(sx, sy, fi, mask_chunks, size)
+    return LanePlan(variant, (W, H), mtx, dist, und_map, bilinear_weight_table(), near, tiles, bmap, bdesc, cpre, ctab, cbits,
                     inv_y0, inv_y1, np.ascontiguousarray(inv_idx), np.ascontiguousarray(inv_fi), np.ascontiguousarray(inv_pack),
                     src_row0, src_row1, gb, ga, frame_tiles, mask_chunks, np.array(starts, np.int32),
                     frame_amap, frame_amap_start, mask_amap, mask_amap_start)

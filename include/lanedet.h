@@ -72,11 +72,12 @@ typedef struct ld_plan_desc {
     const int32_t* mask_chunk_start; /* [n_tiles+1] */
     const uint32_t* frame_amap;      /* per pixel of every frame tile: staged-box byte offset << 10 | fraction */
     const int32_t* frame_amap_start; /* [n_frame_tiles+1] */
-    const uint32_t* mask_amap;       /* same for the mask chunks */
+    const uint32_t* mask_amap;       /* same for the mask chunks, ordered by warp item: [row][128-column group][lane][4] */
     const int32_t* mask_amap_start;  /* [n_mask_chunks+1] */
     const uint32_t* bdesc;           /* [H*(W/32)*4] per output word of the mask: first source bit, step masks, valid pixels */
     int32_t n_mask_chunks;
     int32_t reserved;
+    const uint32_t* cpre;            /* [2048] colour pre-decision per 8x8x8 cell of RGB space, 2 bits: 0 off, 1 on, 2 mixed */
 } ld_plan_desc;
 
 /* One lane of one frame as the window search leaves it (Line.blind_search, Project.py:73-101):
