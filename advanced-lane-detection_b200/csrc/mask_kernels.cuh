@@ -41,9 +41,12 @@ __device__ __forceinline__ bool colour_on_pre(uint32_t rgb, const uint32_t* s_pr
 // bilinear_rgb_off with the doubled weights / byte-permute pack of the frame pass (overlay_kernels.cuh: frame_weights)
 __device__ __forceinline__ uint32_t bilinear_rgb_smem(uint32_t box, uint32_t stride, uint32_t e2) {
     const uint32_t fx = e2 & 31u, fy = (e2 >> 5) & 31u, o = e2 >> 10;
-    const uint32_t tt = (32u - fx) | (fx << 16);
-    const uint32_t wx = (fx | fy) ? tt * (2048u - 64u * fy) : 0xFFFFu, wy = tt * (64u * fy);
-    const uint32_t a = box + (o & ~3u), sh = (o & 3u) * 8u;
+    const uint32_t tt = fx * 0xFFFFu + 32u;                             // (32 - fx) | fx << 16
+    const uint32_t fy64 = fy << 6;
+    uint32_t wx = tt * (2048u - fy64);
+    const uint32_t wy = tt * fy64;
+    if ((e2 & 1023u) == 0u) wx = 0xFFFFu;                               // fx = fy = 0: 2 * 32768 does not fit (frame_weights)
+    const uint32_t a = box + (o & ~3u), sh = o << 3;                    // the funnel shifts use the low five bits: (o & 3) * 8
     uint32_t p0, p1, p2, q0, q1, q2;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p0) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(p1) : "r"(a));
@@ -127,7 +130,7 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
                 for (int item = warp; item < nitems; item += nwarp) {
                     uint4 en = make_uint4(~0u, ~0u, ~0u, ~0u);
                     if (item + nwarp < nitems) en = __ldg(am4 + (item + nwarp) * 32 + lane);   // one item ahead
-                    const int r = item / ncg, cg = item - r * ncg;
+                    const int r = ncg == 1 ? item : (ncg == 2 ? item >> 1 : item / ncg), cg = item - r * ncg;   // chunks are <= 256 px wide
                     const uint32_t es[4] = {e.x, e.y, e.z, e.w};
                     uint32_t words[4];
 #pragma unroll

@@ -327,6 +327,8 @@ __device__ __forceinline__ uint32_t canvas_codes(const uint32_t (&ie)[4], const 
         a0[k] = a1[k] = make_uint4(0u, 0u, 0u, 0u);
         if (ie[k] != 0xFFFFFFFFu) { const uint4* p = cv + (ie[k] >> 17); a0[k] = __ldg(p); a1[k] = __ldg(p + CW); }
     }
+    // (no early exit for all-background taps here: a branch on the loaded words would make the warp wait for them
+    //  before its gather instead of after -- measured 0.34 us/frame slower)
     uint32_t codes = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
