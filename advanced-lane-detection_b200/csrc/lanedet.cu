@@ -321,7 +321,7 @@ extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, 
     if (!ARGS_OK(c, frames, mask, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    const int fpc = n >= 8 * MASK_FPC ? MASK_FPC : (n >= 16 ? 2 : 1);     // small batches: more, shorter CTAs
+    const int fpc = n >= 256 ? MASK_FPC : (n >= 128 ? 2 : 1);             // small batches: more, shorter CTAs (keep >= 3 waves)
     k_mask<<<dim3(d.n_tiles, (n + fpc - 1) / fpc), MASK_THREADS, c->plan->mask_smem, (cudaStream_t)stream>>>(frames, mask, d, n, fpc);
     return check_launch();
 }

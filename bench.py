@@ -279,7 +279,9 @@ def main():
     e2e = world * n * e2e_steps / float(t.item())
     same = bool((pin_out.to("cuda") == out).all().item()) if world == 1 else None
 
-    # ---- roofline of the fused mask kernel, measured live (CUDA events on the launching stream)
+    # ---- per-kernel timings and rooflines, measured live (CUDA events on the launching stream, each kernel alone over
+    #      the same n resident frames).  roofline = the kernel that dominates the step (the frame pass); mask_roofline =
+    #      the fused mask kernel BASELINE.json's metric names.  Algorithmic bytes per frame: SURVEY.md 8(d) / DESIGN.md 4.
     peak, peak_src = peaks()
     alg = eng.plan.mask_algorithmic_bytes
     stage = {}
@@ -295,41 +297,49 @@ def main():
         torch.cuda.synchronize()
         stage[name] = e0.elapsed_time(e1) / reps
 
+    L, h, st = eng.lib, eng._ctx_h, eng._stream()
     mask_t = eng.mask_dev(frames)
-    time_stage("k_mask", lambda: eng.lib.ld_mask(eng._ctx_h, frames.data_ptr(), n, mask_t.data_ptr(), eng._stream()))
-    mask_gbs = alg * n / (stage["k_mask"] * 1e-3) / 1e9
-    traffic = None
-    try:                                                   # dram bytes of k_mask from the committed `ncu --set full` capture
+    time_stage("k_mask", lambda: L.ld_mask(h, frames.data_ptr(), n, mask_t.data_ptr(), st))
+    rec_t = eng.search_dev(mask_t)
+    time_stage("k_search", lambda: L.ld_search(h, mask_t.data_ptr(), n, rec_t.data_ptr(), st))
+    eng.reset()
+    time_stage("k_fit*", lambda: L.ld_fit(h, rec_t.data_ptr(), n, fits.data_ptr(), st))
+    time_stage("k_raster", lambda: L.ld_raster(h, fits.data_ptr(), n, st))
+    time_stage("k_frame_pass_mf<1>", lambda: L.ld_frame_pass(h, frames.data_ptr(), n, out.data_ptr(), st))
+    hist_t = eng.hist_dev(mask_t)
+    time_stage("k_hist", lambda: L.ld_hist(h, mask_t.data_ptr(), n, hist_t.data_ptr(), st))
+    und_t = torch.empty_like(frames)
+    time_stage("k_frame_pass_mf<0> (cv2.undistort alone)", lambda: L.ld_undistort(h, frames.data_ptr(), n, und_t.data_ptr(), st))
+    del und_t
+    eng.check()
+    frame_bytes = 720 * 1280 * 3
+    bytes_per_frame = {"k_mask": alg, "k_search": 115200 + 560, "k_raster": 2 * (722 * 41 * 16), "k_frame_pass_mf<1>": 2 * frame_bytes,
+                       "k_hist": 115200 + 20480, "k_frame_pass_mf<0> (cv2.undistort alone)": 2 * frame_bytes}
+    kernels = {k: {"ms": v, "us_per_frame": 1e3 * v / n,
+                   **({"gbs": bytes_per_frame[k] * n / (v * 1e-3) / 1e9, "frac": bytes_per_frame[k] * n / (v * 1e-3) / 1e9 / peak}
+                      if k in bytes_per_frame else {})} for k, v in stage.items()}
+    traffic = {}
+    try:                                                   # DRAM bytes per frame from the committed `ncu --set full` captures
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f)["k_mask_dram_bytes_per_frame"] * n
+            traffic = json.load(f)
     except Exception:
         pass
-    roofline = {"kernel": "k_mask", "bound": "hbm", "achieved": mask_gbs, "peak": peak, "unit": "GB/s", "frac": mask_gbs / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_frame": alg, "ms_per_launch": stage["k_mask"],
-                "frames_per_launch": n}
-    kernels = None
-    if a.stages or True:
-        rec_t = eng.search_dev(mask_t)
-        time_stage("k_search", lambda: eng.lib.ld_search(eng._ctx_h, mask_t.data_ptr(), n, rec_t.data_ptr(), eng._stream()))
-        eng.reset()
-        time_stage("k_fit*", lambda: eng.lib.ld_fit(eng._ctx_h, rec_t.data_ptr(), n, fits.data_ptr(), eng._stream()))
-        time_stage("k_raster+k_overlay", lambda: eng.lib.ld_overlay(eng._ctx_h, frames.data_ptr(), fits.data_ptr(), n, out.data_ptr(), eng._stream()))
-        hist_t = eng.hist_dev(mask_t)
-        time_stage("k_hist", lambda: eng.lib.ld_hist(eng._ctx_h, mask_t.data_ptr(), n, hist_t.data_ptr(), eng._stream()))
-        und_t = torch.empty_like(frames)
-        time_stage("k_undistort", lambda: eng.lib.ld_undistort(eng._ctx_h, frames.data_ptr(), n, und_t.data_ptr(), eng._stream()))
-        bytes_per_frame = {"k_mask": alg, "k_search": 115200 + 560, "k_raster+k_overlay": 2 * 2764800, "k_hist": 115200 + 20480,
-                           "k_undistort": 2 * 2764800}
-        kernels = {k: {"ms": v, "us_per_frame": 1e3 * v / n,
-                       **({"gbs": bytes_per_frame[k] * n / (v * 1e-3) / 1e9, "frac": bytes_per_frame[k] * n / (v * 1e-3) / 1e9 / peak}
-                          if k in bytes_per_frame else {})} for k, v in stage.items()}
-        eng.check()
+
+    def roof(kernel, alg_bytes, traffic_key):
+        ms_k = stage[kernel]
+        gbs = alg_bytes * n / (ms_k * 1e-3) / 1e9
+        tr = traffic.get(traffic_key)
+        return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                "traffic": tr * n if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_frame": alg_bytes,
+                "ms_per_launch": ms_k, "frames_per_launch": n, "share_of_step": ms_k / (ms / a.steps)}
+
+    roofline = roof("k_frame_pass_mf<1>", 2 * frame_bytes, "k_frame_pass_dram_bytes_per_frame")
+    mask_roofline = roof("k_mask", alg, "k_mask_dram_bytes_per_frame")
 
     if rank == 0:
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             cpu = cpu_baseline_inline()
-        frame_bytes = 720 * 1280 * 3
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
@@ -339,7 +349,7 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * frame_bytes, "d2h_bytes_per_step": n * frame_bytes,
                         "matches_device_path": same, "api": "ld_process_batch_host (pinned host in/out, 32-frame chunks, 3 streams)"},
                 "gpu_launches": launches_per_step * a.steps,
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+                "roofline": roofline, "mask_roofline": mask_roofline, "kernels": kernels, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
