@@ -462,7 +462,7 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
 // buffered: frame i+1 lands while frame i is computed), gathers, blends and stores.
 // MODE 0: cv2.undistort only (helper.py:35-47); MODE 1: undistort + canvas blend + text (process_image).
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
-constexpr int FRAME_STAGES = 4;                 // source boxes in flight
+constexpr int FRAME_STAGES = 4;                 // source boxes in flight (a power of two)
 constexpr int FRAME_BOX_PITCH = 512;            // bytes per staged source row (plan.FRAME_BOX_PITCH): 128 uint32 = the TMA box width
 
 template <int MODE>
@@ -507,36 +507,34 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
     const int CW = WW + 1;                                               // padded canvas geometry (plan.py: inv_pack)
     const size_t cv_frame = (size_t)(H + 2) * CW;
-    // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop)
-    const uint8_t* frame = frames + (size_t)f0 * fbytes;
+    // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop); everything
+    // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
+    // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
     const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f0 * cv_frame;
-    const uint32_t* trow = text + ((size_t)f0 * LD_TEXT_ROWS + (text_row ? y - LD_TEXT_Y0 : 0)) * LD_TEXT_WORDS;
     __syncthreads();                                                     // barriers initialised
 
-    // Producer = thread 0: ONE tensor-map TMA copy stages the whole 512 B x box_rows source box of the next frame into
-    // ring buffer sb, once all 16 warps have released it (empty[sb]).  There is no CTA-wide barrier in the frame loop.
+    // Producer = thread 0: ONE tensor-map TMA copy stages the whole 512 B x box_rows source box of frame f0 + j into ring
+    // buffer j % FRAME_STAGES, once all 16 warps have released it (empty[]).  There is no CTA-wide barrier in the frame loop.
     const uint32_t full0 = smem_u32(&bar[0]), empty0 = smem_u32(&empty[0]);
-    int sb = 0, su = 0, sf = f0;                                         // ring position, ring passes done, next frame to stage
-    auto stage = [&]() {
+    auto stage = [&](int j) {
         if (threadIdx.x == 0) {
+            const int sb = j & (FRAME_STAGES - 1), su = j / FRAME_STAGES;
             if (su > 0) mbar_wait_addr(empty0 + 8u * sb, (uint32_t)((su - 1) & 1));   // use su of buffer sb needs release su - 1
             const uint32_t mb = full0 + 8u * sb;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(box_bytes) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(box0 + sb * box_bytes), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(t.b0 >> 2), "r"(t.sy0), "r"(sf), "r"(mb)
+                         ::"r"(box0 + sb * box_bytes), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(t.b0 >> 2), "r"(t.sy0), "r"(f0 + j), "r"(mb)
                          : "memory");
         }
-        ++sf;
-        if (sb == FRAME_STAGES - 1) { sb = 0; ++su; } else ++sb;
     };
     if (!t.slow) {
 #pragma unroll
-        for (int i = 0; i < FRAME_STAGES - 1; ++i) if (i < nf) stage();
+        for (int j = 0; j < FRAME_STAGES - 1; ++j) if (j < nf) stage(j);
     }
-    int b = 0, parity = 0;                                               // buffer / mbarrier phase of the frame being computed
     for (int i = 0; i < nf; ++i) {
-        if (!t.slow && i + FRAME_STAGES - 1 < nf) stage();
+        const int b = i & (FRAME_STAGES - 1);
+        if (!t.slow && i + FRAME_STAGES - 1 < nf) stage(i + FRAME_STAGES - 1);
         uint32_t codes = 0u;
         if (row_on && inv_row) {
             codes = canvas_codes(ie, cv, CW);                            // issued before the wait and the gather
@@ -544,7 +542,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
         }
         uint32_t c[4];
         if (!t.slow) {
-            mbar_wait_addr(full0 + 8u * b, (uint32_t)parity);
+            mbar_wait_addr(full0 + 8u * b, (uint32_t)((i / FRAME_STAGES) & 1));
             const uint32_t box = box0 + b * box_bytes;
             if (row_on) {
 #pragma unroll
@@ -553,17 +551,18 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");   // this warp is done with buffer b
         } else if (row_on) {
+            const uint8_t* frame = frames + (size_t)(f0 + i) * fbytes;
             const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
         }
-        if (row_on) finish_row<MODE>(c, ie, codes, ngroups, lane, text_row ? trow : nullptr, tw0, orow, rs);
-        frame += fbytes;
+        if (row_on) {
+            const uint32_t* trow = text_row ? text + ((size_t)(f0 + i) * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS : nullptr;
+            finish_row<MODE>(c, ie, codes, ngroups, lane, trow, tw0, orow, rs);
+        }
         orow += fbytes / 4;                                              // W % 32 == 0: a frame is a whole number of words
         cv += cv_frame;
-        trow += LD_TEXT_ROWS * LD_TEXT_WORDS;
-        if (b == FRAME_STAGES - 1) { b = 0; parity ^= 1; } else ++b;
     }
 }
 
