@@ -416,7 +416,10 @@ __device__ __forceinline__ void load_inv4(uint32_t (&ie)[4], int ngroups, int x0
 }
 
 constexpr int FRAME_THREADS = 256;
-constexpr int FRAME_FPC = 16;                   // frames per CTA of the multi-frame pass (upper bound)
+#ifndef LD_FRAME_FPC
+#define LD_FRAME_FPC 32
+#endif
+constexpr int FRAME_FPC = LD_FRAME_FPC;         // frames per CTA of the multi-frame pass (upper bound)
 
 // bilinear_rgb_off with everything that does not depend on the frame hoisted out: po = (tap byte offset & ~3) |
 // (offset & 3) << 30, wx / wy = the dp2a weight pairs of the top / bottom tap row, DOUBLED (see frame_weights) so that
@@ -462,7 +465,10 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
 // buffered: frame i+1 lands while frame i is computed), gathers, blends and stores.
 // MODE 0: cv2.undistort only (helper.py:35-47); MODE 1: undistort + canvas blend + text (process_image).
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
-constexpr int FRAME_STAGES = 4;                 // source boxes in flight (a power of two)
+#ifndef LD_FRAME_STAGES
+#define LD_FRAME_STAGES 4
+#endif
+constexpr int FRAME_STAGES = LD_FRAME_STAGES;   // source boxes in flight (a power of two)
 constexpr int FRAME_BOX_PITCH = 512;            // bytes per staged source row (plan.FRAME_BOX_PITCH): 128 uint32 = the TMA box width
 
 template <int MODE>
@@ -538,7 +544,9 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
         uint32_t codes = 0u;
         if (row_on && inv_row) {
             codes = canvas_codes(ie, cv, CW);                            // issued before the wait and the gather
+#ifdef LD_CANVAS_PREFETCH                                             // measured: 0.08 us/frame SLOWER with the prefetch
             if (i + 1 < nf) canvas_prefetch(ie, cv + cv_frame, CW);
+#endif
         }
         uint32_t c[4];
         if (!t.slow) {
