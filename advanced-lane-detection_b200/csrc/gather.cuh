@@ -51,16 +51,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {      // same, barrier given as a shared-window address
+    // the suspend-time hint lets the hardware park the warp instead of spinning through issue slots the working warps need
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}\n" ::"r"(bar_addr), "r"(parity) : "memory");
+        "}\n" ::"r"(bar_addr), "r"(parity), "r"(20000u) : "memory");
 }
+// keep a loop-invariant value in its register: without this the compiler re-derives lane-dependent constants (S2R, integer
+// division by 3, ...) inside the frame loop instead of holding them
+__device__ __forceinline__ void keep_u32(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep_s32(int& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))

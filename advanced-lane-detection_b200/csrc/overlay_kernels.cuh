@@ -379,21 +379,25 @@ struct RowStore {
         wp = (4 * lane) / 3; wp1 = min(wp + 1, 31);
         const int m = (4 * lane) % 3;
         sel = m == 0 ? 0x4210u : (m == 1 ? 0x5421u : 0x6542u);
+        keep_s32(wp); keep_s32(wp1); keep_u32(sel);
     }
 };
 
 // The tail of a tile row, shared by the frame-pass kernels: canvas blend, text, and the store.  Lane i holds pixels
 // x0 + i + 32 k (k < ngroups) in c[k] as r | g << 8 | b << 16; codes = canvas_codes() of those pixels (0 where the row is
-// outside the inverse warp); orow = this lane's first output word (row start + lane).
+// outside the inverse warp); orow = this lane's first output word (row start + lane); text != nullptr: the row crosses the
+// putText window and its plane row starts at text[trow_word].
 template <int MODE>
 __device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie)[4], uint32_t codes, int ngroups, int lane,
-                                           const uint32_t* __restrict__ trow, int tw0, uint32_t* __restrict__ orow, const RowStore& rs) {
+                                           const uint32_t* __restrict__ text, size_t trow_word, int tw0, uint32_t* __restrict__ orow,
+                                           const RowStore& rs) {
     if (MODE != 0 && codes) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             c[k] = blend_canvas_px(c[k], ie[k], (codes >> (8 * k)) & 255u);
     }
-    if (MODE == 1 && trow) {                                             // tile columns and LD_TEXT_X0 are multiples of 32
+    if (MODE == 1 && text) {                                             // tile columns and LD_TEXT_X0 are multiples of 32
+        const uint32_t* trow = text + trow_word;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int tw = tw0 + k;
@@ -481,12 +485,15 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     const size_t fbytes = (size_t)W * H * 3;
     const int f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
     const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
-    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;             // r = this warp's tile row
+    int lane = threadIdx.x & 31;
+    const int r = threadIdx.x >> 5;                                      // r = this warp's tile row
+    keep_s32(lane);
     const bool row_on = r < t.h;                                         // warp-uniform
     const int ngroups = row_on ? (t.w >> 5) : 0;                         // 32-pixel groups in a tile row (W % 32 == 0)
     const int y = t.y0 + r;
     const uint32_t box_bytes = (uint32_t)(box_rows * FRAME_BOX_PITCH);   // a multiple of 512
-    const uint32_t box0 = (smem_u32(s_boxes) + 127u) & ~127u;
+    uint32_t box0 = (smem_u32(s_boxes) + 127u) & ~127u;
+    keep_u32(box0);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < FRAME_STAGES; ++b) { mbar_init(&bar[b], 1); mbar_init(&empty[b], FRAME_MF_THREADS / 32); }
@@ -512,17 +519,19 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
     const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
     const int CW = WW + 1;                                               // padded canvas geometry (plan.py: inv_pack)
-    const size_t cv_frame = (size_t)(H + 2) * CW;
+    uint32_t cv_frame = (uint32_t)((H + 2) * CW), frame_words = (uint32_t)(fbytes / 4);   // per-frame strides (uint4 / u32 units)
+    keep_u32(cv_frame); keep_u32(frame_words);
     // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop); everything
     // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
     // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
     const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f0 * cv_frame;
+    uint32_t full0 = smem_u32(&bar[0]), empty0 = smem_u32(&empty[0]);
+    keep_u32(full0); keep_u32(empty0);
     __syncthreads();                                                     // barriers initialised
 
     // Producer = thread 0: ONE tensor-map TMA copy stages the whole 512 B x box_rows source box of frame f0 + j into ring
     // buffer j % FRAME_STAGES, once all 16 warps have released it (empty[]).  There is no CTA-wide barrier in the frame loop.
-    const uint32_t full0 = smem_u32(&bar[0]), empty0 = smem_u32(&empty[0]);
     auto stage = [&](int j) {
         if (threadIdx.x == 0) {
             const int sb = j & (FRAME_STAGES - 1), su = j / FRAME_STAGES;
@@ -565,11 +574,10 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             for (int k = 0; k < 4; ++k)
                 c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
         }
-        if (row_on) {
-            const uint32_t* trow = text_row ? text + ((size_t)(f0 + i) * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS : nullptr;
-            finish_row<MODE>(c, ie, codes, ngroups, lane, trow, tw0, orow, rs);
-        }
-        orow += fbytes / 4;                                              // W % 32 == 0: a frame is a whole number of words
+        if (row_on)
+            finish_row<MODE>(c, ie, codes, ngroups, lane, text_row ? text : nullptr,
+                             ((size_t)(f0 + i) * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS, tw0, orow, rs);
+        orow += frame_words;                                             // W % 32 == 0: a frame is a whole number of words
         cv += cv_frame;
     }
 }
@@ -602,7 +610,7 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
             c[k] = __funnelshift_r(a, b, rsh) & 0xFFFFFFu;
         }
         load_inv4(ie, ngroups, t.x0, y, lane, P);
-        finish_row<2>(c, ie, canvas_codes(ie, cv, CW), ngroups, lane, nullptr, 0,
+        finish_row<2>(c, ie, canvas_codes(ie, cv, CW), ngroups, lane, nullptr, 0, 0,
                       reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs);
     }
 }
