@@ -35,6 +35,10 @@ struct ld_plan {
     int n_allocs;
     size_t search_smem, raster_smem, mask_smem, frame_smem;
     int frame_box_rows;        // source rows of the largest frame-pass tile box (the TMA box height)
+    // frame-pass tiles split by what they depend on: `plain` tiles are pure cv2.undistort (no inverse-warp sample, no
+    // putText pixel can fall into them) and need neither the fit nor the canvas; `overlay` tiles are the rest
+    const int32_t* plain_tiles; const int32_t* overlay_tiles;
+    int n_plain, n_overlay;
 };
 
 enum { HOST_CHUNK = 32, PIPE_SUB = 8 };
@@ -176,6 +180,25 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     }
     p->frame_smem = FRAME_STAGES * fs + 128;                             // FRAME_STAGES source boxes in flight
     p->frame_box_rows = box_rows;
+    {
+        int32_t* ids = new (std::nothrow) int32_t[2 * (size_t)desc->n_frame_tiles];
+        if (!ids) { ld_plan_destroy(p); return LD_ERR_ARG; }
+        int32_t* plain = ids; int32_t* over = ids + desc->n_frame_tiles;
+        int np = 0, no = 0;
+        for (int t = 0; t < desc->n_frame_tiles; ++t) {
+            const int x0 = desc->frame_tiles[8 * t], y0 = desc->frame_tiles[8 * t + 1], w = desc->frame_tiles[8 * t + 2], h = desc->frame_tiles[8 * t + 3];
+            bool touched = y0 < LD_TEXT_Y0 + LD_TEXT_ROWS && y0 + h > LD_TEXT_Y0 && x0 < LD_TEXT_X0 + 32 * LD_TEXT_WORDS && x0 + w > LD_TEXT_X0;
+            for (int y = (y0 > desc->inv_y0 ? y0 : desc->inv_y0); !touched && y < y0 + h && y < desc->inv_y1; ++y)
+                for (int x = x0; x < x0 + w; ++x)
+                    if (desc->inv_pack[(size_t)(y - desc->inv_y0) * W + x] != 0xFFFFFFFFu) { touched = true; break; }
+            if (touched) over[no++] = t; else plain[np++] = t;
+        }
+        p->n_plain = np; p->n_overlay = no;
+        rc = upload(p, plain, (size_t)(np ? np : 1), &p->plain_tiles);
+        if (!rc) rc = upload(p, over, (size_t)(no ? no : 1), &p->overlay_tiles);
+        delete[] ids;
+        if (rc) { ld_plan_destroy(p); return rc; }
+    }
     int mow = 0;
     for (int t = 0; t < desc->n_tiles; ++t) {
         const int words = (desc->tiles[8 * t + 1] - desc->tiles[8 * t]) * (W / 32);
@@ -422,7 +445,9 @@ static int frames_per_cta(int m) {
     const int f = m / 8;
     return f < 1 ? 1 : (f > FRAME_FPC ? FRAME_FPC : f);
 }
-static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted) {
+// which = 0: every tile with blend + text; 1: the plain tiles as cv2.undistort; 2: the overlay tiles with blend + text
+static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted,
+                             int which = 0) {
     const PlanDev& d = c->plan->d;
     const uint32_t* planes = c->planes + (size_t)slot * canvas_words(d);
     const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
@@ -434,8 +459,18 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
         CUtensorMap tm;
         int rc;
         if ((rc = frame_tensor_map(c->plan, fin, m, &tm))) return rc;
-        k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, (m + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-            tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows);
+        const dim3 groups(1, (m + fpc - 1) / fpc);
+        if (which == 1) {
+            if (c->plan->n_plain)
+                k_frame_pass_mf<0><<<dim3(c->plan->n_plain, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_tiles);
+        } else if (which == 2) {
+            if (c->plan->n_overlay)
+                k_frame_pass_mf<1><<<dim3(c->plan->n_overlay, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
+                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->overlay_tiles);
+        } else
+            k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
+                tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, nullptr);
     }
     return check_launch();
 }
@@ -537,11 +572,19 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
     const int nsub = sub_batches(M);
     int rc;
     if (nsub < 2) {
-        if ((rc = fit_impl(c, c->rec, M, c->fit, s, frame_offset))) return rc;
-        if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, s));
-        LD_CUDA(cudaEventRecord(c->ev_state, s));
-        if ((rc = launch_raster(c, c->fit, nullptr, nullptr, 0, 30, M, s, 0))) return rc;
-        if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0))) return rc;
+        // The latency-bound chain fit -> raster (few resident warps, ~1 us/frame) runs on the high-priority stream; the
+        // caller's stream meanwhile undistorts the tiles that depend on neither the fit nor the canvas (64 % of them), whose
+        // CTAs fill the issue slots the chain leaves idle.  The overlay tiles follow the raster.
+        LD_CUDA(cudaEventRecord(c->ev_fork, s));
+        LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
+        if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset))) return rc;
+        if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
+        LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
+        if ((rc = launch_raster(c, c->fit, nullptr, nullptr, 0, 30, M, c->s_lat, 0))) return rc;
+        if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, 1))) return rc;
+        if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
+        LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));
+        LD_CUDA(cudaStreamWaitEvent(s, c->ev_join[1], 0));
     } else {
         const int S = (M + nsub - 1) / nsub;
         if ((rc = fork_streams(c, s))) return rc;
@@ -680,7 +723,7 @@ extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* ou
     int rc;
     if ((rc = frame_tensor_map(c->plan, frames, n, &tm))) return rc;
     k_frame_pass_mf<0><<<dim3(d.n_frame_tiles, (n + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(
-        tm, frames, nullptr, nullptr, out, d, n, fpc, c->plan->frame_box_rows);
+        tm, frames, nullptr, nullptr, out, d, n, fpc, c->plan->frame_box_rows, nullptr);
     return check_launch();
 }
 extern "C" int ld_warp(ld_ctx* c, const uint8_t* img, int n, int channels, uint8_t* out, void* stream) {

@@ -467,7 +467,8 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
 // words).  Everything that depends only on the tile -- tap offsets, dp2a weight pairs, inverse-warp entries, output
 // offsets -- is decoded once into registers; per frame the CTA only stages the source box (TMA bulk row copies, double
 // buffered: frame i+1 lands while frame i is computed), gathers, blends and stores.
-// MODE 0: cv2.undistort only (helper.py:35-47); MODE 1: undistort + canvas blend + text (process_image).
+// MODE 0: cv2.undistort only (helper.py:35-47; and, inside process_image, the tiles neither the inverse warp nor putText
+// can touch); MODE 1: undistort + canvas blend + text (process_image).
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
 #ifndef LD_FRAME_STAGES
 #define LD_FRAME_STAGES 4
@@ -478,13 +479,15 @@ constexpr int FRAME_BOX_PITCH = 512;            // bytes per staged source row (
 template <int MODE>
 __global__ void __launch_bounds__(FRAME_MF_THREADS, 2)
 k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes,
-                const uint32_t* __restrict__ text, uint8_t* __restrict__ out, const PlanDev P, int n, int fpc, int box_rows) {
+                const uint32_t* __restrict__ text, uint8_t* __restrict__ out, const PlanDev P, int n, int fpc, int box_rows,
+                const int32_t* __restrict__ tile_ids) {
     extern __shared__ __align__(128) uint8_t s_boxes[];
     __shared__ __align__(8) uint64_t bar[FRAME_STAGES], empty[FRAME_STAGES];     // box landed / box released by all warps
     const int W = P.W, H = P.H, WW = P.WW;
     const size_t fbytes = (size_t)W * H * 3;
     const int f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
-    const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
+    const int tile = tile_ids ? __ldg(tile_ids + blockIdx.x) : (int)blockIdx.x;   // a launch may cover a subset of the tiles
+    const GTile t = load_gtile(P.frame_tiles, tile);
     int lane = threadIdx.x & 31;
     const int r = threadIdx.x >> 5;                                      // r = this warp's tile row
     keep_s32(lane);
@@ -503,7 +506,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     uint32_t po[4], wx[4], wy[4], ie[4];
     {
         uint4 e = make_uint4(0, 0, 0, 0);
-        if (row_on && !t.slow) e = __ldg(reinterpret_cast<const uint4*>(P.frame_amap + P.frame_amap_start[blockIdx.x]) + r * 32 + lane);
+        if (row_on && !t.slow) e = __ldg(reinterpret_cast<const uint4*>(P.frame_amap + P.frame_amap_start[tile]) + r * 32 + lane);
         const uint32_t es[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
