@@ -103,6 +103,10 @@ _SIGNATURES = {
     "ld_margin_search": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "ld_polyfit": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "ld_draw": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "ld_gray": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "ld_sobel_max": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "ld_grad_binary": (C.c_int, [_P, _P, _P, _P, C.c_int, _P] + [C.c_int] * 7 + [_P, _P]),
+    "ld_color_filter": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
 }
 
 

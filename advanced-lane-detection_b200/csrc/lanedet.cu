@@ -13,6 +13,7 @@
 #include "search_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "overlay_kernels.cuh"
+#include "grad_kernels.cuh"
 
 using namespace lanedet;
 
@@ -565,18 +566,20 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
     return join_streams(c, s);
 }
 
+// search_first: the window search has not run yet (process_impl): it joins the latency-bound chain on s_lat
 static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld_frame_fit* fit_out, void* state_out,
-                         cudaStream_t s, int frame_offset) {
+                         cudaStream_t s, int frame_offset, int search_first = 0) {
     const PlanDev& d = c->plan->d;
     const size_t fb = (size_t)d.W * d.H * 3;
     const int nsub = sub_batches(M);
     int rc;
     if (nsub < 2) {
-        // The latency-bound chain fit -> raster (few resident warps, ~1 us/frame) runs on the high-priority stream; the
+        // The latency-bound chain (search ->) fit -> raster (few resident warps, ~1 us/frame) runs on the high-priority stream; the
         // caller's stream meanwhile undistorts the tiles that depend on neither the fit nor the canvas (64 % of them), whose
         // CTAs fill the issue slots the chain leaves idle.  The overlay tiles follow the raster.
         LD_CUDA(cudaEventRecord(c->ev_fork, s));
         LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
+        if (search_first && (rc = ld_search(c, c->mask, M, c->rec, c->s_lat))) return rc;
         if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset))) return rc;
         if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
         LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
@@ -614,6 +617,12 @@ static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, l
     int rc;
     for (int base = 0; base < n; base += c->max_frames) {
         const int M = (n - base) < c->max_frames ? (n - base) : c->max_frames;
+        if (sub_batches(M) < 2) {                                        // mask, then everything else overlapped (postpass_impl)
+            if ((rc = ld_mask(c, frames + base * fb, M, c->mask, s))) return rc;
+            if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
+                                    frame_offset + base, 1))) return rc;
+            continue;
+        }
         if ((rc = prepass_impl(c, frames + base * fb, M, s))) return rc;
         if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
                                 frame_offset + base))) return rc;
@@ -752,6 +761,42 @@ extern "C" int ld_unpack_mask(ld_ctx* c, const uint32_t* mask, int n, uint8_t* b
     if (n == 0) return LD_OK;
     const size_t np = (size_t)c->plan->d.W * c->plan->d.H * n;
     k_unpack_mask<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, bin, np);
+    return check_launch();
+}
+
+// ------------------------------------------------------------------------------------- helper.py gradient / HLS / RGB thresholds
+extern "C" int ld_gray(ld_ctx* c, const uint8_t* img, int n, int warped, uint8_t* gray, void* stream) {
+    if (!ARGS_OK(c, img, gray, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    k_gray<<<dim3((d.W * d.H + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, gray, d, warped ? 1 : 0);
+    return check_launch();
+}
+extern "C" int ld_sobel_max(ld_ctx* c, const uint8_t* gray, int n, uint32_t* maxima, void* stream) {
+    if (!ARGS_OK(c, gray, maxima, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    if (d.W < 2 || d.H < 2) return LD_ERR_ARG;
+    LD_CUDA(cudaMemsetAsync(maxima, 0, sizeof(uint32_t) * 2 * n, (cudaStream_t)stream));
+    k_sobel_max<<<dim3(148, n), 256, 0, (cudaStream_t)stream>>>(gray, maxima, d.W, d.H);
+    return check_launch();
+}
+extern "C" int ld_grad_binary(ld_ctx* c, const uint8_t* img, const uint8_t* gray, const uint32_t* maxima, int n,
+                              const uint8_t* s_table, int s_lo, int s_hi, int sx_lo, int sx_hi, int use_mag, int mag_lo, int mag_hi,
+                              uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, gray, out, n) || !maxima || (s_table && !img)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    k_grad_binary<<<dim3((d.W * d.H + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, gray, maxima, s_table, s_lo, s_hi, sx_lo, sx_hi,
+                                                                                     use_mag ? 1 : 0, mag_lo, mag_hi, out, d.W, d.H);
+    return check_launch();
+}
+extern "C" int ld_color_filter(ld_ctx* c, const uint8_t* img, const uint8_t* and_with, int n, int r_th, int g_th, int b_th,
+                               uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, img, out, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const size_t np = (size_t)c->plan->d.W * c->plan->d.H * n;
+    k_color_filter<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, and_with, r_th, g_th, b_th, out, np);
     return check_launch();
 }
 

@@ -286,6 +286,43 @@ class LaneEngine:
                                               thickness, undist.shape[0], _ptr(out), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ helper.py gradient / HLS / RGB thresholds
+    def _s_table_dev(self):
+        if getattr(self, "_s_table", None) is None:
+            from .plan import hls_s_table
+            self._s_table = self.torch.from_numpy(hls_s_table()).to("cuda:%d" % self.device)
+        return self._s_table
+
+    def gray_dev(self, img, warped=False):
+        """cv2.cvtColor(img, RGB2GRAY) (helper.py:59); of warp(img) when warped (helper.py:109-111)."""
+        img = self._frames(img)
+        out = self._dev((img.shape[0], self.H, self.W), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_gray(self._ctx_h, _ptr(img), img.shape[0], int(bool(warped)), _ptr(out), self._stream()))
+        return out
+
+    def grad_binary_dev(self, img, gray, s_thresh=None, sx_thresh=(20, 100), mag_thresh=None):
+        """img2binary's combined binary (s_thresh and mag_thresh given) or sobelx_filter's abs_bin (both None)."""
+        img = self._frames(img)
+        n = gray.shape[0]
+        mx = self._dev((n, 2), self.torch.int32)
+        _abi.check(self.lib, self.lib.ld_sobel_max(self._ctx_h, _ptr(gray), n, _ptr(mx), self._stream()))
+        out = self._dev((n, self.H, self.W), self.torch.uint8)
+        st = self._s_table_dev() if s_thresh is not None else None
+        s0, s1 = (int(s_thresh[0]), int(s_thresh[1])) if s_thresh is not None else (0, 0)
+        m0, m1 = (int(mag_thresh[0]), int(mag_thresh[1])) if mag_thresh is not None else (0, 0)
+        _abi.check(self.lib, self.lib.ld_grad_binary(self._ctx_h, _ptr(img), _ptr(gray), _ptr(mx), n,
+                                                     _ptr(st) if st is not None else None, s0, s1, int(sx_thresh[0]), int(sx_thresh[1]),
+                                                     int(mag_thresh is not None), m0, m1, _ptr(out), self._stream()))
+        return out
+
+    def color_filter_dev(self, img, r_th, g_th, b_th, and_with=None):
+        """color_filter (helper.py:493-500); AND-ed with `and_with` (combine_bin, helper.py:503-511) when given."""
+        img = self._frames(img)
+        out = self._dev((img.shape[0], self.H, self.W), self.torch.uint8)
+        _abi.check(self.lib, self.lib.ld_color_filter(self._ctx_h, _ptr(img), _ptr(and_with) if and_with is not None else None,
+                                                      img.shape[0], int(r_th), int(g_th), int(b_th), _ptr(out), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ host views
     @staticmethod
     def records_to_numpy(t):

@@ -1,10 +1,11 @@
 """Drop-in for the hot-path functions of the reference's helper.py (same names and argument meaning):
 
-    warp, undistort, luv_lab_filter, sliding_window, skip_sliding_window, draw_area, apply_thresholds
+    warp, undistort, luv_lab_filter, sliding_window, skip_sliding_window, draw_area, apply_thresholds,
+    img2binary, sobelx_filter, color_filter, combine_bin   (the gradient / HLS / RGB thresholds)
 
 Like the reference, the module reads the globals `src`, `dst`, `mtx`, `dist` (helper.py:873-884 assigns them under
 `__main__`; here they have those values from the start and may be re-assigned by the caller).  Everything else of
-helper.py (Sobel / HLS / gamma / equidistant experiments, matplotlib debug plots) is outside the hot path.
+helper.py (gamma / equidistant experiments, window centroids, matplotlib debug plots) is outside the path.
 """
 import numpy as np
 
@@ -51,6 +52,38 @@ def apply_thresholds(image, show=True):
     if show:
         raise NotImplementedError("the matplotlib figure of apply_thresholds(show=True) is outside the hot path; pass show=False")
     return _pipeline().luv_lab_filter(image, (225, 255), (155, 200), False, do_warp=True)
+
+
+def _dev_img(img):
+    eng = _pipeline().engine()
+    return eng, eng.to_device(np.ascontiguousarray(img, dtype=np.uint8))[None]
+
+
+def img2binary(img, s_thresh=(100, 255), sx_thresh=(20, 100)):
+    """helper.py:50-105: (HLS S in s_thresh) | (scaled gradient magnitude in (50, 255)) | (scaled |Sobel x| in sx_thresh)
+    of an undistorted RGB image -> uint8 {0,1}[720,1280].  (dir_bin is identically 1; the `| abs_bin == 1` precedence of
+    helper.py:103 is kept: it evaluates to a plain OR.)"""
+    eng, t = _dev_img(img)
+    return eng.grad_binary_dev(t, eng.gray_dev(t), s_thresh=s_thresh, sx_thresh=sx_thresh, mag_thresh=(50, 255))[0].cpu().numpy()
+
+
+def sobelx_filter(img, sx_thresh=(20, 100)):
+    """helper.py:108-122: warp, gray, Sobel x, scale by the image maximum, threshold -> uint8 {0,1}[720,1280]."""
+    eng, t = _dev_img(img)
+    return eng.grad_binary_dev(t, eng.gray_dev(t, warped=True), sx_thresh=sx_thresh)[0].cpu().numpy()
+
+
+def color_filter(img, r_th=120, g_th=100, b_th=50):
+    """helper.py:493-500: R >= r_th & G >= g_th & B >= b_th."""
+    eng, t = _dev_img(img)
+    return eng.color_filter_dev(t, r_th, g_th, b_th)[0].cpu().numpy()
+
+
+def combine_bin(img, r_th=140, g_th=100, b_th=50, s_thresh=(90, 255), sx_thresh=(20, 100)):
+    """helper.py:503-511: img2binary & color_filter."""
+    eng, t = _dev_img(img)
+    thr = eng.grad_binary_dev(t, eng.gray_dev(t), s_thresh=s_thresh, sx_thresh=sx_thresh, mag_thresh=(50, 255))
+    return eng.color_filter_dev(t, r_th, g_th, b_th, and_with=thr)[0].cpu().numpy()
 
 
 class _LazyResult(dict):

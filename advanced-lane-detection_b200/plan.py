@@ -215,6 +215,18 @@ def colour_tables(l_thresh: Tuple[int, int], b_thresh: Tuple[int, int]):
     return ctab, cbits
 
 
+@functools.lru_cache(maxsize=1)
+def hls_s_table() -> np.ndarray:
+    """u8[2^24]: the S channel of cv2's 8-bit RGB2HLS for every colour, index r << 16 | g << 8 | b (helper.py:90-91).
+    cv2 computes it in float32 with its own rounding; like LUV-L / Lab-b it is a function of the colour alone, so the
+    threshold `s_channel in s_thresh` is exact by construction for any thresholds."""
+    import cv2
+    r, g, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8),
+                          np.arange(256, dtype=np.uint8), indexing="ij")
+    img = np.ascontiguousarray(np.stack([r, g, b], -1).reshape(4096, 4096, 3))
+    return np.ascontiguousarray(cv2.cvtColor(img, cv2.COLOR_RGB2HLS)[..., 2].reshape(-1))
+
+
 @functools.lru_cache(maxsize=8)
 def colour_prefilter(l_thresh: Tuple[int, int], b_thresh: Tuple[int, int]) -> np.ndarray:
     """Coarse form of the same decision: RGB space cut into 32^3 cells of 8x8x8 colours, two bits per cell

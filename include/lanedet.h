@@ -200,6 +200,22 @@ int ld_polyfit(ld_ctx* ctx, const ld_lane_record* rec_dev, int n_records, double
 int ld_draw(ld_ctx* ctx, const uint8_t* undist_dev, const int32_t* verts_dev, const int32_t* counts_dev,
             int max_verts, int thickness, int n, uint8_t* out_dev, void* stream);
 
+/* ---- helper.py gradient / HLS / RGB thresholds (not on the process_image path) ----
+ * cv2.cvtColor(img, RGB2GRAY) (helper.py:59), of warp(img) when warped != 0 (helper.py:109-111) -> u8[n][H][W] */
+int ld_gray(ld_ctx* ctx, const uint8_t* img_dev, int n, int warped, uint8_t* gray_dev, void* stream);
+/* per image: max |Sobel_x| and max (Sobel_x^2 + Sobel_y^2) of a gray image (helper.py:64-68, :76-78) -> u32[n][2] */
+int ld_sobel_max(ld_ctx* ctx, const uint8_t* gray_dev, int n, uint32_t* maxima_dev, void* stream);
+/* img2binary's combined binary (helper.py:50-105: use_mag = 1, s_table_dev = cv2's 8-bit HLS S channel of every colour,
+ * u8[1<<24] indexed r<<16|g<<8|b) or sobelx_filter's abs_bin (helper.py:108-122: use_mag = 0, s_table_dev = NULL)
+ * -> u8[n][H][W] in {0,1}.  img_dev = the RGB frames (only read for the S channel). */
+int ld_grad_binary(ld_ctx* ctx, const uint8_t* img_dev, const uint8_t* gray_dev, const uint32_t* maxima_dev, int n,
+                   const uint8_t* s_table_dev, int s_lo, int s_hi, int sx_lo, int sx_hi, int use_mag, int mag_lo, int mag_hi,
+                   uint8_t* out_dev, void* stream);
+/* color_filter (helper.py:493-500): R >= r_th & G >= g_th & B >= b_th, AND-ed with and_with_dev == 1 when given
+ * (combine_bin, helper.py:503-511) -> u8[n][H][W] in {0,1} */
+int ld_color_filter(ld_ctx* ctx, const uint8_t* img_dev, const uint8_t* and_with_dev, int n, int r_th, int g_th, int b_th,
+                    uint8_t* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

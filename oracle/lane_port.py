@@ -417,6 +417,60 @@ def helper_fill_overlay(undist, dst, src, left_fitx, right_fitx):
 
 
 # --------------------------------------------------------------------------- synthetic sequences
+def helper_img2binary(img, s_thresh=(100, 255), sx_thresh=(20, 100)):
+    """helper.py:50-105, same cv2 / numpy calls in the same order."""
+    gray = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
+    sobelx = cv2.Sobel(gray, cv2.CV_64F, 1, 0)
+    sobely = cv2.Sobel(gray, cv2.CV_64F, 0, 1)
+    abs_sobelx = np.absolute(sobelx)
+    scaled_sobel = np.uint8(255 * abs_sobelx / np.max(abs_sobelx))
+    abs_bin = np.zeros_like(scaled_sobel)
+    abs_bin[(scaled_sobel >= sx_thresh[0]) & (scaled_sobel <= sx_thresh[1])] = 1
+    gradmag = np.sqrt(sobelx ** 2 + sobely ** 2)
+    scale_factor = np.max(gradmag) / 255
+    gradmag = (gradmag / scale_factor).astype(np.uint8)
+    mag_bin = np.zeros_like(gradmag)
+    mag_bin[(gradmag >= 50) & (gradmag <= 255)] = 1
+    absgraddir = np.arctan2(np.absolute(sobely), np.absolute(sobelx))
+    dir_bin = np.zeros_like(absgraddir)
+    dir_bin[(absgraddir >= 0) & (absgraddir <= np.pi / 2)] = 1
+    s_channel = cv2.cvtColor(img, cv2.COLOR_RGB2HLS)[:, :, 2]
+    schannel_bin = np.zeros_like(s_channel)
+    schannel_bin[(s_channel >= s_thresh[0]) & (s_channel <= s_thresh[1])] = 1
+    combined = np.zeros_like(abs_bin)
+    combined[(schannel_bin == 1) | (((mag_bin == 1) & (dir_bin == 1)) | abs_bin == 1)] = 1      # precedence as in helper.py:103
+    return combined
+
+
+HELPER_SRC = ((490, 482), (810, 482), (1250, 720), (0, 720))        # helper.py:880-881
+HELPER_DST = ((0, 0), (1280, 0), (1250, 720), (40, 720))            # helper.py:882-883
+
+
+def helper_sobelx_filter(img, sx_thresh=(20, 100), src=HELPER_SRC, dst=HELPER_DST):
+    """helper.py:108-122 (warp = helper.py:11-21 with the module globals src / dst)"""
+    m = cv2.getPerspectiveTransform(np.float32(src), np.float32(dst))
+    gray = cv2.cvtColor(cv2.warpPerspective(img, m, (W, H), flags=cv2.INTER_NEAREST), cv2.COLOR_RGB2GRAY)
+    abs_sobelx = np.absolute(cv2.Sobel(gray, cv2.CV_64F, 1, 0))
+    scaled_sobel = np.uint8(255 * abs_sobelx / np.max(abs_sobelx))
+    abs_bin = np.zeros_like(scaled_sobel)
+    abs_bin[(scaled_sobel >= sx_thresh[0]) & (scaled_sobel <= sx_thresh[1])] = 1
+    return abs_bin
+
+
+def helper_color_filter(img, r_th=120, g_th=100, b_th=50):
+    """helper.py:493-500"""
+    out = np.zeros_like(img[:, :, 0])
+    out[(img[:, :, 0] >= r_th) & (img[:, :, 1] >= g_th) & (img[:, :, 2] >= b_th)] = 1
+    return out
+
+
+def helper_combine_bin(img, r_th=140, g_th=100, b_th=50, s_thresh=(90, 255), sx_thresh=(20, 100)):
+    """helper.py:503-511"""
+    out = np.zeros_like(img[:, :, 0])
+    out[(helper_img2binary(img, s_thresh, sx_thresh) == 1) & (helper_color_filter(img, r_th, g_th, b_th) == 1)] = 1
+    return out
+
+
 def synth_sequence(stills, n_frames, seed=0):
     """SURVEY.md 8(d) config 2/3 generator: cycle the stills, integer x-shift random walk in
     [-8,8] (edge replicated) and a gain in [0.9,1.1] applied in u8 with saturation."""
