@@ -162,6 +162,17 @@ def cpu_reference_run(steps, warmup, frames_per_proc=8):
             "frames_per_step": procs * frames_per_proc}
 
 
+def cpu_img2binary_ms(n=4):
+    """the reference's helper.img2binary (oracle port) on the host, ms per frame, one process"""
+    from oracle import lane_port as O
+    frames = synth_frames(n, 0)
+    O.helper_img2binary(frames[0])
+    t0 = time.perf_counter()
+    for f in frames:
+        O.helper_img2binary(f)
+    return 1e3 * (time.perf_counter() - t0) / n
+
+
 def cpu_baseline_inline(n=60):
     """single process, cv2 default threads, first n frames of the bench sequence"""
     import cv2
@@ -311,10 +322,15 @@ def main():
     und_t = torch.empty_like(frames)
     time_stage("k_frame_pass_mf<0> (cv2.undistort alone)", lambda: L.ld_undistort(h, frames.data_ptr(), n, und_t.data_ptr(), st))
     del und_t
+    # helper.img2binary: gray -> per-image Sobel maxima -> thresholds, three kernels
+    time_stage("img2binary (k_gray + k_sobel_max + k_grad_binary)",
+               lambda: eng.grad_binary_dev(frames, eng.gray_dev(frames), s_thresh=(100, 255), sx_thresh=(20, 100), mag_thresh=(50, 255)), reps=3)
     eng.check()
     frame_bytes = 720 * 1280 * 3
     bytes_per_frame = {"k_mask": alg, "k_search": 115200 + 560, "k_raster": 2 * (722 * 41 * 16), "k_frame_pass_mf<1>": 2 * frame_bytes,
-                       "k_hist": 115200 + 20480, "k_frame_pass_mf<0> (cv2.undistort alone)": 2 * frame_bytes}
+                       "k_hist": 115200 + 20480, "k_frame_pass_mf<0> (cv2.undistort alone)": 2 * frame_bytes,
+                       # RGB read twice (gray, S channel), gray written once and read twice, binary written once
+                       "img2binary (k_gray + k_sobel_max + k_grad_binary)": 2 * frame_bytes + 4 * 720 * 1280}
     kernels = {k: {"ms": v, "us_per_frame": 1e3 * v / n,
                    **({"gbs": bytes_per_frame[k] * n / (v * 1e-3) / 1e9, "frac": bytes_per_frame[k] * n / (v * 1e-3) / 1e9 / peak}
                       if k in bytes_per_frame else {})} for k, v in stage.items()}
@@ -340,6 +356,7 @@ def main():
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             cpu = cpu_baseline_inline()
+            kernels["img2binary (k_gray + k_sobel_max + k_grad_binary)"]["cpu_port_ms_per_frame"] = cpu_img2binary_ms()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
