@@ -51,7 +51,7 @@ struct ld_ctx {
     ld_lane_record* rec;       // [max][2]
     FitWork* work;             // [max][2]
     ld_frame_fit* fit;         // [max]
-    uint32_t* planes;          // padded canvas [max][H+2][WW+1][4]  (red lo, red hi, green lo, green hi): 64-bit windows of (red without green, green)
+    uint32_t* planes;          // padded, interleaved canvas u64[max][H+2][2 WW + 2] (overlay_kernels.cuh: canvas_codes)
     uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
     TrackState* state;
     int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error
@@ -68,7 +68,7 @@ struct ld_ctx {
 };
 
 // u32 words of one frame's padded canvas (overlay_kernels.cuh: canvas_codes)
-static inline size_t canvas_words(const PlanDev& d) { return (size_t)(d.H + 2) * (d.WW + 1) * 4; }
+static inline size_t canvas_words(const PlanDev& d) { return (size_t)(d.H + 2) * (2 * d.WW + 2) * 2; }
 
 extern "C" int ld_abi_version(void) { return LD_ABI_VERSION; }
 
@@ -407,6 +407,7 @@ extern "C" int ld_fit(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit*
 static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* verts, const int32_t* counts, int max_verts,
                          int thickness, int m, cudaStream_t s, int slot) {
     const PlanDev& d = c->plan->d;
+    if (d.W != 1280 || d.H != 720) return LD_ERR_ARG;                    // RASTER_CW
     k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(
         fit, verts, counts, max_verts, thickness, c->planes + (size_t)slot * canvas_words(d),
         c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);

@@ -19,6 +19,7 @@ namespace lanedet {
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_BAND = 90;                 // canvas rows per CTA (8 bands of a 720-row frame)
 constexpr int MAX_VERTS = 2 * 724;
+constexpr int RASTER_CW = 2 * (1280 / 32) + 2;  // canvas entries per row; the raster is hard-wired to 1280x720 like the reference's windows
 constexpr int RASTER_BIG_ROUND = 4;             // long segments set up per round (one thread each)
 
 #ifdef LD_RASTER_PROF
@@ -27,6 +28,14 @@ __device__ long long g_raster_prof[64][16];
 #else
 #define RPROF(i) do {} while (0)
 #endif
+
+// bit j of a 16-bit value -> bit 2j
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return (x | (x << 1)) & 0x55555555u;
+}
 
 struct BandPlotter {                // sets bits [x1,x2] of canvas row y if the row belongs to this CTA's band
     uint32_t* plane; int WW, W, y_lo, y_hi;
@@ -75,8 +84,8 @@ __device__ __forceinline__ int vertex_x(const double* c, int y) {
     return (int)v;                                              // truncation toward zero
 }
 
-// One CTA = one 90-row band of one frame's canvas.  planes: padded canvas u32[n][H+2][WW+1][4] = (red lo, red hi, green lo, green hi)
-// per entry (red = red without green; rows 0 and H+1 stay zero);
+// One CTA = one 90-row band of one frame's canvas.  planes: padded, interleaved canvas u64[n][H+2][2 WW + 2] (plan.py: inv_pack;
+// red = red without green; rows 0 and H+1 stay zero);
 // text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  Vertices come from the frame's fit + row maps
 // (verts == nullptr) or are given explicitly (ld_draw).  Every CTA lists all vertices (cheap, parallel) and
 // draws only the primitives whose rows can touch its band, one primitive per thread.
@@ -92,8 +101,8 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     RasterShared& R = *reinterpret_cast<RasterShared*>(s_green + RASTER_BAND * WW);
     const int f = blockIdx.y, band = blockIdx.x;
     const int y_lo = band * RASTER_BAND, y_hi = min(H, y_lo + RASTER_BAND);
-    const int CW = WW + 1;                                              // padded canvas: entries per row (see canvas_entries)
-    uint4* out_planes = reinterpret_cast<uint4*>(planes) + ((size_t)f * (H + 2) + y_lo + 1) * CW;
+    constexpr int CW = RASTER_CW;                                       // padded, interleaved canvas: 64-bit entries per row (canvas_codes)
+    uint2* out_planes = reinterpret_cast<uint2*>(planes) + ((size_t)f * (H + 2) + y_lo + 1) * CW;
     BandPlotter red{s_red, WW, W, y_lo, y_hi}, green{s_green, WW, W, y_lo, y_hi};
     const int tid = threadIdx.x;
     const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
@@ -261,14 +270,16 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     __syncthreads();
     RPROF(7);
     for (int i = tid; i < (y_hi - y_lo) * CW; i += RASTER_THREADS) {    // green overwrites red
-        // entry e of a row = the 64-bit window of pixels [32e - 32, 32e + 32) of (red without green, green): two
-        // horizontally adjacent taps always sit in one entry, including the pair (-1, 0) and (W - 1, W)
+        // entry e of a row = the 32 pixels [16e - 16, 16e + 16), (red without green, green) interleaved pixel by pixel: the two
+        // horizontally adjacent taps of any sample (including (-1, 0) and (W - 1, W)) are four consecutive bits of one entry
         const int row = i / CW, e = i - row * CW;
         const uint32_t* sr = s_red + row * WW;
         const uint32_t* sg = s_green + row * WW;
-        const uint32_t g0 = e > 0 ? sg[e - 1] : 0u, g1 = e < WW ? sg[e] : 0u;
-        const uint32_t r0 = e > 0 ? (sr[e - 1] & ~g0) : 0u, r1 = e < WW ? (sr[e] & ~g1) : 0u;
-        out_planes[i] = make_uint4(r0, r1, g0, g1);
+        const int px = 16 * e - 16, w = px >> 5;                        // px = -16, 0, 16, ...; w = -1 for the first entry
+        const uint32_t g_lo = (w >= 0 && w < WW) ? sg[w] : 0u, g_hi = (w + 1 >= 0 && w + 1 < WW) ? sg[w + 1] : 0u;
+        const uint32_t r_lo = (w >= 0 && w < WW) ? sr[w] : 0u, r_hi = (w + 1 >= 0 && w + 1 < WW) ? sr[w + 1] : 0u;
+        const uint32_t g32 = __funnelshift_r(g_lo, g_hi, px & 31), r32 = __funnelshift_r(r_lo, r_hi, px & 31) & ~g32;
+        out_planes[i] = make_uint2(spread16(r32 & 0xFFFFu) | (spread16(g32 & 0xFFFFu) << 1), spread16(r32 >> 16) | (spread16(g32 >> 16) << 1));
     }
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
     RPROF(8);
@@ -311,44 +322,30 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     for (int i = tid; i < LD_TEXT_ROWS * LD_TEXT_WORDS; i += RASTER_THREADS) out_text[i] = s_text[i];
 }
 
-// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170).  cv = this frame's PADDED canvas (plan.py: inv_pack):
-// (H + 2) x (W/32 + 1) entries, entry (r, e) = the 64-bit windows of pixels [32e - 32, 32e + 32) of canvas row r - 1 in the
-// red and in the green plane, zero outside the frame (BORDER_CONSTANT).  The two tap columns b, b + 1 of a pixel come
-// out of one entry with a funnel shift, the two tap rows are consecutive entries rows; there is no border case.
-// An inv_pack entry e is ~0 (pixel not touched by the warp) or entry index << 17 | b << 12 | fy << 5 | fx.
+// + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170).  cv = this frame's PADDED, INTERLEAVED canvas (plan.py:
+// inv_pack): (H + 2) x (W/16 + 2) 64-bit entries, entry (r, e) = the (red-without-green, green) bit pairs of the 32 pixels
+// [16e - 16, 16e + 16) of canvas row r - 1, zero outside the frame (BORDER_CONSTANT).  The two tap columns of a sample are
+// four consecutive bits of one entry (one funnel shift), the two tap rows are consecutive entry rows; no border case.
+// An inv_pack entry e is ~0 (pixel not touched by the warp) or entry index << 15 | shift << 10 | fy << 5 | fx.
 //
-// canvas_codes() fetches the taps of the four pixels a lane owns -- all eight 16-byte loads are issued back to back, and
+// canvas_codes() fetches the taps of the four pixels a lane owns -- all eight 8-byte loads are issued back to back, and
 // the caller runs it BEFORE its gather so their latency hides behind that -- and squeezes each pixel's taps into one
-// byte: red(x, x+1) | green(x, x+1) << 2 of the top tap row, the same << 4 of the bottom row.
-__device__ __forceinline__ uint32_t canvas_codes(const uint32_t (&ie)[4], const uint4* __restrict__ cv, int CW) {
-    uint4 a0[4], a1[4];
+// byte: bits 0..3 = (red, green) of tap (x, top), (x+1, top); bits 4..7 the same for the bottom tap row.
+__device__ __forceinline__ uint32_t canvas_codes(const uint32_t (&ie)[4], const uint2* __restrict__ cv, int CW) {
+    uint2 a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        a0[k] = a1[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (ie[k] != 0xFFFFFFFFu) { const uint4* p = cv + (ie[k] >> 17); a0[k] = __ldg(p); a1[k] = __ldg(p + CW); }
+        a0[k] = a1[k] = make_uint2(0u, 0u);
+        if (ie[k] != 0xFFFFFFFFu) { const uint2* p = cv + (ie[k] >> 15); a0[k] = __ldg(p); a1[k] = __ldg(p + CW); }
     }
-    // (no early exit for all-background taps here: a branch on the loaded words would make the warp wait for them
-    //  before its gather instead of after -- measured 0.34 us/frame slower)
     uint32_t codes = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t b = ie[k] >> 12;                                   // the funnel shifts use its low five bits
-        const uint32_t r0 = __funnelshift_r(a0[k].x, a0[k].y, b) & 3u, g0 = __funnelshift_r(a0[k].z, a0[k].w, b) & 3u;
-        const uint32_t r1 = __funnelshift_r(a1[k].x, a1[k].y, b) & 3u, g1 = __funnelshift_r(a1[k].z, a1[k].w, b) & 3u;
-        codes |= (r0 | (g0 << 2) | (r1 << 4) | (g1 << 6)) << (8 * k);
+        const uint32_t sh = ie[k] >> 10;                                  // the funnel shifts use its low five bits
+        const uint32_t top = __funnelshift_r(a0[k].x, a0[k].y, sh) & 15u, bot = __funnelshift_r(a1[k].x, a1[k].y, sh) & 15u;
+        codes |= (top | (bot << 4)) << (8 * k);
     }
     return codes;
-}
-
-// pull the entries canvas_codes() will read for the NEXT frame towards the SM (no registers held)
-__device__ __forceinline__ void canvas_prefetch(const uint32_t (&ie)[4], const uint4* __restrict__ cv, int CW) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (ie[k] != 0xFFFFFFFFu) {
-            const uint4* p = cv + (ie[k] >> 17);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + CW));
-        }
 }
 
 // Blend one pixel c (r | g << 8 | b << 16) whose taps are `code`.  Most pixels of the trapezoid see four equal taps (all
@@ -357,14 +354,14 @@ __device__ __forceinline__ void canvas_prefetch(const uint32_t (&ie)[4], const u
 // three canvas colours and the float32 blend of cv2.addWeighted.
 __device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, uint32_t code) {
     if (!code) return c;
-    if ((code & 0xCCu) == 0xCCu) {
+    if ((code & 0xAAu) == 0xAAu) {
         const uint32_t g = (c >> 8) & 255u;
         return (c & 0xFF00FFu) | (min(255u, g + 76u + (g & 1u)) << 8);
     }
     const int fx = e & 31, fy = (e >> 5) & 31;
     const int w00 = 32 * (32 - fy) * (32 - fx), w01 = 32 * (32 - fy) * fx, w10 = 32 * fy * (32 - fx), w11 = 32 * fy * fx;
-    const int wr = (code & 1) * w00 + ((code >> 1) & 1) * w01 + ((code >> 4) & 1) * w10 + ((code >> 5) & 1) * w11;
-    const int wg = ((code >> 2) & 1) * w00 + ((code >> 3) & 1) * w01 + ((code >> 6) & 1) * w10 + ((code >> 7) & 1) * w11;
+    const int wr = (code & 1) * w00 + ((code >> 2) & 1) * w01 + ((code >> 4) & 1) * w10 + ((code >> 6) & 1) * w11;
+    const int wg = ((code >> 1) & 1) * w00 + ((code >> 3) & 1) * w01 + ((code >> 5) & 1) * w10 + ((code >> 7) & 1) * w11;
     const uint32_t cr = (uint32_t)(wr * 200 + 16384) >> 15, cg = (uint32_t)(wg * 255 + 16384) >> 15;
     const uint32_t r = blend_u8(c & 255u, cr), g = blend_u8((c >> 8) & 255u, cg);
     return (c & 0xFF0000u) | (g << 8) | r;
@@ -521,14 +518,14 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     const RowStore rs(lane);
     const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
     const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
-    const int CW = WW + 1;                                               // padded canvas geometry (plan.py: inv_pack)
-    uint32_t cv_frame = (uint32_t)((H + 2) * CW), frame_words = (uint32_t)(fbytes / 4);   // per-frame strides (uint4 / u32 units)
+    const int CW = 2 * WW + 2;                                           // padded, interleaved canvas geometry (plan.py: inv_pack)
+    uint32_t cv_frame = (uint32_t)((H + 2) * CW), frame_words = (uint32_t)(fbytes / 4);   // per-frame strides (uint2 / u32 units)
     keep_u32(cv_frame); keep_u32(frame_words);
     // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop); everything
     // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
     // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
-    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f0 * cv_frame;
+    const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f0 * cv_frame;
     uint32_t full0 = smem_u32(&bar[0]), empty0 = smem_u32(&empty[0]);
     keep_u32(full0); keep_u32(empty0);
     __syncthreads();                                                     // barriers initialised
@@ -556,9 +553,6 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
         uint32_t codes = 0u;
         if (row_on && inv_row) {
             codes = canvas_codes(ie, cv, CW);                            // issued before the wait and the gather
-#ifdef LD_CANVAS_PREFETCH                                             // measured: 0.08 us/frame SLOWER with the prefetch
-            if (i + 1 < nf) canvas_prefetch(ie, cv + cv_frame, CW);
-#endif
         }
         uint32_t c[4];
         if (!t.slow) {
@@ -595,8 +589,8 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
     const int f = blockIdx.y;
     const uint8_t* frame = frames + (size_t)f * fbytes;
     uint8_t* out_frame = out + (size_t)f * fbytes;
-    const int CW = WW + 1;
-    const uint4* cv = reinterpret_cast<const uint4*>(planes) + (size_t)f * (H + 2) * CW;
+    const int CW = 2 * WW + 2;
+    const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * (H + 2) * CW;
     const GTile t = load_gtile(P.frame_tiles, blockIdx.x);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ngroups = t.w >> 5;

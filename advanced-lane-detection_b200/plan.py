@@ -514,16 +514,17 @@ def build_plan(variant: Variant = PROJECT, mtx=None, dist=None, size=(1280, 720)
     inv_y0, inv_y1 = (int(trows.min()), int(trows.max()) + 1) if trows.size else (0, 0)
     inv_idx = np.where(touch, ((iy + 1) << 16) | (ix + 1), 0xFFFFFFFF).astype(np.uint32)[inv_y0:inv_y1]
     inv_fi = ifi.astype(np.uint16)[inv_y0:inv_y1]
-    # Packed entry per touched pixel: canvas entry << 17 | first tap's bit << 12 | fraction; 0xFFFFFFFF = no tap inside.
-    # The canvas the kernels keep is PADDED: entry (row r, column e) holds the 64-bit window of pixels [32e - 32, 32e + 32)
-    # of canvas row r - 1, for r in [0, H + 2) and e in [0, W/32 + 1); rows 0 and H + 1 and everything outside the frame
-    # are zero (BORDER_CONSTANT).  Every tap pair (ix, ix + 1) x (iy, iy + 1) of a touched pixel (ix >= -1, iy >= -1) is
-    # then bits b, b + 1 of entries (iy + 1, (ix + 32) >> 5) and (iy + 2, ...), b = (ix + 32) & 31: one code path.
-    CW = W // 32 + 1
-    entry = ((iy + 1).astype(np.int64) * CW + ((ix + 32) >> 5))
-    packed = (entry << 17) | (((ix + 32) & 31).astype(np.int64) << 12) | ifi
-    if (H + 2) * CW >= (1 << 15):
-        packed = np.zeros_like(packed)                                # entry index would not fit 15 bits (4K): the overlay is 720p-only
+    # Packed entry per touched pixel: canvas entry << 15 | bit shift << 10 | fraction; 0xFFFFFFFF = no tap inside.
+    # The canvas the kernels keep is PADDED and INTERLEAVED: entry (row r, column e) is 64 bits holding, for the 32 pixels
+    # [16e - 16, 16e + 16) of canvas row r - 1, the pairs (red-without-green, green) -- bit 2j = red, bit 2j + 1 = green of
+    # pixel 16e - 16 + j -- for r in [0, H + 2) and e in [0, W/16 + 2); rows 0 and H + 1 and everything outside the frame are
+    # zero (BORDER_CONSTANT).  The tap pair (ix, ix + 1), ix >= -1, is the four bits 2j .. 2j + 3 of entry ((ix + 16) >> 4)
+    # with j = (ix + 16) & 15 (one funnel shift); the second tap row is the entry one row down: one code path, no border case.
+    CW = W // 16 + 2
+    entry = ((iy + 1).astype(np.int64) * CW + ((ix + 16) >> 4))
+    packed = (entry << 15) | ((2 * ((ix + 16) & 15)).astype(np.int64) << 10) | ifi
+    if (H + 2) * CW >= (1 << 16):
+        packed = np.zeros_like(packed)                                # entry index would not fit 16 bits (4K): the overlay is 720p-only
     inv_pack = np.where(~touch, 0xFFFFFFFF, packed & 0xFFFFFFFF).astype(np.uint32)[inv_y0:inv_y1]
     gb, ga = glyph_atlas()
     frame_tiles = gather_tiles(sx, sy, size, [(0, y, W, 16) for y in range(0, H, 16)], 128, fixed_stride=FRAME_BOX_PITCH)

@@ -62,7 +62,7 @@ typedef struct ld_plan_desc {
     int32_t inv_y0, inv_y1;          /* output rows the inverse warp can touch */
     const uint32_t* inv_idx;         /* [(inv_y1-inv_y0)*W] */
     const uint16_t* inv_fi;          /* [(inv_y1-inv_y0)*W] */
-    const uint32_t* inv_pack;        /* [(inv_y1-inv_y0)*W] padded-canvas entry << 17 | bit << 12 | fraction; ~0 = untouched */
+    const uint32_t* inv_pack;        /* [(inv_y1-inv_y0)*W] padded-canvas entry << 15 | bit shift << 10 | fraction; ~0 = untouched */
     const uint32_t* glyph_bits;      /* [n_glyphs*40*12] */
     const int32_t* glyph_adv;        /* [n_glyphs] */
     int32_t n_glyphs;
