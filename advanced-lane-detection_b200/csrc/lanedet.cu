@@ -32,7 +32,7 @@ static thread_local char g_cuda_err[256] = "";
 struct ld_plan {
     int device;
     PlanDev d;
-    void* allocs[32];
+    void* allocs[40];
     int n_allocs;
     size_t search_smem, raster_smem, mask_smem, frame_smem;
     int frame_box_rows;        // source rows of the largest frame-pass tile box (the TMA box height)
@@ -40,6 +40,10 @@ struct ld_plan {
     // putText pixel can fall into them) and need neither the fit nor the canvas; `overlay` tiles are the rest
     const int32_t* plain_tiles; const int32_t* overlay_tiles;
     int n_plain, n_overlay;
+    // The shared pass (process_image only): the tiles from row share_y0 down are undistorted ONCE for the mask and the
+    // overlay (k_frame_pass_mf<3> -> k_mask_b, k_blend_px); `text` tiles are the overlay tiles above share_y0 (putText).
+    const int32_t* share_tiles; const int32_t* text_tiles; const int32_t* plain_top_tiles;   // plain_top = plain tiles above share_y0
+    int n_share, n_text, n_plain_top, shared_ok;
 };
 
 enum { HOST_CHUNK = 32, PIPE_SUB = 8 };
@@ -53,6 +57,8 @@ struct ld_ctx {
     ld_frame_fit* fit;         // [max]
     uint32_t* planes;          // padded, interleaved canvas u64[max][H+2][2 WW + 2] (overlay_kernels.cuh: canvas_codes)
     uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
+    uint32_t* und_bits;        // shared pass: colour decision of the undistorted pixels, [max][H - share_y0][WW] (+ pad)
+    uint32_t* und_px;          // shared pass: the undistorted pixels in lane order, [max][n_share][16][4][32]
     TrackState* state;
     int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error
     int* flags_host;           // pinned mirror
@@ -88,7 +94,7 @@ extern "C" const char* ld_last_cuda_error(void) { return g_cuda_err; }
 template <class T>
 static int upload(ld_plan* p, const T* host, size_t count, const T** dev) {
     void* d = nullptr;
-    if (p->n_allocs >= 32) return LD_ERR_ARG;
+    if (p->n_allocs >= 40) return LD_ERR_ARG;
     LD_CUDA(cudaMalloc(&d, count * sizeof(T) + 64));
     LD_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
     p->allocs[p->n_allocs++] = d;
@@ -197,8 +203,56 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         p->n_plain = np; p->n_overlay = no;
         rc = upload(p, plain, (size_t)(np ? np : 1), &p->plain_tiles);
         if (!rc) rc = upload(p, over, (size_t)(no ? no : 1), &p->overlay_tiles);
+        // shared pass: first tile row that holds a pixel the bird's-eye warp samples or the inverse warp touches
+        int first_row = H;
+        for (int t = 0; t < desc->n_tiles; ++t)
+            if (desc->tiles[8 * t + 5] > 0 && desc->tiles[8 * t + 3] < first_row) first_row = desc->tiles[8 * t + 3];
+        if (desc->inv_y1 > desc->inv_y0 && desc->inv_y0 < first_row) first_row = desc->inv_y0;
+        d.share_y0 = first_row / 16 * 16;
+        int ns = 0, nt = 0;
+        for (int t = 0; t < desc->n_frame_tiles && !rc; ++t)
+            if (desc->frame_tiles[8 * t + 1] >= d.share_y0) plain[ns++] = t;          // (re-using the scratch arrays)
+        if (!rc) rc = upload(p, plain, (size_t)(ns ? ns : 1), &p->share_tiles);
+        for (int k = 0; k < no; ++k)
+            if (desc->frame_tiles[8 * over[k] + 1] < d.share_y0) plain[nt++] = over[k];
+        if (!rc) rc = upload(p, plain, (size_t)(nt ? nt : 1), &p->text_tiles);
+        p->n_share = ns; p->n_text = nt;
+        int npt = 0;
+        for (int t = 0; t < desc->n_frame_tiles; ++t) {                  // everything above share_y0 that is not a text tile
+            if (desc->frame_tiles[8 * t + 1] >= d.share_y0) continue;
+            bool is_text = false;
+            for (int k = 0; k < no; ++k) is_text = is_text || over[k] == t;
+            if (!is_text) plain[npt++] = t;
+        }
+        if (!rc) rc = upload(p, plain, (size_t)(npt ? npt : 1), &p->plain_top_tiles);
+        p->n_plain_top = npt;
         delete[] ids;
         if (rc) { ld_plan_destroy(p); return rc; }
+    }
+    {   // bdesc_g: bdesc with the first source bit re-based from the band's box to the und_bits plane
+        const size_t nw = (size_t)H * (W / 32);
+        uint32_t* g = new (std::nothrow) uint32_t[nw * 4];
+        if (!g) { ld_plan_destroy(p); return LD_ERR_ARG; }
+        memcpy(g, desc->bdesc, nw * 16);
+        bool ok = W == 1280 && H == 720 && p->n_share > 0;
+        for (int t = 0; t < desc->n_tiles; ++t) {
+            const int y0 = desc->tiles[8 * t], y1 = desc->tiles[8 * t + 1], u0 = desc->tiles[8 * t + 2], v0 = desc->tiles[8 * t + 3];
+            const int pitch = desc->tiles[8 * t + 4] * 32;
+            for (size_t wi = (size_t)y0 * (W / 32); wi < (size_t)y1 * (W / 32); ++wi) {
+                uint32_t& first = g[4 * wi];
+                if (first == 0xFFFFFFFFu) continue;                      // border word
+                if (first == 0xFFFFFFFEu || pitch <= 0) { ok = false; continue; }   // general homography: only the fused k_mask handles it
+                const int ny = v0 + (int)(first / (uint32_t)pitch), nx = u0 + (int)(first % (uint32_t)pitch);
+                if (ny < d.share_y0) { ok = false; continue; }
+                first = (uint32_t)((ny - d.share_y0) * W + nx);
+            }
+        }
+        const uint32_t* gd = nullptr;
+        rc = upload(p, g, nw * 4, &gd);
+        delete[] g;
+        if (rc) { ld_plan_destroy(p); return rc; }
+        d.bdesc_g = reinterpret_cast<const uint4*>(gd);
+        p->shared_ok = ok ? 1 : 0;
     }
     int mow = 0;
     for (int t = 0; t < desc->n_tiles; ++t) {
@@ -217,6 +271,8 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
     // carveout, otherwise an SM has to drain before a kernel with a different carveout can start on it.
     LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -270,6 +326,10 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     CTX_ALLOC(c->fit, sizeof(ld_frame_fit) * max_frames);
     CTX_ALLOC(c->planes, canvas_words(d) * 4 * max_frames);
     CTX_ALLOC(c->text, (size_t)LD_TEXT_ROWS * LD_TEXT_WORDS * 4 * max_frames);
+    if (plan->shared_ok) {
+        CTX_ALLOC(c->und_bits, (size_t)(d.H - d.share_y0) * d.WW * 4 * max_frames + 64);
+        CTX_ALLOC(c->und_px, (size_t)plan->n_share * 16 * 128 * 4 * max_frames);
+    }
     CTX_ALLOC(c->state, sizeof(TrackState));
     CTX_ALLOC(c->flags, 16 * sizeof(int));
     for (int b = 0; b < 2; ++b) {
@@ -313,7 +373,7 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     cudaSetDevice(c->plan->device);
     cudaDeviceSynchronize();
     cudaFree(c->mask); cudaFree(c->rec); cudaFree(c->work); cudaFree(c->fit); cudaFree(c->planes);
-    cudaFree(c->text); cudaFree(c->state); cudaFree(c->flags);
+    cudaFree(c->text); cudaFree(c->und_bits); cudaFree(c->und_px); cudaFree(c->state); cudaFree(c->flags);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->stage_in[b]); cudaFree(c->stage_out[b]);
         if (c->ev_in[b]) cudaEventDestroy(c->ev_in[b]);
@@ -447,7 +507,9 @@ static int frames_per_cta(int m) {
     const int f = m / 8;
     return f < 1 ? 1 : (f > FRAME_FPC ? FRAME_FPC : f);
 }
-// which = 0: every tile with blend + text; 1: the plain tiles as cv2.undistort; 2: the overlay tiles with blend + text
+// which = 0: every tile with blend + text; 1: the plain tiles as cv2.undistort; 2: the overlay tiles with blend + text;
+// 3: the shared pass over the share tiles (undistorted pixels -> c->und_px, their colour bits -> c->und_bits; fout unused);
+// 4: the text tiles (overlay tiles above share_y0) with blend + text; 5: the plain tiles above share_y0 as cv2.undistort
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted,
                              int which = 0) {
     const PlanDev& d = c->plan->d;
@@ -465,14 +527,26 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
         if (which == 1) {
             if (c->plan->n_plain)
                 k_frame_pass_mf<0><<<dim3(c->plan->n_plain, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_tiles);
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_tiles, nullptr, nullptr);
         } else if (which == 2) {
             if (c->plan->n_overlay)
                 k_frame_pass_mf<1><<<dim3(c->plan->n_overlay, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->overlay_tiles);
+                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->overlay_tiles, nullptr, nullptr);
+        } else if (which == 3) {
+            k_frame_pass_mf<3><<<dim3(c->plan->n_share, groups.y), FRAME_MF_THREADS, c->plan->frame_smem + MASK_PRE_WORDS * 4, s>>>(
+                tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->share_tiles,
+                c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, c->und_px + (size_t)slot * c->plan->n_share * 16 * 128);
+        } else if (which == 5) {
+            if (c->plan->n_plain_top)
+                k_frame_pass_mf<0><<<dim3(c->plan->n_plain_top, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_top_tiles, nullptr, nullptr);
+        } else if (which == 4) {
+            if (c->plan->n_text)
+                k_frame_pass_mf<1><<<dim3(c->plan->n_text, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
+                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->text_tiles, nullptr, nullptr);
         } else
             k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, nullptr);
+                tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, nullptr, nullptr, nullptr);
     }
     return check_launch();
 }
@@ -551,7 +625,13 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
     const int nsub = sub_batches(M);
     int rc;
     if (nsub < 2) {
-        if ((rc = ld_mask(c, fin, M, c->mask, s))) return rc;
+        if (c->plan->shared_ok) {
+            // shared pass: undistort the tiles under share_y0 once (pixels -> und_px, colour bits -> und_bits), then pick the
+            // mask out of the bit plane; the overlay later blends the canvas onto und_px instead of gathering again
+            if ((rc = launch_frame_pass(c, fin, M, nullptr, s, 0, 0, 3))) return rc;
+            k_mask_b<<<dim3(d.n_tiles, M), MASK_THREADS, (size_t)d.max_out_words * 2 + 16, s>>>(c->und_bits, c->mask, d);
+            if ((rc = check_launch())) return rc;
+        } else if ((rc = ld_mask(c, fin, M, c->mask, s))) return rc;
         return ld_search(c, c->mask, M, c->rec, s);
     }
     const int S = (M + nsub - 1) / nsub;
@@ -585,8 +665,13 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
         LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
         if ((rc = launch_raster(c, c->fit, nullptr, nullptr, 0, 30, M, c->s_lat, 0))) return rc;
-        if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, 1))) return rc;
-        if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
+        if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, (c->plan->shared_ok && !search_first) ? 5 : 1))) return rc;
+        if (c->plan->shared_ok && !search_first) {
+            // the shared pass of ld_prepass left the undistorted pixels of the share tiles in und_px: blend, do not gather again
+            k_blend_px<<<dim3(c->plan->n_share, M), FRAME_THREADS, 0, c->s_lat>>>(c->und_px, c->planes, fout, d, c->plan->share_tiles);
+            if ((rc = check_launch())) return rc;
+            if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 4))) return rc;
+        } else if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
         LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));
         LD_CUDA(cudaStreamWaitEvent(s, c->ev_join[1], 0));
     } else {
@@ -618,7 +703,7 @@ static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, l
     int rc;
     for (int base = 0; base < n; base += c->max_frames) {
         const int M = (n - base) < c->max_frames ? (n - base) : c->max_frames;
-        if (sub_batches(M) < 2) {                                        // mask, then everything else overlapped (postpass_impl)
+        if (sub_batches(M) < 2 && !c->plan->shared_ok) {                 // mask, then everything else overlapped (postpass_impl)
             if ((rc = ld_mask(c, frames + base * fb, M, c->mask, s))) return rc;
             if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
                                     frame_offset + base, 1))) return rc;
@@ -733,7 +818,7 @@ extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* ou
     int rc;
     if ((rc = frame_tensor_map(c->plan, frames, n, &tm))) return rc;
     k_frame_pass_mf<0><<<dim3(d.n_frame_tiles, (n + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(
-        tm, frames, nullptr, nullptr, out, d, n, fpc, c->plan->frame_box_rows, nullptr);
+        tm, frames, nullptr, nullptr, out, d, n, fpc, c->plan->frame_box_rows, nullptr, nullptr, nullptr);
     return check_launch();
 }
 extern "C" int ld_warp(ld_ctx* c, const uint8_t* img, int n, int channels, uint8_t* out, void* stream) {

@@ -227,6 +227,76 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
     }
 }
 
+// ============================ K1b: the mask out of the shared pass's bit plane ========================
+// Inside process_image the undistorted pixels under plan.share_y0 are computed ONCE (k_frame_pass_mf<3>,
+// overlay_kernels.cuh) for both the mask and the overlay; their colour decisions land in und_bits
+// (u32[n][H - share_y0][W/32]).  This kernel is k_mask's phase B over that plane: per OUTPUT WORD a 64-bit window
+// (plan.bdesc_g: first source bit as a global index) is cut out and expanded.  One CTA = one band of one frame.
+__global__ void __launch_bounds__(MASK_THREADS)
+k_mask_b(const uint32_t* __restrict__ und_bits, uint32_t* __restrict__ mask, const PlanDev P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int n_jobs;
+    uint16_t* s_job = reinterpret_cast<uint16_t*>(smem_raw);
+    const int tile = blockIdx.x, f = blockIdx.y;
+    const int4 t0 = P.tiles[2 * tile];
+    const int y0 = t0.x, y1 = t0.y;
+    const uint32_t* bits = und_bits + (size_t)f * (P.H - P.share_y0) * P.WW;
+    if (threadIdx.x == 0) n_jobs = 0;
+    __syncthreads();
+    const int out_words = (y1 - y0) * P.WW;
+    uint32_t* out = mask + ((size_t)f * P.H + y0) * P.WW;
+    const uint4* bd = P.bdesc_g + (size_t)y0 * P.WW;
+#pragma unroll 2
+    for (int wi = threadIdx.x; wi < out_words; wi += MASK_THREADS) {
+        const uint4 d = __ldg(bd + wi);
+        uint32_t o = 0;
+        bool job = false;
+        if (d.x != BDESC_BORDER) {
+            const uint32_t* p = bits + (d.x >> 5);
+            const uint32_t sh = d.x & 31;
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+            const int span = __popc(d.y) + __popc(d.z) + 1;                          // source bits the word reads (<= 63)
+            const uint32_t mlo = span >= 32 ? 0xFFFFFFFFu : (1u << span) - 1u;
+            const uint32_t mhi = span <= 32 ? 0u : (1u << (span - 32)) - 1u;
+            lo &= mlo; hi &= mhi;
+            if ((lo | hi) == 0u) o = 0u;
+            else if (lo == mlo && hi == mhi) o = d.w;
+            else job = true;
+        }
+        if (job) s_job[atomicAdd(&n_jobs, 1)] = (uint16_t)wi;
+        else out[wi] = o;
+    }
+    __syncthreads();
+    const int nj = n_jobs;
+    for (int k = threadIdx.x; k < nj; k += MASK_THREADS) {
+        const int wi = s_job[k];
+        const uint4 d = __ldg(bd + wi);
+        const uint32_t* p = bits + (d.x >> 5);
+        const uint32_t sh = d.x & 31;
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh), o = 0;
+        if (d.z == 0u) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                o = __funnelshift_r(o, lo, 1);             // append source bit 0 at the top; after 32 steps bit i = pixel i
+                const uint32_t st = (d.y >> i) & 1u;
+                lo = __funnelshift_r(lo, hi, st);
+                hi >>= st;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                o = __funnelshift_r(o, lo, 1);
+                const uint32_t st = ((d.y >> i) & 1u) + ((d.z >> i) & 1u);
+                lo = __funnelshift_r(lo, hi, st);
+                hi >>= st;
+            }
+        }
+        out[wi] = o & d.w;
+    }
+}
+
 // ============================ K2: column histogram of the eight 90-row bands ========================
 // np.sum(image[win_top:win_bottom, :], axis=0) (Project.py:83).  A warp owns a 32-column word
 // column of one band: lane r holds the mask word of row r, bit b of all 32 rows is gathered with

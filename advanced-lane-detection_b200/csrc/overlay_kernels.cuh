@@ -12,6 +12,7 @@
 #include "fit_math.h"
 #include "gather.cuh"
 #include "raster_math.h"
+#include "mask_kernels.cuh"                        // colour_on_pre (the shared pass decides the mask colours)
 #include <cuda.h>                                // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 
 namespace lanedet {
@@ -465,7 +466,11 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
 // offsets -- is decoded once into registers; per frame the CTA only stages the source box (TMA bulk row copies, double
 // buffered: frame i+1 lands while frame i is computed), gathers, blends and stores.
 // MODE 0: cv2.undistort only (helper.py:35-47; and, inside process_image, the tiles neither the inverse warp nor putText
-// can touch); MODE 1: undistort + canvas blend + text (process_image).
+// can touch); MODE 1: undistort + canvas blend + text (process_image); MODE 3: the SHARED pass of process_image over the
+// tiles below plan.share_y0 -- the undistorted pixels are needed twice there, by the mask (every bird's-eye pixel is a copy
+// of one of them) and by the overlay, so they are computed once: their colour decision goes to a bit plane (und_bits,
+// k_mask_b picks the mask out of it) and the pixels themselves to a scratch buffer in lane order (und_px, k_blend_px adds
+// the canvas later).
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
 #ifndef LD_FRAME_STAGES
 #define LD_FRAME_STAGES 4
@@ -477,7 +482,7 @@ template <int MODE>
 __global__ void __launch_bounds__(FRAME_MF_THREADS, 2)
 k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes,
                 const uint32_t* __restrict__ text, uint8_t* __restrict__ out, const PlanDev P, int n, int fpc, int box_rows,
-                const int32_t* __restrict__ tile_ids) {
+                const int32_t* __restrict__ tile_ids, uint32_t* __restrict__ und_bits, uint32_t* __restrict__ und_px) {
     extern __shared__ __align__(128) uint8_t s_boxes[];
     __shared__ __align__(8) uint64_t bar[FRAME_STAGES], empty[FRAME_STAGES];     // box landed / box released by all warps
     const int W = P.W, H = P.H, WW = P.WW;
@@ -494,6 +499,10 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     const uint32_t box_bytes = (uint32_t)(box_rows * FRAME_BOX_PITCH);   // a multiple of 512
     uint32_t box0 = (smem_u32(s_boxes) + 127u) & ~127u;
     keep_u32(box0);
+    // MODE 3: the colour pre-decision table sits behind the ring of boxes
+    const uint32_t* s_pre = reinterpret_cast<const uint32_t*>(s_boxes + (box0 - smem_u32(s_boxes)) + FRAME_STAGES * box_bytes);
+    if (MODE == 3)
+        for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += FRAME_MF_THREADS) const_cast<uint32_t*>(s_pre)[i] = __ldg(P.cpre + i);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < FRAME_STAGES; ++b) { mbar_init(&bar[b], 1); mbar_init(&empty[b], FRAME_MF_THREADS / 32); }
@@ -512,9 +521,9 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             po[k] = (o & ~3u) | (o << 30);
         }
     }
-    if (MODE != 0) load_inv4(ie, ngroups, t.x0, y, lane, P);
+    if (MODE == 1) load_inv4(ie, ngroups, t.x0, y, lane, P);
     else { ie[0] = ie[1] = ie[2] = ie[3] = 0xFFFFFFFFu; }
-    const bool inv_row = MODE != 0 && __any_sync(0xffffffffu, (ie[0] & ie[1] & ie[2] & ie[3]) != 0xFFFFFFFFu);   // warp-uniform
+    const bool inv_row = MODE == 1 && __any_sync(0xffffffffu, (ie[0] & ie[1] & ie[2] & ie[3]) != 0xFFFFFFFFu);   // warp-uniform
     const RowStore rs(lane);
     const int tw0 = (t.x0 - LD_TEXT_X0) >> 5;
     const bool text_row = MODE == 1 && row_on && y >= LD_TEXT_Y0 && y < LD_TEXT_Y0 + LD_TEXT_ROWS && tw0 + 3 >= 0 && tw0 < LD_TEXT_WORDS;
@@ -525,6 +534,12 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
     // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
+    if (MODE == 3) {
+        // und_px: u32[n][share tiles][16 rows][4][32] (pixel l + 32k of the row at [k][l]); und_bits: u32[n][H - share_y0][WW]
+        frame_words = gridDim.x * 16u * 128u;
+        orow = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + r * 128 + lane;
+        und_bits += (size_t)f0 * (H - P.share_y0) * WW + (size_t)(y - P.share_y0) * WW + (t.x0 >> 5);
+    }
     const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f0 * cv_frame;
     uint32_t full0 = smem_u32(&bar[0]), empty0 = smem_u32(&empty[0]);
     keep_u32(full0); keep_u32(empty0);
@@ -571,11 +586,48 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             for (int k = 0; k < 4; ++k)
                 c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
         }
-        if (row_on)
+        if (MODE == 3) {
+            if (row_on) {
+                uint32_t words[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    words[k] = __ballot_sync(0xffffffffu, k < ngroups && colour_on_pre(c[k], s_pre, P.ctab, P.cbits));
+                    if (k < ngroups) orow[32 * k] = c[k];
+                }
+                if (lane < ngroups) und_bits[lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
+            }
+            und_bits += (size_t)(H - P.share_y0) * WW;
+        } else if (row_on)
             finish_row<MODE>(c, ie, codes, ngroups, lane, text_row ? text : nullptr,
                              ((size_t)(f0 + i) * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS, tw0, orow, rs);
         orow += frame_words;                                             // W % 32 == 0: a frame is a whole number of words
         cv += cv_frame;
+    }
+}
+
+// Second half of the shared pass: the undistorted pixels of a share tile come back from und_px (lane order, one u32 per
+// pixel), get the canvas blend and go out as packed RGB.  One CTA = one tile of one frame, warp w = rows w, w + 8.
+__global__ void __launch_bounds__(FRAME_THREADS)
+k_blend_px(const uint32_t* __restrict__ und_px, const uint32_t* __restrict__ planes, uint8_t* __restrict__ out, const PlanDev P,
+           const int32_t* __restrict__ tile_ids) {
+    const int W = P.W, H = P.H, WW = P.WW;
+    const int f = blockIdx.y;
+    uint8_t* out_frame = out + (size_t)f * W * H * 3;
+    const int CW = 2 * WW + 2;
+    const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * (H + 2) * CW;
+    const GTile t = load_gtile(P.frame_tiles, __ldg(tile_ids + blockIdx.x));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ngroups = t.w >> 5;
+    const RowStore rs(lane);
+    const uint32_t* px = und_px + ((size_t)f * gridDim.x + blockIdx.x) * (16u * 128u);
+    for (int r = warp; r < t.h; r += FRAME_THREADS / 32) {
+        const int y = t.y0 + r;
+        uint32_t c[4], ie[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = k < ngroups ? __ldg(px + r * 128 + 32 * k + lane) : 0u;
+        load_inv4(ie, ngroups, t.x0, y, lane, P);
+        finish_row<2>(c, ie, canvas_codes(ie, cv, CW), ngroups, lane, nullptr, 0, 0,
+                      reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs);
     }
 }
 
