@@ -37,6 +37,7 @@ struct PlanDev {
     const uint4* bdesc;              // per output mask word: (first source bit | BORDER | FALLBACK, step1, step2, valid)
     int max_out_words;
     int share_y0;                    // first row of the tiles whose undistorted pixels both the mask and the overlay need (multiple of 16)
+    const uint8_t* share_groups;     // [(H - share_y0)][W/128]: bit k = the row's 32-pixel group k of that 128-column tile holds a sampled pixel
     const uint4* bdesc_g;            // bdesc with the first source bit as an index into und_bits ((ny - share_y0) * W + nx)
     int mask_box_bytes;              // shared-memory bytes of the largest mask chunk box, rounded up to 128
 };

@@ -252,6 +252,21 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         delete[] g;
         if (rc) { ld_plan_destroy(p); return rc; }
         d.bdesc_g = reinterpret_cast<const uint4*>(gd);
+        // which 32-pixel groups of the share rows hold a pixel the bird's-eye warp samples (only those need a colour decision)
+        const int srows = H - d.share_y0, tcols = (W + 127) / 128;
+        uint8_t* sg = new (std::nothrow) uint8_t[(size_t)(srows > 0 ? srows : 1) * tcols];
+        if (!sg) { ld_plan_destroy(p); return LD_ERR_ARG; }
+        memset(sg, 0, (size_t)(srows > 0 ? srows : 1) * tcols);
+        for (size_t i = 0; i < npix; ++i) {
+            const int32_t sidx = desc->near_map[i];
+            if (sidx < 0) continue;
+            const int ny = sidx / W, nx = sidx % W;
+            if (ny < d.share_y0) { ok = false; continue; }
+            sg[(size_t)(ny - d.share_y0) * tcols + (nx >> 7)] |= (uint8_t)(1u << ((nx >> 5) & 3));
+        }
+        rc = upload(p, sg, (size_t)(srows > 0 ? srows : 1) * tcols, &d.share_groups);
+        delete[] sg;
+        if (rc) { ld_plan_destroy(p); return rc; }
         p->shared_ok = ok ? 1 : 0;
     }
     int mow = 0;
@@ -668,7 +683,9 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, (c->plan->shared_ok && !search_first) ? 5 : 1))) return rc;
         if (c->plan->shared_ok && !search_first) {
             // the shared pass of ld_prepass left the undistorted pixels of the share tiles in und_px: blend, do not gather again
-            k_blend_px<<<dim3(c->plan->n_share, M), FRAME_THREADS, 0, c->s_lat>>>(c->und_px, c->planes, fout, d, c->plan->share_tiles);
+            const int bf = frames_per_cta(M);
+            k_blend_px<<<dim3(c->plan->n_share, (M + bf - 1) / bf), FRAME_THREADS, 0, c->s_lat>>>(c->und_px, c->planes, fout, d,
+                                                                                                 c->plan->share_tiles, M, bf);
             if ((rc = check_launch())) return rc;
             if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 4))) return rc;
         } else if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;

@@ -534,7 +534,9 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
     // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
+    uint32_t gmask = 0;                                                  // MODE 3: which 32-pixel groups of the row hold a pixel the bird's-eye warp samples
     if (MODE == 3) {
+        if (row_on) gmask = __ldg(P.share_groups + (size_t)(y - P.share_y0) * (W / 128) + (t.x0 >> 7));
         // und_px: u32[n][share tiles][16 rows][4][32] (pixel l + 32k of the row at [k][l]); und_bits: u32[n][H - share_y0][WW]
         frame_words = gridDim.x * 16u * 128u;
         orow = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + r * 128 + lane;
@@ -591,7 +593,8 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
                 uint32_t words[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    words[k] = __ballot_sync(0xffffffffu, k < ngroups && colour_on_pre(c[k], s_pre, P.ctab, P.cbits));
+                    words[k] = 0u;
+                    if ((gmask >> k) & 1u) words[k] = __ballot_sync(0xffffffffu, colour_on_pre(c[k], s_pre, P.ctab, P.cbits));   // warp-uniform
                     if (k < ngroups) orow[32 * k] = c[k];
                 }
                 if (lane < ngroups) und_bits[lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
@@ -606,28 +609,46 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
 }
 
 // Second half of the shared pass: the undistorted pixels of a share tile come back from und_px (lane order, one u32 per
-// pixel), get the canvas blend and go out as packed RGB.  One CTA = one tile of one frame, warp w = rows w, w + 8.
+// pixel), get the canvas blend and go out as packed RGB.  One CTA = one tile of up to `fpc` consecutive frames, warp w =
+// rows w, w + 8; the inverse-warp entries of the thread's pixels are loaded once per CTA.
 __global__ void __launch_bounds__(FRAME_THREADS)
 k_blend_px(const uint32_t* __restrict__ und_px, const uint32_t* __restrict__ planes, uint8_t* __restrict__ out, const PlanDev P,
-           const int32_t* __restrict__ tile_ids) {
+           const int32_t* __restrict__ tile_ids, int n, int fpc) {
     const int W = P.W, H = P.H, WW = P.WW;
-    const int f = blockIdx.y;
-    uint8_t* out_frame = out + (size_t)f * W * H * 3;
+    const int f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
     const int CW = 2 * WW + 2;
-    const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f * (H + 2) * CW;
     const GTile t = load_gtile(P.frame_tiles, __ldg(tile_ids + blockIdx.x));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    keep_s32(lane);
+    const int warp = threadIdx.x >> 5;
     const int ngroups = t.w >> 5;
     const RowStore rs(lane);
-    const uint32_t* px = und_px + ((size_t)f * gridDim.x + blockIdx.x) * (16u * 128u);
-    for (int r = warp; r < t.h; r += FRAME_THREADS / 32) {
-        const int y = t.y0 + r;
-        uint32_t c[4], ie[4];
+    uint32_t ie[2][4];
+    bool inv_row[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c[k] = k < ngroups ? __ldg(px + r * 128 + 32 * k + lane) : 0u;
-        load_inv4(ie, ngroups, t.x0, y, lane, P);
-        finish_row<2>(c, ie, canvas_codes(ie, cv, CW), ngroups, lane, nullptr, 0, 0,
-                      reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs);
+    for (int j = 0; j < 2; ++j) {
+        const int r = warp + 8 * j;
+        load_inv4(ie[j], r < t.h ? ngroups : 0, t.x0, t.y0 + r, lane, P);
+        inv_row[j] = __any_sync(0xffffffffu, (ie[j][0] & ie[j][1] & ie[j][2] & ie[j][3]) != 0xFFFFFFFFu);
+    }
+    uint32_t frame_words = (uint32_t)((size_t)W * H * 3 / 4), cv_frame = (uint32_t)((H + 2) * CW), px_frame = gridDim.x * 16u * 128u;
+    keep_u32(frame_words); keep_u32(cv_frame); keep_u32(px_frame);
+    const uint32_t* px = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + warp * 128 + lane;
+    const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f0 * cv_frame;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * W * H * 3 + ((size_t)(t.y0 + warp) * W + t.x0) * 3) + lane;
+    for (int i = 0; i < nf; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (warp + 8 * j >= t.h) continue;                           // warp-uniform
+            const uint32_t codes = inv_row[j] ? canvas_codes(ie[j], cv, CW) : 0u;
+            uint32_t c[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] = k < ngroups ? __ldg(px + j * (8 * 128) + 32 * k) : 0u;
+            finish_row<2>(c, ie[j], codes, ngroups, lane, nullptr, 0, 0, orow + (size_t)j * 8 * (W * 3 / 4), rs);
+        }
+        px += px_frame;
+        cv += cv_frame;
+        orow += frame_words;
     }
 }
 
