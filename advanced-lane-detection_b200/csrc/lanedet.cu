@@ -409,6 +409,29 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     return LD_OK;
 }
 
+// LD_TIMELINE=1: CUDA events around every stage of prepass / postpass, printed by ld_check (tuning aid)
+static int g_timeline = -1;
+static cudaEvent_t g_tl_ev[16];
+static const char* g_tl_name[16];
+static int g_tl_n = 0;
+static void tl_mark(const char* name, cudaStream_t s) {
+    if (g_timeline < 0) { const char* e = getenv("LD_TIMELINE"); g_timeline = e ? atoi(e) : 0; }
+    if (!g_timeline || g_tl_n >= 16) return;
+    if (!g_tl_ev[g_tl_n]) cudaEventCreate(&g_tl_ev[g_tl_n]);
+    cudaEventRecord(g_tl_ev[g_tl_n], s);
+    g_tl_name[g_tl_n++] = name;
+}
+static void tl_print() {
+    if (g_timeline <= 0 || g_tl_n < 2) { g_tl_n = 0; return; }
+    cudaDeviceSynchronize();
+    for (int i = 1; i < g_tl_n; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_tl_ev[0], g_tl_ev[i]);
+        fprintf(stderr, "[timeline] %-22s +%8.3f ms\n", g_tl_name[i], ms);
+    }
+    g_tl_n = 0;
+}
+
 static inline int check_launch() {
     LD_CUDA(cudaGetLastError());
     return LD_OK;
@@ -598,6 +621,36 @@ extern "C" int ld_frame_pass(ld_ctx* c, const uint8_t* frames, int n, uint8_t* o
     return n ? launch_frame_pass(c, frames, n, out, (cudaStream_t)stream, 0, 0) : LD_OK;
 }
 
+// The launches ld_process_batch is made of, one at a time (measurement / profiling of the real step):
+// which = 3 shared pass (frames -> und_px, und_bits), 7 k_mask_b (und_bits -> the context's mask), 5 plain tiles above
+// share_y0 (frames -> out), 6 k_blend_px (und_px + canvas -> out), 4 text tiles (frames + canvas + text -> out).
+extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint8_t* out, void* stream) {
+    if (!c || n < 0 || n > c->max_frames || !c->plan->shared_ok) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (which == 3 || which == 4 || which == 5) {
+        if (!frames || (which != 3 && !out)) return LD_ERR_ARG;
+        return launch_frame_pass(c, frames, n, out, s, 0, 0, which);
+    }
+    if (which == 7) {
+        k_mask_b<<<dim3(d.n_tiles, n), MASK_THREADS, (size_t)d.max_out_words * 2 + 16, s>>>(c->und_bits, c->mask, d);
+        return check_launch();
+    }
+    if (which == 6) {
+        if (!out) return LD_ERR_ARG;
+        const int bf = frames_per_cta(n);
+        k_blend_px<<<dim3(c->plan->n_share, (n + bf - 1) / bf), FRAME_THREADS, 0, s>>>(c->und_px, c->planes, out, d, c->plan->share_tiles, n, bf);
+        return check_launch();
+    }
+    return LD_ERR_ARG;
+}
+extern "C" const uint32_t* ld_ctx_mask(ld_ctx* c) { return c ? c->mask : nullptr; }   // the context's packed masks (device), [max_frames][H][W/32]
+extern "C" int ld_stage_tiles(ld_ctx* c, int which) {                   // tiles a stage covers (for byte accounting)
+    if (!c) return -1;
+    return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? c->plan->n_text : which == 5 ? c->plan->n_plain_top : -1;
+}
+
 extern "C" int ld_draw(ld_ctx* c, const uint8_t* undist, const int32_t* verts, const int32_t* counts, int max_verts,
                        int thickness, int n, uint8_t* out, void* stream) {
     if (!ARGS_OK(c, undist, out, n) || !verts || !counts || max_verts < 0 || thickness < 0 || thickness > 30 || (thickness & 1))
@@ -640,14 +693,19 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
     const int nsub = sub_batches(M);
     int rc;
     if (nsub < 2) {
+        tl_mark("start", s);
         if (c->plan->shared_ok) {
             // shared pass: undistort the tiles under share_y0 once (pixels -> und_px, colour bits -> und_bits), then pick the
             // mask out of the bit plane; the overlay later blends the canvas onto und_px instead of gathering again
             if ((rc = launch_frame_pass(c, fin, M, nullptr, s, 0, 0, 3))) return rc;
+            tl_mark("shared pass", s);
             k_mask_b<<<dim3(d.n_tiles, M), MASK_THREADS, (size_t)d.max_out_words * 2 + 16, s>>>(c->und_bits, c->mask, d);
             if ((rc = check_launch())) return rc;
+            tl_mark("mask_b", s);
         } else if ((rc = ld_mask(c, fin, M, c->mask, s))) return rc;
-        return ld_search(c, c->mask, M, c->rec, s);
+        rc = ld_search(c, c->mask, M, c->rec, s);
+        tl_mark("search", s);
+        return rc;
     }
     const int S = (M + nsub - 1) / nsub;
     if ((rc = fork_streams(c, s))) return rc;
@@ -679,15 +737,20 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset))) return rc;
         if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
         LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
+        tl_mark("fit (s_lat)", c->s_lat);
         if ((rc = launch_raster(c, c->fit, nullptr, nullptr, 0, 30, M, c->s_lat, 0))) return rc;
+        tl_mark("raster (s_lat)", c->s_lat);
         if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, (c->plan->shared_ok && !search_first) ? 5 : 1))) return rc;
+        tl_mark("plain tiles (s)", s);
         if (c->plan->shared_ok && !search_first) {
             // the shared pass of ld_prepass left the undistorted pixels of the share tiles in und_px: blend, do not gather again
             const int bf = frames_per_cta(M);
             k_blend_px<<<dim3(c->plan->n_share, (M + bf - 1) / bf), FRAME_THREADS, 0, c->s_lat>>>(c->und_px, c->planes, fout, d,
                                                                                                  c->plan->share_tiles, M, bf);
             if ((rc = check_launch())) return rc;
+            tl_mark("blend_px (s_lat)", c->s_lat);
             if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 4))) return rc;
+            tl_mark("text tiles (s_lat)", c->s_lat);
         } else if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
         LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));
         LD_CUDA(cudaStreamWaitEvent(s, c->ev_join[1], 0));
@@ -753,6 +816,7 @@ extern "C" int ld_process_batch(ld_ctx* c, const uint8_t* frames, int n, uint8_t
 
 extern "C" int ld_check(ld_ctx* c, void* stream, int* first_bad_frame) {
     if (!c) return LD_ERR_ARG;
+    tl_print();
     cudaStream_t s = (cudaStream_t)stream;
     LD_CUDA(cudaMemcpyAsync(c->flags_host, c->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     LD_CUDA(cudaStreamSynchronize(s));

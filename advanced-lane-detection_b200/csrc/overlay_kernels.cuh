@@ -611,7 +611,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
 // Second half of the shared pass: the undistorted pixels of a share tile come back from und_px (lane order, one u32 per
 // pixel), get the canvas blend and go out as packed RGB.  One CTA = one tile of up to `fpc` consecutive frames, warp w =
 // rows w, w + 8; the inverse-warp entries of the thread's pixels are loaded once per CTA.
-__global__ void __launch_bounds__(FRAME_THREADS)
+__global__ void __launch_bounds__(FRAME_THREADS, 4)
 k_blend_px(const uint32_t* __restrict__ und_px, const uint32_t* __restrict__ planes, uint8_t* __restrict__ out, const PlanDev P,
            const int32_t* __restrict__ tile_ids, int n, int fpc) {
     const int W = P.W, H = P.H, WW = P.WW;
@@ -636,17 +636,32 @@ k_blend_px(const uint32_t* __restrict__ und_px, const uint32_t* __restrict__ pla
     const uint32_t* px = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + warp * 128 + lane;
     const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f0 * cv_frame;
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * W * H * 3 + ((size_t)(t.y0 + warp) * W + t.x0) * 3) + lane;
+    // the pixels of the next frame are fetched while the current one is blended (the kernel is a load -> blend -> store chain
+    // with little else to hide the HBM latency behind)
+    uint32_t nx[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nx[j][k] = (k < ngroups && warp + 8 * j < t.h && nf > 0) ? __ldg(px + j * (8 * 128) + 32 * k) : 0u;
     for (int i = 0; i < nf; ++i) {
+        uint32_t cur[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cur[j][k] = nx[j][k];
+        px += px_frame;
+        if (i + 1 < nf) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k < ngroups && warp + 8 * j < t.h) nx[j][k] = __ldg(px + j * (8 * 128) + 32 * k);
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             if (warp + 8 * j >= t.h) continue;                           // warp-uniform
             const uint32_t codes = inv_row[j] ? canvas_codes(ie[j], cv, CW) : 0u;
-            uint32_t c[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) c[k] = k < ngroups ? __ldg(px + j * (8 * 128) + 32 * k) : 0u;
-            finish_row<2>(c, ie[j], codes, ngroups, lane, nullptr, 0, 0, orow + (size_t)j * 8 * (W * 3 / 4), rs);
+            finish_row<2>(cur[j], ie[j], codes, ngroups, lane, nullptr, 0, 0, orow + (size_t)j * 8 * (W * 3 / 4), rs);
         }
-        px += px_frame;
         cv += cv_frame;
         orow += frame_words;
     }

@@ -163,6 +163,18 @@ class LaneEngine:
         frames = self._frames(frames)
         _abi.check(self.lib, self.lib.ld_prepass(self._ctx_h, _ptr(frames), frames.shape[0], self._stream()))
 
+    def context_masks(self, n):
+        """copy of the packed masks the last prepass / process call left in the context: int32[n, H, W/32] (device)"""
+        out = self._dev((n, self.H, self.WW), self.torch.int32)
+        src = self.lib.ld_ctx_mask(self._ctx_h)
+        # wrap the raw device pointer through the CUDA array interface
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (n, self.H, self.WW), "typestr": "<i4", "data": (int(src), False), "version": 3}
+        out.copy_(self.torch.as_tensor(raw, device="cuda:%d" % self.device))
+        return out
+
     def postpass_dev(self, frames, out=None, fits=None, state_out=None):
         """fit (tracker order!) + overlay of the range given to prepass_dev; state_out = CUDA uint8 blob or None"""
         frames = self._frames(frames)

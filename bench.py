@@ -252,7 +252,8 @@ def main():
         else:
             sharding.process_sharded(eng, frames, rank, world, out=out)
 
-    launches_per_step = 1 + 4 + 5                        # state reset; k_mask, k_search, k_raster, k_frame_pass_mf; 5 fit kernels
+    # state reset; shared pass, k_mask_b, k_search; 5 fit kernels; k_raster; plain tiles, k_blend_px, text tiles
+    launches_per_step = 1 + 3 + 5 + 1 + 3
 
     for _ in range(a.warmup):
         step()
@@ -316,7 +317,15 @@ def main():
     eng.reset()
     time_stage("k_fit*", lambda: L.ld_fit(h, rec_t.data_ptr(), n, fits.data_ptr(), st))
     time_stage("k_raster", lambda: L.ld_raster(h, fits.data_ptr(), n, st))
-    time_stage("k_frame_pass_mf<1>", lambda: L.ld_frame_pass(h, frames.data_ptr(), n, out.data_ptr(), st))
+    # the launches the step is really made of (ld_stage): shared pass -> k_mask_b -> ... plain tiles, k_blend_px, text tiles
+    SH, PL, BL, TX = "k_frame_pass_mf<3> (shared pass)", "k_frame_pass_mf<0> (plain tiles)", "k_blend_px", "k_frame_pass_mf<1> (text tiles)"
+    time_stage(SH, lambda: L.ld_stage(h, 3, frames.data_ptr(), n, None, st))
+    time_stage("k_mask_b", lambda: L.ld_stage(h, 7, None, n, None, st))
+    time_stage(PL, lambda: L.ld_stage(h, 5, frames.data_ptr(), n, out.data_ptr(), st))
+    time_stage(BL, lambda: L.ld_stage(h, 6, None, n, out.data_ptr(), st))
+    time_stage(TX, lambda: L.ld_stage(h, 4, frames.data_ptr(), n, out.data_ptr(), st))
+    n_share, n_plain, n_text = L.ld_stage_tiles(h, 3), L.ld_stage_tiles(h, 5), L.ld_stage_tiles(h, 4)
+    time_stage("k_frame_pass_mf<1> (whole frame: ld_frame_pass / ld_overlay)", lambda: L.ld_frame_pass(h, frames.data_ptr(), n, out.data_ptr(), st))
     hist_t = eng.hist_dev(mask_t)
     time_stage("k_hist", lambda: L.ld_hist(h, mask_t.data_ptr(), n, hist_t.data_ptr(), st))
     und_t = torch.empty_like(frames)
@@ -327,7 +336,12 @@ def main():
                lambda: eng.grad_binary_dev(frames, eng.gray_dev(frames), s_thresh=(100, 255), sx_thresh=(20, 100), mag_thresh=(50, 255)), reps=3)
     eng.check()
     frame_bytes = 720 * 1280 * 3
-    bytes_per_frame = {"k_mask": alg, "k_search": 115200 + 560, "k_raster": 2 * (722 * 41 * 16), "k_frame_pass_mf<1>": 2 * frame_bytes,
+    tile_px = 128 * 16
+    bytes_per_frame = {"k_mask": alg, "k_search": 115200 + 560, "k_raster": 722 * 82 * 8,
+                       "k_frame_pass_mf<1> (whole frame: ld_frame_pass / ld_overlay)": 2 * frame_bytes,
+                       SH: n_share * tile_px * (3 + 4) + 43520,          # source pixels read, u32 pixels + decision bits written
+                       "k_mask_b": 43520 + 115200, PL: n_plain * tile_px * 6, TX: n_text * tile_px * 6,
+                       BL: n_share * tile_px * (4 + 3) + 722 * 82 * 8,   # u32 pixels + canvas read, RGB written
                        "k_hist": 115200 + 20480, "k_frame_pass_mf<0> (cv2.undistort alone)": 2 * frame_bytes,
                        # RGB read twice (gray, S channel), gray written once and read twice, binary written once
                        "img2binary (k_gray + k_sobel_max + k_grad_binary)": 2 * frame_bytes + 4 * 720 * 1280}
@@ -349,8 +363,12 @@ def main():
                 "traffic": tr * n if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_frame": alg_bytes,
                 "ms_per_launch": ms_k, "frames_per_launch": n, "share_of_step": ms_k / (ms / a.steps)}
 
-    roofline = roof("k_frame_pass_mf<1>", 2 * frame_bytes, "k_frame_pass_dram_bytes_per_frame")
+    # the dominant launch of the step: the larger of the two big frame-pass launches
+    dom = SH if stage[SH] >= stage[PL] else PL
+    roofline = roof(dom, bytes_per_frame[dom], "k_frame_pass_shared_dram_bytes_per_frame" if dom == SH else "k_frame_pass_plain_dram_bytes_per_frame")
     mask_roofline = roof("k_mask", alg, "k_mask_dram_bytes_per_frame")
+    mask_roofline["note"] = ("the fused mask kernel of ld_mask (north-star kernel 1), timed alone; inside ld_process_batch the mask comes "
+                             "from the shared pass + k_mask_b")
 
     if rank == 0:
         cpu = None

@@ -148,6 +148,15 @@ int ld_overlay(ld_ctx* ctx, const uint8_t* frames_dev, const ld_frame_fit* fit_d
  * (Project.py:294, 167-170, 320-332). */
 int ld_raster(ld_ctx* ctx, const ld_frame_fit* fit_dev, int n, void* stream);
 int ld_frame_pass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
+/* The individual launches ld_process_batch is made of, for measurement and profiling (n <= max_frames, 1280x720 plans):
+ * which = 3 shared pass: the tiles from plan row share_y0 down are undistorted once for the mask AND the overlay (pixels and
+ * their colour decisions stay in the context); 7: the packed mask out of those decisions (context mask); 5: the plain tiles
+ * above share_y0 (pure cv2.undistort) -> out; 6: canvas blend onto the shared pixels -> out; 4: the putText tiles -> out.
+ * ld_stage_tiles: how many 128x16 tiles stage `which` covers. */
+int ld_stage(ld_ctx* ctx, int which, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
+int ld_stage_tiles(ld_ctx* ctx, int which);
+/* the packed masks ld_prepass / ld_process_batch / ld_stage(7) leave in the context: device u32[max_frames][H][W/32] */
+const uint32_t* ld_ctx_mask(ld_ctx* ctx);
 /* process_image for n consecutive frames (Project.py:289-334).  fit_dev may be NULL. */
 int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev,
                      ld_frame_fit* fit_dev, void* stream);

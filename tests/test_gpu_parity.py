@@ -300,3 +300,28 @@ def test_config5_independent_streams(engines, stills, golden):
     assert np.concatenate(parts_a).tobytes() == ref_a.tobytes()
     assert np.concatenate(parts_b).tobytes() != ref_a.tobytes()
     e1.close(); e2.close()
+
+
+def test_shared_pass_equals_fused_kernels(engines, stills):
+    """ld_process_batch takes the mask from the shared pass (k_frame_pass_mf<3> -> k_mask_b) and blends onto its pixels
+    (k_blend_px); ld_mask (fused k_mask) and ld_overlay (whole-frame k_frame_pass_mf<1>) must give the same bytes."""
+    eng = engines("project")
+    rng = np.random.default_rng(11)
+    frames = np.stack([stills("test1"), stills("test5"), rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8),
+                       np.full((720, 1280, 3), 255, np.uint8), stills("straight_lines2")])
+    dev = eng.to_device(frames)
+    eng.reset()
+    out_t, fit_t = eng.process_dev(dev)
+    try:
+        eng.check()
+    except TypeError:
+        pass                                                    # the noise / white frames have no lanes; masks and pixels still compare
+    assert (eng.context_masks(len(frames)) == eng.mask_dev(dev)).all()
+    ok = eng.fits_to_numpy(fit_t)["status"] == 0
+    assert ok.sum() >= 3
+    assert (out_t[torch_idx(ok, out_t)] == eng.overlay_dev(dev, fit_t)[torch_idx(ok, out_t)]).all()
+
+
+def torch_idx(mask, like):
+    import torch
+    return torch.as_tensor(np.nonzero(mask)[0], device=like.device)

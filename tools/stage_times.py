@@ -54,6 +54,12 @@ def main():
     if hasattr(L, "ld_raster"):
         t("k_raster", lambda: L.ld_raster(h, fits.data_ptr(), n, s))
         t("k_frame_pass", lambda: L.ld_frame_pass(h, frames.data_ptr(), n, out.data_ptr(), s))
+    if hasattr(L, "ld_stage"):                                            # the launches process_batch is really made of
+        t("shared pass k_frame_pass_mf<3>", lambda: L.ld_stage(h, 3, frames.data_ptr(), n, None, s))
+        t("k_mask_b", lambda: L.ld_stage(h, 7, None, n, None, s))
+        t("plain tiles k_frame_pass_mf<0>", lambda: L.ld_stage(h, 5, frames.data_ptr(), n, out.data_ptr(), s))
+        t("k_blend_px", lambda: L.ld_stage(h, 6, None, n, out.data_ptr(), s))
+        t("text tiles k_frame_pass_mf<1>", lambda: L.ld_stage(h, 4, frames.data_ptr(), n, out.data_ptr(), s))
     und = torch.empty_like(frames)
     t("k_undistort", lambda: L.ld_undistort(h, frames.data_ptr(), n, und.data_ptr(), s))
     eng.reset()
