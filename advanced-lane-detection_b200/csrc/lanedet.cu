@@ -739,6 +739,7 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
         tl_mark("fit (s_lat)", c->s_lat);
         if ((rc = launch_raster(c, c->fit, nullptr, nullptr, 0, 30, M, c->s_lat, 0))) return rc;
+        LD_CUDA(cudaEventRecord(c->ev_rast[0], c->s_lat));
         tl_mark("raster (s_lat)", c->s_lat);
         if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, (c->plan->shared_ok && !search_first) ? 5 : 1))) return rc;
         tl_mark("plain tiles (s)", s);
@@ -749,8 +750,10 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
                                                                                                  c->plan->share_tiles, M, bf);
             if ((rc = check_launch())) return rc;
             tl_mark("blend_px (s_lat)", c->s_lat);
-            if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 4))) return rc;
-            tl_mark("text tiles (s_lat)", c->s_lat);
+            // the putText tiles only need the raster's text plane: they follow the plain tiles on the caller's stream
+            LD_CUDA(cudaStreamWaitEvent(s, c->ev_rast[0], 0));
+            if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, 4))) return rc;
+            tl_mark("text tiles (s)", s);
         } else if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
         LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));
         LD_CUDA(cudaStreamWaitEvent(s, c->ev_join[1], 0));
