@@ -34,6 +34,42 @@ k_gray(const uint8_t* __restrict__ img, uint8_t* __restrict__ gray, const PlanDe
     gray[(size_t)f * npix + i] = (uint8_t)v;
 }
 
+// unwarped cv2.cvtColor(RGB2GRAY), four pixels (three input words, one output word) per thread; n_quads = pixels / 4
+__global__ void __launch_bounds__(256)
+k_gray4(const uint32_t* __restrict__ img, uint32_t* __restrict__ gray, size_t n_quads) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_quads) return;
+    const uint32_t a = __ldg(img + 3 * q), b = __ldg(img + 3 * q + 1), c = __ldg(img + 3 * q + 2);   // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+    const uint32_t g0 = gray_u8(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
+    const uint32_t g1 = gray_u8(a >> 24, b & 255u, (b >> 8) & 255u);
+    const uint32_t g2 = gray_u8((b >> 16) & 255u, b >> 24, c & 255u);
+    const uint32_t g3 = gray_u8((c >> 8) & 255u, (c >> 16) & 255u, c >> 24);
+    gray[q] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+}
+
+// Sobel derivatives of the four pixels x0 .. x0+3 (x0 % 4 == 0, W % 4 == 0) of row y: three rows x (left byte, word, right byte)
+struct Sobel4 { int sx[4], sy[4]; };
+__device__ __forceinline__ void row6(const uint8_t* __restrict__ row, int W, int x0, int (&v)[6]) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
+    v[0] = x0 == 0 ? (int)((w >> 8) & 255u) : (int)row[x0 - 1];          // BORDER_REFLECT_101: -1 -> 1
+    v[1] = w & 255u; v[2] = (w >> 8) & 255u; v[3] = (w >> 16) & 255u; v[4] = w >> 24;
+    v[5] = x0 + 4 == W ? (int)((w >> 16) & 255u) : (int)row[x0 + 4];     // W -> W - 2
+}
+__device__ __forceinline__ Sobel4 sobel4_at(const uint8_t* __restrict__ g, int W, int H, int x0, int y) {
+    const int ym = y == 0 ? 1 : y - 1, yp = y == H - 1 ? H - 2 : y + 1;
+    int a[6], b[6], c[6];
+    row6(g + (size_t)ym * W, W, x0, a);
+    row6(g + (size_t)y * W, W, x0, b);
+    row6(g + (size_t)yp * W, W, x0, c);
+    Sobel4 r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r.sx[k] = (a[k + 2] + 2 * b[k + 2] + c[k + 2]) - (a[k] + 2 * b[k] + c[k]);
+        r.sy[k] = (c[k] + 2 * c[k + 1] + c[k + 2]) - (a[k] + 2 * a[k + 1] + a[k + 2]);
+    }
+    return r;
+}
+
 // 3x3 Sobel derivatives at (x, y) with BORDER_REFLECT_101 (index -1 -> 1, n -> n-2)
 __device__ __forceinline__ void sobel_at(const uint8_t* __restrict__ g, int W, int H, int x, int y, int& sx, int& sy) {
     const int xm = x == 0 ? 1 : x - 1, xp = x == W - 1 ? W - 2 : x + 1;
@@ -52,11 +88,14 @@ k_sobel_max(const uint8_t* __restrict__ gray, uint32_t* __restrict__ mx, int W, 
     const int f = blockIdx.y, npix = W * H;
     const uint8_t* g = gray + (size_t)f * npix;
     uint32_t ma = 0, mm = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
-        int sx, sy;
-        sobel_at(g, W, H, i % W, i / W, sx, sy);
-        ma = max(ma, (uint32_t)abs(sx));
-        mm = max(mm, (uint32_t)(sx * sx + sy * sy));
+    const int qw = W / 4;                                               // W % 4 == 0 (plans require W % 32 == 0)
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npix / 4; q += gridDim.x * blockDim.x) {
+        const Sobel4 sb = sobel4_at(g, W, H, (q % qw) * 4, q / qw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ma = max(ma, (uint32_t)abs(sb.sx[k]));
+            mm = max(mm, (uint32_t)(sb.sx[k] * sb.sx[k] + sb.sy[k] * sb.sy[k]));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -72,27 +111,51 @@ __global__ void __launch_bounds__(256)
 k_grad_binary(const uint8_t* __restrict__ img, const uint8_t* __restrict__ gray, const uint32_t* __restrict__ mx,
               const uint8_t* __restrict__ s_table, int s_lo, int s_hi, int sx_lo, int sx_hi, int use_mag, int mag_lo, int mag_hi,
               uint8_t* __restrict__ out, int W, int H) {
-    const int f = blockIdx.y, npix = W * H;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
-    int sx, sy;
-    sobel_at(gray + (size_t)f * npix, W, H, i % W, i / W, sx, sy);
+    const int f = blockIdx.y, npix = W * H, qw = W / 4;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;                // four pixels per thread
+    if (q >= npix / 4) return;
+    const Sobel4 sb = sobel4_at(gray + (size_t)f * npix, W, H, (q % qw) * 4, q / qw);
     const uint32_t max_abs = __ldg(mx + 2 * f), max_m2 = __ldg(mx + 2 * f + 1);
-    // np.uint8(255 * abs_sobelx / np.max(abs_sobelx))   (helper.py:68); a flat image (0/0 = nan) casts to 0
-    const int scaled = max_abs ? (int)(__dmul_rn(255.0, (double)abs(sx)) / (double)max_abs) : 0;
-    bool on = scaled >= sx_lo && scaled <= sx_hi;
-    if (use_mag) {
-        // gradmag = np.sqrt(sobelx**2 + sobely**2); (gradmag / (np.max(gradmag) / 255)).astype(np.uint8)   (helper.py:76-80)
-        const double scale = __ddiv_rn(__dsqrt_rn((double)max_m2), 255.0);
-        const int gm = max_m2 ? (int)__ddiv_rn(__dsqrt_rn((double)(sx * sx + sy * sy)), scale) : 0;
-        on = on || (gm >= mag_lo && gm <= mag_hi);
-    }
+    uint32_t rgb[4] = {0u, 0u, 0u, 0u};
     if (s_table) {
-        const uint8_t* p = img + ((size_t)f * npix + i) * 3;
-        const int s = __ldg(s_table + (((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | p[2]));
-        on = on || (s >= s_lo && s <= s_hi);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(img + ((size_t)f * npix + 4 * (size_t)q) * 3);
+        const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);   // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+        rgb[0] = ((a & 255u) << 16) | (a & 0xFF00u) | ((a >> 16) & 255u);                                  // r << 16 | g << 8 | b
+        rgb[1] = ((a >> 24) << 16) | ((b & 255u) << 8) | ((b >> 8) & 255u);
+        rgb[2] = (((b >> 16) & 255u) << 16) | ((b >> 24) << 8) | (c & 255u);
+        rgb[3] = (((c >> 8) & 255u) << 16) | (((c >> 16) & 255u) << 8) | (c >> 24);
     }
-    out[(size_t)f * npix + i] = on ? 1 : 0;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int sx = sb.sx[k], sy = sb.sy[k];
+        // np.uint8(255 * abs_sobelx / np.max(abs_sobelx))   (helper.py:68).  The exact quotient 255 a / max is a fraction with a
+        // denominator <= 1020: when it is not an integer it is at least 1/1020 away from one, far more than float64 rounding can
+        // bridge, so truncating the float64 quotient equals the integer division.  A flat image (0/0 = nan) casts to 0.
+        const int scaled = max_abs ? (int)((255u * (uint32_t)abs(sx)) / max_abs) : 0;
+        bool on = scaled >= sx_lo && scaled <= sx_hi;
+        if (use_mag) {
+            // gradmag = np.sqrt(sobelx**2 + sobely**2); (gradmag / (np.max(gradmag) / 255)).astype(np.uint8)   (helper.py:76-80).
+            // v = 255 sqrt(m2 / M2): gm >= k  <=>  65025 m2 >= k^2 M2 unless the two sides are EQUAL (v is exactly the integer k;
+            // only then can the float64 pipeline land on either side) -- equal cases take numpy's float64 operations.
+            const uint64_t m2 = (uint64_t)(sx * sx + sy * sy) * 65025ull;
+            const uint64_t lo2 = (uint64_t)(mag_lo * mag_lo) * max_m2, hi2 = (uint64_t)((mag_hi + 1) * (mag_hi + 1)) * max_m2;
+            bool mag_on;
+            if (max_m2 == 0u) mag_on = 0 >= mag_lo && 0 <= mag_hi;
+            else if (m2 == lo2 || m2 == hi2 || mag_lo < 0) {
+                const double scale = __ddiv_rn(__dsqrt_rn((double)max_m2), 255.0);
+                const int gm = (int)(unsigned char)(int)__ddiv_rn(__dsqrt_rn((double)(sx * sx + sy * sy)), scale);
+                mag_on = gm >= mag_lo && gm <= mag_hi;
+            } else mag_on = m2 > lo2 && (mag_hi >= 255 || m2 < hi2);      // gm <= mag_hi  <=>  v < mag_hi + 1
+            on = on || mag_on;
+        }
+        if (s_table) {
+            const int sv = __ldg(s_table + rgb[k]);
+            on = on || (sv >= s_lo && sv <= s_hi);
+        }
+        packed |= (on ? 1u : 0u) << (8 * k);
+    }
+    reinterpret_cast<uint32_t*>(out + (size_t)f * npix)[q] = packed;
 }
 
 // color_filter (helper.py:493-500), optionally AND-ed with another binary (combine_bin, helper.py:503-511)

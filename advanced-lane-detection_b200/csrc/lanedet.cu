@@ -939,7 +939,12 @@ extern "C" int ld_gray(ld_ctx* c, const uint8_t* img, int n, int warped, uint8_t
     if (!ARGS_OK(c, img, gray, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    k_gray<<<dim3((d.W * d.H + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, gray, d, warped ? 1 : 0);
+    if (!warped && !(((uintptr_t)img | (uintptr_t)gray) & 3)) {          // four pixels per thread, word loads / stores
+        const size_t nq = (size_t)d.W * d.H * n / 4;
+        k_gray4<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(img),
+                                                                               reinterpret_cast<uint32_t*>(gray), nq);
+    } else
+        k_gray<<<dim3((d.W * d.H + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, gray, d, warped ? 1 : 0);
     return check_launch();
 }
 extern "C" int ld_sobel_max(ld_ctx* c, const uint8_t* gray, int n, uint32_t* maxima, void* stream) {
@@ -957,7 +962,8 @@ extern "C" int ld_grad_binary(ld_ctx* c, const uint8_t* img, const uint8_t* gray
     if (!ARGS_OK(c, gray, out, n) || !maxima || (s_table && !img)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    k_grad_binary<<<dim3((d.W * d.H + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, gray, maxima, s_table, s_lo, s_hi, sx_lo, sx_hi,
+    if (((uintptr_t)gray | (uintptr_t)out | (uintptr_t)img) & 3) return LD_ERR_ARG;   // word loads / stores
+    k_grad_binary<<<dim3((d.W * d.H / 4 + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, gray, maxima, s_table, s_lo, s_hi, sx_lo, sx_hi,
                                                                                      use_mag ? 1 : 0, mag_lo, mag_hi, out, d.W, d.H);
     return check_launch();
 }
