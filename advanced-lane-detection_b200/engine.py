@@ -175,7 +175,13 @@ class LaneEngine:
         out.copy_(self.torch.as_tensor(raw, device="cuda:%d" % self.device))
         return out
 
-    def postpass_dev(self, frames, out=None, fits=None, state_out=None):
+    def plain_pass_dev(self, frames, out):
+        """The tiles of the range given to prepass_dev that depend on neither the fit nor the canvas (pure cv2.undistort),
+        written into `out` ahead of postpass_dev(..., skip_plain=True).  Returns False when the plan has no such split."""
+        frames = self._frames(frames)
+        return self.lib.ld_stage(self._ctx_h, 5, _ptr(frames), frames.shape[0], _ptr(out), self._stream()) == _abi.LD_OK
+
+    def postpass_dev(self, frames, out=None, fits=None, state_out=None, skip_plain=False):
         """fit (tracker order!) + overlay of the range given to prepass_dev; state_out = CUDA uint8 blob or None"""
         frames = self._frames(frames)
         n = frames.shape[0]
@@ -183,8 +189,9 @@ class LaneEngine:
             out = self.torch.empty_like(frames)
         if fits is None:
             fits = self._dev((n, _abi.FIT_DTYPE.itemsize), self.torch.uint8)
-        _abi.check(self.lib, self.lib.ld_postpass(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits),
-                                                  _ptr(state_out) if state_out is not None else None, self._stream()))
+        _abi.check(self.lib, self.lib.ld_postpass_flags(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits),
+                                                        _ptr(state_out) if state_out is not None else None, self._stream(),
+                                                        1 if skip_plain else 0))
         return out, fits
 
     def wait_state(self, stream):

@@ -5,8 +5,8 @@ own contiguous frame range with no communication.  Only `Line` tracking is order
 fit stage of rank r needs the trackers as rank r-1 left them.  That state is one small blob
 (LaneEngine.export_state, ~1.6 KB); it is handed down the chain rank 0 -> 1 -> ... with
 torch.distributed point-to-point send/recv (NCCL over NVLink on a GPU box, gloo on CPU tests).
-While a rank waits for its predecessor it has already finished mask + search for its range, so
-the chain only serialises the fit stage (tens of microseconds per rank).
+While a rank waits for its predecessor it has already finished mask + search for its range and undistorts
+the tiles that depend on neither the fit nor the canvas, so the chain only serialises the fit stage.
 """
 from __future__ import annotations
 
@@ -43,6 +43,10 @@ def process_sharded(engine, frames_dev, rank: int, world: int, group=None, out=N
     import torch
     import torch.distributed as dist
     engine.prepass_dev(frames_dev)                              # mask + search: no tracker access, runs on every rank at once
+    if out is None:
+        out = torch.empty_like(frames_dev)
+    # the tiles that need neither the fit nor the canvas are undistorted while this rank waits for its predecessor's state
+    plain_done = rank > 0 and engine.plain_pass_dev(frames_dev, out)
     nbytes = engine.lib.ld_state_size()
     blob_in = torch.empty(nbytes, dtype=torch.uint8, device=frames_dev.device)
     blob_out = torch.empty(nbytes, dtype=torch.uint8, device=frames_dev.device) if rank + 1 < world else None
@@ -55,7 +59,7 @@ def process_sharded(engine, frames_dev, rank: int, world: int, group=None, out=N
     def run(state):
         if state is not None:
             engine.import_state_dev(state)
-        result["v"] = engine.postpass_dev(frames_dev, out=out, fits=fits, state_out=blob_out)
+        result["v"] = engine.postpass_dev(frames_dev, out=out, fits=fits, state_out=blob_out, skip_plain=plain_done)
         return blob_out
 
     def send(state):

@@ -166,6 +166,11 @@ int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out
  * (ld_state_import).  If state_out_dev is not NULL the updated blob is copied there right after the fit stage and
  * ld_wait_state makes `stream` wait for exactly that copy, so it can be sent on while the overlay still runs. */
 int ld_prepass(ld_ctx* ctx, const uint8_t* frames_dev, int n, void* stream);
+/* ld_postpass_flags: LD_POST_SKIP_PLAIN = the caller has already written the plain tiles of this range with
+ * ld_stage(ctx, 5, ...) -- what a sharded rank does while it waits for its predecessor's tracker state. */
+enum { LD_POST_SKIP_PLAIN = 1 };
+int ld_postpass_flags(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, ld_frame_fit* fit_dev,
+                      void* state_out, void* stream, int flags);
 int ld_postpass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, ld_frame_fit* fit_dev,
                 void* state_out_dev, void* stream);
 int ld_wait_state(ld_ctx* ctx, void* stream);
