@@ -220,6 +220,8 @@ def main():
         print(json.dumps(line))
         return
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"                   # NCCL prints its version banner on STDOUT; this script's stdout is one JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
