@@ -181,7 +181,7 @@ class LaneEngine:
         frames = self._frames(frames)
         return self.lib.ld_stage(self._ctx_h, 5, _ptr(frames), frames.shape[0], _ptr(out), self._stream()) == _abi.LD_OK
 
-    def postpass_dev(self, frames, out=None, fits=None, state_out=None, skip_plain=False):
+    def postpass_dev(self, frames, out=None, fits=None, state_out=None, skip_plain=False, fit_first=False):
         """fit (tracker order!) + overlay of the range given to prepass_dev; state_out = CUDA uint8 blob or None"""
         frames = self._frames(frames)
         n = frames.shape[0]
@@ -191,7 +191,7 @@ class LaneEngine:
             fits = self._dev((n, _abi.FIT_DTYPE.itemsize), self.torch.uint8)
         _abi.check(self.lib, self.lib.ld_postpass_flags(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits),
                                                         _ptr(state_out) if state_out is not None else None, self._stream(),
-                                                        1 if skip_plain else 0))
+                                                        (1 if skip_plain else 0) | (2 if fit_first else 0)))
         return out, fits
 
     def wait_state(self, stream):

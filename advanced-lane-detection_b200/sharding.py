@@ -59,7 +59,8 @@ def process_sharded(engine, frames_dev, rank: int, world: int, group=None, out=N
     def run(state):
         if state is not None:
             engine.import_state_dev(state)
-        result["v"] = engine.postpass_dev(frames_dev, out=out, fits=fits, state_out=blob_out, skip_plain=plain_done)
+        result["v"] = engine.postpass_dev(frames_dev, out=out, fits=fits, state_out=blob_out, skip_plain=plain_done,
+                                          fit_first=world > 1)
         return blob_out
 
     def send(state):

@@ -168,7 +168,9 @@ int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out
 int ld_prepass(ld_ctx* ctx, const uint8_t* frames_dev, int n, void* stream);
 /* ld_postpass_flags: LD_POST_SKIP_PLAIN = the caller has already written the plain tiles of this range with
  * ld_stage(ctx, 5, ...) -- what a sharded rank does while it waits for its predecessor's tracker state. */
-enum { LD_POST_SKIP_PLAIN = 1 };
+enum { LD_POST_SKIP_PLAIN = 1,      /* ... */
+       LD_POST_FIT_FIRST = 2 };     /* do not start the plain tiles before the fit stage is done (the first rank of a sharded run:
+                                       its successors wait for that stage) */
 int ld_postpass_flags(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, ld_frame_fit* fit_dev,
                       void* state_out, void* stream, int flags);
 int ld_postpass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, ld_frame_fit* fit_dev,
