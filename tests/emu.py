@@ -105,3 +105,33 @@ def emu_mask_words(plan, frame):
                     off += ((inc1 >> i) & 1) + ((inc2 >> i) & 1)
                 out[y, w] = word & valid
     return np.unpackbits(out.view(np.uint8), axis=1, bitorder="little").reshape(H, W)
+
+
+def emu_canvas_entries(plan, red, green):
+    """the padded, interleaved canvas k_raster writes (overlay_kernels.cuh): u64[H + 2][W/16 + 2], entry (r, e) = the
+    (red-without-green, green) bit pairs of pixels [16e - 16, 16e + 16) of canvas row r - 1"""
+    W, H = plan.size
+    CW = W // 16 + 2
+    r = np.zeros((H + 2, W + 64), np.uint64)
+    g = np.zeros((H + 2, W + 64), np.uint64)
+    r[1:H + 1, 16:16 + W] = (red & ~green).astype(np.uint64)
+    g[1:H + 1, 16:16 + W] = green.astype(np.uint64)
+    ent = np.zeros((H + 2, CW), np.uint64)
+    for j in range(32):
+        cols = 16 * np.arange(CW) + j                       # padded column of pixel 16e - 16 + j
+        ent |= (r[:, cols] << np.uint64(2 * j)) | (g[:, cols] << np.uint64(2 * j + 1))
+    return ent
+
+
+def emu_canvas_codes(plan, ent):
+    """what canvas_codes() reads through inv_pack: per touched pixel the byte (red, green) of taps (x, top), (x+1, top),
+    (x, bottom), (x+1, bottom); returns (codes u8[rows, W], touched bool[rows, W])"""
+    W, H = plan.size
+    CW = W // 16 + 2
+    e = plan.inv_pack.astype(np.int64)
+    touched = e != 0xFFFFFFFF
+    idx, sh = np.where(touched, e >> 15, 0), np.where(touched, (e >> 10) & 31, 0)
+    flat = ent.reshape(-1)
+    top = (flat[idx] >> sh.astype(np.uint64)) & np.uint64(15)
+    bot = (flat[idx + CW] >> sh.astype(np.uint64)) & np.uint64(15)
+    return (top | (bot << np.uint64(4))).astype(np.uint8), touched

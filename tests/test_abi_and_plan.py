@@ -154,3 +154,70 @@ def test_partition():
     assert sum(b - a for a, b in S.partition(1261, 8)) == 1261
     with pytest.raises(ValueError):
         S.partition(5, 0)
+
+
+def test_colour_prefilter_is_a_sound_coarsening(pkg):
+    """every 8x8x8 cell the 2-bit pre-decision calls all-off / all-on really is; mixed cells are the only ones left to ctab"""
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    for l, b in (((215, 255), (145, 200)), ((210, 255), (143, 200))):
+        pre = P.colour_prefilter(l, b)
+        assert pre.dtype == np.uint32 and pre.shape == (2048,)
+        L, Bc = P._all_colour_channels()
+        on = ((L >= l[0]) & (L <= l[1])) | ((Bc >= b[0]) & (Bc <= b[1]))
+        r, g, bb = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")
+        idx = (r >> 3) | ((g >> 3) << 5) | ((bb >> 3) << 10)              # the kernel's index (mask_kernels.cuh: colour_on_pre)
+        code = (pre[idx >> 4] >> ((idx & 15) * 2).astype(np.uint32)) & 3
+        assert set(np.unique(code)) <= {0, 1, 2}
+        assert not on[code == 0].any() and on[code == 1].all()
+        assert 0.01 < (code == 2).mean() < 0.2
+
+
+@pytest.mark.parametrize("variant", ["project", "harder"])
+def test_gather_maps_and_canvas_encoding(pkg, variant):
+    """the re-ordered gather tables and the packed inverse map decode to the same taps as the plain per-pixel tables"""
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    plan = P.build_plan(P.VARIANTS[variant])
+    W, H = plan.size
+    m = plan.und_map.astype(np.int64)
+    fi = m & 1023
+    sx = ((m >> 10) & 2047) - 1024 + np.arange(W)[None, :]
+    sy = ((m >> 21) & 2047) - 1024 + np.arange(H)[:, None]
+    # frame tiles: lane-strided order [row][lane][k] = column lane + 32 k, fixed 512-byte pitch
+    ft = plan.frame_tiles.view(np.uint32).astype(np.int64)
+    assert ((ft[:, 7] & 0x7FFFFFFF) == P.FRAME_BOX_PITCH).all() and (ft[:, 4] % 16 == 0).all()
+    for t in (0, 137, len(ft) - 1):
+        x0, y0, w, h, b0, sy0 = ft[t, :6]
+        e = plan.frame_amap[plan.frame_amap_start[t]:plan.frame_amap_start[t + 1]].astype(np.int64).reshape(h, 32, 4)
+        cols = np.arange(32)[:, None] + 32 * np.arange(4)[None, :]
+        off = (sy[y0:y0 + h, x0:x0 + w] - sy0) * P.FRAME_BOX_PITCH + sx[y0:y0 + h, x0:x0 + w] * 3 - b0
+        want = ((off << 10) | fi[y0:y0 + h, x0:x0 + w])
+        assert (e == want[:, cols]).all()
+        assert off.min() >= 0 and (off % P.FRAME_BOX_PITCH).max() + 12 <= P.FRAME_BOX_PITCH     # every 3-word tap read stays inside its row
+    # mask chunks: warp items [row][128-column group][lane][k]
+    mc = plan.mask_chunks.view(np.uint32).astype(np.int64)
+    for c in (0, len(mc) // 2, len(mc) - 1):
+        x0, y0, w, h, b0, sy0 = mc[c, :6]
+        stride = mc[c, 7] & 0x7FFFFFFF
+        ncg = (w + 127) // 128
+        e = plan.mask_amap[plan.mask_amap_start[c]:plan.mask_amap_start[c + 1]].astype(np.int64).reshape(h, ncg, 32, 4)
+        off = (sy[y0:y0 + h, x0:x0 + w] - sy0) * stride + sx[y0:y0 + h, x0:x0 + w] * 3 - b0
+        want = np.full((h, ncg * 128), 0xFFFFFFFF, np.int64)
+        want[:, :w] = (off << 10) | fi[y0:y0 + h, x0:x0 + w]
+        assert (e == want.reshape(h, ncg, 4, 32).transpose(0, 1, 3, 2)).all()
+    # inverse map: the packed entry addresses the same four taps as (inv_idx, inv_fi) in the padded, interleaved canvas
+    rng = np.random.default_rng(9)
+    red = rng.integers(0, 2, (H, W), dtype=np.uint8)
+    green = rng.integers(0, 2, (H, W), dtype=np.uint8)
+    codes, touched = emu.emu_canvas_codes(plan, emu.emu_canvas_entries(plan, red, green))
+    idx = plan.inv_idx.astype(np.int64)
+    assert (touched == (idx != 0xFFFFFFFF)).all()
+    ty, tx = np.where(touched, (idx >> 16) - 1, 0), np.where(touched, (idx & 0xFFFF) - 1, 0)
+    rpad = np.zeros((H + 2, W + 2), np.uint8)
+    gpad = np.zeros((H + 2, W + 2), np.uint8)
+    rpad[1:-1, 1:-1] = red & ~green
+    gpad[1:-1, 1:-1] = green
+    want = np.zeros_like(codes)
+    for bit, (oy, ox, pl) in enumerate(((0, 0, rpad), (0, 0, gpad), (0, 1, rpad), (0, 1, gpad), (1, 0, rpad), (1, 0, gpad), (1, 1, rpad), (1, 1, gpad))):
+        want |= (pl[ty + oy + 1, tx + ox + 1] << bit).astype(np.uint8)
+    assert (codes[touched] == want[touched]).all()
+    assert ((plan.inv_pack[touched] & 1023) == plan.inv_fi[touched]).all()
