@@ -70,18 +70,6 @@ __device__ __forceinline__ Sobel4 sobel4_at(const uint8_t* __restrict__ g, int W
     return r;
 }
 
-// 3x3 Sobel derivatives at (x, y) with BORDER_REFLECT_101 (index -1 -> 1, n -> n-2)
-__device__ __forceinline__ void sobel_at(const uint8_t* __restrict__ g, int W, int H, int x, int y, int& sx, int& sy) {
-    const int xm = x == 0 ? 1 : x - 1, xp = x == W - 1 ? W - 2 : x + 1;
-    const int ym = y == 0 ? 1 : y - 1, yp = y == H - 1 ? H - 2 : y + 1;
-    const uint8_t* r0 = g + (size_t)ym * W;
-    const uint8_t* r1 = g + (size_t)y * W;
-    const uint8_t* r2 = g + (size_t)yp * W;
-    const int a = r0[xm], b = r0[x], c = r0[xp], d = r1[xm], e = r1[xp], p = r2[xm], q = r2[x], r = r2[xp];
-    sx = (c + 2 * e + r) - (a + 2 * d + p);
-    sy = (p + 2 * q + r) - (a + 2 * b + c);
-}
-
 // per-frame maxima: mx[2f] = max |sobelx| (helper.py:68), mx[2f+1] = max (sobelx^2 + sobely^2) (helper.py:78: sqrt is monotone)
 __global__ void __launch_bounds__(256)
 k_sobel_max(const uint8_t* __restrict__ gray, uint32_t* __restrict__ mx, int W, int H) {

@@ -38,34 +38,12 @@ __device__ __forceinline__ bool colour_on_pre(uint32_t rgb, const uint32_t* s_pr
     return colour_on(rgb, ctab, cbits);
 }
 
-// bilinear_rgb_off with the doubled weights / byte-permute pack of the frame pass (overlay_kernels.cuh: frame_weights)
+// one pixel from a plan.gather_offsets entry (tap byte offset << 10 | fy << 5 | fx), weights decoded on the fly
 __device__ __forceinline__ uint32_t bilinear_rgb_smem(uint32_t box, uint32_t stride, uint32_t e2) {
-    const uint32_t fx = e2 & 31u, fy = (e2 >> 5) & 31u, o = e2 >> 10;
-    const uint32_t tt = fx * 0xFFFFu + 32u;                             // (32 - fx) | fx << 16
-    const uint32_t fy64 = fy << 6;
-    uint32_t wx = tt * (2048u - fy64);
-    const uint32_t wy = tt * fy64;
-    if ((e2 & 1023u) == 0u) wx = 0xFFFFu;                               // fx = fy = 0: 2 * 32768 does not fit (frame_weights)
-    const uint32_t a = box + (o & ~3u), sh = o << 3;                    // the funnel shifts use the low five bits: (o & 3) * 8
-    uint32_t p0, p1, p2, q0, q1, q2;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p0) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(p1) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(p2) : "r"(a));
-    const uint32_t a2 = a + stride;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q0) : "r"(a2));
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(q1) : "r"(a2));
-    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(q2) : "r"(a2));
-    const uint32_t lt = __funnelshift_r(p0, p1, sh), ht = __funnelshift_r(p1, p2, sh);   // r0 g0 b0 r1 | g1 b1 . .
-    const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
-    const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11
-    const uint32_t GBt = __byte_perm(lt, ht, 0x5241), GBb = __byte_perm(lb, hb, 0x5241);   // g0 g1 b0 b1
-    uint32_t r = __dp2a_lo(wx, R, 32768u);
-    r = __dp2a_hi(wy, R, r);
-    uint32_t g = __dp2a_lo(wx, GBt, 32768u);
-    g = __dp2a_lo(wy, GBb, g);
-    uint32_t b = __dp2a_hi(wx, GBt, 32768u);
-    b = __dp2a_hi(wy, GBb, b);
-    return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);
+    uint32_t wx, wy;
+    frame_weights(e2 & 31u, (e2 >> 5) & 31u, wx, wy);
+    const uint32_t o = e2 >> 10;
+    return bilinear_taps(box + (o & ~3u), stride, o << 3, wx, wy);
 }
 
 __global__ void __launch_bounds__(MASK_THREADS, 3)

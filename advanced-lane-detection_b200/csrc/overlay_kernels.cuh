@@ -423,40 +423,10 @@ constexpr int FRAME_THREADS = 256;
 #endif
 constexpr int FRAME_FPC = LD_FRAME_FPC;         // frames per CTA of the multi-frame pass (upper bound)
 
-// bilinear_rgb_off with everything that does not depend on the frame hoisted out: po = (tap byte offset & ~3) |
-// (offset & 3) << 30, wx / wy = the dp2a weight pairs of the top / bottom tap row, DOUBLED (see frame_weights) so that
-// each channel's rounded result is byte 2 of its accumulator and two byte permutes pack the pixel.
+// one pixel with everything that does not depend on the frame hoisted out: po = (tap byte offset & ~3) | (offset & 3) << 30,
+// wx / wy = the dp2a weight pairs of the top / bottom tap row (gather.cuh: frame_weights)
 __device__ __forceinline__ uint32_t bilinear_rgb_pre(uint32_t box, uint32_t stride, uint32_t po, uint32_t wx, uint32_t wy) {
-    const uint32_t a = box + (po & 0x3FFFFFFFu), sh = po >> 27;
-    uint32_t p0, p1, p2, q0, q1, q2;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p0) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(p1) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(p2) : "r"(a));
-    const uint32_t a2 = a + stride;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q0) : "r"(a2));
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(q1) : "r"(a2));
-    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(q2) : "r"(a2));
-    const uint32_t lt = __funnelshift_r(p0, p1, sh), ht = __funnelshift_r(p1, p2, sh);   // r0 g0 b0 r1 | g1 b1 . .
-    const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
-    const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11
-    const uint32_t GBt = __byte_perm(lt, ht, 0x5241), GBb = __byte_perm(lb, hb, 0x5241);   // g0 g1 b0 b1
-    uint32_t r = __dp2a_lo(wx, R, 32768u);
-    r = __dp2a_hi(wy, R, r);
-    uint32_t g = __dp2a_lo(wx, GBt, 32768u);
-    g = __dp2a_lo(wy, GBb, g);
-    uint32_t b = __dp2a_hi(wx, GBt, 32768u);
-    b = __dp2a_hi(wy, GBb, b);
-    return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);           // (r >> 16) | (g >> 16) << 8 | (b >> 16) << 16
-}
-
-// OpenCV's four bilinear weights of fraction (fx, fy) are the exact integers 32(32-fy)(32-fx), 32(32-fy)fx, 32 fy (32-fx),
-// 32 fy fx (sum 2^15); out = (sum w p + 2^14) >> 15.  Doubling them gives out = (sum 2w p + 2^15) >> 16 = byte 2 of
-// the accumulator.  Only w00 = 2^15 (fx = fy = 0, a single tap) does not fit 16 bits doubled; 65535 p + 2^15 >> 16 = p
-// for every p <= 255, so 65535 is exact there.
-__device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t& wx, uint32_t& wy) {
-    const uint32_t tt = (32u - fx) | (fx << 16);
-    wx = (fx | fy) ? tt * (2048u - 64u * fy) : 0xFFFFu;
-    wy = tt * (64u * fy);
+    return bilinear_taps(box + (po & 0x3FFFFFFFu), stride, po >> 27, wx, wy);
 }
 
 // K4b / stand-alone undistort, multi-frame form.  One CTA = one 128x16 output tile (plan.frame_tiles) of up to

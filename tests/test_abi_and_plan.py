@@ -221,3 +221,22 @@ def test_gather_maps_and_canvas_encoding(pkg, variant):
         want |= (pl[ty + oy + 1, tx + ox + 1] << bit).astype(np.uint8)
     assert (codes[touched] == want[touched]).all()
     assert ((plan.inv_pack[touched] & 1023) == plan.inv_fi[touched]).all()
+
+
+def test_bilinear_weights_closed_form_and_doubling(pkg):
+    """gather.cuh: frame_weights -- OpenCV's 8U bilinear table equals 32(32-fy)(32-fx) ... in closed form, and the doubled
+    weights (65535 for the single-tap case) with >> 16 give the same pixel as the table with >> 15"""
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    tab = P.bilinear_weight_table().astype(np.int64) & 0xFFFF          # [1024, 4] = w00 w01 w10 w11, index fy << 5 | fx
+    fy, fx = np.divmod(np.arange(1024), 32)
+    closed = np.stack([32 * (32 - fy) * (32 - fx), 32 * (32 - fy) * fx, 32 * fy * (32 - fx), 32 * fy * fx], 1)
+    assert (tab == closed).all() and (tab.sum(1) == 32768).all()
+    dbl = np.minimum(2 * closed, 65535)
+    assert ((2 * closed > 65535).sum(1) <= 1).all() and (2 * closed > 65535).sum() == 1      # only w00 of fraction (0, 0)
+    rng = np.random.default_rng(2)
+    taps = rng.integers(0, 256, (1024, 64, 4))
+    taps[:, 0] = 255
+    taps[:, 1] = 0
+    want = (np.einsum("fk,fnk->fn", closed, taps) + 16384) >> 15
+    got = (np.einsum("fk,fnk->fn", dbl, taps) + 32768) >> 16
+    assert (want == got).all() and got.max() <= 255
