@@ -94,6 +94,8 @@ _SIGNATURES = {
     "ld_postpass": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "ld_postpass_flags": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int]),
     "ld_wait_state": (C.c_int, [_P, _P]),
+    "ld_halo_set": (C.c_int, [_P, _P, C.c_int, _P]),
+    "ld_ctx_records": (_P, [_P]),
     "ld_check": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "ld_state_reset": (C.c_int, [_P, _P]),
     "ld_state_size": (C.c_size_t, []),

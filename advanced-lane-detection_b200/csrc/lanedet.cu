@@ -46,15 +46,17 @@ struct ld_plan {
     int n_share, n_text, n_plain_top, shared_ok;
 };
 
-enum { HOST_CHUNK = 32, PIPE_SUB = 8 };
+enum { HOST_CHUNK = 32, PIPE_SUB = 8, HALO_MAX = 32 };               // HALO_MAX: look-back records a sharded rank may put in front of its range
 
 struct ld_ctx {
     ld_plan* plan;
     int max_frames;
     uint32_t* mask;            // [max][H][WW]
-    ld_lane_record* rec;       // [max][2]
-    FitWork* work;             // [max][2]
-    ld_frame_fit* fit;         // [max]
+    // [max][2] / [max][2] / [max]; each has HALO_MAX more slots IN FRONT (rec[-2h..0), ...) for the look-back halo of ld_halo_set
+    ld_lane_record* rec;
+    FitWork* work;
+    ld_frame_fit* fit;
+    int halo;                  // frames of look-back records waiting in front of rec (consumed by the next ld_postpass_flags(USE_HALO))
     uint32_t* planes;          // padded, interleaved canvas u64[max][H+2][2 WW + 2] (overlay_kernels.cuh: canvas_codes)
     uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
     uint32_t* und_bits;        // shared pass: colour decision of the undistorted pixels, [max][H - share_y0][WW] (+ pad)
@@ -336,9 +338,12 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
         }                                                       \
     } while (0)
     CTX_ALLOC(c->mask, mw * 4 * max_frames);
-    CTX_ALLOC(c->rec, sizeof(ld_lane_record) * 2 * max_frames);
-    CTX_ALLOC(c->work, sizeof(FitWork) * 2 * max_frames);
-    CTX_ALLOC(c->fit, sizeof(ld_frame_fit) * max_frames);
+    CTX_ALLOC(c->rec, sizeof(ld_lane_record) * 2 * (max_frames + HALO_MAX));
+    c->rec += 2 * HALO_MAX;                                             // the halo slots sit in front
+    CTX_ALLOC(c->work, sizeof(FitWork) * 2 * (max_frames + HALO_MAX));
+    c->work += 2 * HALO_MAX;
+    CTX_ALLOC(c->fit, sizeof(ld_frame_fit) * (max_frames + HALO_MAX));
+    c->fit += HALO_MAX;
     CTX_ALLOC(c->planes, canvas_words(d) * 4 * max_frames);
     CTX_ALLOC(c->text, (size_t)LD_TEXT_ROWS * LD_TEXT_WORDS * 4 * max_frames);
     if (plan->shared_ok) {
@@ -387,7 +392,10 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     if (!c) return LD_ERR_ARG;
     cudaSetDevice(c->plan->device);
     cudaDeviceSynchronize();
-    cudaFree(c->mask); cudaFree(c->rec); cudaFree(c->work); cudaFree(c->fit); cudaFree(c->planes);
+    cudaFree(c->mask); cudaFree(c->planes);
+    if (c->rec) cudaFree(c->rec - 2 * HALO_MAX);
+    if (c->work) cudaFree(c->work - 2 * HALO_MAX);
+    if (c->fit) cudaFree(c->fit - HALO_MAX);
     cudaFree(c->text); cudaFree(c->und_bits); cudaFree(c->und_px); cudaFree(c->state); cudaFree(c->flags);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->stage_in[b]); cudaFree(c->stage_out[b]);
@@ -483,18 +491,27 @@ extern "C" int ld_polyfit(ld_ctx* c, const ld_lane_record* rec, int n, double* c
     return check_launch();
 }
 
-static int fit_impl(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, cudaStream_t s, int frame_offset) {
-    if (!ARGS_OK(c, rec, fit, n) || n > c->max_frames) return LD_ERR_ARG;
+// halo > 0 (only with rec == c->rec, fit == c->fit): the `halo` look-back records ld_halo_set put in front of the range are
+// fitted first, from EMPTY trackers.  A deque(maxlen=F) median of medians depends on the last 2(F-1) frames only, so after
+// >= 2(F-1) look-back frames without an empty lane the trackers are exactly what the predecessor would hand over.
+static int fit_impl(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, cudaStream_t s, int frame_offset, int halo = 0) {
+    if (!ARGS_OK(c, rec, fit, n) || n > c->max_frames || halo < 0 || halo > HALO_MAX) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
+    if (halo) {
+        if (rec != c->rec || fit != c->fit) return LD_ERR_ARG;
+        k_state_reset<<<1, 128, 0, s>>>(c->state);
+        rec -= 2 * halo; fit -= halo; n += halo; frame_offset -= halo;
+    }
+    FitWork* work = c->work - 2 * halo;
     LD_CUDA(cudaMemsetAsync(c->flags, 0, sizeof(int), s));              // any_fail = 0
     LD_CUDA(cudaMemsetAsync(c->flags + 1, 0x7F, sizeof(int), s));       // first_bad = 0x7f7f7f7f
     const int t = 64, g2 = (2 * n + t - 1) / t, g1 = (n + t - 1) / t;
-    k_fit1<<<g2, t, 0, s>>>(rec, c->work, n, c->flags);
-    k_fit_fallback<<<1, 32, 0, s>>>(rec, c->work, fit, c->state, n, d.depth, d.top_anchor, c->flags, c->flags + 1);
-    k_fit2<<<g2, t, 0, s>>>(c->work, c->state, n, d.depth, d.top_anchor, c->flags + 1);
-    k_fit3<<<g1, t, 0, s>>>(rec, c->work, c->state, fit, n, d, c->flags + 1);
-    k_state_update<<<1, 32, 0, s>>>(rec, c->work, fit, c->state, n, d.depth, c->flags + 1, c->flags + 2, frame_offset);
+    k_fit1<<<g2, t, 0, s>>>(rec, work, n, c->flags);
+    k_fit_fallback<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, d.top_anchor, c->flags, c->flags + 1);
+    k_fit2<<<g2, t, 0, s>>>(work, c->state, n, d.depth, d.top_anchor, c->flags + 1);
+    k_fit3<<<g1, t, 0, s>>>(rec, work, c->state, fit, n, d, c->flags + 1);
+    k_state_update<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, c->flags + 1, c->flags + 2, frame_offset);
     return check_launch();
 }
 extern "C" int ld_fit(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, void* stream) {
@@ -723,7 +740,7 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
 // search_first: the window search has not run yet (process_impl): it joins the latency-bound chain on s_lat
 // skip_plain: the caller already ran the plain tiles of this range (ld_stage(5), e.g. while waiting for its predecessor's state)
 static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld_frame_fit* fit_out, void* state_out,
-                         cudaStream_t s, int frame_offset, int search_first = 0, int skip_plain = 0, int fit_first = 0) {
+                         cudaStream_t s, int frame_offset, int search_first = 0, int skip_plain = 0, int fit_first = 0, int halo = 0) {
     const PlanDev& d = c->plan->d;
     const size_t fb = (size_t)d.W * d.H * 3;
     const int nsub = sub_batches(M);
@@ -735,7 +752,7 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         LD_CUDA(cudaEventRecord(c->ev_fork, s));
         LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
         if (search_first && (rc = ld_search(c, c->mask, M, c->rec, c->s_lat))) return rc;
-        if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset))) return rc;
+        if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset, halo))) return rc;
         if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
         LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
         tl_mark("fit (s_lat)", c->s_lat);
@@ -817,9 +834,21 @@ extern "C" int ld_postpass(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out
 extern "C" int ld_postpass_flags(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, void* state_out,
                                  void* stream, int flags) {
     if (!ARGS_OK(c, frames, out, n) || n > c->max_frames) return LD_ERR_ARG;
+    int halo = 0;
+    if (flags & LD_POST_USE_HALO) { halo = c->halo; c->halo = 0; if (halo <= 0 || sub_batches(n) > 1) return LD_ERR_ARG; }
     return n ? postpass_impl(c, frames, n, out, fit_out, state_out, (cudaStream_t)stream, 0, 0, flags & LD_POST_SKIP_PLAIN,
-                             flags & LD_POST_FIT_FIRST) : LD_OK;
+                             flags & LD_POST_FIT_FIRST, halo) : LD_OK;
 }
+// Look-back halo for frame-range sharding without a serial hand-off: the lane records of the `n_halo` frames just before
+// this context's range (the predecessor's last records, ld_ctx_records of ITS context + 2 * (its n - n_halo)) are placed in
+// front of the range; the next ld_postpass_flags(..., LD_POST_USE_HALO) fits them first from empty trackers.
+extern "C" int ld_halo_set(ld_ctx* c, const ld_lane_record* halo_dev, int n_halo, void* stream) {
+    if (!c || !halo_dev || n_halo < 1 || n_halo > HALO_MAX) return LD_ERR_ARG;
+    LD_CUDA(cudaMemcpyAsync(c->rec - 2 * n_halo, halo_dev, sizeof(ld_lane_record) * 2 * n_halo, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    c->halo = n_halo;
+    return LD_OK;
+}
+extern "C" const ld_lane_record* ld_ctx_records(ld_ctx* c) { return c ? c->rec : nullptr; }   // records of the last ld_prepass (device)
 extern "C" int ld_wait_state(ld_ctx* c, void* stream) {
     if (!c) return LD_ERR_ARG;
     LD_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_state, 0));

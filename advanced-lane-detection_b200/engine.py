@@ -166,13 +166,7 @@ class LaneEngine:
     def context_masks(self, n):
         """copy of the packed masks the last prepass / process call left in the context: int32[n, H, W/32] (device)"""
         out = self._dev((n, self.H, self.WW), self.torch.int32)
-        src = self.lib.ld_ctx_mask(self._ctx_h)
-        # wrap the raw device pointer through the CUDA array interface
-        class _Raw:
-            pass
-        raw = _Raw()
-        raw.__cuda_array_interface__ = {"shape": (n, self.H, self.WW), "typestr": "<i4", "data": (int(src), False), "version": 3}
-        out.copy_(self.torch.as_tensor(raw, device="cuda:%d" % self.device))
+        out.copy_(self._raw_view(self.lib.ld_ctx_mask(self._ctx_h), (n, self.H, self.WW), "<i4"))
         return out
 
     def plain_pass_dev(self, frames, out):
@@ -181,7 +175,24 @@ class LaneEngine:
         frames = self._frames(frames)
         return self.lib.ld_stage(self._ctx_h, 5, _ptr(frames), frames.shape[0], _ptr(out), self._stream()) == _abi.LD_OK
 
-    def postpass_dev(self, frames, out=None, fits=None, state_out=None, skip_plain=False, fit_first=False):
+    def _raw_view(self, ptr, shape, typestr):
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+        return self.torch.as_tensor(raw, device="cuda:%d" % self.device)
+
+    def context_records(self, n):
+        """VIEW (no copy) of the lane records the last prepass left in the context: uint8[n, 2, 280] on the device"""
+        return self._raw_view(self.lib.ld_ctx_records(self._ctx_h), (n, 2, _abi.RECORD_DTYPE.itemsize), "|u1")
+
+    def halo_set(self, records):
+        """lane records (uint8[h, 2, 280], device) of the h frames just before the range given to prepass_dev; the next
+        postpass_dev(use_halo=True) rebuilds the trackers from them instead of importing a predecessor's state"""
+        records = records.contiguous()
+        _abi.check(self.lib, self.lib.ld_halo_set(self._ctx_h, _ptr(records), records.shape[0], self._stream()))
+
+    def postpass_dev(self, frames, out=None, fits=None, state_out=None, skip_plain=False, fit_first=False, use_halo=False):
         """fit (tracker order!) + overlay of the range given to prepass_dev; state_out = CUDA uint8 blob or None"""
         frames = self._frames(frames)
         n = frames.shape[0]
@@ -191,7 +202,7 @@ class LaneEngine:
             fits = self._dev((n, _abi.FIT_DTYPE.itemsize), self.torch.uint8)
         _abi.check(self.lib, self.lib.ld_postpass_flags(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits),
                                                         _ptr(state_out) if state_out is not None else None, self._stream(),
-                                                        (1 if skip_plain else 0) | (2 if fit_first else 0)))
+                                                        (1 if skip_plain else 0) | (2 if fit_first else 0) | (4 if use_halo else 0)))
         return out, fits
 
     def wait_state(self, stream):

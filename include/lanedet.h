@@ -168,7 +168,8 @@ int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out
 int ld_prepass(ld_ctx* ctx, const uint8_t* frames_dev, int n, void* stream);
 /* ld_postpass_flags: LD_POST_SKIP_PLAIN = the caller has already written the plain tiles of this range with
  * ld_stage(ctx, 5, ...) -- what a sharded rank does while it waits for its predecessor's tracker state. */
-enum { LD_POST_SKIP_PLAIN = 1,      /* ... */
+enum { LD_POST_USE_HALO = 4,        /* fit the look-back records of ld_halo_set first, from empty trackers (see ld_halo_set) */
+       LD_POST_SKIP_PLAIN = 1,      /* ... */
        LD_POST_FIT_FIRST = 2 };     /* do not start the plain tiles before the fit stage is done (the first rank of a sharded run:
                                        its successors wait for that stage) */
 int ld_postpass_flags(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, ld_frame_fit* fit_dev,
@@ -176,6 +177,12 @@ int ld_postpass_flags(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* ou
 int ld_postpass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, ld_frame_fit* fit_dev,
                 void* state_out_dev, void* stream);
 int ld_wait_state(ld_ctx* ctx, void* stream);
+/* Look-back halo: Line's deque(maxlen=F) medians make frame k depend on the window searches of frames
+ * k-2(F-1)..k only, so a rank that is given the lane records of the >= 2(F-1) frames before its range (none of them with an
+ * empty lane) rebuilds its predecessor's trackers itself and needs no hand-off.  ld_ctx_records: device pointer to the
+ * records ld_prepass left in the context ([n][2]); ld_halo_set copies n_halo (<= 32) frames' records in front of the range. */
+int ld_halo_set(ld_ctx* ctx, const ld_lane_record* halo_records_dev, int n_halo, void* stream);
+const ld_lane_record* ld_ctx_records(ld_ctx* ctx);
 /* Same with host buffers: chunks are copied in, processed and copied out on three streams.
  * Synchronous; returns LD_ERR_EMPTY_LANE like the reference raises.  fits_host may be NULL. */
 int ld_process_batch_host(ld_ctx* ctx, const uint8_t* frames_host, int n, uint8_t* out_host,

@@ -325,3 +325,29 @@ def test_shared_pass_equals_fused_kernels(engines, stills):
 def torch_idx(mask, like):
     import torch
     return torch.as_tensor(np.nonzero(mask)[0], device=like.device)
+
+
+def test_halo_rebuilds_tracker_state(engines, stills):
+    """sharding without a hand-off: 30 look-back lane records in front of a range, fitted from empty trackers, give the
+    same fits, frames and follow-up behaviour as processing the video from its start"""
+    eng = engines("project")
+    names = ["straight_lines1", "straight_lines2", "test1", "test2", "test3", "test4", "test5", "test6"]
+    seq = np.stack(list(O.synth_sequence([stills(n) for n in names], 48, seed=4)))
+    dev = eng.to_device(seq)
+    eng.reset()
+    out_full, fit_full = eng.process_dev(dev)
+    eng.check()
+    rec_full = eng.context_records(48).clone()
+    fits_full = eng.fits_to_numpy(fit_full).copy()
+    eng.reset()
+    eng.process_dev(dev[40:48])                                 # leave unrelated trackers behind: the halo path must not use them
+    eng.prepass_dev(dev[31:40])
+    eng.halo_set(rec_full[1:31])
+    out_a, fit_a = eng.postpass_dev(dev[31:40], use_halo=True)
+    out_b, fit_b = eng.process_dev(dev[40:48])                  # continues from the rebuilt trackers
+    eng.check()
+    for got_t, lo, hi in ((fit_a, 31, 40), (fit_b, 40, 48)):
+        got = eng.fits_to_numpy(got_t)
+        for k in ("fit", "fit1", "fit2", "bottom", "top", "offset", "mean_curv"):
+            assert (got[k] == fits_full[k][lo:hi]).all(), (k, lo)
+    assert (out_a == out_full[31:40]).all() and (out_b == out_full[40:48]).all()
