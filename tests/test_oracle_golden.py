@@ -63,3 +63,20 @@ def test_sequence(key, variant, golden, stills):
             assert [len(orc.left.fity), len(orc.right.fity)] == rec["n_fit_points"], i
             assert r.offset == unhex(rec["offset"]) and r.mean_curv == unhex(rec["mean_curv"]), i
             assert hashlib.md5(r.out.tobytes()).hexdigest() == rec["out_md5"], i
+
+
+def test_lookback_halo_property(stills):
+    """What sharding.py's look-back halo relies on: Line's deque(maxlen=15) medians make frame k depend on the searches of
+    frames k-28..k only, so trackers started from scratch 28 frames early reproduce every later fit bit for bit."""
+    names = ["straight_lines1", "straight_lines2", "test1", "test2", "test3", "test4", "test5", "test6"]
+    seq = list(O.synth_sequence([stills(n) for n in names], 52, seed=0))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        whole = O.LaneOracle("project")
+        ref = [whole.process(f, render=False) for f in seq]
+        a, halo = 40, 28
+        late = O.LaneOracle("project")
+        got = [late.process(f, render=False) for f in seq[a - halo:]][halo:]
+    for g, r in zip(got, ref[a:]):
+        assert np.array_equal(np.asarray(g.fit), np.asarray(r.fit))
+        assert g.offset == r.offset and g.mean_curv == r.mean_curv

@@ -89,3 +89,15 @@ def test_two_rank_handoff_matches_single_process(tmp_path):
             want.append([list(map(float, r.fit[0])), list(map(float, r.fit[1]))])
     assert got.shape == (N_FRAMES, 2, 3)
     assert (got == np.array(want)).all()
+
+
+def test_halo_decision_is_symmetric():
+    """both ends of a rank boundary decide from the same `ok` flags: any empty lane in the halo -> serial hand-off"""
+    import importlib
+    import numpy as np
+    S = importlib.import_module("advanced-lane-detection_b200.sharding")
+    ok = np.ones((S.HALO, 2), np.int32)
+    assert S.halo_is_valid(ok)
+    ok[7, 1] = 0
+    assert not S.halo_is_valid(ok)
+    assert S.HALO >= 2 * (15 - 1) and S.HALO <= 32            # Project.py:350 frame_num = 15; ld_halo_set takes at most 32
