@@ -10,6 +10,7 @@
 #pragma once
 #include "common.cuh"
 #include "fit_math.h"
+#include "search_math.h"
 
 namespace lanedet {
 
@@ -18,28 +19,8 @@ constexpr int SEARCH_WARPS = SEARCH_THREADS / 32;
 
 struct Box { int x0, x1, r0, r1; };       // inclusive column / row ranges
 
-__device__ __forceinline__ uint32_t col_mask(int w, int x0, int x1) {   // bits of word w inside [x0,x1]
-    const int lo = max(x0 - 32 * w, 0), hi = min(x1 - 32 * w, 31);
-    if (lo > 31 || hi < 0 || lo > hi) return 0u;
-    return (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
-}
-__device__ __forceinline__ uint32_t bitpos_sum(uint32_t v) {             // sum of the indices of set bits
-    return __popc(v & 0xAAAAAAAAu) + (__popc(v & 0xCCCCCCCCu) << 1) + (__popc(v & 0xF0F0F0F0u) << 2) +
-           (__popc(v & 0xFF00FF00u) << 3) + (__popc(v & 0xFFFF0000u) << 4);
-}
-// pixel count and sum of x of mask row `row` restricted to columns [x0, x1]
-__device__ __forceinline__ void row_count_sx(const uint32_t* s_mask, int WW, int W, int row, int x0, int x1,
-                                             uint32_t& cnt, uint32_t& sx) {
-    cnt = 0; sx = 0;
-    x0 = max(x0, 0); x1 = min(x1, W - 1);
-    if (x0 > x1) return;
-    for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
-        const uint32_t v = s_mask[row * WW + w] & col_mask(w, x0, x1);
-        const uint32_t c = __popc(v);
-        cnt += c;
-        sx += bitpos_sum(v) + 32u * w * c;
-    }
-}
+using lanesearch::row_count_sx;                 // per-row count / sum of x by word popcounts (search_math.h)
+
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -90,33 +71,10 @@ __device__ __forceinline__ void stage_mask(const uint32_t* __restrict__ mask, ui
     for (int i = threadIdx.x; i < words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
-// Column histogram of rows [r0, r1), r1 - r0 <= 127, of the 32 columns of word-column wc, by ONE thread: the rows are
-// added bit-parallel into seven bit planes (a ripple-carry counter per column, 32 columns per operation), then each
-// column's 7-bit count is read out of the planes.  np.sum(image[r0:r1, :], axis=0) (Project.py:83) for 32 columns costs
-// ~15 integer operations per row this way; the ballot transpose it replaces took a whole warp ~3 instructions per row
-// and column.  Counts are stored as u16 pairs with a rotation that keeps the 32 threads of a warp on 32 banks.
+// np.sum(image[r0:r1, :], axis=0) (Project.py:83) for the 32 columns of word-column wc by ONE thread: bit-sliced counters
+// (search_math.h); the ballot transpose this replaced took a whole warp ~3 instructions per row and column.
 __device__ __forceinline__ void thread_hist_rows(const uint32_t* s_mask, int WW, int r0, int r1, int wc, uint16_t* hist) {
-    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0;
-    for (int r = r0; r < r1; ++r) {
-        uint32_t c = s_mask[r * WW + wc], t;
-        t = p0 & c; p0 ^= c; c = t;
-        t = p1 & c; p1 ^= c; c = t;
-        t = p2 & c; p2 ^= c; c = t;
-        t = p3 & c; p3 ^= c; c = t;
-        t = p4 & c; p4 ^= c; c = t;
-        t = p5 & c; p5 ^= c; c = t;
-        p6 ^= c;
-    }
-    uint32_t* out = reinterpret_cast<uint32_t*>(hist) + wc * 16;
-#pragma unroll 4
-    for (int jj = 0; jj < 16; ++jj) {
-        const int j = (jj + (wc >> 1)) & 15, b = 2 * j;                   // columns 32 wc + b, + b + 1
-        const uint32_t q0 = p0 >> b, q1 = p1 >> b, q2 = p2 >> b, q3 = p3 >> b, q4 = p4 >> b, q5 = p5 >> b, q6 = p6 >> b;
-        const uint32_t lo = (q0 & 1u) | ((q1 & 1u) << 1) | ((q2 & 1u) << 2) | ((q3 & 1u) << 3) | ((q4 & 1u) << 4) | ((q5 & 1u) << 5) | ((q6 & 1u) << 6);
-        const uint32_t hi = ((q0 >> 1) & 1u) | (((q1 >> 1) & 1u) << 1) | (((q2 >> 1) & 1u) << 2) | (((q3 >> 1) & 1u) << 3) |
-                            (((q4 >> 1) & 1u) << 4) | (((q5 >> 1) & 1u) << 5) | (((q6 >> 1) & 1u) << 6);
-        out[j] = lo | (hi << 16);
-    }
+    lanesearch::hist_rows_bitsliced(s_mask, WW, r0, r1, wc, hist);
 }
 
 // histograms of `nb` row ranges (r0[i], r1[i]) into hist + i*W, one thread per (range, word-column); whole CTA participates

@@ -144,3 +144,18 @@ extern "C" int hs_stamp_ok(int dx, int dy, int thickness) {
     build_stamp(dx, dy, thickness, hw.data(), st, cv);
     return st.ok;
 }
+
+#include "../../advanced-lane-detection_b200/csrc/search_math.h"
+
+extern "C" {
+
+// np.sum(mask[r0:r1, :], axis=0) through the bit-sliced per-word-column counters of k_search; hist = u16[W]
+void hs_hist_rows(const uint32_t* mask, int W, int r0, int r1, uint16_t* hist) {
+    for (int wc = 0; wc < W / 32; ++wc) lanesearch::hist_rows_bitsliced(mask, W / 32, r0, r1, wc, hist);
+}
+
+// count and sum of x of the set pixels of row `row` with x0 <= x <= x1
+void hs_row_count_sx(const uint32_t* mask, int W, int row, int x0, int x1, uint32_t* cnt, uint32_t* sx) {
+    lanesearch::row_count_sx(mask, W / 32, W, row, x0, x1, *cnt, *sx);
+}
+}

@@ -158,3 +158,25 @@ def test_lane_shaped_canvases_match_cv2(hs):
         ref = np.zeros((H, W), np.uint8)
         cv2.fillPoly(ref, pts, 1)
         assert (ref == _fillpoly(hs, p)).all(), it
+
+
+def test_bitsliced_histogram_and_row_sums(hs):
+    """search_math.h (the integer core of k_search): column counts by bit-sliced counters == np.sum(axis=0) for every band
+    height the kernels use, and per-row count / sum-of-x by word popcounts == numpy on random windows"""
+    import ctypes
+    rng = np.random.default_rng(12)
+    W, H = 1280, 720
+    for density in (0.02, 0.5, 1.0):
+        mask = (rng.random((H, W)) < density).astype(np.uint8)
+        packed = np.ascontiguousarray(np.packbits(mask, axis=1, bitorder="little").view("<u4"))
+        for r0, r1 in ((630, 720), (0, 90), (200, 270), (100, 178), (646, 720), (5, 132), (300, 301), (400, 400)):
+            hist = np.zeros(W, np.uint16)
+            hs.hs_hist_rows(packed.ctypes.data_as(ctypes.c_void_p), W, r0, r1, hist.ctypes.data_as(ctypes.c_void_p))
+            assert (hist == mask[r0:r1].sum(0)).all(), (density, r0, r1)
+        cnt, sx = ctypes.c_uint32(), ctypes.c_uint32()
+        for _ in range(300):
+            row = int(rng.integers(0, H))
+            x0, x1 = sorted(int(v) for v in rng.integers(-70, W + 70, 2))
+            hs.hs_row_count_sx(packed.ctypes.data_as(ctypes.c_void_p), W, row, x0, x1, ctypes.byref(cnt), ctypes.byref(sx))
+            xs = np.nonzero(mask[row, max(x0, 0):max(min(x1, W - 1) + 1, 0)])[0] + max(x0, 0)
+            assert cnt.value == xs.size and sx.value == int(xs.sum()), (row, x0, x1)
