@@ -96,6 +96,12 @@ _SIGNATURES = {
     "ld_wait_state": (C.c_int, [_P, _P]),
     "ld_halo_set": (C.c_int, [_P, _P, C.c_int, _P]),
     "ld_ctx_records": (_P, [_P]),
+    "ld_ctx_halo_slots": (_P, [_P, C.c_int]),
+    "ld_halo_arrives": (C.c_int, [_P, C.c_int, _P]),
+    "ld_tail_check": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "ld_halo_status": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ld_warmup": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "ld_process_range_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "ld_check": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "ld_state_reset": (C.c_int, [_P, _P]),
     "ld_state_size": (C.c_size_t, []),

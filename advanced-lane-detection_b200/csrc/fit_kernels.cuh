@@ -64,26 +64,31 @@ __device__ __forceinline__ void do_fit1(FitWork& w) {
 }
 
 // value j of a deque-like series at batch position k-back (back = 0 is frame k itself): the batch
-// entries come from `work`, older ones from the carried state.  Returns false if out of history.
+// entries come from `work`, older ones from the carried state.  Returns the number of entries.
+// lo > 0 (look-back warm-up, see k_halo_start): the trackers start EMPTY at batch frame lo -- frames before it do not exist
+// and nothing is carried.
 template <class GetBatch>
 __device__ __forceinline__ int gather_window(int k, int depth, int n_hist, const double* carried, GetBatch get,
-                                             double* out) {
+                                             double* out, int lo = 0) {
     int m = 0;
     for (int back = depth - 1; back >= 0; --back) {
         const int j = k - back;
-        if (j >= 0) out[m++] = get(j);
-        else if (n_hist + j >= 0) out[m++] = carried[n_hist + j];
+        if (j >= lo) out[m++] = get(j);
+        else if (lo == 0 && n_hist + j >= 0) out[m++] = carried[n_hist + j];
     }
     return m;
 }
+__device__ __forceinline__ int batch_lo(const int* __restrict__ start) { return start ? *start : 0; }
 
 // ---- pass 1: first fit of every frame whose search succeeded (frame-parallel) --------------------
-__global__ void k_fit1(const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work, int n, int* __restrict__ any_fail) {
+__global__ void k_fit1(const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work, int n, int* __restrict__ any_fail,
+                       const int* __restrict__ start) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (frame, lane)
     if (i >= 2 * n) return;
     FitWork& w = work[i];
     const ld_lane_record& r = rec[i];
     w.in.valid = 0;
+    if ((i >> 1) < batch_lo(start)) return;                     // before the warm-up start: the frame does not exist
     if (!r.ok) { atomicOr(any_fail, 1); return; }
 #pragma unroll
     for (int m = 0; m < 8; ++m) w.in.mom[m] = r.mom[m];
@@ -96,25 +101,27 @@ __global__ void k_fit1(const ld_lane_record* __restrict__ rec, FitWork* __restri
 // ---- pass 1b: serial walk over the frames whose search failed (one thread per lane) ---------------
 __global__ void k_fit_fallback(const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work,
                                ld_frame_fit* __restrict__ fit, const TrackState* __restrict__ st, int n, int depth,
-                               int top_anchor, const int* __restrict__ any_fail, int* __restrict__ first_bad) {
+                               int top_anchor, const int* __restrict__ any_fail, int* __restrict__ first_bad,
+                               const int* __restrict__ start) {
     const int L = threadIdx.x;
     if (L >= 2 || !*any_fail) return;
     const TrackLane& T = st->lane[L];
-    for (int k = 0; k < n; ++k) {
+    const int lo = batch_lo(start);
+    for (int k = lo; k < n; ++k) {
         if (rec[2 * k + L].ok) continue;
         FitWork& w = work[2 * k + L];
         // x_inds = self.x, y_inds = self.y (Project.py:98-100): last frame's arrays with its anchors,
         // then .astype(np.float32) (Project.py:308-311)
         FitInput prev; double pb, pt; int prev_n;
-        if (k == 0) { prev = T.pts; pb = T.last_bottom; pt = T.last_top; prev_n = T.n_points; if (!T.has_points) prev.valid = 0; }
+        if (k == lo) { prev = T.pts; pb = T.last_bottom; pt = T.last_top; prev_n = T.n_points; if (!T.has_points || lo > 0) prev.valid = 0; }
         else {
             const FitWork& p = work[2 * (k - 1) + L];
             prev = p.in;
             if (prev.valid) {                                   // anchors of frame k-1 = medians at k-1
                 double tmp[LD_MAX_DEPTH];
-                int m = gather_window(k - 1, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp);
+                int m = gather_window(k - 1, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp, lo);
                 pb = lanefit::median_small(tmp, m);
-                m = gather_window(k - 1, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp);
+                m = gather_window(k - 1, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp, lo);
                 pt = lanefit::median_small(tmp, m);
             }
             prev_n = prev.n_points + 1 + (top_anchor ? 1 : 0);
@@ -132,7 +139,7 @@ __global__ void k_fit_fallback(const ld_lane_record* __restrict__ rec, FitWork* 
         // Line.fity of a fallback frame = the previous frame's fity (its anchors included)
         for (int i = 0; i < LD_ROWMAP_WORDS; ++i) {
             uint32_t v;
-            if (k == 0) v = T.rowmap[i];
+            if (k == lo) v = T.rowmap[i];
             else if (rec[2 * (k - 1) + L].ok) {
                 v = rec[2 * (k - 1) + L].rowmap[i];
                 if (i == (720 >> 5)) v |= 1u << (720 & 31);
@@ -145,17 +152,18 @@ __global__ void k_fit_fallback(const ld_lane_record* __restrict__ rec, FitWork* 
 
 // ---- pass 2: anchors (deque medians) + second fit (frame-parallel) --------------------------------
 __global__ void k_fit2(FitWork* __restrict__ work, const TrackState* __restrict__ st, int n, int depth, int top_anchor,
-                       const int* __restrict__ first_bad) {
+                       const int* __restrict__ first_bad, const int* __restrict__ start) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
     const int k = i >> 1, L = i & 1;
-    if (k >= *first_bad) return;
+    const int lo = batch_lo(start);
+    if (k >= *first_bad || k < lo) return;
     const TrackLane& T = st->lane[L];
     FitWork& w = work[i];
     double tmp[LD_MAX_DEPTH];
-    int m = gather_window(k, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp);
+    int m = gather_window(k, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp, lo);
     w.mb = lanefit::median_small(tmp, m);                       // np.median(self.bottom_x)
-    m = gather_window(k, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp);
+    m = gather_window(k, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp, lo);
     w.mt = lanefit::median_small(tmp, m);
     lanefit::PowerSums ps = sums_of(w.in);
     lanefit::sums_add_level(ps, 720.0, 1.0, lanefit::dd_make(w.mb));          // np.append(self.x, bottom); (self.y, 720)
@@ -192,10 +200,12 @@ __device__ __forceinline__ unsigned long long centi_round(double av) {
 // ---- pass 3: deque medians of A,B,C, car_pos, curvature, text (frame-parallel, one thread per frame)
 __global__ void k_fit3(const ld_lane_record* __restrict__ rec, const FitWork* __restrict__ work,
                        const TrackState* __restrict__ st, ld_frame_fit* __restrict__ fit, int n, const PlanDev P,
-                       const int* __restrict__ first_bad) {
+                       const int* __restrict__ first_bad, const int* __restrict__ start) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     ld_frame_fit& o = fit[k];
+    const int lo = batch_lo(start);
+    if (k < lo) { o.status = LD_ERR_ARG; return; }              // look-back frame before the warm-up start: no result
     if (k >= *first_bad) { o.status = (k == *first_bad) ? LD_ERR_EMPTY_LANE : LD_ERR_ARG; return; }
     o.status = LD_OK;
     const int depth = P.depth;
@@ -203,11 +213,11 @@ __global__ void k_fit3(const ld_lane_record* __restrict__ rec, const FitWork* __
         const TrackLane& T = st->lane[L];
         const FitWork& w = work[2 * k + L];
         double tmp[LD_MAX_DEPTH];
-        int m = gather_window(k, depth, T.n_hist, T.A, [&](int j) { return work[2 * j + L].fit2[0]; }, tmp);
+        int m = gather_window(k, depth, T.n_hist, T.A, [&](int j) { return work[2 * j + L].fit2[0]; }, tmp, lo);
         o.fit[L][0] = lanefit::median_small(tmp, m);
-        m = gather_window(k, depth, T.n_hist, T.B, [&](int j) { return work[2 * j + L].fit2[1]; }, tmp);
+        m = gather_window(k, depth, T.n_hist, T.B, [&](int j) { return work[2 * j + L].fit2[1]; }, tmp, lo);
         o.fit[L][1] = lanefit::median_small(tmp, m);
-        m = gather_window(k, depth, T.n_hist, T.C, [&](int j) { return work[2 * j + L].fit2[2]; }, tmp);
+        m = gather_window(k, depth, T.n_hist, T.C, [&](int j) { return work[2 * j + L].fit2[2]; }, tmp, lo);
         o.fit[L][2] = lanefit::median_small(tmp, m);
         for (int c = 0; c < 3; ++c) { o.fit1[L][c] = w.fit1[c]; o.fit2[L][c] = w.fit2[c]; }
         o.bottom[L] = w.mb; o.top[L] = w.mt;
@@ -260,20 +270,23 @@ __global__ void k_fit3(const ld_lane_record* __restrict__ rec, const FitWork* __
 // ---- pass 4: roll the trackers forward to the end of the valid part of the batch (one thread per lane)
 __global__ void k_state_update(const ld_lane_record* __restrict__ rec, const FitWork* __restrict__ work,
                                const ld_frame_fit* __restrict__ fit, TrackState* __restrict__ st, int n, int depth,
-                               const int* __restrict__ first_bad, int* __restrict__ last_bad_out, int frame_offset) {
+                               const int* __restrict__ first_bad, int* __restrict__ last_bad_out, int frame_offset,
+                               const int* __restrict__ start, int n_lookback, int* __restrict__ halo_invalid) {
     const int L = threadIdx.x;
     if (L == 0 && *first_bad < n && *last_bad_out < 0) *last_bad_out = frame_offset + *first_bad;   // sticky until ld_check reports it
+    if (L == 0 && halo_invalid && *first_bad < n_lookback) *halo_invalid = 1;   // the fit stage stopped inside the look-back frames
     if (L >= 2) return;
     const int nv = min(n, *first_bad);
-    if (nv <= 0) return;
+    const int lo = batch_lo(start);
+    if (nv <= lo) return;
     TrackLane& T = st->lane[L];
     double nb[LD_MAX_DEPTH], nt[LD_MAX_DEPTH], nA[LD_MAX_DEPTH], nB[LD_MAX_DEPTH], nC[LD_MAX_DEPTH];
     const int k = nv - 1;
-    const int m = gather_window(k, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, nb);
-    gather_window(k, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, nt);
-    gather_window(k, depth, T.n_hist, T.A, [&](int j) { return work[2 * j + L].fit2[0]; }, nA);
-    gather_window(k, depth, T.n_hist, T.B, [&](int j) { return work[2 * j + L].fit2[1]; }, nB);
-    gather_window(k, depth, T.n_hist, T.C, [&](int j) { return work[2 * j + L].fit2[2]; }, nC);
+    const int m = gather_window(k, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, nb, lo);
+    gather_window(k, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, nt, lo);
+    gather_window(k, depth, T.n_hist, T.A, [&](int j) { return work[2 * j + L].fit2[0]; }, nA, lo);
+    gather_window(k, depth, T.n_hist, T.B, [&](int j) { return work[2 * j + L].fit2[1]; }, nB, lo);
+    gather_window(k, depth, T.n_hist, T.C, [&](int j) { return work[2 * j + L].fit2[2]; }, nC, lo);
     for (int i = 0; i < m; ++i) { T.bottom[i] = nb[i]; T.top[i] = nt[i]; T.A[i] = nA[i]; T.B[i] = nB[i]; T.C[i] = nC[i]; }
     T.n_hist = m;
     T.has_points = 1;
@@ -288,6 +301,31 @@ __global__ void k_state_update(const ld_lane_record* __restrict__ rec, const Fit
 __global__ void k_state_reset(TrackState* st) {
     uint32_t* p = reinterpret_cast<uint32_t*>(st);
     for (int i = threadIdx.x; i < (int)(sizeof(TrackState) / 4); i += blockDim.x) p[i] = 0;
+}
+
+// Sharding: where in a look-back can trackers start from EMPTY and be exactly the predecessor's trackers at its
+// end?  At any frame s whose `depth` (= frame_num) frames s..s+depth-1 have no empty lane, provided >= need = 2(depth-1)
+// look-back frames follow s: then every deque window that survives into the range is made of first fits that depend on
+// their own frame only, and every empty-lane fallback further on starts from exact points and anchors (an empty lane re-uses
+// the previous frame's points + anchors, Project.py:98-100 -- the one recursion that reaches further back than the medians).
+// rec: the records of the first `m` of `total` look-back frames.  Picks the LATEST such s -> *start (the fit kernels treat
+// earlier frames as non-existent); none -> *start = 0, *invalid = 1.  check == 0: the look-back starts the video, s = 0.
+__global__ void k_halo_start(const ld_lane_record* __restrict__ rec, int m, int total, int depth, int need, int check,
+                             int* __restrict__ start, int* __restrict__ invalid) {
+    __shared__ int best;
+    if (threadIdx.x == 0) best = -1;
+    __syncthreads();
+    if (check)
+        for (int s = threadIdx.x; s + depth <= m && s + need <= total; s += blockDim.x) {
+            bool clean = true;
+            for (int i = 2 * s; i < 2 * (s + depth); ++i) clean = clean && rec[i].ok != 0;
+            if (clean) atomicMax(&best, s);
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *start = (check && best > 0) ? best : 0;
+        *invalid = (check && best < 0) ? 1 : 0;
+    }
 }
 
 // np.polyfit(y, x, 2) of plain pixel sets with float64 rcond (helper.py:309-310, 362-363)

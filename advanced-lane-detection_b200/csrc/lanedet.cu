@@ -29,6 +29,18 @@ static thread_local char g_cuda_err[256] = "";
         }                                                                                      \
     } while (0)
 
+// the same, running `cleanup` first (the create functions destroy what they have built so far)
+#define LD_CUDA_OR(expr, cleanup)                                                              \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                     cudaGetErrorString(_e));                                                  \
+            cleanup;                                                                           \
+            return LD_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
 struct ld_plan {
     int device;
     PlanDev d;
@@ -62,7 +74,8 @@ struct ld_ctx {
     uint32_t* und_bits;        // shared pass: colour decision of the undistorted pixels, [max][H - share_y0][WW] (+ pad)
     uint32_t* und_px;          // shared pass: the undistorted pixels in lane order, [max][n_share][16][4][32]
     TrackState* state;
-    int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error
+    int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error, [4] halo invalid,
+                               // [5] tail invalid (the records this rank hands on), [6] scratch last_bad of ld_warmup
     int* flags_host;           // pinned mirror
     // host pipeline
     cudaStream_t s_in, s_comp, s_out;
@@ -70,6 +83,10 @@ struct ld_ctx {
     // intra-batch pipeline: pixel-heavy kernels on s_pix, the latency-bound search/fit/raster chain on s_lat
     cudaStream_t s_pix, s_lat;
     cudaEvent_t ev_fork, ev_state, ev_join[2], ev_mask[PIPE_SUB], ev_rast[PIPE_SUB];
+    // sharding: ev_halo_in = the look-back records have landed in front of rec (the next fit stage waits for it, nothing else does);
+    // ev_valid[0/1] = the pinned copies of flags[4] (halo invalid) / flags[5] (tail invalid) are readable
+    cudaEvent_t ev_halo_in, ev_valid[2];
+    int halo_wait;             // ev_halo_in was recorded for the next ld_postpass_flags(LD_POST_USE_HALO)
     uint8_t* stage_in[2];
     uint8_t* stage_out[2];
     int chunk;
@@ -142,16 +159,16 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         const int rows = desc->frame_tiles[8 * t + 6] & 0xFFFF, stride = desc->frame_tiles[8 * t + 7] & 0x7FFFFFFF;
         if (desc->frame_tiles[8 * t + 7] < 0) continue;                  // slow tile: no staged box
         // every staged box is one tensor-map TMA copy of FRAME_BOX_PITCH bytes x box_rows rows
-        if (stride != FRAME_BOX_PITCH || desc->frame_tiles[8 * t + 2] > 128 || (desc->frame_tiles[8 * t + 4] & 15)) return LD_ERR_ARG;
+        if (stride != FRAME_BOX_PITCH || desc->frame_tiles[8 * t + 2] > 128 || (desc->frame_tiles[8 * t + 4] & 15)) { ld_plan_destroy(p); return LD_ERR_ARG; }
         if (rows > box_rows) box_rows = rows;
     }
-    if (box_rows > 64) return LD_ERR_ARG;
+    if (box_rows > 64) { ld_plan_destroy(p); return LD_ERR_ARG; }
     fs = (size_t)box_rows * FRAME_BOX_PITCH;
     for (int t = 0; t < desc->n_mask_chunks; ++t) {
         const size_t b = (size_t)(desc->mask_chunks[8 * t + 6] & 0xFFFF) * (size_t)(desc->mask_chunks[8 * t + 7] & 0x7FFFFFFF);
         if (b > ms) ms = b;
     }
-    if (ms > 96 * 1024) return LD_ERR_ARG;                               // k_mask double-buffers its chunk boxes
+    if (ms > 96 * 1024) { ld_plan_destroy(p); return LD_ERR_ARG; }                              // k_mask double-buffers its chunk boxes
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
@@ -285,24 +302,24 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     // The opt-in limit is a per-function, per-device attribute shared by every plan: always raise it to
     // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
     if (p->mask_smem > 220 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }
-    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
     // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
     // carveout, otherwise an SM has to drain before a kernel with a different carveout can start on it.
-    LD_CUDA(cudaFuncSetAttribute(k_mask, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LD_CUDA(cudaFuncSetAttribute(k_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LD_CUDA(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LD_CUDA(cudaFuncSetAttribute(k_fit1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LD_CUDA(cudaFuncSetAttribute(k_fit2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LD_CUDA(cudaFuncSetAttribute(k_fit3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_mask, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_fit1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_fit2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_fit3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
     if (W == 1280 && H == 720) {        // search / raster stage the whole 115,200-byte mask plane per CTA
-        LD_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
-        LD_CUDA(cudaFuncSetAttribute(k_margin_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem));
-        LD_CUDA(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->raster_smem));
+        LD_CUDA_OR(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem), ld_plan_destroy(p));
+        LD_CUDA_OR(cudaFuncSetAttribute(k_margin_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->search_smem), ld_plan_destroy(p));
+        LD_CUDA_OR(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->raster_smem), ld_plan_destroy(p));
     }
     *out = p;
     return LD_OK;
@@ -357,32 +374,34 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
         CTX_ALLOC(c->stage_out[b], fb * c->chunk);
     }
 #undef CTX_ALLOC
-    LD_CUDA(cudaMallocHost((void**)&c->flags_host, 16 * sizeof(int)));
-    LD_CUDA(cudaMemset(c->planes, 0, canvas_words(d) * 4 * max_frames));  // the border rows of every canvas stay zero for good
-    LD_CUDA(cudaMemset(c->state, 0, sizeof(TrackState)));
-    LD_CUDA(cudaMemset(c->flags, 0, 16 * sizeof(int)));
-    LD_CUDA(cudaMemset(c->flags + 2, 0xFF, sizeof(int)));       // last_bad = -1
-    LD_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-    LD_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
-    LD_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    LD_CUDA(cudaStreamCreateWithFlags(&c->s_pix, cudaStreamNonBlocking));
+    LD_CUDA_OR(cudaMallocHost((void**)&c->flags_host, 16 * sizeof(int)), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaMemset(c->planes, 0, canvas_words(d) * 4 * max_frames), ld_ctx_destroy(c));  // the border rows of every canvas stay zero for good
+    LD_CUDA_OR(cudaMemset(c->state, 0, sizeof(TrackState)), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaMemset(c->flags, 0, 16 * sizeof(int)), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaMemset(c->flags + 2, 0xFF, sizeof(int)), ld_ctx_destroy(c));       // last_bad = -1
+    LD_CUDA_OR(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaStreamCreateWithFlags(&c->s_pix, cudaStreamNonBlocking), ld_ctx_destroy(c));
     {   // the latency-bound chain gets the highest priority: its few CTAs take SM slots as soon as they free up and run
         // concurrently with the bandwidth-bound kernel instead of queueing behind its whole grid
         int lo = 0, hi = 0;
-        LD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        LD_CUDA(cudaStreamCreateWithPriority(&c->s_lat, cudaStreamNonBlocking, hi));
+        LD_CUDA_OR(cudaDeviceGetStreamPriorityRange(&lo, &hi), ld_ctx_destroy(c));
+        LD_CUDA_OR(cudaStreamCreateWithPriority(&c->s_lat, cudaStreamNonBlocking, hi), ld_ctx_destroy(c));
     }
-    LD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    LD_CUDA(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
-    for (int b = 0; b < 2; ++b) LD_CUDA(cudaEventCreateWithFlags(&c->ev_join[b], cudaEventDisableTiming));
+    LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming), ld_ctx_destroy(c));
+    LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_halo_in, cudaEventDisableTiming), ld_ctx_destroy(c));
+    for (int b = 0; b < 2; ++b) LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_valid[b], cudaEventDisableTiming), ld_ctx_destroy(c));
+    for (int b = 0; b < 2; ++b) LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_join[b], cudaEventDisableTiming), ld_ctx_destroy(c));
     for (int b = 0; b < PIPE_SUB; ++b) {
-        LD_CUDA(cudaEventCreateWithFlags(&c->ev_mask[b], cudaEventDisableTiming));
-        LD_CUDA(cudaEventCreateWithFlags(&c->ev_rast[b], cudaEventDisableTiming));
+        LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_mask[b], cudaEventDisableTiming), ld_ctx_destroy(c));
+        LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_rast[b], cudaEventDisableTiming), ld_ctx_destroy(c));
     }
     for (int b = 0; b < 2; ++b) {
-        LD_CUDA(cudaEventCreateWithFlags(&c->ev_in[b], cudaEventDisableTiming));
-        LD_CUDA(cudaEventCreateWithFlags(&c->ev_comp[b], cudaEventDisableTiming));
-        LD_CUDA(cudaEventCreateWithFlags(&c->ev_out[b], cudaEventDisableTiming));
+        LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_in[b], cudaEventDisableTiming), ld_ctx_destroy(c));
+        LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_comp[b], cudaEventDisableTiming), ld_ctx_destroy(c));
+        LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_out[b], cudaEventDisableTiming), ld_ctx_destroy(c));
     }
     *out = c;
     return LD_OK;
@@ -411,6 +430,8 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     if (c->s_lat) cudaStreamDestroy(c->s_lat);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_state) cudaEventDestroy(c->ev_state);
+    if (c->ev_halo_in) cudaEventDestroy(c->ev_halo_in);
+    for (int b = 0; b < 2; ++b) if (c->ev_valid[b]) cudaEventDestroy(c->ev_valid[b]);
     for (int b = 0; b < 2; ++b) if (c->ev_join[b]) cudaEventDestroy(c->ev_join[b]);
     for (int b = 0; b < PIPE_SUB; ++b) { if (c->ev_mask[b]) cudaEventDestroy(c->ev_mask[b]); if (c->ev_rast[b]) cudaEventDestroy(c->ev_rast[b]); }
     delete c;
@@ -494,25 +515,41 @@ extern "C" int ld_polyfit(ld_ctx* c, const ld_lane_record* rec, int n, double* c
 // halo > 0 (only with rec == c->rec, fit == c->fit): the `halo` look-back records ld_halo_set put in front of the range are
 // fitted first, from EMPTY trackers.  A deque(maxlen=F) median of medians depends on the last 2(F-1) frames only, so after
 // >= 2(F-1) look-back frames without an empty lane the trackers are exactly what the predecessor would hand over.
-static int fit_impl(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, cudaStream_t s, int frame_offset, int halo = 0) {
-    if (!ARGS_OK(c, rec, fit, n) || n > c->max_frames || halo < 0 || halo > HALO_MAX) return LD_ERR_ARG;
-    if (n == 0) return LD_OK;
+// warm = 0: plain batch, trackers carried.  warm = 1: the first `look` frames of the batch are look-back frames fitted from EMPTY
+// trackers starting at the frame k_halo_start picks (check = 0: at frame 0, the look-back starts the video); `look_total` = length
+// of the whole look-back when only its first chunk is in this batch.  flags[7] = the start, flags[4] = no exact start exists.
+static int fit_core(ld_ctx* c, const ld_lane_record* rec, FitWork* work, int n, ld_frame_fit* fit, cudaStream_t s, int frame_offset,
+                    int warm, int look, int look_total, int check, int* last_bad_out) {
     const PlanDev& d = c->plan->d;
-    if (halo) {
-        if (rec != c->rec || fit != c->fit) return LD_ERR_ARG;
+    const int* start = nullptr;
+    if (warm) {
         k_state_reset<<<1, 128, 0, s>>>(c->state);
-        rec -= 2 * halo; fit -= halo; n += halo; frame_offset -= halo;
+        k_halo_start<<<1, 64, 0, s>>>(rec, look, look_total, d.depth, 2 * (d.depth - 1), check, c->flags + 7, c->flags + 4);
+        start = c->flags + 7;
     }
-    FitWork* work = c->work - 2 * halo;
     LD_CUDA(cudaMemsetAsync(c->flags, 0, sizeof(int), s));              // any_fail = 0
     LD_CUDA(cudaMemsetAsync(c->flags + 1, 0x7F, sizeof(int), s));       // first_bad = 0x7f7f7f7f
     const int t = 64, g2 = (2 * n + t - 1) / t, g1 = (n + t - 1) / t;
-    k_fit1<<<g2, t, 0, s>>>(rec, work, n, c->flags);
-    k_fit_fallback<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, d.top_anchor, c->flags, c->flags + 1);
-    k_fit2<<<g2, t, 0, s>>>(work, c->state, n, d.depth, d.top_anchor, c->flags + 1);
-    k_fit3<<<g1, t, 0, s>>>(rec, work, c->state, fit, n, d, c->flags + 1);
-    k_state_update<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, c->flags + 1, c->flags + 2, frame_offset);
+    k_fit1<<<g2, t, 0, s>>>(rec, work, n, c->flags, start);
+    k_fit_fallback<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, d.top_anchor, c->flags, c->flags + 1, start);
+    k_fit2<<<g2, t, 0, s>>>(work, c->state, n, d.depth, d.top_anchor, c->flags + 1, start);
+    k_fit3<<<g1, t, 0, s>>>(rec, work, c->state, fit, n, d, c->flags + 1, start);
+    k_state_update<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, c->flags + 1, last_bad_out ? last_bad_out : c->flags + 2, frame_offset,
+                                    start, warm ? look : 0, warm ? c->flags + 4 : nullptr);
+    if (warm) {
+        LD_CUDA(cudaMemcpyAsync(c->flags_host + 4, c->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, s));
+        LD_CUDA(cudaEventRecord(c->ev_valid[0], s));
+    }
     return check_launch();
+}
+// halo > 0 (only with rec == c->rec, fit == c->fit): the `halo` look-back records in front of the range (ld_halo_set /
+// ld_halo_arrives) are fitted first, from EMPTY trackers.  A deque(maxlen=F) median of medians depends on the last 2(F-1) frames
+// only, so after such a halo the trackers are exactly what the predecessor would hand over (k_halo_start has the precise rule).
+static int fit_impl(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, cudaStream_t s, int frame_offset, int halo = 0) {
+    if (!ARGS_OK(c, rec, fit, n) || n > c->max_frames || halo < 0 || halo > HALO_MAX) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    if (halo && (rec != c->rec || fit != c->fit)) return LD_ERR_ARG;
+    return fit_core(c, rec - 2 * halo, c->work - 2 * halo, n + halo, fit - halo, s, frame_offset - halo, halo ? 1 : 0, halo, halo, 1, nullptr);
 }
 extern "C" int ld_fit(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit* fit, void* stream) {
     return fit_impl(c, rec, n, fit, (cudaStream_t)stream, 0);
@@ -751,6 +788,10 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         // CTAs fill the issue slots the chain leaves idle.  The overlay tiles follow the raster.
         LD_CUDA(cudaEventRecord(c->ev_fork, s));
         LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
+        if (halo && c->halo_wait) {                                      // look-back records still on their way (ld_halo_arrives):
+            LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_halo_in, 0));   // only the fit chain waits, the plain tiles start now
+            c->halo_wait = 0;
+        }
         if (search_first && (rc = ld_search(c, c->mask, M, c->rec, c->s_lat))) return rc;
         if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset, halo))) return rc;
         if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
@@ -849,6 +890,56 @@ extern "C" int ld_halo_set(ld_ctx* c, const ld_lane_record* halo_dev, int n_halo
     return LD_OK;
 }
 extern "C" const ld_lane_record* ld_ctx_records(ld_ctx* c) { return c ? c->rec : nullptr; }   // records of the last ld_prepass (device)
+// The slots in front of the context's records, for a transfer that delivers the look-back records in place (NCCL receive,
+// cudaMemcpyPeerAsync): ld_ctx_halo_slots = where the n_halo frames' records go; ld_halo_arrives = they are being written by
+// work queued on `stream` -- the next ld_postpass_flags(LD_POST_USE_HALO) uses them and only its fit stage waits for that work.
+extern "C" ld_lane_record* ld_ctx_halo_slots(ld_ctx* c, int n_halo) {
+    return (c && n_halo >= 1 && n_halo <= HALO_MAX) ? c->rec - 2 * n_halo : nullptr;
+}
+extern "C" int ld_halo_arrives(ld_ctx* c, int n_halo, void* stream) {
+    if (!c || n_halo < 1 || n_halo > HALO_MAX) return LD_ERR_ARG;
+    LD_CUDA(cudaEventRecord(c->ev_halo_in, (cudaStream_t)stream));
+    c->halo = n_halo;
+    c->halo_wait = 1;
+    return LD_OK;
+}
+// The sender's side of the same decision: are the last n_halo of the n records ld_prepass left a halo its successor can
+// rebuild the trackers from (k_halo_valid)?  Both ends look at the same records, so they agree without a handshake.
+extern "C" int ld_tail_check(ld_ctx* c, int n, int n_halo, void* stream) {
+    if (!c || n_halo < 1 || n_halo > HALO_MAX || n < n_halo || n > c->max_frames) return LD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int depth = c->plan->d.depth;
+    k_halo_start<<<1, 64, 0, s>>>(c->rec + 2 * (n - n_halo), n_halo, n_halo, depth, 2 * (depth - 1), 1, c->flags + 8, c->flags + 5);
+    LD_CUDA(cudaMemcpyAsync(c->flags_host + 5, c->flags + 5, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LD_CUDA(cudaEventRecord(c->ev_valid[1], s));
+    return check_launch();
+}
+// Waits for the last halo / tail decisions (not for the rest of the step) and returns them: 1 = the halo could NOT rebuild the
+// trackers exactly, the range has to be fitted again from a longer look-back or the predecessor's tracker blob.
+extern "C" int ld_halo_status(ld_ctx* c, int* halo_invalid, int* tail_invalid) {
+    if (!c) return LD_ERR_ARG;
+    LD_CUDA(cudaEventSynchronize(c->ev_valid[0]));
+    LD_CUDA(cudaEventSynchronize(c->ev_valid[1]));
+    if (halo_invalid) *halo_invalid = c->flags_host[4];
+    if (tail_invalid) *tail_invalid = c->flags_host[5];
+    return LD_OK;
+}
+// Zero-communication sharding (SURVEY 8e "recompute"): a rank that holds the n frames BEFORE its range runs mask + search + fit
+// on them from empty trackers (no raster, no overlay, nothing written out); after n >= 2 (frame_num - 1) such frames whose
+// first `check_frames` (frame_num; 0 = the look-back starts at the first frame of the video, nothing to check) have no empty
+// lane the trackers are exactly what a single GPU would carry into the range (k_halo_valid).  Follow with ld_process_batch.
+static int warmup_impl(ld_ctx* c, const uint8_t* frames, int n, int n_total, int check, cudaStream_t s) {
+    int rc;
+    if ((rc = prepass_impl(c, frames, n, s))) return rc;
+    // an empty lane on a fresh tracker inside a look-back that does NOT start the video is not the reference's TypeError (the
+    // real tracker had points there): it only makes the halo invalid, so its frame index goes to a scratch slot
+    return fit_core(c, c->rec, c->work, n, c->fit, s, 0, 1, n, n_total, check, check ? c->flags + 6 : nullptr);
+}
+extern "C" int ld_warmup(ld_ctx* c, const uint8_t* frames, int n, int check_frames, void* stream) {
+    if (!c || !frames || n < 1 || n > c->max_frames || check_frames < 0 || check_frames > n) return LD_ERR_ARG;
+    if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
+    return warmup_impl(c, frames, n, n, check_frames ? 1 : 0, (cudaStream_t)stream);
+}
 extern "C" int ld_wait_state(ld_ctx* c, void* stream) {
     if (!c) return LD_ERR_ARG;
     LD_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_state, 0));
@@ -874,34 +965,68 @@ extern "C" int ld_check(ld_ctx* c, void* stream, int* first_bad_frame) {
     return LD_OK;
 }
 
-extern "C" int ld_process_batch_host(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fits) {
-    if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
-    LD_CUDA(cudaSetDevice(c->plan->device));
+// Host buffers: chunks are copied in (s_in), processed (s_comp) and copied out (s_out) on three streams, two staging buffers
+// each way.  With a look-back (lookback != NULL: the n_lookback frames before `frames` in the video) the trackers are first
+// rebuilt from empty by mask + search + fit of those frames (warmup_impl), chunk by chunk through the same pipeline.
+static int process_host_impl(ld_ctx* c, const uint8_t* lookback, int n_lookback, int check_frames, const uint8_t* frames, int n,
+                             uint8_t* out, ld_frame_fit* fits, int* halo_invalid) {
     const PlanDev& d = c->plan->d;
     const size_t fb = (size_t)d.W * d.H * 3;
     int chunk_i = 0, rc = LD_OK;
-    for (int done = 0; done < n; done += c->chunk, ++chunk_i) {
-        const int m = (n - done) < c->chunk ? (n - done) : c->chunk;
+    cudaError_t ce = cudaSuccess;
+#define HOST_TRY(expr) do { if (!rc && ce == cudaSuccess) { ce = (expr); if (ce != cudaSuccess) \
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(ce)); } } while (0)
+    const int total = n_lookback + n;
+    for (int pos = 0; pos < total && !rc && ce == cudaSuccess; ++chunk_i) {
+        const bool warm = pos < n_lookback;
+        const int done = warm ? pos : pos - n_lookback, left = warm ? n_lookback - pos : total - pos;
+        const int m = left < c->chunk ? left : c->chunk;
+        const uint8_t* src = (warm ? lookback : frames) + (size_t)done * fb;
         const int b = chunk_i & 1;
         if (chunk_i >= 2) {
-            LD_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_comp[b], 0));        // stage_in[b] consumed by chunk i-2
-            LD_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_out[b], 0));       // stage_out[b] drained by chunk i-2
+            HOST_TRY(cudaStreamWaitEvent(c->s_in, c->ev_comp[b], 0));        // stage_in[b] consumed by chunk i-2
+            HOST_TRY(cudaStreamWaitEvent(c->s_comp, c->ev_out[b], 0));       // stage_out[b] drained by chunk i-2
         }
-        LD_CUDA(cudaMemcpyAsync(c->stage_in[b], frames + done * fb, m * fb, cudaMemcpyHostToDevice, c->s_in));
-        LD_CUDA(cudaEventRecord(c->ev_in[b], c->s_in));
-        LD_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_in[b], 0));
-        if ((rc = process_impl(c, c->stage_in[b], m, c->stage_out[b], nullptr, c->s_comp, done))) break;
-        if (fits) LD_CUDA(cudaMemcpyAsync(fits + done, c->fit, sizeof(ld_frame_fit) * m, cudaMemcpyDeviceToHost, c->s_comp));
-        LD_CUDA(cudaEventRecord(c->ev_comp[b], c->s_comp));
-        LD_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_comp[b], 0));
-        LD_CUDA(cudaMemcpyAsync(out + done * fb, c->stage_out[b], m * fb, cudaMemcpyDeviceToHost, c->s_out));
-        LD_CUDA(cudaEventRecord(c->ev_out[b], c->s_out));
+        HOST_TRY(cudaMemcpyAsync(c->stage_in[b], src, m * fb, cudaMemcpyHostToDevice, c->s_in));
+        HOST_TRY(cudaEventRecord(c->ev_in[b], c->s_in));
+        HOST_TRY(cudaStreamWaitEvent(c->s_comp, c->ev_in[b], 0));
+        if (ce != cudaSuccess) break;
+        if (warm) {
+            if (pos == 0) rc = warmup_impl(c, c->stage_in[b], m, n_lookback, check_frames ? 1 : 0, c->s_comp);
+            else if (!(rc = prepass_impl(c, c->stage_in[b], m, c->s_comp)))
+                rc = fit_core(c, c->rec, c->work, m, c->fit, c->s_comp, 0, 0, 0, 0, 0, check_frames ? c->flags + 6 : nullptr);
+            HOST_TRY(cudaEventRecord(c->ev_comp[b], c->s_comp));
+        } else {
+            rc = process_impl(c, c->stage_in[b], m, c->stage_out[b], nullptr, c->s_comp, done);
+            if (fits) HOST_TRY(cudaMemcpyAsync(fits + done, c->fit, sizeof(ld_frame_fit) * m, cudaMemcpyDeviceToHost, c->s_comp));
+            HOST_TRY(cudaEventRecord(c->ev_comp[b], c->s_comp));
+            HOST_TRY(cudaStreamWaitEvent(c->s_out, c->ev_comp[b], 0));
+            HOST_TRY(cudaMemcpyAsync(out + done * fb, c->stage_out[b], m * fb, cudaMemcpyDeviceToHost, c->s_out));
+            HOST_TRY(cudaEventRecord(c->ev_out[b], c->s_out));
+        }
+        pos += m;
     }
-    LD_CUDA(cudaStreamSynchronize(c->s_in));
+#undef HOST_TRY
+    // never return with copies from / to the caller's buffers still in flight
+    cudaStreamSynchronize(c->s_in);
     const int st = ld_check(c, c->s_comp, &c->flags_host[8]);   // flags_host[8] = index of the offending frame
-    LD_CUDA(cudaStreamSynchronize(c->s_out));
+    cudaStreamSynchronize(c->s_out);
+    if (halo_invalid) *halo_invalid = n_lookback ? c->flags_host[4] : 0;
+    if (ce != cudaSuccess) return LD_ERR_CUDA;
     if (rc) return rc;
     return st;
+}
+extern "C" int ld_process_batch_host(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fits) {
+    if (!ARGS_OK(c, frames, out, n)) return LD_ERR_ARG;
+    LD_CUDA(cudaSetDevice(c->plan->device));
+    return process_host_impl(c, nullptr, 0, 0, frames, n, out, fits, nullptr);
+}
+extern "C" int ld_process_range_host(ld_ctx* c, const uint8_t* lookback, int n_lookback, int check_frames, const uint8_t* frames,
+                                     int n, uint8_t* out, ld_frame_fit* fits, int* halo_invalid) {
+    if (!ARGS_OK(c, frames, out, n) || n_lookback < 0 || (n_lookback && !lookback) || check_frames < 0 || check_frames > n_lookback)
+        return LD_ERR_ARG;
+    LD_CUDA(cudaSetDevice(c->plan->device));
+    return process_host_impl(c, lookback, n_lookback, check_frames, frames, n, out, fits, halo_invalid);
 }
 
 // ------------------------------------------------------------------------------------- tracker state

@@ -192,6 +192,55 @@ class LaneEngine:
         records = records.contiguous()
         _abi.check(self.lib, self.lib.ld_halo_set(self._ctx_h, _ptr(records), records.shape[0], self._stream()))
 
+    is_cuda = True
+
+    def new_like(self, frames):
+        return self.torch.empty_like(frames)
+
+    def new_fits(self, n):
+        return self._dev((n, _abi.FIT_DTYPE.itemsize), self.torch.uint8)
+
+    def new_state_blob(self):
+        """device buffer for one tracker blob (export_state_dev / import_state_dev)"""
+        return self._dev((self.lib.ld_state_size(),), self.torch.uint8)
+
+    def records_ok(self, n):
+        """host int32[n, 2]: the `ok` flags of the records the last prepass left in the context (synchronises)"""
+        off = _abi.RECORD_DTYPE.fields["ok"][1]
+        r = self.context_records(n)[:, :, off:off + 4].contiguous().cpu().numpy()
+        return r.view(np.int32).reshape(n, 2)
+
+    def halo_slots(self, h):
+        """VIEW of the h record slots in front of the context's records (uint8[h, 2, 280], device): a transfer may deliver the
+        look-back records there directly; announce it with halo_arrives(h, stream)"""
+        ptr = self.lib.ld_ctx_halo_slots(self._ctx_h, int(h))
+        if not ptr:
+            raise ValueError("halo of %d frames is not supported" % h)
+        return self._raw_view(ptr, (h, 2, _abi.RECORD_DTYPE.itemsize), "|u1")
+
+    def halo_arrives(self, h, stream):
+        """the h look-back records are being written into halo_slots(h) by work queued on `stream` (torch stream): the next
+        postpass_dev(use_halo=True) uses them; only its fit stage waits for that work"""
+        _abi.check(self.lib, self.lib.ld_halo_arrives(self._ctx_h, int(h), C.c_void_p(stream.cuda_stream)))
+
+    def tail_check(self, n, h):
+        """decide on the device whether the last h of the n records of the last prepass_dev are a usable halo for the successor"""
+        _abi.check(self.lib, self.lib.ld_tail_check(self._ctx_h, int(n), int(h), self._stream()))
+
+    def halo_status(self):
+        """(halo_invalid, tail_invalid) of the last step; waits for those two device decisions only"""
+        a, b = C.c_int(0), C.c_int(0)
+        _abi.check(self.lib, self.lib.ld_halo_status(self._ctx_h, C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
+
+    def warmup_dev(self, lookback, starts_video=False):
+        """Zero-communication sharding: rebuild the trackers from the frames just before this rank's range (mask + search + fit
+        from empty trackers, nothing drawn).  The device starts the trackers at the latest look-back frame from which the
+        result is exact (frame_num frames without an empty lane, 2 (frame_num - 1) frames before the range) -- or at frame 0 when
+        the look-back starts the video.  Verdict (an exact start exists): halo_status()[0] is False."""
+        lookback = self._frames(lookback)
+        _abi.check(self.lib, self.lib.ld_warmup(self._ctx_h, _ptr(lookback), lookback.shape[0], 0 if starts_video else 1, self._stream()))
+
     def postpass_dev(self, frames, out=None, fits=None, state_out=None, skip_plain=False, fit_first=False, use_halo=False):
         """fit (tracker order!) + overlay of the range given to prepass_dev; state_out = CUDA uint8 blob or None"""
         frames = self._frames(frames)
@@ -233,6 +282,18 @@ class LaneEngine:
         st = self.lib.ld_process_batch_host(self._ctx_h, _ptr(pin_in), n, _ptr(pin_out),
                                             _ptr(pin_fit) if pin_fit is not None else None)
         _abi.check(self.lib, st)
+
+    def process_range_pinned(self, pin_lookback, pin_in, pin_out, pin_fit=None, starts_video=False):
+        """process_pinned for one rank's range of a sharded video: pin_lookback = the frames before the range (None: the range
+        starts the video), warmed up through the same pipeline.  Returns True if no exact tracker start exists in the
+        look-back (see warmup_dev): pass a longer one."""
+        h = 0 if pin_lookback is None else pin_lookback.shape[0]
+        bad = C.c_int(0)
+        st = self.lib.ld_process_range_host(self._ctx_h, _ptr(pin_lookback) if h else None, h, 0 if (starts_video or not h) else 1,
+                                            _ptr(pin_in), pin_in.shape[0], _ptr(pin_out), _ptr(pin_fit) if pin_fit is not None else None,
+                                            C.byref(bad))
+        _abi.check(self.lib, st)
+        return bool(bad.value)
 
     # ------------------------------------------------------------------ tracker state
     def reset(self):

@@ -1,28 +1,41 @@
 """Frame-range sharding of one video over the GPUs of a box.
 
-The per-pixel stages (mask, search, overlay) are frame-independent, so every rank runs them on its
-own contiguous frame range with no communication.  Only `Line` tracking is order dependent, and only
-through `deque(maxlen=frame_num)` medians: frame k depends on the window searches of frames
-k-2(F-1)..k.  Two ways to give rank r the trackers "as rank r-1 left them":
+The per-pixel stages (mask, search, overlay) are frame-independent, so every rank runs them on its own contiguous frame
+range with no communication.  Only `Line` tracking is order dependent, and only through `deque(maxlen=frame_num)` medians
+(Project.py:122-138): frame k depends on the window searches of frames k-2(F-1)..k.  Three ways to give rank r the trackers
+"as rank r-1 left them", all bit-identical to one GPU walking the whole video:
 
-* look-back halo (default): rank r-1 sends the lane records (280 B per lane and frame) of its last
-  HALO frames right after its own prepass; rank r fits them first, from empty trackers, and so
-  rebuilds the state itself.  No rank waits for another rank's fit stage.  Exact whenever none of
-  the HALO frames has an empty lane (an empty lane re-uses the previous frame's points, a recursion
-  that can reach further back); both sides see the same records and take the same decision.
-* serial hand-off (fallback, and for ranges shorter than the halo): the tracker blob
-  (LaneEngine.export_state, ~1.6 KB) travels rank 0 -> 1 -> ... after each rank's fit stage.
+* ``lookback`` (default; zero communication): rank r is handed the HALO frames before its range together with the range (the
+  host has the decoded video anyway) and runs mask + search + fit over them from empty trackers -- 2.4 % extra work for
+  1260-frame ranges, no exchange, no synchronisation between ranks at all (LaneEngine.warmup_dev / ld_warmup).
+* ``records`` (NVLink): rank r-1 sends the lane records (280 B per lane and frame, 17 KB per boundary) of its last HALO
+  frames right after its own mask + search; they land directly in the slots in front of rank r's records, and only rank r's
+  fit stage waits for them -- its tiles that need neither fit nor canvas are undistorted meanwhile.  One batched
+  isend/irecv per step on a process group of its own, queued on a side stream; the host never waits inside a step.
+* ``serial``: the 1.6 KB tracker blob travels rank 0 -> 1 -> ... after each rank's fit stage (LaneEngine.export_state_dev).
+  The reference protocol the other two are checked against, and the repair path of ``records``.
 
-While a rank waits it has finished mask + search for its range and undistorts the tiles that depend on
-neither the fit nor the canvas.  torch.distributed point-to-point over NCCL/NVLink (gloo on CPU tests).
+Trackers started EMPTY at look-back frame s are exact from the range's first frame on iff frames s..s+frame_num-1 have no empty
+lane and at least 2 (frame_num - 1) look-back frames follow s (an empty lane re-uses the previous frame's points and anchors,
+Project.py:98-100: the one recursion that reaches further back).  The device picks the latest such s itself
+(fit_kernels.cuh: k_halo_start) while the step runs optimistically; the host reads the verdict "no such s" one step later
+(ShardedRun.finish, called by the next step) and only then -- rarely -- repairs: ``lookback`` asks for a longer look-back
+(`fetch_lookback`), ``records`` falls back to the tracker blob for that boundary (sender and receiver judge the same records
+by the same rule, so they agree without a handshake).
 """
 from __future__ import annotations
 
+import contextlib
 import os
-from typing import List, Tuple
+from typing import Callable, List, Optional, Tuple
 
 HALO = 30                    # >= 2 * (frame_num - 1) = 28 for Project.py's frame_num = 15 (harder: 5 -> 8)
-_OK_OFFSET = 160             # byte offset of ld_lane_record.ok (u64 mom[8] + u32 rowmap[24])
+HALO_SLOTS = 32              # look-back record slots in front of a context's records (csrc/lanedet.cu: HALO_MAX)
+MODES = ("lookback", "records", "serial")
+
+
+class ShardingError(RuntimeError):
+    pass
 
 
 def partition(n_frames: int, world: int) -> List[Tuple[int, int]]:
@@ -38,6 +51,11 @@ def partition(n_frames: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+def lookback_range(start: int, halo: int = HALO) -> Tuple[int, int]:
+    """[lo, start): the frames a rank whose range begins at `start` is handed in front of it"""
+    return max(0, start - halo), start
+
+
 def handoff_chain(rank: int, world: int, recv_fn, send_fn, run_ordered):
     """Generic chain: receive predecessor state (rank > 0), run the ordered stage, send to the successor.
     `recv_fn()` returns the state, `run_ordered(state_or_None)` returns the new state, `send_fn(state)` ships it."""
@@ -48,98 +66,293 @@ def handoff_chain(rank: int, world: int, recv_fn, send_fn, run_ordered):
     return new_state
 
 
-def halo_is_valid(ok_flags) -> bool:
-    """ok_flags: the `ok` field of the halo frames' records, any int array [h, 2]: usable iff no lane is empty"""
-    return bool((ok_flags != 0).all())
+def choose_warmup_start(ok_flags, depth: int, at_video_start: bool = False) -> Optional[int]:
+    """Host form of k_halo_start.  ok_flags: the `ok` field of the look-back frames' records, any int array [k, 2], oldest frame
+    first.  The latest frame s the trackers can start from EMPTY and be exact: frames s..s+depth-1 without an empty lane and at
+    least 2(depth-1) look-back frames from s on -- or frame 0 when the look-back reaches the first frame of the video.
+    None: no exact start, a longer look-back (or the predecessor's tracker blob) is needed."""
+    k = len(ok_flags)
+    if at_video_start:
+        return 0
+    clean = [bool(ok_flags[i][0]) and bool(ok_flags[i][1]) for i in range(k)]
+    need = 2 * (depth - 1)
+    for s in range(k - need, -1, -1):
+        if s + depth <= k and all(clean[s:s + depth]):
+            return s
+    return None
 
 
-def _ok_flags_async(records, stream):
-    """start the copy of the `ok` fields of uint8[h, 2, 280] device records to pinned host memory on `stream`;
-    returns the host tensor (int32[h, 2]), valid after stream.synchronize()"""
-    import torch
-    host = torch.empty((records.shape[0], 2), dtype=torch.int32, pin_memory=True)
-    with torch.cuda.stream(stream):
-        flags = records[:, :, _OK_OFFSET:_OK_OFFSET + 4].contiguous().view(torch.int32).reshape(records.shape[0], 2)
-        host.copy_(flags, non_blocking=True)
-    return host
+def halo_is_valid(ok_flags, depth: int) -> bool:
+    return choose_warmup_start(ok_flags, depth) is not None
 
 
-def _all_ranges_longer_than(engine, n, halo, world, group):
-    """True iff every rank's range holds more than `halo` frames (one tiny all_gather per distinct n, cached)"""
-    import torch
-    import torch.distributed as dist
-    cache = engine.__dict__.setdefault("_shard_range_cache", {})
-    key = (n, halo, world)
-    if key not in cache:
-        mine = torch.tensor([n], dtype=torch.int64, device="cuda:%d" % engine.device)
-        every = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(every, mine, group=group)
-        cache[key] = min(int(t.item()) for t in every) > halo
-    return cache[key]
+class _CudaStreams:
+    def __init__(self, device):
+        import torch
+        self.torch, self.device = torch, device
+
+    def new(self):
+        return self.torch.cuda.Stream(device=self.device)
+
+    def current(self):
+        return self.torch.cuda.current_stream(self.device)
+
+    def use(self, stream):
+        return self.torch.cuda.stream(stream)
 
 
-def process_sharded(engine, frames_dev, rank: int, world: int, group=None, out=None, fits=None, halo=None):
-    """Run this rank's frame range of a video whose ranges are laid out rank after rank.
-    frames_dev: this rank's frames (CUDA uint8 [n,H,W,3], n <= engine.max_frames).
-    halo: look-back frames (None = HALO, or env LD_SHARD_HALO; 0 = always the serial hand-off); every rank must pass the same.
+class _NoStream:
+    def wait_stream(self, other):
+        pass
+
+
+class _HostStreams:
+    """stand-in when the engine is not a CUDA engine (the gloo CPU tests drive the protocol with a host model of the engine)"""
+    def new(self):
+        return _NoStream()
+
+    def current(self):
+        return _NoStream()
+
+    def use(self, stream):
+        return contextlib.nullcontext()
+
+
+class DistTransport:
+    """torch.distributed point-to-point (NCCL over NVLink on the box, gloo in the CPU tests)."""
+
+    def __init__(self, world: int, group=None, dedicated: bool = True):
+        import torch.distributed as dist
+        self.dist = dist
+        # a process group of its own: point-to-point calls on the default group are queued behind one another and behind the
+        # caller's collectives (ProcessGroupNCCL serialises un-batched send/recv on one communicator)
+        self.group = dist.new_group(ranks=list(range(world))) if (group is None and dedicated and world > 1) else group
+
+    def exchange(self, send_t, dst, recv_t, src):
+        """send and receive as ONE batch (one NCCL group call) on the current stream; returns once queued"""
+        dist = self.dist
+        ops = []
+        if send_t is not None:
+            ops.append(dist.P2POp(dist.isend, send_t, dst, self.group))
+        if recv_t is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_t, src, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()                                    # NCCL: orders the current STREAM after the transfer, not the host
+
+    def send(self, t, dst):
+        self.dist.send(t, dst, group=self.group)
+
+    def recv(self, t, src):
+        self.dist.recv(t, src, group=self.group)
+
+
+class LocalTransport:
+    """Ranks played one after the other inside ONE process (single-GPU tests): a send parks a copy in a mailbox, the matching
+    receive (issued later, ranks are stepped in order) picks it up.  Copies are stream ordered through events."""
+
+    def __init__(self):
+        self.box = {}
+
+    def _put(self, key, t):
+        import torch
+        ev = torch.cuda.Event() if t.is_cuda else None
+        c = t.clone()
+        if ev is not None:
+            ev.record()
+        self.box.setdefault(key, []).append((c, ev))
+
+    def _get(self, key, t):
+        import torch
+        c, ev = self.box[key].pop(0)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        t.copy_(c)
+
+    def bind(self, rank):
+        return _LocalEnd(self, rank)
+
+
+class _LocalEnd:
+    def __init__(self, hub, rank):
+        self.hub, self.rank = hub, rank
+
+    def exchange(self, send_t, dst, recv_t, src):
+        if send_t is not None:
+            self.hub._put(("x", self.rank, dst), send_t)
+        if recv_t is not None:
+            self.hub._get(("x", src, self.rank), recv_t)
+
+    def send(self, t, dst):
+        self.hub._put(("b", self.rank, dst), t)
+
+    def recv(self, t, src):
+        self.hub._get(("b", src, self.rank), t)
+
+
+class ShardedRun:
+    """One rank's side of a sharded video.  Persistent: streams, blob buffers and the transport are made once; a step queues
+    work and returns, the host never waits inside it.
+
+        run = ShardedRun(engine, rank, world)                         # mode from LD_SHARD_MODE, default "lookback"
+        out, fits = run.step(frames_dev, out=out, lookback=lookback_dev)   # lookback: the <= HALO frames before the range
+        ...                                                           # further steps (each first settles the one before)
+        run.finish()                                                  # results of the last step are final after this
+
+    `fetch_lookback(k) -> (frames_dev, at_video_start)`: the k frames before this rank's range (fewer at the start of the
+    video); only called when the verdict on the regular look-back comes back negative (``lookback`` mode repair)."""
+
+    def __init__(self, engine, rank: int, world: int, mode: Optional[str] = None, halo: Optional[int] = None, transport=None,
+                 group=None, fetch_lookback: Optional[Callable] = None, lookback_starts_video: bool = False):
+        self.engine, self.rank, self.world = engine, int(rank), int(world)
+        self.mode = mode or os.environ.get("LD_SHARD_MODE", "lookback")
+        if self.mode not in MODES:
+            raise ValueError("sharding mode %r (expected one of %s)" % (self.mode, ", ".join(MODES)))
+        self.halo = int(os.environ.get("LD_SHARD_HALO", HALO)) if halo is None else int(halo)
+        self.depth = int(engine.variant.frame_num)
+        if self.mode == "records" and not 2 * (self.depth - 1) <= self.halo <= HALO_SLOTS:
+            raise ValueError("records mode needs %d <= halo <= %d" % (2 * (self.depth - 1), HALO_SLOTS))
+        self.fetch_lookback, self.lookback_starts_video = fetch_lookback, bool(lookback_starts_video)
+        self.S = _CudaStreams(engine.device) if getattr(engine, "is_cuda", True) else _HostStreams()
+        self.side = self.S.new()
+        self.transport = transport
+        if self.transport is None and self.world > 1 and self.mode != "lookback":
+            self.transport = DistTransport(self.world, group)
+        self.blob_in = self.blob_out = None
+        if self.mode != "lookback" and self.world > 1:
+            self.blob_in, self.blob_out = engine.new_state_blob(), engine.new_state_blob()
+        self.pending = None
+        self.repairs = 0                                    # steps whose optimistic result had to be fitted again
+
+    # ------------------------------------------------------------------ public
+    def step(self, frames_dev, out=None, fits=None, lookback=None):
+        """Queue this rank's range of the next video (or the next repetition of it); returns (out, fits) like
+        LaneEngine.process_dev.  The results are final once the next step() or finish() has returned."""
+        self.finish()
+        eng = self.engine
+        n = frames_dev.shape[0]
+        if out is None:
+            out = eng.new_like(frames_dev)
+        if fits is None:
+            fits = eng.new_fits(n)
+        self.S.current().wait_stream(self.side)             # last step's transfers are out of the buffers this one rewrites
+        if self.world == 1:
+            eng.reset()
+            eng.process_dev(frames_dev, out=out, fits=fits)
+        elif self.mode == "lookback":
+            self._step_lookback(frames_dev, out, fits, lookback)
+        elif self.mode == "records":
+            self._step_records(frames_dev, out, fits)
+        else:
+            self._step_serial(frames_dev, out, fits)
+        self.pending = (frames_dev, out, fits, lookback)
+        return out, fits
+
+    def finish(self):
+        """Settle the last step: read the device's verdict on its halo and, if negative, fit the range again from exact
+        trackers.  Waits for that step's fit stage only, not for its overlay."""
+        if self.pending is None or self.world == 1:
+            self.pending = None
+            return
+        frames_dev, out, fits, lookback = self.pending
+        self.pending = None
+        if self.mode == "lookback":
+            self._finish_lookback(frames_dev, out, fits, lookback)
+        elif self.mode == "records":
+            self._finish_records(frames_dev, out, fits)
+
+    # ------------------------------------------------------------------ lookback: zero communication
+    def _checked(self, lookback):
+        return lookback is not None and lookback.shape[0] > 0 and not self.lookback_starts_video
+
+    def _step_lookback(self, frames_dev, out, fits, lookback):
+        eng = self.engine
+        if lookback is None or lookback.shape[0] == 0:
+            eng.reset()                                     # the range starts the video
+        else:
+            if not self.lookback_starts_video and lookback.shape[0] < 2 * (self.depth - 1):
+                raise ValueError("look-back of %d frames; frame_num = %d needs %d" % (lookback.shape[0], self.depth, 2 * (self.depth - 1)))
+            eng.warmup_dev(lookback, starts_video=self.lookback_starts_video)
+        eng.process_dev(frames_dev, out=out, fits=fits)
+
+    def _finish_lookback(self, frames_dev, out, fits, lookback):
+        eng = self.engine
+        if not self._checked(lookback) or not eng.halo_status()[0]:
+            return
+        if self.fetch_lookback is None:
+            raise ShardingError("the look-back holds an empty lane in its first %d frames, so the trackers cannot be rebuilt from "
+                                "it exactly; pass fetch_lookback= (a longer look-back) or use mode='records' / 'serial'" % self.depth)
+        k = lookback.shape[0]
+        while True:                                         # the slow path: it may wait for the device
+            k = min(2 * k, eng.max_frames)
+            lb, at_start = self.fetch_lookback(k)
+            eng.warmup_dev(lb, starts_video=at_start)
+            if not eng.halo_status()[0]:
+                break
+            if at_start or lb.shape[0] >= eng.max_frames:
+                raise ShardingError("no exact tracker start within %d look-back frames" % lb.shape[0])
+        eng.process_dev(frames_dev, out=out, fits=fits)
+        self.repairs += 1
+
+    # ------------------------------------------------------------------ records: look-back records over NVLink
+    def _step_records(self, frames_dev, out, fits):
+        eng, n, h, rank, world = self.engine, frames_dev.shape[0], self.halo, self.rank, self.world
+        if rank + 1 < world and n < h:
+            raise ValueError("a range of %d frames cannot hand on a halo of %d; use mode='serial'" % (n, h))
+        main = self.S.current()
+        if rank == 0:
+            eng.reset()                                     # the other ranks rebuild their trackers from the halo
+        eng.prepass_dev(frames_dev)                         # mask + search of the range: no tracker access
+        send_t = eng.context_records(n)[n - h:] if rank + 1 < world else None
+        recv_t = eng.halo_slots(h) if rank > 0 else None
+        self.side.wait_stream(main)
+        with self.S.use(self.side):
+            self.transport.exchange(send_t, rank + 1, recv_t, rank - 1)
+        if rank > 0:
+            eng.halo_arrives(h, self.side)                  # only the fit stage waits for the records
+        if rank + 1 < world:
+            eng.tail_check(n, h)
+        eng.postpass_dev(frames_dev, out=out, fits=fits, use_halo=rank > 0)
+
+    def _finish_records(self, frames_dev, out, fits):
+        eng, rank, world = self.engine, self.rank, self.world
+        halo_bad, tail_bad = eng.halo_status()
+        if rank > 0 and halo_bad:                           # my predecessor judged the same records: it is sending its trackers
+            self.transport.recv(self.blob_in, rank - 1)
+            eng.import_state_dev(self.blob_in)
+            eng.postpass_dev(frames_dev, out=out, fits=fits, skip_plain=True)   # the range's records are still in the context
+            self.repairs += 1
+        if rank + 1 < world and tail_bad:                   # trackers at the end of my (possibly re-fitted) range
+            eng.export_state_dev(self.blob_out)
+            self.transport.send(self.blob_out, rank + 1)
+
+    # ------------------------------------------------------------------ serial: tracker blob down the chain
+    def _step_serial(self, frames_dev, out, fits):
+        eng, rank, world = self.engine, self.rank, self.world
+        if rank == 0:
+            eng.reset()
+        eng.prepass_dev(frames_dev)
+        plain_done = rank > 0 and eng.plain_pass_dev(frames_dev, out)   # while the predecessors fit
+        if rank > 0:
+            self.transport.recv(self.blob_in, rank - 1)
+            eng.import_state_dev(self.blob_in)
+        need = rank + 1 < world
+        eng.postpass_dev(frames_dev, out=out, fits=fits, state_out=self.blob_out if need else None, skip_plain=bool(plain_done),
+                         fit_first=need)
+        if need:                                            # ship the blob as soon as the fit stage is done
+            eng.wait_state(self.side)
+            with self.S.use(self.side):
+                self.transport.send(self.blob_out, rank + 1)
+
+
+def process_sharded(engine, frames_dev, rank: int, world: int, group=None, out=None, fits=None, halo=None, mode=None, lookback=None):
+    """One-call form: runs (and settles) this rank's range with a ShardedRun cached on the engine.
     Returns (out, fits) like LaneEngine.process_dev."""
-    import torch
-    import torch.distributed as dist
-    n = frames_dev.shape[0]
-    if halo is None:
-        halo = int(os.environ.get("LD_SHARD_HALO", HALO))
-    use_halo = world > 1 and 0 < halo <= 32 and _all_ranges_longer_than(engine, n, halo, world, group)
-    dev = frames_dev.device
-    main = torch.cuda.current_stream(dev)
-    nbytes = engine.lib.ld_state_size()
-    rec_bytes = engine.context_records(1).shape[2]
-    side_r, side_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-
-    # 1. the predecessor's last records can land at any time: post the receive first
-    halo_buf = halo_ok = None
-    if use_halo and rank > 0:
-        halo_buf = torch.empty((halo, 2, rec_bytes), dtype=torch.uint8, device=dev)
-        side_r.wait_stream(main)
-        with torch.cuda.stream(side_r):
-            dist.recv(halo_buf, src=rank - 1, group=group)
-        halo_ok = _ok_flags_async(halo_buf, side_r)
-    # 2. mask + search of this range: no tracker access, runs on every rank at once
-    engine.prepass_dev(frames_dev)
-    if out is None:
-        out = torch.empty_like(frames_dev)
-    tail = tail_ok = None
-    if use_halo and rank + 1 < world:
-        tail = engine.context_records(n)[n - halo:].clone()
-        side_s.wait_stream(main)
-        with torch.cuda.stream(side_s):
-            dist.send(tail, dst=rank + 1, group=group)          # goes out as soon as this rank's prepass is done
-        tail_ok = _ok_flags_async(tail, side_s)
-    # 3. the tiles that need neither the fit nor the canvas: while the records travel / the predecessor fits
-    plain_done = (use_halo or rank > 0) and engine.plain_pass_dev(frames_dev, out)
-    # 4. both ends of a hand-off look at the same records and take the same decision
-    tail_valid = halo_valid = False
-    if tail_ok is not None:
-        side_s.synchronize()
-        tail_valid = halo_is_valid(tail_ok.numpy())
-    if halo_ok is not None:
-        side_r.synchronize()
-        halo_valid = halo_is_valid(halo_ok.numpy())
-    if halo_valid:
-        engine.halo_set(halo_buf)                               # rebuild the predecessor's trackers from its last records
-    elif rank > 0:                                              # serial hand-off: wait for the predecessor's trackers
-        blob_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        dist.recv(blob_in, src=rank - 1, group=group)
-        engine.import_state_dev(blob_in)
-    need_blob = rank + 1 < world and not tail_valid             # the successor cannot rebuild the state itself
-    blob_out = torch.empty(nbytes, dtype=torch.uint8, device=dev) if need_blob else None
-    result = engine.postpass_dev(frames_dev, out=out, fits=fits, state_out=blob_out, skip_plain=bool(plain_done),
-                                 fit_first=need_blob, use_halo=halo_valid)
-    if need_blob:
-        side_b = torch.cuda.Stream(device=dev)                  # ship the blob as soon as the fit stage is done,
-        engine.wait_state(side_b)                               # while this rank's overlay is still running
-        with torch.cuda.stream(side_b):
-            dist.send(blob_out, dst=rank + 1, group=group)
-        main.wait_stream(side_b)
-    main.wait_stream(side_s)                                    # the buffers of the in-flight transfers outlive them
-    main.wait_stream(side_r)
-    return result
+    key = (rank, world, mode, halo)
+    run = engine.__dict__.get("_sharded_run")
+    if run is None or engine.__dict__.get("_sharded_key") != key:
+        run = ShardedRun(engine, rank, world, mode=mode, halo=halo, group=group)
+        engine.__dict__["_sharded_run"], engine.__dict__["_sharded_key"] = run, key
+    res = run.step(frames_dev, out=out, fits=fits, lookback=lookback)
+    run.finish()
+    return res

@@ -183,6 +183,30 @@ int ld_wait_state(ld_ctx* ctx, void* stream);
  * records ld_prepass left in the context ([n][2]); ld_halo_set copies n_halo (<= 32) frames' records in front of the range. */
 int ld_halo_set(ld_ctx* ctx, const ld_lane_record* halo_records_dev, int n_halo, void* stream);
 const ld_lane_record* ld_ctx_records(ld_ctx* ctx);
+/* Transfers that deliver the look-back records IN PLACE (NCCL receive, cudaMemcpyPeerAsync): ld_ctx_halo_slots = device
+ * address of the n_halo (<= 32) frames' records in front of the context's own; ld_halo_arrives = they are being written by
+ * work queued on `stream`: the next ld_postpass_flags(LD_POST_USE_HALO) uses them, and only its fit stage waits for `stream`
+ * (the tiles that need neither fit nor canvas start at once). */
+ld_lane_record* ld_ctx_halo_slots(ld_ctx* ctx, int n_halo);
+int ld_halo_arrives(ld_ctx* ctx, int n_halo, void* stream);
+/* Was a halo good enough?  Trackers rebuilt from empty equal the predecessor's iff the first frame_num look-back frames have no
+ * empty lane (an empty lane re-uses the previous frame's points + anchors, Project.py:98-100 -- the one recursion that reaches
+ * further back than the deque(maxlen=frame_num) medians of Project.py:122-138).  The fit stage decides this on the device for
+ * the halo it used; ld_tail_check decides the same for the last n_halo of the n records ld_prepass left, i.e. for what this
+ * rank hands to its successor -- both ends see the same records and agree without a handshake.  ld_halo_status waits for these
+ * two decisions only (not for the step) and returns them: 1 = invalid, re-fit that range from a longer look-back or from the
+ * predecessor's tracker blob (ld_state_export / ld_state_import + ld_postpass). */
+int ld_tail_check(ld_ctx* ctx, int n, int n_halo, void* stream);
+int ld_halo_status(ld_ctx* ctx, int* halo_invalid, int* tail_invalid);
+/* Zero-communication sharding ("recompute the look-back"): frames_dev = the n frames just before this rank's range.
+ * Resets the trackers and runs mask + search + fit over them (no raster, no overlay, no output); follow with ld_process_batch
+ * over the range.  check_frames = how many leading look-back frames must have no empty lane (frame_num; 0 when the look-back
+ * starts at the first frame of the video); the verdict comes back through ld_halo_status. */
+int ld_warmup(ld_ctx* ctx, const uint8_t* frames_dev, int n, int check_frames, void* stream);
+/* ld_process_batch_host for one rank's range of a sharded video: lookback_host = the n_lookback frames before the range (NULL /
+ * 0: none, trackers are left as they are), warmed up through the same three-stream pipeline; *halo_invalid as above. */
+int ld_process_range_host(ld_ctx* ctx, const uint8_t* lookback_host, int n_lookback, int check_frames, const uint8_t* frames_host,
+                          int n, uint8_t* out_host, ld_frame_fit* fits_host, int* halo_invalid);
 /* Same with host buffers: chunks are copied in, processed and copied out on three streams.
  * Synchronous; returns LD_ERR_EMPTY_LANE like the reference raises.  fits_host may be NULL. */
 int ld_process_batch_host(ld_ctx* ctx, const uint8_t* frames_host, int n, uint8_t* out_host,
