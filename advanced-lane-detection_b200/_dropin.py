@@ -131,10 +131,13 @@ class Pipeline:
                 return [], [], False
 
             def blind_search(self, nonzerox, nonzeroy, image):
-                rec, mask_dev = pipeline._search_binary(image)
-                r = rec[0, 1 if self is pipeline.right else 0]
-                if r["ok"]:
-                    x, y = pipeline._window_pixels(mask_dev, r)
+                x, y = [], []
+                if self.detected is False:                      # Project.py:79: a detected line skips the window search
+                    rec, mask_dev = pipeline._search_binary(image)
+                    r = rec[0, 1 if self is pipeline.right else 0]
+                    if r["ok"]:
+                        x, y = pipeline._window_pixels(mask_dev, r)
+                if np.sum(x) > 0:                               # Project.py:96-100
                     self.detected = True
                 else:
                     x, y = self.x, self.y
@@ -153,41 +156,73 @@ class Pipeline:
         self.Line = Line
         self.left = None
         self.right = None
+        self._created = 0
+        self._pin = None
         self.left = Line()
         self.right = Line()
 
     # ------------------------------------------------------------------ engines
-    def engine(self, l_thresh=None, b_thresh=None) -> LaneEngine:
-        key = (tuple(l_thresh or self.variant.l_thresh), tuple(b_thresh or self.variant.b_thresh))
-        if key not in self._engines:
-            self._engines[key] = LaneEngine(self.variant, self.mtx, self.dist, max_frames=8, l_thresh=key[0], b_thresh=key[1])
-        return self._engines[key]
+    MAX_ENGINES = 4                                         # distinct (thresholds, calibration) plans kept alive
+
+    def engine(self, l_thresh=None, b_thresh=None, mtx=None, dist=None) -> LaneEngine:
+        """the LaneEngine for these thresholds and this calibration (default: the pipeline's own); least recently used
+        engines beyond MAX_ENGINES are closed -- each one holds a plan, a context and streams on the device"""
+        mtx = self.mtx if mtx is None else np.asarray(mtx, np.float64)
+        dist = self.dist if dist is None else np.asarray(dist, np.float64)
+        key = (tuple(l_thresh or self.variant.l_thresh), tuple(b_thresh or self.variant.b_thresh), mtx.tobytes(), dist.tobytes())
+        eng = self._engines.pop(key, None)
+        if eng is None:
+            eng = LaneEngine(self.variant, mtx, dist, max_frames=8, l_thresh=key[0], b_thresh=key[1])
+            default = self._default_key()
+            while len(self._engines) >= self.MAX_ENGINES:
+                victim = next(k for k in self._engines if k != default)
+                self._engines.pop(victim).close()
+        self._engines[key] = eng                            # most recently used last
+        return eng
+
+    def _default_key(self):
+        return (tuple(self.variant.l_thresh), tuple(self.variant.b_thresh), self.mtx.tobytes(), self.dist.tobytes())
 
     def _lines_created(self, line):
-        # `left = Line(); right = Line()` at module level resets the trackers (Project.py:351-352)
+        # `left = Line(); right = Line()` (Project.py:351-352): the latest pair of Line objects are the trackers process_image
+        # updates -- first of a pair = left, second = right -- and creating them resets the tracker state on the GPU
+        self._created += 1
+        if self._created % 2:
+            self.left = line
+        else:
+            self.right = line
         for e in self._engines.values():
             e.reset()
 
     def reset(self):
-        self.left = self.Line()
-        self.right = self.Line()
-        return self.left, self.right
+        self._created += self._created % 2                  # start a fresh pair
+        left, right = self.Line(), self.Line()
+        return left, right
 
     # ------------------------------------------------------------------ process_image
     def process_image(self, img, plot=False):
+        """Project.py:289-334 for one frame: ONE ld_process_batch_host call (pinned staging in and out, one synchronisation),
+        then the two lane records (560 B) for the host mirrors of `left` / `right`."""
         eng = self.engine()
-        frame = eng.to_device(np.ascontiguousarray(img, dtype=np.uint8))[None]
-        mask = eng.mask_dev(frame)
-        rec_dev = eng.search_dev(mask)
-        fit_dev = eng.fit_dev(rec_dev)
-        out = eng.overlay_dev(frame, fit_dev)
-        eng.check()                                     # TypeError("expected 1D vector for x") like the reference
-        fit = eng.fits_to_numpy(fit_dev)[0]
-        rec = eng.records_to_numpy(rec_dev)[0]
-        state = np.frombuffer(eng.export_state(), dtype=np.uint8)
+        torch = eng.torch
+        if self._pin is None:
+            shape = (1, eng.H, eng.W, 3)
+            self._pin = (torch.empty(shape, dtype=torch.uint8, pin_memory=True), torch.empty(shape, dtype=torch.uint8, pin_memory=True),
+                         torch.empty((1, _abi.FIT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True),
+                         torch.empty((1, 2, _abi.RECORD_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True))
+        pin_in, pin_out, pin_fit, pin_rec = self._pin
+        img = np.asarray(img)
+        if img.shape != (eng.H, eng.W, 3) or img.dtype != np.uint8:
+            raise ValueError("expected a uint8 frame of shape (%d, %d, 3)" % (eng.H, eng.W))
+        pin_in.numpy()[0] = img
+        eng.process_pinned(pin_in, pin_out, pin_fit)        # TypeError("expected 1D vector for x") like the reference
+        pin_rec.copy_(eng.context_records(1))               # device -> pinned: synchronous
+        fit = pin_fit.numpy().copy().view(_abi.FIT_DTYPE).reshape(1)[0]
+        rec = pin_rec.numpy().copy().view(_abi.RECORD_DTYPE).reshape(1, 2)[0]
+        mask = eng.context_masks(1)                         # stays on the device; only read if somebody asks for Line.x / .y
         for lane, line in enumerate((self.left, self.right)):
-            self._update_line(line, lane, fit, rec[lane], mask, state)
-        return out[0].cpu().numpy()
+            self._update_line(line, lane, fit, rec[lane], mask, None)
+        return pin_out.numpy()[0].copy()
 
     def _update_line(self, line, lane, fit, rec, mask_dev, state_blob):
         v = self.variant
@@ -256,7 +291,7 @@ class Pipeline:
         return eng.warp_dev(t)[0].cpu().numpy()
 
     def undistort(self, img, mtx=None, dist=None):
-        eng = self.engine()
+        eng = self.engine(mtx=mtx, dist=dist)               # a caller's own calibration gets its own plan
         t = eng.to_device(np.ascontiguousarray(img, dtype=np.uint8))
         return eng.undistort_dev(t)[0].cpu().numpy()
 

@@ -276,9 +276,19 @@ class LaneEngine:
         fits = self._pin_fit[:n].numpy().copy().view(_abi.FIT_DTYPE).reshape(n) if want_fits else None
         return out, fits
 
+    def _host_frames(self, t, what):
+        """host frame buffers go to the C ABI as raw pointers: refuse anything that is not a dense uint8 [n, H, W, 3] block"""
+        if t.is_cuda or t.dtype != self.torch.uint8 or not t.is_contiguous() or tuple(t.shape[1:]) != (self.H, self.W, 3):
+            raise ValueError("%s: expected a contiguous host uint8 tensor [n, %d, %d, 3]" % (what, self.H, self.W))
+        return t
+
     def process_pinned(self, pin_in, pin_out, pin_fit=None):
         """The timed end-to-end call of bench.py: pinned host in -> pinned host out, synchronous."""
+        self._host_frames(pin_in, "pin_in")
+        self._host_frames(pin_out, "pin_out")
         n = pin_in.shape[0]
+        if pin_out.shape[0] < n or (pin_fit is not None and (not pin_fit.is_contiguous() or pin_fit.numel() < n * _abi.FIT_DTYPE.itemsize)):
+            raise ValueError("output buffers are smaller than the input")
         st = self.lib.ld_process_batch_host(self._ctx_h, _ptr(pin_in), n, _ptr(pin_out),
                                             _ptr(pin_fit) if pin_fit is not None else None)
         _abi.check(self.lib, st)
@@ -288,6 +298,13 @@ class LaneEngine:
         starts the video), warmed up through the same pipeline.  Returns True if no exact tracker start exists in the
         look-back (see warmup_dev): pass a longer one."""
         h = 0 if pin_lookback is None else pin_lookback.shape[0]
+        self._host_frames(pin_in, "pin_in")
+        self._host_frames(pin_out, "pin_out")
+        if h:
+            self._host_frames(pin_lookback, "pin_lookback")
+        if pin_out.shape[0] < pin_in.shape[0] or (pin_fit is not None and (not pin_fit.is_contiguous() or
+                                                                            pin_fit.numel() < pin_in.shape[0] * _abi.FIT_DTYPE.itemsize)):
+            raise ValueError("output buffers are smaller than the input")
         bad = C.c_int(0)
         st = self.lib.ld_process_range_host(self._ctx_h, _ptr(pin_lookback) if h else None, h, 0 if (starts_video or not h) else 1,
                                             _ptr(pin_in), pin_in.shape[0], _ptr(pin_out), _ptr(pin_fit) if pin_fit is not None else None,

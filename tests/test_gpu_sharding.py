@@ -25,7 +25,7 @@ def rig(stills):
     S = importlib.import_module("advanced-lane-detection_b200.sharding")
     ref = pkg.LaneEngine("project", max_frames=TOTAL)
     ranks = [pkg.LaneEngine("project", max_frames=TOTAL) for _ in range(WORLD)]
-    base = np.stack(list(O.synth_sequence([stills(n) for n in NAMES], TOTAL, seed=11)))
+    base = np.ascontiguousarray(np.stack(list(O.synth_sequence([stills(n) for n in NAMES], TOTAL, seed=11))))
     yield S, ref, ranks, base
     for e in [ref] + ranks:
         e.close()
@@ -116,10 +116,12 @@ def test_host_range_pipeline_matches(rig):
     fits = torch.empty((PER_RANK, fit_full.shape[1]), dtype=torch.uint8).pin_memory()
     bad = eng.process_range_pinned(pin[10:40], pin[40:80], out, fits)
     assert not bad
-    assert (out == out_full[40:80].cpu()).all() and (fits == fit_full[40:80].cpu()).all()
+    assert (fits == fit_full[40:80].cpu()).all()
+    diff = [i for i in range(PER_RANK) if not (out[i] == out_full[40 + i].cpu()).all()]
+    assert not diff, "frames %s differ" % diff
     seq = base.copy()
     seq[15] = 0
-    pin2 = torch.from_numpy(seq).pin_memory()
+    pin2 = torch.from_numpy(np.ascontiguousarray(seq)).pin_memory()
     assert eng.process_range_pinned(pin2[10:40], pin2[40:80], out, fits)          # flagged: no 15 clean frames start at look-back frame 0, 1 or 2
     assert not eng.process_range_pinned(pin2[0:40], pin2[40:80], out, fits, starts_video=True)   # whole prefix: exact by construction
     ref.reset()
