@@ -101,6 +101,7 @@ _SIGNATURES = {
     "ld_tail_check": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ld_halo_status": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ld_warmup": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "ld_process_range": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "ld_process_range_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "ld_check": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "ld_state_reset": (C.c_int, [_P, _P]),

@@ -776,12 +776,17 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
 
 // search_first: the window search has not run yet (process_impl): it joins the latency-bound chain on s_lat
 // skip_plain: the caller already ran the plain tiles of this range (ld_stage(5), e.g. while waiting for its predecessor's state)
+// look > 0 (ld_process_range): the prepass covered `look` look-back frames in workspace slots [0, look) in front of the M range
+// frames in slots [look, look + M); the fit stage walks all of them from EMPTY trackers (fit_core, warm), everything after it
+// touches the range only.  fin / fout = first frame of the RANGE.
 static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld_frame_fit* fit_out, void* state_out,
-                         cudaStream_t s, int frame_offset, int search_first = 0, int skip_plain = 0, int fit_first = 0, int halo = 0) {
+                         cudaStream_t s, int frame_offset, int search_first = 0, int skip_plain = 0, int fit_first = 0, int halo = 0,
+                         int look = 0, int look_check = 0) {
     const PlanDev& d = c->plan->d;
     const size_t fb = (size_t)d.W * d.H * 3;
     const int nsub = sub_batches(M);
     int rc;
+    if (look && (nsub >= 2 || !c->plan->shared_ok || search_first || halo)) return LD_ERR_ARG;
     if (nsub < 2) {
         // The latency-bound chain (search ->) fit -> raster (few resident warps, ~1 us/frame) runs on the high-priority stream; the
         // caller's stream meanwhile undistorts the tiles that depend on neither the fit nor the canvas (64 % of them), whose
@@ -793,11 +798,13 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
             c->halo_wait = 0;
         }
         if (search_first && (rc = ld_search(c, c->mask, M, c->rec, c->s_lat))) return rc;
-        if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset, halo))) return rc;
+        if (look) {
+            if ((rc = fit_core(c, c->rec, c->work, look + M, c->fit, c->s_lat, frame_offset - look, 1, look, look, look_check, nullptr))) return rc;
+        } else if ((rc = fit_impl(c, c->rec, M, c->fit, c->s_lat, frame_offset, halo))) return rc;
         if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
         LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
         tl_mark("fit (s_lat)", c->s_lat);
-        if ((rc = launch_raster(c, c->fit, nullptr, nullptr, 0, 30, M, c->s_lat, 0))) return rc;
+        if ((rc = launch_raster(c, c->fit + look, nullptr, nullptr, 0, 30, M, c->s_lat, look))) return rc;
         LD_CUDA(cudaEventRecord(c->ev_rast[0], c->s_lat));
         tl_mark("raster (s_lat)", c->s_lat);
         // LD_POST_FIT_FIRST (sharded runs): the plain tiles start when the fit stage is done -- run beside them the tiny fit
@@ -805,18 +812,18 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         // vs 4.39 ms per 1260 frames.)
         if (fit_first) LD_CUDA(cudaStreamWaitEvent(s, c->ev_state, 0));
         if (!(skip_plain && c->plan->shared_ok && !search_first) &&
-            (rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, (c->plan->shared_ok && !search_first) ? 5 : 1))) return rc;
+            (rc = launch_frame_pass(c, fin, M, fout, s, look, 0, (c->plan->shared_ok && !search_first) ? 5 : 1))) return rc;
         tl_mark("plain tiles (s)", s);
         if (c->plan->shared_ok && !search_first) {
             // the shared pass of ld_prepass left the undistorted pixels of the share tiles in und_px: blend, do not gather again
             const int bf = frames_per_cta(M);
-            k_blend_px<<<dim3(c->plan->n_share, (M + bf - 1) / bf), FRAME_THREADS, 0, c->s_lat>>>(c->und_px, c->planes, fout, d,
-                                                                                                 c->plan->share_tiles, M, bf);
+            k_blend_px<<<dim3(c->plan->n_share, (M + bf - 1) / bf), FRAME_THREADS, 0, c->s_lat>>>(
+                c->und_px + (size_t)look * c->plan->n_share * 16 * 128, c->planes + (size_t)look * canvas_words(d), fout, d, c->plan->share_tiles, M, bf);
             if ((rc = check_launch())) return rc;
             tl_mark("blend_px (s_lat)", c->s_lat);
             // the putText tiles only need the raster's text plane: they follow the plain tiles on the caller's stream
             LD_CUDA(cudaStreamWaitEvent(s, c->ev_rast[0], 0));
-            if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, 4))) return rc;
+            if ((rc = launch_frame_pass(c, fin, M, fout, s, look, 0, 4))) return rc;
             tl_mark("text tiles (s)", s);
         } else if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
         LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));
@@ -837,7 +844,7 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         }
         if ((rc = join_streams(c, s))) return rc;
     }
-    if (fit_out) LD_CUDA(cudaMemcpyAsync(fit_out, c->fit, sizeof(ld_frame_fit) * M, cudaMemcpyDeviceToDevice, s));
+    if (fit_out) LD_CUDA(cudaMemcpyAsync(fit_out, c->fit + look, sizeof(ld_frame_fit) * M, cudaMemcpyDeviceToDevice, s));
     return LD_OK;
 }
 
@@ -934,6 +941,24 @@ static int warmup_impl(ld_ctx* c, const uint8_t* frames, int n, int n_total, int
     // an empty lane on a fresh tracker inside a look-back that does NOT start the video is not the reference's TypeError (the
     // real tracker had points there): it only makes the halo invalid, so its frame index goes to a scratch slot
     return fit_core(c, c->rec, c->work, n, c->fit, s, 0, 1, n, n_total, check, check ? c->flags + 6 : nullptr);
+}
+// The same in ONE pass when the look-back frames sit right in front of the range in memory (frames_dev = n_lookback + n frames):
+// mask + search run once over all of them, the fit stage walks all of them from empty trackers, raster and overlay touch the
+// range only -- the look-back costs its share of the prepass (2.4 % of it for 30 + 1260 frames) and not a single extra launch.
+extern "C" int ld_process_range(ld_ctx* c, const uint8_t* frames, int n_lookback, int check_frames, int n, uint8_t* out,
+                                ld_frame_fit* fit_out, void* stream) {
+    if (!ARGS_OK(c, frames, out, n) || n_lookback < 0 || n_lookback + n > c->max_frames || check_frames < 0) return LD_ERR_ARG;
+    if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    if (!n_lookback || !c->plan->shared_ok) {                            // nothing to merge (or a plan without the shared pass): two steps
+        int rc;
+        if (n_lookback && (rc = warmup_impl(c, frames, n_lookback, n_lookback, check_frames ? 1 : 0, (cudaStream_t)stream))) return rc;
+        return process_impl(c, frames + (size_t)n_lookback * c->plan->d.W * c->plan->d.H * 3, n, out, fit_out, (cudaStream_t)stream, 0);
+    }
+    int rc;
+    if ((rc = prepass_impl(c, frames, n_lookback + n, (cudaStream_t)stream))) return rc;
+    return postpass_impl(c, frames + (size_t)n_lookback * c->plan->d.W * c->plan->d.H * 3, n, out, fit_out, nullptr, (cudaStream_t)stream, 0,
+                         0, 0, 0, 0, n_lookback, check_frames ? 1 : 0);
 }
 extern "C" int ld_warmup(ld_ctx* c, const uint8_t* frames, int n, int check_frames, void* stream) {
     if (!c || !frames || n < 1 || n > c->max_frames || check_frames < 0 || check_frames > n) return LD_ERR_ARG;

@@ -241,6 +241,27 @@ class LaneEngine:
         lookback = self._frames(lookback)
         _abi.check(self.lib, self.lib.ld_warmup(self._ctx_h, _ptr(lookback), lookback.shape[0], 0 if starts_video else 1, self._stream()))
 
+    def process_range_dev(self, lookback, frames, out=None, fits=None, starts_video=False):
+        """warmup_dev(lookback) + process_dev(frames).  When `lookback` ends exactly where `frames` begins in memory (two views of
+        one buffer, lookback + range <= max_frames) both run as ONE pass without a single extra launch (ld_process_range)."""
+        frames = self._frames(frames)
+        n = frames.shape[0]
+        if out is None:
+            out = self.torch.empty_like(frames)
+        if fits is None:
+            fits = self.new_fits(n)
+        if lookback is None or lookback.shape[0] == 0:
+            self.reset()
+            return self.process_dev(frames, out=out, fits=fits)
+        lookback = self._frames(lookback)
+        h = lookback.shape[0]
+        if lookback.data_ptr() + lookback.numel() == frames.data_ptr() and h + n <= self.max_frames:
+            _abi.check(self.lib, self.lib.ld_process_range(self._ctx_h, _ptr(lookback), h, 0 if starts_video else 1, n, _ptr(out), _ptr(fits),
+                                                           self._stream()))
+            return out, fits
+        self.warmup_dev(lookback, starts_video=starts_video)
+        return self.process_dev(frames, out=out, fits=fits)
+
     def postpass_dev(self, frames, out=None, fits=None, state_out=None, skip_plain=False, fit_first=False, use_halo=False):
         """fit (tracker order!) + overlay of the range given to prepass_dev; state_out = CUDA uint8 blob or None"""
         frames = self._frames(frames)

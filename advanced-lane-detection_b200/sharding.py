@@ -141,10 +141,10 @@ class DistTransport:
                 w.wait()                                    # NCCL: orders the current STREAM after the transfer, not the host
 
     def send(self, t, dst):
-        self.dist.send(t, dst, group=self.group)
+        self.exchange(t, dst, None, None)                   # a batch of one: un-batched P2P calls are serialised per group
 
     def recv(self, t, src):
-        self.dist.recv(t, src, group=self.group)
+        self.exchange(None, None, t, src)
 
 
 class LocalTransport:
@@ -272,7 +272,8 @@ class ShardedRun:
         else:
             if not self.lookback_starts_video and lookback.shape[0] < 2 * (self.depth - 1):
                 raise ValueError("look-back of %d frames; frame_num = %d needs %d" % (lookback.shape[0], self.depth, 2 * (self.depth - 1)))
-            eng.warmup_dev(lookback, starts_video=self.lookback_starts_video)
+            eng.process_range_dev(lookback, frames_dev, out=out, fits=fits, starts_video=self.lookback_starts_video)
+            return
         eng.process_dev(frames_dev, out=out, fits=fits)
 
     def _finish_lookback(self, frames_dev, out, fits, lookback):

@@ -326,7 +326,7 @@ def main():
     frames, lookback = dev_all[h:], (dev_all[:h] if h else None)
     out = torch.empty_like(frames)
     fits = torch.empty((n, pkg._abi.FIT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    eng = pkg.LaneEngine("project", device=local, max_frames=n)
+    eng = pkg.LaneEngine("project", device=local, max_frames=n + HALO)
 
     def fetch_from(pin_src_names, seed_base):
         def fetch(k):                                        # repair path of the look-back protocol: more frames of the predecessor
@@ -356,8 +356,8 @@ def main():
     value = world * n * a.steps / (ms / 1e3)
     repairs = run.repairs
     # kernels of one step: state reset; shared pass, k_mask_b, k_search; 5 fit kernels; k_raster; plain tiles, k_blend_px, text
-    # tiles; a sharded rank adds the look-back warm-up (reset, shared pass, k_mask_b, k_search, k_halo_start, 5 fit kernels)
-    launches_per_step = (1 + 3 + 5 + 1 + 3) if (world == 1 or rank == 0 and mode == "lookback") else {"lookback": 12 + 10, "records": 12 + 3, "serial": 13}[mode]
+    # tiles (rank 0 prints: its range starts the video, so it has no look-back; the other ranks of a 'lookback' run add k_halo_start)
+    launches_per_step = (1 + 3 + 5 + 1 + 3) if (world == 1 or mode != "records") else 14
 
     # ---- sharded results against the serial protocol and against each other, then the other protocols' rates
     shard = None
@@ -387,7 +387,7 @@ def main():
 
     # ---- end to end through the C ABI host call (pinned host -> pinned host); at N > 1 the look-back travels with the range
     def e2e_call():
-        if world == 1:
+        if pin_look is None:                                 # the range starts the video: fresh trackers
             eng.reset()
             eng.process_pinned(pin_in, pin_out)
             return False
@@ -422,7 +422,7 @@ def main():
         pin3, h3 = make_inputs(HARDER_STILLS, 100)
         d3 = pin3[HALO - h3:].to(dev)
         del pin3
-        eng3 = pkg.LaneEngine("harder", device=local, max_frames=n)
+        eng3 = pkg.LaneEngine("harder", device=local, max_frames=n + HALO)
         run3 = sharding.ShardedRun(eng3, rank, world, mode=mode, halo=HALO, fetch_lookback=fetch_from(HARDER_STILLS, 100))
         fits3 = torch.empty_like(fits)
         step3 = lambda: run3.step(d3[h3:], out=out, fits=fits3, lookback=d3[:h3] if h3 else None)

@@ -203,6 +203,11 @@ int ld_halo_status(ld_ctx* ctx, int* halo_invalid, int* tail_invalid);
  * over the range.  check_frames = how many leading look-back frames must have no empty lane (frame_num; 0 when the look-back
  * starts at the first frame of the video); the verdict comes back through ld_halo_status. */
 int ld_warmup(ld_ctx* ctx, const uint8_t* frames_dev, int n, int check_frames, void* stream);
+/* ld_warmup + ld_process_batch in one pass for look-back frames that sit right in front of the range in memory: frames_dev =
+ * n_lookback + n frames (<= max_frames), out_dev / fit_dev = the n frames of the range.  Not one extra launch: mask + search run
+ * once over all frames, the fit stage walks them from empty trackers, raster and overlay touch the range only. */
+int ld_process_range(ld_ctx* ctx, const uint8_t* frames_dev, int n_lookback, int check_frames, int n, uint8_t* out_dev,
+                     ld_frame_fit* fit_dev, void* stream);
 /* ld_process_batch_host for one rank's range of a sharded video: lookback_host = the n_lookback frames before the range (NULL /
  * 0: none, trackers are left as they are), warmed up through the same three-stream pipeline; *halo_invalid as above. */
 int ld_process_range_host(ld_ctx* ctx, const uint8_t* lookback_host, int n_lookback, int check_frames, const uint8_t* frames_host,

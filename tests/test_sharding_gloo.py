@@ -212,6 +212,10 @@ class ModelEngine:
         except TypeError:
             assert self.flags[0]                                # only a flagged look-back may start with an empty lane
 
+    def process_range_dev(self, lookback, frames, out=None, fits=None, starts_video=False):
+        self.warmup_dev(lookback, starts_video)
+        return self.process_dev(frames, out, fits)
+
     def process_dev(self, frames, out=None, fits=None):
         self.prepass_dev(frames)
         self._run(self.rec, out, fits)
