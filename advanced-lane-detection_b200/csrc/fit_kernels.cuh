@@ -98,55 +98,86 @@ __global__ void k_fit1(const ld_lane_record* __restrict__ rec, FitWork* __restri
     do_fit1(w);
 }
 
-// ---- pass 1b: serial walk over the frames whose search failed (one thread per lane) ---------------
-__global__ void k_fit_fallback(const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work,
-                               ld_frame_fit* __restrict__ fit, const TrackState* __restrict__ st, int n, int depth,
-                               int top_anchor, const int* __restrict__ any_fail, int* __restrict__ first_bad,
-                               const int* __restrict__ start) {
-    const int L = threadIdx.x;
-    if (L >= 2 || !*any_fail) return;
-    const TrackLane& T = st->lane[L];
-    const int lo = batch_lo(start);
-    for (int k = lo; k < n; ++k) {
-        if (rec[2 * k + L].ok) continue;
-        FitWork& w = work[2 * k + L];
-        // x_inds = self.x, y_inds = self.y (Project.py:98-100): last frame's arrays with its anchors,
-        // then .astype(np.float32) (Project.py:308-311)
-        FitInput prev; double pb, pt; int prev_n;
-        if (k == lo) { prev = T.pts; pb = T.last_bottom; pt = T.last_top; prev_n = T.n_points; if (!T.has_points || lo > 0) prev.valid = 0; }
-        else {
-            const FitWork& p = work[2 * (k - 1) + L];
-            prev = p.in;
-            if (prev.valid) {                                   // anchors of frame k-1 = medians at k-1
-                double tmp[LD_MAX_DEPTH];
-                int m = gather_window(k - 1, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp, lo);
-                pb = lanefit::median_small(tmp, m);
-                m = gather_window(k - 1, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp, lo);
-                pt = lanefit::median_small(tmp, m);
-            }
-            prev_n = prev.n_points + 1 + (top_anchor ? 1 : 0);
+// ---- pass 1b: the frames whose search failed (one CTA, dependency rounds) ---------------------------
+// An empty lane re-uses the previous frame's points with that frame's anchors (Project.py:98-100), and those anchors are
+// medians over the first fits of the `depth` frames before.  So (frame k, lane L) can be resolved as soon as every failed
+// frame among k-depth..k-1 of the same lane is: isolated failures -- the common case -- all resolve in the FIRST round, in
+// parallel (each costs a full polyfit; walked one after the other they were 8.7 of the 12 ms of a 1260-frame harder-challenge
+// batch with 236 empty lanes); only a run of consecutive failures is inherently serial, one round per frame.
+// state[2n]: 0 = resolved (search succeeded, or done), 1 = pending, 2 = being resolved in this round.  list[2n]: this round's items.
+__device__ __forceinline__ void fallback_item(int k, int L, int lo, const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work,
+                                              ld_frame_fit* __restrict__ fit, const TrackLane& T, int depth, int top_anchor,
+                                              int* __restrict__ first_bad) {
+    FitWork& w = work[2 * k + L];
+    // x_inds = self.x, y_inds = self.y (Project.py:98-100): last frame's arrays with its anchors,
+    // then .astype(np.float32) (Project.py:308-311)
+    FitInput prev; double pb = 0.0, pt = 0.0; int prev_n;
+    if (k == lo) { prev = T.pts; pb = T.last_bottom; pt = T.last_top; prev_n = T.n_points; if (!T.has_points || lo > 0) prev.valid = 0; }
+    else {
+        const FitWork& p = work[2 * (k - 1) + L];
+        prev = p.in;
+        if (prev.valid) {                                   // anchors of frame k-1 = medians at k-1
+            double tmp[LD_MAX_DEPTH];
+            int m = gather_window(k - 1, depth, T.n_hist, T.bottom, [&](int j) { return work[2 * j + L].bi; }, tmp, lo);
+            pb = lanefit::median_small(tmp, m);
+            m = gather_window(k - 1, depth, T.n_hist, T.top, [&](int j) { return work[2 * j + L].ti; }, tmp, lo);
+            pt = lanefit::median_small(tmp, m);
         }
-        if (!prev.valid) {                                      // np.polyfit(array(None)) -> TypeError
-            w.in.valid = 0;
-            atomicMin(first_bad, k);
-            return;
+        prev_n = prev.n_points + 1 + (top_anchor ? 1 : 0);
+    }
+    if (!prev.valid) {                                      // np.polyfit(array(None)) -> TypeError
+        w.in.valid = 0;
+        atomicMin(first_bad, k);
+        return;
+    }
+    w.in = prev;
+    w.in.c720 += 1.0; w.in.s720 = LD_ADD(w.in.s720, (double)(float)pb);
+    if (top_anchor) { w.in.c0 += 1.0; w.in.s0 = LD_ADD(w.in.s0, (double)(float)pt); }
+    w.in.n_points = prev_n;
+    do_fit1(w);
+    // Line.fity of a fallback frame = the previous frame's fity (its anchors included)
+    for (int i = 0; i < LD_ROWMAP_WORDS; ++i) {
+        uint32_t v;
+        if (k == lo) v = T.rowmap[i];
+        else if (rec[2 * (k - 1) + L].ok) {
+            v = rec[2 * (k - 1) + L].rowmap[i];
+            if (i == (720 >> 5)) v |= 1u << (720 & 31);
+            if (i == 0 && top_anchor) v |= 1u;
+        } else v = fit[k - 1].rowmap[L][i];
+        fit[k].rowmap[L][i] = v;
+    }
+}
+
+constexpr int FALLBACK_THREADS = 256;
+__global__ void __launch_bounds__(FALLBACK_THREADS)
+k_fit_fallback(const ld_lane_record* __restrict__ rec, FitWork* __restrict__ work, ld_frame_fit* __restrict__ fit,
+               const TrackState* __restrict__ st, int n, int depth, int top_anchor, const int* __restrict__ any_fail,
+               int* __restrict__ first_bad, const int* __restrict__ start, unsigned char* __restrict__ state, int* __restrict__ list) {
+    if (!*any_fail) return;
+    __shared__ int n_ready;
+    const int lo = batch_lo(start), tid = threadIdx.x;
+    for (int i = tid; i < 2 * n; i += FALLBACK_THREADS) state[i] = ((i >> 1) >= lo && !rec[i].ok) ? 1 : 0;
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) n_ready = 0;
+        __syncthreads();
+        for (int i = tid; i < 2 * n; i += FALLBACK_THREADS) {
+            if (state[i] != 1) continue;
+            const int k = i >> 1, L = i & 1;
+            bool ready = true;
+            for (int j = max(lo, k - depth); j < k; ++j) ready = ready && state[2 * j + L] == 0;
+            if (ready) list[atomicAdd(&n_ready, 1)] = i;
         }
-        w.in = prev;
-        w.in.c720 += 1.0; w.in.s720 = LD_ADD(w.in.s720, (double)(float)pb);
-        if (top_anchor) { w.in.c0 += 1.0; w.in.s0 = LD_ADD(w.in.s0, (double)(float)pt); }
-        w.in.n_points = prev_n;
-        do_fit1(w);
-        // Line.fity of a fallback frame = the previous frame's fity (its anchors included)
-        for (int i = 0; i < LD_ROWMAP_WORDS; ++i) {
-            uint32_t v;
-            if (k == lo) v = T.rowmap[i];
-            else if (rec[2 * (k - 1) + L].ok) {
-                v = rec[2 * (k - 1) + L].rowmap[i];
-                if (i == (720 >> 5)) v |= 1u << (720 & 31);
-                if (i == 0 && top_anchor) v |= 1u;
-            } else v = fit[k - 1].rowmap[L][i];
-            fit[k].rowmap[L][i] = v;
+        __syncthreads();
+        const int nr = n_ready;
+        if (nr == 0) break;                                 // nothing pending (the earliest pending item is always ready)
+        for (int q = tid; q < nr; q += FALLBACK_THREADS) {
+            const int i = list[q];
+            fallback_item(i >> 1, i & 1, lo, rec, work, fit, st->lane[i & 1], depth, top_anchor, first_bad);
         }
+        __syncthreads();
+        for (int q = tid; q < nr; q += FALLBACK_THREADS) state[list[q]] = 0;
+        __syncthreads();
     }
 }
 

@@ -74,6 +74,8 @@ struct ld_ctx {
     uint32_t* und_bits;        // shared pass: colour decision of the undistorted pixels, [max][H - share_y0][WW] (+ pad)
     uint32_t* und_px;          // shared pass: the undistorted pixels in lane order, [max][n_share][16][4][32]
     TrackState* state;
+    unsigned char* fb_state;   // k_fit_fallback scratch: [2 (max + HALO_MAX)] item states, [2 (max + HALO_MAX)] ready list
+    int* fb_list;
     int* flags;                // [0] any_fail, [1] first_bad, [2] last_bad (sticky result), [3] poly_error, [4] halo invalid,
                                // [5] tail invalid (the records this rank hands on), [6] scratch last_bad of ld_warmup
     int* flags_host;           // pinned mirror
@@ -368,6 +370,8 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
         CTX_ALLOC(c->und_px, (size_t)plan->n_share * 16 * 128 * 4 * max_frames);
     }
     CTX_ALLOC(c->state, sizeof(TrackState));
+    CTX_ALLOC(c->fb_state, (size_t)2 * (max_frames + HALO_MAX));
+    CTX_ALLOC(c->fb_list, sizeof(int) * 2 * (max_frames + HALO_MAX));
     CTX_ALLOC(c->flags, 16 * sizeof(int));
     for (int b = 0; b < 2; ++b) {
         CTX_ALLOC(c->stage_in[b], fb * c->chunk);
@@ -416,6 +420,7 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     if (c->work) cudaFree(c->work - 2 * HALO_MAX);
     if (c->fit) cudaFree(c->fit - HALO_MAX);
     cudaFree(c->text); cudaFree(c->und_bits); cudaFree(c->und_px); cudaFree(c->state); cudaFree(c->flags);
+    cudaFree(c->fb_state); cudaFree(c->fb_list);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->stage_in[b]); cudaFree(c->stage_out[b]);
         if (c->ev_in[b]) cudaEventDestroy(c->ev_in[b]);
@@ -531,7 +536,7 @@ static int fit_core(ld_ctx* c, const ld_lane_record* rec, FitWork* work, int n, 
     LD_CUDA(cudaMemsetAsync(c->flags + 1, 0x7F, sizeof(int), s));       // first_bad = 0x7f7f7f7f
     const int t = 64, g2 = (2 * n + t - 1) / t, g1 = (n + t - 1) / t;
     k_fit1<<<g2, t, 0, s>>>(rec, work, n, c->flags, start);
-    k_fit_fallback<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, d.top_anchor, c->flags, c->flags + 1, start);
+    k_fit_fallback<<<1, FALLBACK_THREADS, 0, s>>>(rec, work, fit, c->state, n, d.depth, d.top_anchor, c->flags, c->flags + 1, start, c->fb_state, c->fb_list);
     k_fit2<<<g2, t, 0, s>>>(work, c->state, n, d.depth, d.top_anchor, c->flags + 1, start);
     k_fit3<<<g1, t, 0, s>>>(rec, work, c->state, fit, n, d, c->flags + 1, start);
     k_state_update<<<1, 32, 0, s>>>(rec, work, fit, c->state, n, d.depth, c->flags + 1, last_bad_out ? last_bad_out : c->flags + 2, frame_offset,
