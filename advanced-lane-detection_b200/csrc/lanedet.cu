@@ -461,7 +461,8 @@ static void tl_print() {
     for (int i = 1; i < g_tl_n; ++i) {
         float ms = 0;
         cudaEventElapsedTime(&ms, g_tl_ev[0], g_tl_ev[i]);
-        fprintf(stderr, "[timeline] %-22s +%8.3f ms\n", g_tl_name[i], ms);
+        const char* rk = getenv("RANK");
+        fprintf(stderr, "[timeline rank %s] %-22s +%8.3f ms\n", rk ? rk : "0", g_tl_name[i], ms);
     }
     g_tl_n = 0;
 }

@@ -85,45 +85,78 @@ def synth_frames(n, seed, lo=0, hi=None, names=STILLS, out=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region (B200_PROFILING.md's clocks line).  The region is
+    a few tens of milliseconds, far below nvidia-smi's start-up time, so a thread polls NVML directly (about every millisecond);
+    nvidia-smi -lms is the fallback when NVML cannot be loaded."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu):
-        self.gpu, self.lines, self.proc = gpu, [], None
+    def __init__(self, gpu, uuid=None):
+        self.gpu, self.uuid = gpu, uuid
+        self.sm, self.max_mhz, self.reasons, self.lines = [], None, set(), []
+        self.handle = self.nv = self.proc = self.thread = None
+        self.stop = threading.Event()
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = nv.nvmlDeviceGetHandleByUUID(uuid) if uuid else nv.nvmlDeviceGetHandleByIndex(gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.nv = nv
+        except Exception:
+            self.handle = None
+
+    def _poll(self):
+        nv, h = self.nv, self.handle
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for bit, name in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def __enter__(self):
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+            time.sleep(0.5)                                 # let nvidia-smi come up before the timed region starts
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
-            self.t.join(timeout=2)
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
         for ln in self.lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 8:
                 continue
             try:
-                sm.append(float(p[1]))
-                mx = max(mx, float(p[2]))
+                self.sm.append(float(p[1]))
+                self.max_mhz = max(self.max_mhz or 0, float(p[2]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    self.reasons.add(name)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.handle is not None else "nvidia-smi"}
 
 
 def peaks():
@@ -262,8 +295,11 @@ def main():
         print(json.dumps(line))
         return
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"                   # NCCL prints its version banner on STDOUT; this script's stdout is one JSON line
+    # This script's stdout is ONE JSON line, but libraries write there too (NCCL prints its version banner on stdout at the
+    # VERSION and WARN debug levels): keep the real stdout aside and point file descriptor 1 at stderr until the line is printed.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -275,6 +311,10 @@ def main():
     sharding = importlib.import_module(PKG + ".sharding")
     n = a.frames
     dev = torch.device("cuda", local)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
 
     def barrier():
         if world > 1:
@@ -343,7 +383,7 @@ def main():
     run.finish()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, gpu_uuid) as clocks:
         barrier()
         ev0.record()
         for _ in range(a.steps):
@@ -405,15 +445,16 @@ def main():
     # the platform's ceiling for this traffic pattern, same run: plain pinned copies of the same buffers both ways at once, no kernels
     scratch = torch.empty_like(out)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(2):
+    pcie_fps = 0.0
+    for _ in range(3):                                       # best of three rounds (the first one also warms the copy engines up)
+        barrier()
+        t0 = time.perf_counter()
         with torch.cuda.stream(s1):
             scratch.copy_(pin_in, non_blocking=True)
         with torch.cuda.stream(s2):
             pin_out.copy_(frames, non_blocking=True)
-    torch.cuda.synchronize()
-    pcie_fps = world * n * 2 / reduce_max(time.perf_counter() - t0)
+        torch.cuda.synchronize()
+        pcie_fps = max(pcie_fps, world * n / reduce_max(time.perf_counter() - t0))
     del scratch
 
     # ---- config 3: the harder pipeline (frame_num = 5), sharded the same way
@@ -454,7 +495,8 @@ def main():
         line.update(single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg))
     line["configs"] = cfg
     if rank == 0:
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
