@@ -115,6 +115,8 @@ _SIGNATURES = {
     "ld_unpack_mask": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_margin_search": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "ld_polyfit": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "ld_polyfit_points": (C.c_int, [_P, _P, _P, C.c_int, C.c_double, _P, _P, _P]),
+    "ld_tracked_search": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "ld_draw": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "ld_gray": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "ld_sobel_max": (C.c_int, [_P, _P, C.c_int, _P, _P]),

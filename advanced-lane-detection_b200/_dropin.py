@@ -109,6 +109,8 @@ class Pipeline:
 
             @property
             def fity(self):
+                if self._xy_override and self._xy_override[1] is not None:
+                    return self._xy_override[1]
                 return self._points_with_anchors()[1]
 
             @property
@@ -150,8 +152,41 @@ class Pipeline:
                 return self.x[idx], self.y[idx]
 
             def get_fit(self):
-                raise NotImplementedError("Line.get_fit runs on the GPU inside process_image (ld_fit); "
-                                          "it cannot be driven point-list by point-list")
+                """Project.py:113-141 (harder:154-182) driven by hand: the caller has set self.x / self.y (as process_image does at
+                Project.py:308-311); the two np.polyfit calls run on the GPU (ld_polyfit_points), the deque medians are the
+                scalar bookkeeping of this mirror object.  Inside process_image the same stage runs batched on the device
+                (ld_fit) with the trackers kept there; a Line driven by hand keeps its history in these deques."""
+                v = pipeline.variant
+                eng = pipeline.engine()
+                x, y = self.x, self.y
+                if x is None or y is None:
+                    raise TypeError("expected 1D vector for x")          # np.polyfit(None, None, 2)
+                x, y = np.asarray(x), np.asarray(y)
+                fit1, rank = eng.polyfit_points(y, x)
+                pipeline._rank_warning(rank)
+                self.fit = fit1
+                bottom, top = self.get_intercepts()
+                self.bottom_x.append(bottom)
+                self.current_bottom_x = np.median(self.bottom_x)
+                x, y = np.append(x, self.current_bottom_x), np.append(y, 720)
+                if v.top_anchor:                                          # harder:163-171 keeps the bottom anchor only
+                    self.top_x.append(top)
+                    self.current_top_x = np.median(self.top_x)
+                    x, y = np.append(x, self.current_top_x), np.append(y, 0)
+                else:
+                    self.current_top_x = top
+                order = np.argsort(y)
+                x, y = x[order], y[order]
+                fit2, rank = eng.polyfit_points(y, x)
+                pipeline._rank_warning(rank)
+                self.A.append(fit2[0])
+                self.B.append(fit2[1])
+                self.C.append(fit2[2])
+                self._pts, self._anchors = None, None
+                self._xy_override = (x, y)
+                self.fit = [np.median(self.A), np.median(self.B), np.median(self.C)]
+                self._manual_fity = y
+                return self.fit, self.fit[0] * y ** 2 + self.fit[1] * y + self.fit[2], y
 
         self.Line = Line
         self.left = None
@@ -224,11 +259,15 @@ class Pipeline:
             self._update_line(line, lane, fit, rec[lane], mask, None)
         return pin_out.numpy()[0].copy()
 
+    @staticmethod
+    def _rank_warning(rank):
+        if rank < 3:
+            warnings.warn("Polyfit may be poorly conditioned", RankWarning, stacklevel=3)
+
     def _update_line(self, line, lane, fit, rec, mask_dev, state_blob):
         v = self.variant
         for k in (1, 2):
-            if fit["rank%d" % k][lane] < 3:
-                warnings.warn("Polyfit may be poorly conditioned", RankWarning, stacklevel=3)
+            self._rank_warning(fit["rank%d" % k][lane])
         prev = line._points_with_anchors if line._pts is not None else None
         prev_snapshot = None
         if not rec["ok"] and prev is not None:

@@ -369,4 +369,46 @@ __global__ void k_polyfit(const ld_lane_record* __restrict__ rec, int n, double*
     rank[i] = rec[i].mom[0] ? r.rank : 0;
 }
 
+// np.polyfit(y, x, 2) of CALLER-SUPPLIED points (Line.get_fit as a stand-alone call, Project.py:113-141: self.x / self.y set by
+// the caller).  x, y: float64[n] (float32 inputs convert exactly); eps = the machine epsilon of the caller's y dtype (np.polyfit:
+// rcond = len(x) * finfo(x.dtype).eps).  One CTA: every thread accumulates the eight power sums of its points in double-double
+// (products y^k and x y^k by two_prod: exact to ~1e-32 relative), a tree reduction adds them up, thread 0 solves.
+constexpr int POINTS_THREADS = 256;
+__global__ void __launch_bounds__(POINTS_THREADS)
+k_polyfit_points(const double* __restrict__ x, const double* __restrict__ y, int n, double eps, double* __restrict__ coef,
+                 int* __restrict__ rank) {
+    __shared__ lanefit::dd red[8][POINTS_THREADS];
+    lanefit::dd acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = lanefit::dd_make(0.0);
+    for (int i = threadIdx.x; i < n; i += POINTS_THREADS) {
+        const double yi = y[i], xi = x[i];
+        lanefit::dd yk = lanefit::dd_make(1.0);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            acc[k] = lanefit::dd_add(acc[k], yk);
+            if (k < 3) acc[5 + k] = lanefit::dd_add(acc[5 + k], lanefit::dd_mul_d(yk, xi));
+            yk = lanefit::dd_mul_d(yk, yi);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) red[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    for (int step = POINTS_THREADS / 2; step > 0; step >>= 1) {
+        if ((int)threadIdx.x < step)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) red[q][threadIdx.x] = lanefit::dd_add(red[q][threadIdx.x], red[q][threadIdx.x + step]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        lanefit::PowerSums ps;
+        for (int k = 0; k < 5; ++k) ps.S[k] = red[k][0];
+        for (int k = 0; k < 3; ++k) ps.T[k] = red[5 + k][0];
+        ps.n = (double)n;
+        const lanefit::FitResult r = lanefit::polyfit2(ps, eps);
+        coef[0] = r.c[0]; coef[1] = r.c[1]; coef[2] = r.c[2];
+        *rank = r.rank;
+    }
+}
+
 }  // namespace lanedet

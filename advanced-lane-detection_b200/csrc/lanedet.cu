@@ -511,6 +511,31 @@ extern "C" int ld_margin_search(ld_ctx* c, const uint32_t* mask, const double* f
     return check_launch();
 }
 
+// np.polyfit(y, x, 2) of caller-supplied points: the stand-alone Line.get_fit (Project.py:113-141)
+extern "C" int ld_polyfit_points(ld_ctx* c, const double* x, const double* y, int n, double eps, double* coef, int32_t* rank, void* stream) {
+    if (!c || !x || !y || !coef || !rank || n < 1 || !(eps > 0.0)) return LD_ERR_ARG;
+    k_polyfit_points<<<1, POINTS_THREADS, 0, (cudaStream_t)stream>>>(x, y, n, eps, coef, rank);
+    return check_launch();
+}
+
+// helper.skip_sliding_window as a tracked search over a sequence (helper.py:331-403): see k_tracked_search.
+extern "C" int ld_tracked_search(ld_ctx* c, const uint32_t* mask, int n, const double* init_fits, ld_lane_record* rec, double* fits,
+                                 int32_t* source, void* stream) {
+    if (!ARGS_OK(c, mask, rec, n) || !fits || !source || n > c->max_frames) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    PlanDev d = c->plan->d;
+    if (d.H != 720 || d.W != 1280) return LD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    // the fallback of every frame, in parallel: helper.sliding_window (helper.py:224-328) + its two polyfits
+    d.search_mode = LD_SEARCH_HELPER; d.margin = 50; d.minpix = 40;
+    k_search<<<n, SEARCH_THREADS, c->plan->search_smem, s>>>(mask, c->rec, d, nullptr);
+    double* win_fit = reinterpret_cast<double*>(c->work);               // scratch: the fit stage is not running
+    int32_t* win_rank = reinterpret_cast<int32_t*>(win_fit + (size_t)6 * n);
+    k_polyfit<<<(2 * n + 63) / 64, 64, 0, s>>>(c->rec, 2 * n, win_fit, win_rank);
+    k_tracked_search<<<1, SEARCH_THREADS, 0, s>>>(mask, n, init_fits, c->rec, win_fit, win_rank, rec, fits, source, d);
+    return check_launch();
+}
+
 extern "C" int ld_polyfit(ld_ctx* c, const ld_lane_record* rec, int n, double* coef, int32_t* rank, void* stream) {
     if (!ARGS_OK(c, rec, coef, n) || !rank) return LD_ERR_ARG;
     if (n == 0) return LD_OK;

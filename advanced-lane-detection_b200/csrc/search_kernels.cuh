@@ -284,4 +284,88 @@ k_margin_search(const uint32_t* __restrict__ mask, const double* __restrict__ fi
     write_records(rec + (size_t)f * 2, S, 0, 10, nullptr);
 }
 
+// helper.skip_sliding_window driven frame by frame (helper.py:331-403): frame k's two polyfits are the centre
+// lines of frame k+1's +-100 px bands -- the one true fit -> selection recursion of the reference, so the frames of a sequence
+// are walked in order by ONE CTA.  Everything that does not depend on the previous frame is done beforehand, in parallel:
+// win_rec / win_fit = helper.sliding_window of every frame (k_search in helper mode + k_polyfit), which the walk falls back to
+// when the band search returns None (fewer than 10 pixels in either lane, helper.py:357-359) -- what helper.refine's caller does
+// by calling it again with skip=False.  source[k]: 0 = band search, 1 = window search, 2 = both returned None (the fits of the
+// frame before are kept, as a caller holding on to its last good fits would).
+struct TrackedShared {
+    double fit[2][3], next[2][3];
+    int have, ok;
+};
+__global__ void __launch_bounds__(SEARCH_THREADS)
+k_tracked_search(const uint32_t* __restrict__ mask, int n, const double* __restrict__ init_fits,
+                 const ld_lane_record* __restrict__ win_rec, const double* __restrict__ win_fit, const int* __restrict__ win_rank,
+                 ld_lane_record* __restrict__ rec_out, double* __restrict__ fits_out, int32_t* __restrict__ source_out, const PlanDev P) {
+    const int W = P.W, H = P.H, WW = P.WW;
+    __shared__ SearchShared S;
+    __shared__ TrackedShared T;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 6) {
+        T.fit[threadIdx.x / 3][threadIdx.x % 3] = init_fits ? init_fits[threadIdx.x] : 0.0;
+        if (threadIdx.x == 0) T.have = init_fits != nullptr;
+    }
+    for (int k = 0; k < n; ++k) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (int)(sizeof(SearchShared) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&S)[i] = 0;
+        __syncthreads();
+        const uint32_t* m = mask + (size_t)k * H * WW;                   // read through L2: only the two bands are touched
+        if (T.have) {
+            for (int L = 0; L < 2; ++L) {
+                const double* c = T.fit[L];
+                uint64_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int row = threadIdx.x; row < H; row += blockDim.x) {
+                    // left_fit[0]*(nonzeroy**2) + left_fit[1]*nonzeroy + left_fit[2]  -/+ margin   (helper.py:340-348)
+                    const double centre = lanefit::eval_fit(c, (double)row);
+                    const double lo = LD_SUB(centre, 100.0), hi = LD_ADD(centre, 100.0);
+                    const double x0d = fmax(floor(lo) + 1.0, 0.0), x1d = fmin(ceil(hi) - 1.0, (double)(W - 1));
+                    if (!(x0d <= x1d)) continue;                           // also rejects NaN
+                    uint32_t cnt, sx;
+                    row_count_sx(m, WW, W, row, (int)x0d, (int)x1d, cnt, sx);
+                    if (cnt) {
+                        const uint64_t y = row, y2 = y * y;
+                        a[0] += cnt; a[1] += y * cnt; a[2] += y2 * cnt; a[3] += y2 * y * cnt; a[4] += y2 * y2 * cnt;
+                        a[5] += sx; a[6] += y * sx; a[7] += y2 * sx;
+                        atomicOr(&S.rowmap[L][row >> 5], 1u << (row & 31));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint64_t v = warp_sum_u64(a[q]);
+                    if (lane == 0 && v) atomicAdd(&S.mom[L][q], (unsigned long long)v);
+                }
+            }
+        }
+        __syncthreads();
+        const bool band_ok = T.have && S.mom[0][0] >= 10ull && S.mom[1][0] >= 10ull;      // helper.py:357-359
+        const bool win_ok = win_rec[2 * k].ok && win_rec[2 * k + 1].ok;                    // helper.py:302-304
+        if (band_ok) {
+            if (threadIdx.x < 2) {                                        // np.polyfit(lefty, leftx, 2) (helper.py:362-363)
+                const lanefit::FitResult r = lanefit::polyfit2(lanefit::sums_from_moments(reinterpret_cast<const uint64_t*>(S.mom[threadIdx.x])),
+                                                               2.220446049250313e-16);
+                T.next[threadIdx.x][0] = r.c[0]; T.next[threadIdx.x][1] = r.c[1]; T.next[threadIdx.x][2] = r.c[2];
+            }
+            write_records(rec_out + (size_t)k * 2, S, 0, 10, nullptr);
+        } else {
+            if (threadIdx.x < 6 && win_ok) T.next[threadIdx.x / 3][threadIdx.x % 3] = win_fit[(size_t)k * 6 + threadIdx.x];
+            // the record of the frame: the window search's selection (what the fits were made from, or what failed)
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(win_rec + (size_t)k * 2);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(rec_out + (size_t)k * 2);
+            for (int i = threadIdx.x; i < (int)(2 * sizeof(ld_lane_record) / 4); i += blockDim.x) dst[i] = src[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            const int L = threadIdx.x / 3, j = threadIdx.x % 3;
+            if (band_ok || win_ok) T.fit[L][j] = T.next[L][j];
+            fits_out[(size_t)k * 6 + threadIdx.x] = (band_ok || win_ok || T.have) ? T.fit[L][j] : nan("");
+        }
+        if (threadIdx.x == 0) {
+            source_out[k] = band_ok ? 0 : (win_ok ? 1 : 2);
+            if (band_ok || win_ok) T.have = 1;
+        }
+    }
+}
+
 }  // namespace lanedet

@@ -399,6 +399,38 @@ class LaneEngine:
                                                        self._stream()))
         return out
 
+    def tracked_search_dev(self, mask, init_fits=None):
+        """helper.skip_sliding_window as a tracked search over a sequence of packed masks (int32[n,H,W/32], frame order): frame k's
+        fits set frame k+1's bands, on the device.  init_fits = float64[2,3] (CUDA) or None.  Returns (records uint8[n,2,280],
+        fits float64[n,2,3], source int32[n]: 0 band search, 1 window-search fallback, 2 neither found 10 pixels per lane)."""
+        n = mask.shape[0]
+        rec = self._dev((n, 2, _abi.RECORD_DTYPE.itemsize), self.torch.uint8)
+        fits = self._dev((n, 2, 3), self.torch.float64)
+        source = self._dev((n,), self.torch.int32)
+        _abi.check(self.lib, self.lib.ld_tracked_search(self._ctx_h, _ptr(mask), n, _ptr(init_fits) if init_fits is not None else None,
+                                                        _ptr(rec), _ptr(fits), _ptr(source), self._stream()))
+        return rec, fits, source
+
+    def polyfit_points(self, y, x):
+        """np.polyfit(y, x, 2) of host point arrays on the device (the stand-alone Line.get_fit): returns (float64[3], rank).
+        rcond follows numpy: len(y) * eps of y's floating dtype (float64 for integer input)."""
+        y, x = np.asarray(y), np.asarray(x)
+        if y.ndim != 1:
+            raise TypeError("expected 1D vector for x")              # numpy's message: polyfit's `x` is our y
+        if x.ndim != 1 or x.shape[0] != y.shape[0]:
+            raise TypeError("expected x and y to have same length")
+        if y.size == 0:
+            raise TypeError("expected non-empty vector for x")
+        eps = float(np.finfo(y.dtype).eps) if np.issubdtype(y.dtype, np.floating) else float(np.finfo(np.float64).eps)
+        dev = "cuda:%d" % self.device
+        yd = self.torch.as_tensor(np.ascontiguousarray(y, np.float64)).to(dev)
+        xd = self.torch.as_tensor(np.ascontiguousarray(x, np.float64)).to(dev)
+        coef = self._dev((3,), self.torch.float64)
+        rank = self._dev((1,), self.torch.int32)
+        _abi.check(self.lib, self.lib.ld_polyfit_points(self._ctx_h, _ptr(xd), _ptr(yd), int(y.shape[0]), eps, _ptr(coef), _ptr(rank),
+                                                        self._stream()))
+        return coef.cpu().numpy(), int(rank.item())
+
     def polyfit_dev(self, records):
         n = records.numel() // _abi.RECORD_DTYPE.itemsize
         coef = self._dev((n, 3), self.torch.float64)

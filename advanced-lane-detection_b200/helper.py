@@ -1,6 +1,7 @@
 """Drop-in for the hot-path functions of the reference's helper.py (same names and argument meaning):
 
     warp, undistort, luv_lab_filter, sliding_window, skip_sliding_window, draw_area, apply_thresholds,
+    tracked_search  (skip_sliding_window over a whole sequence with the fit -> band recursion on the device),
     img2binary, sobelx_filter, color_filter, combine_bin   (the gradient / HLS / RGB thresholds)
 
 Like the reference, the module reads the globals `src`, `dst`, `mtx`, `dist` (helper.py:873-884 assigns them under
@@ -184,6 +185,41 @@ def skip_sliding_window(binary_warped, left_fit, right_fit):
     if res is None:
         return None
     return _LazyResult(res[0], res[1])
+
+
+def tracked_search(binaries, left_fit=None, right_fit=None):
+    """helper.skip_sliding_window as a TRACKED search over a whole sequence of bird's-eye binaries (helper.py:331-403): frame
+    k's two fits are the centre lines of frame k+1's +-100 px bands, the recursion runs on the device (ld_tracked_search).
+    A frame whose band search would return None (fewer than 10 pixels in a lane) falls back to sliding_window, as a caller
+    of helper.refine does with skip=False; if that returns None too the last fits are carried over.
+    binaries: uint8[n,720,1280] in {0,1}; left_fit / right_fit: the fits to start from (None: frame 0 starts with
+    sliding_window).  Returns a list of n dicts {left_fit, right_fit, left_fitx, right_fitx, n_left, n_right, source}
+    (source: 'band', 'window' or None when neither search found the lanes; the fits are then those of the frame before, or
+    None while there has never been one)."""
+    pipe = _pipeline()
+    eng = pipe.engine()
+    binaries = np.ascontiguousarray(binaries, dtype=np.uint8)
+    if binaries.ndim == 2:
+        binaries = binaries[None]
+    out = []
+    init = None
+    if left_fit is not None and right_fit is not None:
+        init = eng.torch.as_tensor(np.asarray([left_fit, right_fit], dtype=np.float64)).to("cuda:%d" % eng.device)
+    for a in range(0, binaries.shape[0], eng.max_frames):       # chunks of the context's size; the fits carry over
+        chunk = eng.to_device(binaries[a:a + eng.max_frames])
+        rec_t, fits_t, src_t = eng.tracked_search_dev(eng.pack_dev(chunk), init)
+        rec, fits, src = eng.records_to_numpy(rec_t), fits_t.cpu().numpy(), src_t.cpu().numpy()
+        for k in range(chunk.shape[0]):
+            lf, rf = fits[k]
+            have = not np.isnan(lf[0])
+            out.append({"left_fit": lf.copy() if have else None, "right_fit": rf.copy() if have else None,
+                        "left_fitx": lf[0] * ploty ** 2 + lf[1] * ploty + lf[2] if have else None,
+                        "right_fitx": rf[0] * ploty ** 2 + rf[1] * ploty + rf[2] if have else None,
+                        "n_left": int(rec[k, 0]["mom"][0]), "n_right": int(rec[k, 1]["mom"][0]),
+                        "source": ("band", "window", None)[int(src[k])]})
+        if not np.isnan(fits[-1]).any():
+            init = fits_t[-1].contiguous()
+    return out
 
 
 def draw_area(undist, dst, src, left_fitx, right_fitx):

@@ -242,10 +242,24 @@ int ld_unpack_mask(ld_ctx* ctx, const uint32_t* mask_dev, int n, uint8_t* bin_de
  * previous fits (fits_dev = double[n][2][3]) -> ld_lane_record[n][2] (ok = at least 10 pixels). */
 int ld_margin_search(ld_ctx* ctx, const uint32_t* mask_dev, const double* fits_dev, int n,
                      ld_lane_record* rec_dev, void* stream);
+/* The same as a TRACKED search over a sequence (helper.py:331-403): the two polyfits of frame k are the centre lines
+ * of frame k+1's bands -- the reference's one fit -> selection recursion, walked on the device in frame order.  When a band
+ * search returns None (< 10 pixels in either lane, helper.py:357-359) the frame falls back to helper.sliding_window
+ * (helper.py:224-328), as a caller of helper.refine does with skip=False; when that returns None too, the last fits are kept.
+ * init_fits_dev = double[2][3] to start from, or NULL (frame 0 starts with the window search).  Out: rec_dev[n][2] (the selection
+ * each frame's fits were made from), fits_dev = double[n][2][3] (the fits AFTER frame k), source_dev = int32[n]: 0 band search,
+ * 1 window search, 2 none (fits carried over; NaN while there has never been a fit).  n <= max_frames. */
+int ld_tracked_search(ld_ctx* ctx, const uint32_t* mask_dev, int n, const double* init_fits_dev, ld_lane_record* rec_dev,
+                      double* fits_dev, int32_t* source_dev, void* stream);
 /* np.polyfit(y, x, 2) of each record's pixel set with rcond = n*2^-52 (helper.py:309-310,362-363)
  * -> double[n_records][3], int32 rank[n_records] */
 int ld_polyfit(ld_ctx* ctx, const ld_lane_record* rec_dev, int n_records, double* coef_dev,
                int32_t* rank_dev, void* stream);
+/* np.polyfit(y, x, 2) of caller-supplied points -- Line.get_fit driven by hand (Project.py:113-141: the caller sets self.x / self.y):
+ * x_dev, y_dev = double[n] on the device, eps = machine epsilon of the caller's y dtype (np.polyfit: rcond = len(x) * eps)
+ * -> coef_dev = double[3], rank_dev = int32[1]. */
+int ld_polyfit_points(ld_ctx* ctx, const double* x_dev, const double* y_dev, int n, double eps, double* coef_dev,
+                      int32_t* rank_dev, void* stream);
 /* draw_area with explicit polygon vertices (Project.py:144-170; helper.py:758-779 when
  * thickness == 0): verts_dev = int32[n][max_verts][2] (x,y after np.int_), counts_dev = int32[n].
  * `undist_dev` is ALREADY undistorted. */

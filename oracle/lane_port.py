@@ -406,6 +406,32 @@ def helper_margin_search(mask, left_fit, right_fit):
             "nonzerox": nx, "nonzeroy": ny, "left_lane_inds": out[0], "right_lane_inds": out[1]}
 
 
+def helper_tracked_search(masks, left_fit=None, right_fit=None, margin_search=helper_margin_search, window_search=helper_sliding_window):
+    """The driver loop helper.refine is written for (helper.py:381-403 takes the last fits and `skip`): the band search of
+    helper.skip_sliding_window with the fits of the frame before; when it returns None (helper.py:357-359) the frame is searched
+    again with helper.sliding_window (skip=False); when that returns None too the last fits are kept.  `margin_search` /
+    `window_search` are injectable so that oracle/make_golden_tracked.py can run this same loop over the REFERENCE's functions.
+    Returns per frame (left_fit, right_fit, n_left, n_right, source) with source 0 band / 1 window / 2 none."""
+    fits, out = (None if left_fit is None or right_fit is None else (np.asarray(left_fit, float), np.asarray(right_fit, float))), []
+    for m in masks:
+        ret, source = None, 2
+        if fits is not None:
+            ret = margin_search(m, fits[0], fits[1])
+            source = 0
+        if ret is None:
+            ret = window_search(m)
+            source = 1
+        if ret is None:
+            out.append((None if fits is None else fits[0], None if fits is None else fits[1], None, None, 2))
+            continue
+        li, ri = ret["left_lane_inds"], ret["right_lane_inds"]
+        n_l = int(li.sum()) if li.dtype == bool else int(li.size)
+        n_r = int(ri.sum()) if ri.dtype == bool else int(ri.size)
+        fits = (np.asarray(ret["left_fit"], float), np.asarray(ret["right_fit"], float))
+        out.append((fits[0], fits[1], n_l, n_r, source))
+    return out
+
+
 def helper_fill_overlay(undist, dst, src, left_fitx, right_fitx):
     """helper.draw_area, helper.py:758-779."""
     canvas = np.zeros((H, W, 3), np.uint8)

@@ -109,3 +109,46 @@ def test_helper_module(stills):
     out = Hp.draw_area(und, Hp.dst, Hp.src, want["left_fitx"], want["right_fitx"])
     ref = O.helper_fill_overlay(und, Hp.dst, Hp.src, want["left_fitx"], want["right_fitx"])
     assert np.abs(out.astype(np.int16) - ref.astype(np.int16)).max() <= 1
+
+
+def test_line_get_fit_driven_by_hand(stills, golden):
+    """Line.get_fit as a stand-alone call (Project.py:113-141): the caller runs the searches, sets .x / .y as process_image does
+    (Project.py:308-311) and asks for the fit.  Checked against the same steps written with np.polyfit and deques."""
+    from collections import deque
+    P = importlib.import_module(PKG + ".Project")
+    orc = O.LaneOracle("project")
+    seq = golden["sequences"]["project_seed0_40"]
+    frames = list(O.synth_sequence([stills(s) for s in seq["stills"]], 4, seed=seq["seed"]))
+    left, right = P.Line(), P.Line()                            # the pattern of Project.py:351-352: the new pair replaces the old one
+    assert P._pipeline.left is left and P._pipeline.right is right
+    ref = {id(left): [deque(maxlen=15) for _ in range(5)], id(right): [deque(maxlen=15) for _ in range(5)]}
+    for f in frames:
+        mask = O.binary_birdseye(O.undistort(f, orc.mtx, orc.dist), orc.v)
+        nzx, nzy = np.nonzero(np.transpose(mask))
+        for line in (left, right):
+            line.detected = False
+            x, y, line.detected = line.blind_search(nzx, nzy, mask)
+            line.x, line.y = np.array(x).astype(np.float32), np.array(y).astype(np.float32)
+            wx, wy = line.x.copy(), line.y.copy()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                fit, fitx, fity = line.get_fit()
+                bq, tq, A, B, C = ref[id(line)]                 # Project.py:118-139 with numpy
+                f1 = np.polyfit(wy, wx, 2)
+                bq.append(f1[0] * 720 ** 2 + f1[1] * 720 + f1[2])
+                tq.append(f1[2])
+                wx = np.append(np.append(wx, np.median(bq)), np.median(tq))
+                wy = np.append(np.append(wy, 720), 0)
+                order = np.argsort(wy)
+                wx, wy = wx[order], wy[order]
+                f2 = np.polyfit(wy, wx, 2)
+            A.append(f2[0]); B.append(f2[1]); C.append(f2[2])
+            want = np.array([np.median(A), np.median(B), np.median(C)])
+            assert (np.abs(np.array(fit) - want) <= 1e-9 * np.abs(want)).all()
+            assert (fity == wy).all() and np.abs(fitx - (want[0] * wy ** 2 + want[1] * wy + want[2])).max() < 1e-6
+            assert abs(line.current_bottom_x - np.median(bq)) <= 1e-9 * abs(np.median(bq))
+            assert len(line.A) == len(A) and (line.fity == wy).all()
+    fresh = P.Line()
+    with pytest.raises(TypeError, match="expected 1D vector for x"):
+        fresh.get_fit()                                         # np.polyfit(None, None, 2), the reference's failure mode
+    P.reset()
