@@ -62,7 +62,7 @@ class FrameFit(C.Structure):
                 ("rank1", C.c_int32 * 2), ("rank2", C.c_int32 * 2), ("detected", C.c_int32 * 2),
                 ("n_points", C.c_int32 * 2), ("status", C.c_int32), ("n_text", C.c_int32 * 2),
                 ("text", (C.c_uint8 * LD_TEXT_MAX_GLYPHS) * 2), ("rowmap", (C.c_uint32 * LD_ROWMAP_WORDS) * 2),
-                ("pad", C.c_int32)]
+                ("near_integer", C.c_int32)]
 
 
 RECORD_DTYPE = np.dtype(LaneRecord)

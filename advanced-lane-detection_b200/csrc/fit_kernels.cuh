@@ -295,7 +295,15 @@ __global__ void k_fit3(const ld_lane_record* __restrict__ rec, const FitWork* __
         if (p < LD_TEXT_MAX_GLYPHS) o.text[1][p++] = 14;
         o.n_text[1] = p;
     }
-    o.pad = 0;
+    // how many polygon vertices could truncate differently from the reference's (see ld_frame_fit.near_integer)
+    int near = 0;
+    for (int L = 0; L < 2; ++L)
+        for (int w = 0; w < LD_ROWMAP_WORDS; ++w)
+            for (uint32_t m = o.rowmap[L][w]; m; m &= m - 1) {
+                const double v = lanefit::eval_fit(o.fit[L], (double)(w * 32 + __ffs(m) - 1));
+                near += fabs(v - rint(v)) < 1e-6;
+            }
+    o.near_integer = near;
 }
 
 // ---- pass 4: roll the trackers forward to the end of the valid part of the batch (one thread per lane)

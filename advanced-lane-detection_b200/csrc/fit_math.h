@@ -1,5 +1,5 @@
 // fit_math.h -- the fp64 / double-double arithmetic of the lane fit, shared by the CUDA kernels
-// (lane_fit.cuh) and by the CPU-only fuzz harness under tests/hostsim (which exists so this
+// (fit_kernels.cuh, search_kernels.cuh) and by the CPU-only fuzz harness under tests/hostsim (which exists so this
 // arithmetic can be checked against numpy in a container without a GPU; the package never loads it).
 //
 // What it reproduces: np.polyfit(y, x, 2) as called at Project.py:118 and :133

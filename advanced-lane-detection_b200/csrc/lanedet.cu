@@ -71,6 +71,7 @@ struct ld_ctx {
     int halo;                  // frames of look-back records waiting in front of rec (consumed by the next ld_postpass_flags(USE_HALO))
     uint32_t* planes;          // padded, interleaved canvas u64[max][H+2][2 WW + 2] (overlay_kernels.cuh: canvas_codes)
     uint32_t* text;            // [max][TEXT_ROWS][TEXT_WORDS]
+    RasterPrep* prep;          // [max] vertices + prepared long segments of every frame's polygon (k_raster_prep -> k_raster)
     uint32_t* und_bits;        // shared pass: colour decision of the undistorted pixels, [max][H - share_y0][WW] (+ pad)
     uint32_t* und_px;          // shared pass: the undistorted pixels in lane order, [max][n_share][16][4][32]
     TrackState* state;
@@ -365,6 +366,7 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     c->fit += HALO_MAX;
     CTX_ALLOC(c->planes, canvas_words(d) * 4 * max_frames);
     CTX_ALLOC(c->text, (size_t)LD_TEXT_ROWS * LD_TEXT_WORDS * 4 * max_frames);
+    CTX_ALLOC(c->prep, sizeof(RasterPrep) * (size_t)max_frames);
     if (plan->shared_ok) {
         CTX_ALLOC(c->und_bits, (size_t)(d.H - d.share_y0) * d.WW * 4 * max_frames + 64);
         CTX_ALLOC(c->und_px, (size_t)plan->n_share * 16 * 128 * 4 * max_frames);
@@ -420,7 +422,7 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     if (c->work) cudaFree(c->work - 2 * HALO_MAX);
     if (c->fit) cudaFree(c->fit - HALO_MAX);
     cudaFree(c->text); cudaFree(c->und_bits); cudaFree(c->und_px); cudaFree(c->state); cudaFree(c->flags);
-    cudaFree(c->fb_state); cudaFree(c->fb_list);
+    cudaFree(c->fb_state); cudaFree(c->fb_list); cudaFree(c->prep);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->stage_in[b]); cudaFree(c->stage_out[b]);
         if (c->ev_in[b]) cudaEventDestroy(c->ev_in[b]);
@@ -591,8 +593,10 @@ static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* vert
                          int thickness, int m, cudaStream_t s, int slot) {
     const PlanDev& d = c->plan->d;
     if (d.W != 1280 || d.H != 720) return LD_ERR_ARG;                    // RASTER_CW
+    // once per frame: vertices + the set-up of the long segments; then one CTA per 90-row band draws
+    k_raster_prep<<<m, RASTER_THREADS, 0, s>>>(fit, verts, counts, max_verts, thickness, c->prep + slot, d);
     k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(
-        fit, verts, counts, max_verts, thickness, c->planes + (size_t)slot * canvas_words(d),
+        fit, c->prep + slot, thickness, c->planes + (size_t)slot * canvas_words(d),
         c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);
     return check_launch();
 }

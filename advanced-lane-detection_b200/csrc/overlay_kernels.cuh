@@ -53,12 +53,20 @@ struct BandPlotter {                // sets bits [x1,x2] of canvas row y if the 
     }
 };
 
+constexpr int RASTER_MAX_BIG = 16;             // long segments per frame whose set-up k_raster_prep does ahead of the band CTAs
+
+// Per frame, written once by k_raster_prep and read by the eight band CTAs of k_raster: the polygon's vertices and the
+// ThickSetup records of its long red segments (lane gaps, the connector between the lanes).
+struct RasterPrep {
+    int n_verts, n_big, bad, pad;
+    int big_idx[RASTER_MAX_BIG];                // segment i = vertex i -> i + 1
+    laneraster::ThickSetup big[RASTER_MAX_BIG];
+    int vx[MAX_VERTS], vy[MAX_VERTS];
+};
+
 struct RasterShared {
-    int n_verts, overflow, cut, n_jobs, n_big, n_bigedge;
-    int count[2];
+    int n_verts, overflow, n_jobs, n_big, n_bigedge, pad;
     int hw[16];
-    uint32_t rowmask[2][LD_ROWMAP_WORDS];
-    int prefix[2][LD_ROWMAP_WORDS];
     int vx[MAX_VERTS], vy[MAX_VERTS];
     int cnt[RASTER_BAND];
     alignas(8) int cross[RASTER_BAND * LD_MAX_CROSSINGS];        // also the ThickSetup records of the long red segments
@@ -85,15 +93,107 @@ __device__ __forceinline__ int vertex_x(const double* c, int y) {
     return (int)v;                                              // truncation toward zero
 }
 
+// The rare general paths of k_raster, kept out of line so that their register appetite (64-bit divisions, the quad's corners)
+// does not spill the common path: a long segment k_raster_prep had no room for, and a short segment no stamp covers.
+__device__ __noinline__ void raster_setup_slow(int W, int H, int x0, int y0, int x1, int y1, int thickness, laneraster::ThickSetup* T) {
+    laneraster::thick_segment_setup(W, H, x0, y0, x1, y1, thickness, *T);
+}
+__device__ __noinline__ void raster_segment_slow(BandPlotter* red, int W, int H, int x0, int y0, int x1, int y1, int thickness, const int* hw,
+                                                 bool first, int lane, int y_lo, int y_hi) {
+    laneraster::thick_segment_part(*red, W, H, x0, y0, x1, y1, thickness, hw, first, lane, 32, y_lo, y_hi);
+}
+
+// Set-up half of the raster, once per frame (the band CTAs of k_raster used to repeat all of it eight times, and the long
+// segments' set-up -- clipping, the quad's corners, four outline DDAs, the scan edges: some thirty 64-bit and double divisions
+// -- ran on ONE thread while 255 waited: 46 % of k_raster's time).  Lists the polygon's vertices -- left lane descending y,
+// then right lane ascending y (Project.py:153-157), x = np.int_(fit(y)) -- from the frame's fit and row maps (verts == nullptr)
+// or copies the caller's (ld_draw), finds the long red segments and prepares them, one warp each.
+__global__ void __launch_bounds__(RASTER_THREADS)
+k_raster_prep(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts, const int32_t* __restrict__ counts,
+              int max_verts, int thickness, RasterPrep* __restrict__ prep, const PlanDev P) {
+    __shared__ uint32_t rowmask[2][LD_ROWMAP_WORDS];
+    __shared__ int prefix[2][LD_ROWMAP_WORDS], count[2], s_cut, s_nbig;
+    const int W = P.W, H = P.H;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    RasterPrep& R = prep[f];
+    const bool bad = fit && fit[f].status != LD_OK;
+    if (tid == 0) {
+        s_nbig = 0;
+        int cut = -1;                                                   // harder:192-197 drops y <= max(min lefty, min righty)
+        if (fit && !bad && P.clip_polygon) {
+            int mn[2];
+            for (int l = 0; l < 2; ++l) {
+                mn[l] = 1 << 20;
+                for (int w = 0; w < LD_ROWMAP_WORDS; ++w)
+                    if (fit[f].rowmap[l][w]) { mn[l] = w * 32 + __ffs(fit[f].rowmap[l][w]) - 1; break; }
+            }
+            cut = max(mn[0], mn[1]);
+        }
+        s_cut = cut;
+    }
+    __syncthreads();
+    int nv = 0;
+    if (verts) {
+        nv = min(counts[f], min(max_verts, MAX_VERTS));
+        for (int i = tid; i < nv; i += RASTER_THREADS) {
+            R.vx[i] = verts[((size_t)f * max_verts + i) * 2];
+            R.vy[i] = verts[((size_t)f * max_verts + i) * 2 + 1];
+        }
+    } else if (!bad) {
+        const ld_frame_fit& F = fit[f];
+        if (tid < 2 * LD_ROWMAP_WORDS) {                                // rows kept per lane (bits above the cut)
+            const int L = tid / LD_ROWMAP_WORDS, w = tid % LD_ROWMAP_WORDS;
+            uint32_t m = F.rowmap[L][w];
+            const int cut = s_cut;
+            if (cut >= w * 32 + 31) m = 0;
+            else if (cut >= w * 32) m &= ~((2u << (cut - w * 32)) - 1u);
+            rowmask[L][w] = m;
+        }
+        __syncthreads();
+        if (tid < 2 * LD_ROWMAP_WORDS) {
+            const int L = tid / LD_ROWMAP_WORDS, w = tid % LD_ROWMAP_WORDS;
+            int sum = 0;
+            for (int k = 0; k < w; ++k) sum += __popc(rowmask[L][k]);
+            prefix[L][w] = sum;
+            if (w == LD_ROWMAP_WORDS - 1) count[L] = sum + __popc(rowmask[L][w]);
+        }
+        __syncthreads();
+        for (int t = tid; t < 2 * LD_ROWMAP_WORDS * 32; t += RASTER_THREADS) {
+            const int L = t / (LD_ROWMAP_WORDS * 32), y = t % (LD_ROWMAP_WORDS * 32);
+            const uint32_t m = rowmask[L][y >> 5];
+            if (!((m >> (y & 31)) & 1u)) continue;
+            const int rank = prefix[L][y >> 5] + __popc(m & ((1u << (y & 31)) - 1u));
+            const int slot = L ? count[0] + rank : count[0] - 1 - rank;
+            R.vx[slot] = vertex_x(F.fit[L], y);
+            R.vy[slot] = y;
+        }
+        nv = count[0] + count[1];
+    }
+    __syncthreads();                                                     // the vertices are in global memory, visible to the CTA
+    // long red segments: everything k_raster's pass 1 sends to its `big` list, whatever band it touches
+    if (thickness >= 2)
+        for (int i = tid; i + 1 < nv; i += RASTER_THREADS)
+            if (max(abs(R.vx[i + 1] - R.vx[i]), abs(R.vy[i + 1] - R.vy[i])) > 24) {
+                const int k = atomicAdd(&s_nbig, 1);
+                if (k < RASTER_MAX_BIG) R.big_idx[k] = i;
+            }
+    __syncthreads();
+    const int nb = min(s_nbig, (int)RASTER_MAX_BIG);
+    for (int k = tid >> 5; k < nb; k += RASTER_THREADS / 32)
+        if ((tid & 31) == 0) {
+            const int i = R.big_idx[k];
+            laneraster::thick_segment_setup(W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.big[k]);
+        }
+    if (tid == 0) { R.n_verts = nv; R.n_big = nb; R.bad = bad ? 1 : 0; R.pad = 0; }
+}
+
 // One CTA = one 90-row band of one frame's canvas.  planes: padded, interleaved canvas u64[n][H+2][2 WW + 2] (plan.py: inv_pack;
 // red = red without green; rows 0 and H+1 stay zero);
-// text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  Vertices come from the frame's fit + row maps
-// (verts == nullptr) or are given explicitly (ld_draw).  Every CTA lists all vertices (cheap, parallel) and
-// draws only the primitives whose rows can touch its band, one primitive per thread.
+// text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  The vertices and the prepared long segments come from
+// k_raster_prep; every CTA draws only the primitives whose rows can touch its band, expensive ones one per warp.
 __global__ void __launch_bounds__(RASTER_THREADS, 4)
-k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts, const int32_t* __restrict__ counts,
-         int max_verts, int thickness, uint32_t* __restrict__ planes, uint32_t* __restrict__ text, const PlanDev P,
-         int* __restrict__ poly_error) {
+k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ prep, int thickness, uint32_t* __restrict__ planes,
+         uint32_t* __restrict__ text, const PlanDev P, int* __restrict__ poly_error) {
     extern __shared__ uint32_t smem[];
     const int W = P.W, H = P.H, WW = P.WW;
     uint32_t* s_red = smem;                                             // RASTER_BAND*WW
@@ -107,73 +207,24 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
     BandPlotter red{s_red, WW, W, y_lo, y_hi}, green{s_green, WW, W, y_lo, y_hi};
     const int tid = threadIdx.x;
     const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
+    const RasterPrep& Q = prep[f];
 
     RPROF(0);
+    const int nv = Q.n_verts;
+    const bool bad = Q.bad != 0;
+    for (int i = tid; i < nv; i += RASTER_THREADS) { R.vx[i] = Q.vx[i]; R.vy[i] = Q.vy[i]; }     // issued first: their latency hides behind the clear
     for (int i = tid; i < 2 * RASTER_BAND * WW; i += RASTER_THREADS) s_red[i] = 0;
     for (int i = tid; i < RASTER_BAND; i += RASTER_THREADS) R.cnt[i] = 0;
-    const bool bad = fit && fit[f].status != LD_OK;
     const int radius = min(thickness / 2, 15);
     if (tid == 0) {
         R.overflow = 0;
-        R.n_verts = 0;
+        R.n_verts = nv;
         R.n_jobs = 0;
         R.n_big = 0;
         R.n_bigedge = 0;
         laneraster::circle_half_widths(radius, R.hw);
-        int cut = -1;                                                   // harder:192-197 drops y <= max(min lefty, min righty)
-        if (fit && !bad && P.clip_polygon) {
-            int mn[2];
-            for (int l = 0; l < 2; ++l) {
-                mn[l] = 1 << 20;
-                for (int w = 0; w < LD_ROWMAP_WORDS; ++w)
-                    if (fit[f].rowmap[l][w]) { mn[l] = w * 32 + __ffs(fit[f].rowmap[l][w]) - 1; break; }
-            }
-            cut = max(mn[0], mn[1]);
-        }
-        R.cut = cut;
     }
     __syncthreads();
-
-    // ---- vertices: left lane descending y, then right lane ascending y (Project.py:153-157)
-    if (verts) {
-        const int nv = min(counts[f], min(max_verts, MAX_VERTS));
-        for (int i = tid; i < nv; i += RASTER_THREADS) {
-            R.vx[i] = verts[((size_t)f * max_verts + i) * 2];
-            R.vy[i] = verts[((size_t)f * max_verts + i) * 2 + 1];
-        }
-        if (tid == 0) R.n_verts = nv;
-    } else if (!bad) {
-        const ld_frame_fit& F = fit[f];
-        if (tid < 2 * LD_ROWMAP_WORDS) {                                // rows kept per lane (bits above the cut)
-            const int L = tid / LD_ROWMAP_WORDS, w = tid % LD_ROWMAP_WORDS;
-            uint32_t m = F.rowmap[L][w];
-            const int cut = R.cut;
-            if (cut >= w * 32 + 31) m = 0;
-            else if (cut >= w * 32) m &= ~((2u << (cut - w * 32)) - 1u);
-            R.rowmask[L][w] = m;
-        }
-        __syncthreads();
-        if (tid < 2 * LD_ROWMAP_WORDS) {
-            const int L = tid / LD_ROWMAP_WORDS, w = tid % LD_ROWMAP_WORDS;
-            int s = 0;
-            for (int k = 0; k < w; ++k) s += __popc(R.rowmask[L][k]);
-            R.prefix[L][w] = s;
-            if (w == LD_ROWMAP_WORDS - 1) R.count[L] = s + __popc(R.rowmask[L][w]);
-        }
-        __syncthreads();
-        for (int t = tid; t < 2 * LD_ROWMAP_WORDS * 32; t += RASTER_THREADS) {
-            const int L = t / (LD_ROWMAP_WORDS * 32), y = t % (LD_ROWMAP_WORDS * 32);
-            const uint32_t m = R.rowmask[L][y >> 5];
-            if (!((m >> (y & 31)) & 1u)) continue;
-            const int rank = R.prefix[L][y >> 5] + __popc(m & ((1u << (y & 31)) - 1u));
-            const int slot = L ? R.count[0] + rank : R.count[0] - 1 - rank;
-            R.vx[slot] = vertex_x(F.fit[L], y);
-            R.vy[slot] = y;
-        }
-        if (tid == 0) R.n_verts = R.count[0] + R.count[1];
-    }
-    __syncthreads();
-    const int nv = R.n_verts;
     RPROF(1);
 
     // ---- red: cv2.polylines(canvas, pts, False, (200,0,0), thickness) (Project.py:160-161)
@@ -211,8 +262,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         for (int k = warp; k < R.n_jobs; k += RASTER_THREADS / 32) {
             const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
             if (type == 0)
-                laneraster::thick_segment_part(red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, lane, 32,
-                                               y_lo, y_hi);
+                raster_segment_slow(&red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, lane, y_lo, y_hi);
             else if (type == 3)
                 laneraster::draw_stamp_part(red, stamps[laneraster::stamp_index(R.vx[i + 1] - R.vx[i], R.vy[i + 1] - R.vy[i])], R.vx[i],
                                             R.vy[i], lane, 32);
@@ -228,9 +278,16 @@ k_raster(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts
         for (int k0 = 0; k0 < R.n_big; k0 += RASTER_BIG_ROUND) {
             const int nb = min(RASTER_BIG_ROUND, R.n_big - k0);
             __syncthreads();
-            if ((tid & 31) == 0 && (tid >> 5) < nb) {
+            if ((tid >> 5) < nb) {                                       // one warp per segment: copy the record k_raster_prep made
                 const int i = R.big[k0 + (tid >> 5)];
-                laneraster::thick_segment_setup(W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, ts[tid >> 5]);
+                int found = -1;
+                for (int q = 0; q < Q.n_big; ++q) if (Q.big_idx[q] == i) found = q;
+                if (found >= 0) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.big[found]);
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(&ts[tid >> 5]);
+                    for (int w = tid & 31; w < (int)(sizeof(laneraster::ThickSetup) / 4); w += 32) dst[w] = src[w];
+                } else if ((tid & 31) == 0)                              // more long segments than the prep kernel holds: set up here
+                    raster_setup_slow(W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, &ts[tid >> 5]);
             }
             __syncthreads();
             for (int k = 0; k < nb; ++k)
@@ -440,7 +497,9 @@ __device__ __forceinline__ uint32_t bilinear_rgb_pre(uint32_t box, uint32_t stri
 // tiles below plan.share_y0 -- the undistorted pixels are needed twice there, by the mask (every bird's-eye pixel is a copy
 // of one of them) and by the overlay, so they are computed once: their colour decision goes to a bit plane (und_bits,
 // k_mask_b picks the mask out of it) and the pixels themselves to a scratch buffer in lane order (und_px, k_blend_px adds
-// the canvas later).
+// the canvas later).  (Writing the share tiles' pixels straight into the output frames and blending only the 32-pixel groups
+// the canvas touches in place was tried in round 2: 2.99 instead of 4.81 MB of traffic per frame, but the packed store in the
+// shared pass and the read-modify-write chain cost more issue slots than the bytes saved: 4.14 against 4.00 ms per step.)
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
 #ifndef LD_FRAME_STAGES
 #define LD_FRAME_STAGES 4

@@ -1,5 +1,5 @@
 // raster_math.h -- integer rasterisers behind draw_area (Project.py:144-170), shared by the CUDA
-// raster kernel (lane_raster.cuh) and the CPU-only fuzz harness under tests/hostsim.
+// raster kernel (overlay_kernels.cuh: k_raster) and the CPU-only fuzz harness under tests/hostsim.
 //
 // The reference draws with  cv2.polylines(canvas, pts, False, (200,0,0), thickness=30)  and
 // cv2.fillPoly(canvas, pts, (0,255,0))  (Project.py:160-164).  OpenCV is not in /root/reference;

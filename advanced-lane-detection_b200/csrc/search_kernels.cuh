@@ -264,7 +264,7 @@ k_margin_search(const uint32_t* __restrict__ mask, const double* __restrict__ fi
             const double centre = lanefit::eval_fit(c, (double)row);
             const double lo = LD_SUB(centre, 100.0), hi = LD_ADD(centre, 100.0);
             const double x0d = fmax(floor(lo) + 1.0, 0.0), x1d = fmin(ceil(hi) - 1.0, (double)(W - 1));
-            if (!(x0d <= x1d)) continue;                                   // also rejects NaN
+            if (!(x0d <= x1d) || centre != centre) continue;               // a NaN centre selects nothing (fmax / fmin would drop the NaN)
             uint32_t cnt, sx;
             row_count_sx(s_mask, WW, W, row, (int)x0d, (int)x1d, cnt, sx);
             if (cnt) {
@@ -321,7 +321,7 @@ k_tracked_search(const uint32_t* __restrict__ mask, int n, const double* __restr
                     const double centre = lanefit::eval_fit(c, (double)row);
                     const double lo = LD_SUB(centre, 100.0), hi = LD_ADD(centre, 100.0);
                     const double x0d = fmax(floor(lo) + 1.0, 0.0), x1d = fmin(ceil(hi) - 1.0, (double)(W - 1));
-                    if (!(x0d <= x1d)) continue;                           // also rejects NaN
+                    if (!(x0d <= x1d) || centre != centre) continue;       // a NaN centre selects nothing (fmax / fmin would drop the NaN)
                     uint32_t cnt, sx;
                     row_count_sx(m, WW, W, row, (int)x0d, (int)x1d, cnt, sx);
                     if (cnt) {

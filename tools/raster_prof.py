@@ -25,7 +25,7 @@ buf = (ctypes.c_longlong * (64 * 16))()
 eng.lib.ld_debug_raster_prof.argtypes = [ctypes.c_void_p]
 assert eng.lib.ld_debug_raster_prof(buf) == 0
 a = np.array(buf[:], dtype=np.int64).reshape(64, 16)
-names = ["clear+cut", "verts", "classify(red pass1)", "jobs(pass2)", "big segs", "green edges", "big edges", "sort+spans", "store"]
+names = ["clear + load vertices", "classify (red pass 1)", "jobs (red pass 2)", "long segments", "green edges", "long edges", "sort + spans", "store"]
 d = np.diff(a[:, :9], axis=1)
 print("phase cycles per CTA (frame, band) -- mean / max over 64 CTAs")
 for i in range(8):
