@@ -33,7 +33,7 @@ struct PlanDev {
     int n_mask_chunks;
     const uint32_t* frame_amap; const int32_t* frame_amap_start;
     const uint32_t* mask_amap; const int32_t* mask_amap_start;
-    const void* stamps;              // laneraster::Stamp[STAMP_N] for thickness 30 (raster_math.h)
+    const void* stamps;              // StampTable (overlay_kernels.cuh): the thick-line stamps of raster_math.h for thickness 30
     const uint4* bdesc;              // per output mask word: (first source bit | BORDER | FALLBACK, step1, step2, valid)
     int max_out_words;
     int share_y0;                    // first row of the tiles whose undistorted pixels both the mask and the overlay need (multiple of 16)

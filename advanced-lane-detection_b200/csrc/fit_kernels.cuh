@@ -295,15 +295,29 @@ __global__ void k_fit3(const ld_lane_record* __restrict__ rec, const FitWork* __
         if (p < LD_TEXT_MAX_GLYPHS) o.text[1][p++] = 14;
         o.n_text[1] = p;
     }
-    // how many polygon vertices could truncate differently from the reference's (see ld_frame_fit.near_integer)
+    o.near_integer = -1;                                        // not evaluated yet (k_near_integer, after the overlay)
+}
+
+// ld_frame_fit.near_integer: how many polygon vertices np.int_(fit(y)) (Project.py:139, :160) have fit(y) within 1e-6 of an
+// integer -- the only ones that could truncate to a different pixel than the reference's, whose np.polyfit differs from this
+// fit in the 10th digit.  One CTA per frame, off the critical chain (1440 evaluations per frame were 0.08 us/frame inside k_fit3).
+__global__ void __launch_bounds__(128)
+k_near_integer(ld_frame_fit* __restrict__ fit, int n) {
+    ld_frame_fit& o = fit[blockIdx.x];
+    if (o.status != LD_OK) return;
     int near = 0;
-    for (int L = 0; L < 2; ++L)
-        for (int w = 0; w < LD_ROWMAP_WORDS; ++w)
-            for (uint32_t m = o.rowmap[L][w]; m; m &= m - 1) {
-                const double v = lanefit::eval_fit(o.fit[L], (double)(w * 32 + __ffs(m) - 1));
-                near += fabs(v - rint(v)) < 1e-6;
-            }
-    o.near_integer = near;
+    for (int t = threadIdx.x; t < 2 * LD_ROWMAP_WORDS * 32; t += blockDim.x) {
+        const int L = t / (LD_ROWMAP_WORDS * 32), y = t % (LD_ROWMAP_WORDS * 32);
+        if (!((o.rowmap[L][y >> 5] >> (y & 31)) & 1u)) continue;
+        const double v = lanefit::eval_fit(o.fit[L], (double)y);
+        near += fabs(v - rint(v)) < 1e-6;
+    }
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    if (near) atomicAdd(&total, near);
+    __syncthreads();
+    if (threadIdx.x == 0) o.near_integer = total;
 }
 
 // ---- pass 4: roll the trackers forward to the end of the valid part of the batch (one thread per lane)

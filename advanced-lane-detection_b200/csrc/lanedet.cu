@@ -196,15 +196,24 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     d.mask_chunks = reinterpret_cast<const int4*>(mc);
     d.bdesc = reinterpret_cast<const uint4*>(bd);
     {   // stamps of the short thick-line steps (translation invariant away from the border), built with the same host/device code
-        static laneraster::Stamp stamps[laneraster::STAMP_N];
+        static laneraster::Stamp stamp;
+        static StampTable table;
         int hw[16];
         laneraster::circle_half_widths(15, hw);
         laneraster::StampCanvas cv;
+        memset(&table, 0, sizeof(table));
         for (int dy = -laneraster::STAMP_K; dy <= laneraster::STAMP_K; ++dy)
-            for (int dx = -laneraster::STAMP_K; dx <= laneraster::STAMP_K; ++dx)
-                laneraster::build_stamp(dx, dy, 30, hw, stamps[laneraster::stamp_index(dx, dy)], cv);
-        const laneraster::Stamp* sd = nullptr;
-        if ((rc = upload(p, stamps, (size_t)laneraster::STAMP_N, &sd))) { ld_plan_destroy(p); return rc; }
+            for (int dx = -laneraster::STAMP_K; dx <= laneraster::STAMP_K; ++dx) {
+                const int si = laneraster::stamp_index(dx, dy);
+                laneraster::build_stamp(dx, dy, 30, hw, stamp, cv);
+                if (stamp.ok) table.ok |= 1ull << si;
+                for (int r = 0; r < laneraster::STAMP_ROWS; ++r) {
+                    table.x1[si * laneraster::STAMP_ROWS + r] = (signed char)stamp.x1[r];
+                    table.x2[si * laneraster::STAMP_ROWS + r] = (signed char)stamp.x2[r];
+                }
+            }
+        const StampTable* sd = nullptr;
+        if ((rc = upload(p, &table, (size_t)1, &sd))) { ld_plan_destroy(p); return rc; }
         d.stamps = sd;
     }
     p->frame_smem = FRAME_STAGES * fs + 128;                             // FRAME_STAGES source boxes in flight
@@ -301,7 +310,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     d.mask_box_bytes = (int)((ms + 127) / 128 * 128);
     p->mask_smem = (((size_t)mb + 4) * 4 + (size_t)mow * 2 + 15) / 16 * 16 + MASK_PRE_WORDS * 4 + 2 * (size_t)d.mask_box_bytes + 32;
     p->search_smem = (size_t)H * d.WW * 4 + (size_t)9 * W * 2;
-    p->raster_smem = (size_t)2 * RASTER_BAND * d.WW * 4 + sizeof(RasterShared);   // text plane (6.7 KB) aliases the red plane
+    p->raster_smem = (size_t)2 * RASTER_BAND * d.WW * 4 + sizeof(RasterShared);   // interleaved band canvas (the text plane, 6.7 KB, aliases it) + lists
     // The opt-in limit is a per-function, per-device attribute shared by every plan: always raise it to
     // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
     if (p->mask_smem > 220 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }
@@ -861,6 +870,7 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
             if ((rc = launch_frame_pass(c, fin, M, fout, s, look, 0, 4))) return rc;
             tl_mark("text tiles (s)", s);
         } else if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
+        k_near_integer<<<M, 128, 0, c->s_lat>>>(c->fit + look, M);      // the vertex guard of ld_frame_fit, off the critical chain
         LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));
         LD_CUDA(cudaStreamWaitEvent(s, c->ev_join[1], 0));
     } else {

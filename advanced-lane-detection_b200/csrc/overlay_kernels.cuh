@@ -30,28 +30,33 @@ __device__ long long g_raster_prof[64][16];
 #define RPROF(i) do {} while (0)
 #endif
 
-// bit j of a 16-bit value -> bit 2j
-__device__ __forceinline__ uint32_t spread16(uint32_t x) {
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    return (x | (x << 1)) & 0x55555555u;
-}
-
-struct BandPlotter {                // sets bits [x1,x2] of canvas row y if the row belongs to this CTA's band
-    uint32_t* plane; int WW, W, y_lo, y_hi;
+// The band's canvas in shared memory is INTERLEAVED from the start: word w of a row holds the 16 pixels [16 w, 16 w + 16),
+// bit 2 j = red of pixel j, bit 2 j + 1 = green -- the layout the blend kernels sample (canvas_codes) -- so that the band is
+// stored with a copy instead of a bit-spreading pass.  A plotter sets the `bit` (0 red, 1 green) of pixels [x1, x2] of row y
+// if the row belongs to this CTA's band.
+struct BandPlotter {
+    uint32_t* plane; uint32_t sel; int CWW, W, y_lo, y_hi;              // sel = 0x55555555 (red) / 0xAAAAAAAA (green); CWW = words per row
     __device__ __forceinline__ void span(int y, int x1, int x2) {
         if (y < y_lo || y >= y_hi) return;
         x1 = max(x1, 0); x2 = min(x2, W - 1);
         if (x1 > x2) return;
-        const int w1 = x1 >> 5, w2 = x2 >> 5;
-        uint32_t* row = plane + (y - y_lo) * WW;
-        if (w1 == w2) { atomicOr(row + w1, (0xFFFFFFFFu << (x1 & 31)) & (0xFFFFFFFFu >> (31 - (x2 & 31)))); return; }
-        atomicOr(row + w1, 0xFFFFFFFFu << (x1 & 31));
-        for (int w = w1 + 1; w < w2; ++w) atomicOr(row + w, 0xFFFFFFFFu);
-        atomicOr(row + w2, 0xFFFFFFFFu >> (31 - (x2 & 31)));
+        const int w1 = x1 >> 4, w2 = x2 >> 4;
+        uint32_t* row = plane + (y - y_lo) * CWW;
+        const uint32_t first = (0xFFFFFFFFu << (2 * (x1 & 15))) & sel, last = (0xFFFFFFFFu >> (30 - 2 * (x2 & 15))) & sel;
+        if (w1 == w2) { atomicOr(row + w1, first & last); return; }
+        atomicOr(row + w1, first);
+        for (int w = w1 + 1; w < w2; ++w) atomicOr(row + w, sel);
+        atomicOr(row + w2, last);
     }
 };
+
+// The stamps of raster_math.h in the form k_raster keeps in shared memory (built once by ld_plan_create): row offsets as bytes,
+// bit s of `ok` = stamp s exists (a step whose raster is not one interval per row has none).
+struct StampTable {
+    signed char x1[laneraster::STAMP_N * laneraster::STAMP_ROWS], x2[laneraster::STAMP_N * laneraster::STAMP_ROWS];
+    unsigned long long ok;
+};
+static_assert(sizeof(StampTable) % 8 == 0, "StampTable is copied as 64-bit words");
 
 constexpr int RASTER_MAX_BIG = 16;             // long segments per frame whose set-up k_raster_prep does ahead of the band CTAs
 
@@ -69,9 +74,15 @@ struct RasterShared {
     int hw[16];
     int vx[MAX_VERTS], vy[MAX_VERTS];
     int cnt[RASTER_BAND];
-    alignas(8) int cross[RASTER_BAND * LD_MAX_CROSSINGS];        // also the ThickSetup records of the long red segments
-    unsigned short job[2 * MAX_VERTS];       // segment index | type << 14
-    unsigned short big[MAX_VERTS], bigedge[MAX_VERTS];
+    // the red phase's job list is consumed before the long segments' ThickSetup records and then the green phase's crossing lists
+    // take its place; the list of long red segments is consumed before the list of long polygon edges is written
+    union {
+        unsigned short job[2 * MAX_VERTS];   // segment index | type << 14
+        alignas(8) int cross[RASTER_BAND * LD_MAX_CROSSINGS];
+    };
+    union { unsigned short big[MAX_VERTS], bigedge[MAX_VERTS]; };
+    // the thick-line stamps (plan: 49 x 40 rows of x1, x2; they fit a byte) next to the code that draws dozens of them per band
+    alignas(16) StampTable st;
 };
 
 static_assert(sizeof(laneraster::ThickSetup) * RASTER_BIG_ROUND <= sizeof(int) * RASTER_BAND * LD_MAX_CROSSINGS,
@@ -196,24 +207,24 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
          uint32_t* __restrict__ text, const PlanDev P, int* __restrict__ poly_error) {
     extern __shared__ uint32_t smem[];
     const int W = P.W, H = P.H, WW = P.WW;
-    uint32_t* s_red = smem;                                             // RASTER_BAND*WW
-    uint32_t* s_green = s_red + RASTER_BAND * WW;
-    uint32_t* s_text = s_red;                                           // TEXT_ROWS*TEXT_WORDS: band 0, after the planes are stored
-    RasterShared& R = *reinterpret_cast<RasterShared*>(s_green + RASTER_BAND * WW);
+    uint32_t* s_canvas = smem;                                          // [RASTER_BAND][2 WW] interleaved (BandPlotter)
+    uint32_t* s_text = smem;                                            // TEXT_ROWS*TEXT_WORDS: band 0, after the canvas is stored
+    RasterShared& R = *reinterpret_cast<RasterShared*>(smem + 2 * RASTER_BAND * WW);
     const int f = blockIdx.y, band = blockIdx.x;
     const int y_lo = band * RASTER_BAND, y_hi = min(H, y_lo + RASTER_BAND);
     constexpr int CW = RASTER_CW;                                       // padded, interleaved canvas: 64-bit entries per row (canvas_codes)
     uint2* out_planes = reinterpret_cast<uint2*>(planes) + ((size_t)f * (H + 2) + y_lo + 1) * CW;
-    BandPlotter red{s_red, WW, W, y_lo, y_hi}, green{s_green, WW, W, y_lo, y_hi};
+    BandPlotter red{s_canvas, 0x55555555u, 2 * WW, W, y_lo, y_hi}, green{s_canvas, 0xAAAAAAAAu, 2 * WW, W, y_lo, y_hi};
     const int tid = threadIdx.x;
-    const laneraster::Stamp* __restrict__ stamps = static_cast<const laneraster::Stamp*>(P.stamps);
     const RasterPrep& Q = prep[f];
 
     RPROF(0);
     const int nv = Q.n_verts;
     const bool bad = Q.bad != 0;
     for (int i = tid; i < nv; i += RASTER_THREADS) { R.vx[i] = Q.vx[i]; R.vy[i] = Q.vy[i]; }     // issued first: their latency hides behind the clear
-    for (int i = tid; i < 2 * RASTER_BAND * WW; i += RASTER_THREADS) s_red[i] = 0;
+    for (int i = tid; i < (int)(sizeof(StampTable) / 8); i += RASTER_THREADS)
+        reinterpret_cast<unsigned long long*>(&R.st)[i] = __ldg(static_cast<const unsigned long long*>(P.stamps) + i);
+    for (int i = tid; i < 2 * RASTER_BAND * WW; i += RASTER_THREADS) s_canvas[i] = 0;
     for (int i = tid; i < RASTER_BAND; i += RASTER_THREADS) R.cnt[i] = 0;
     const int radius = min(thickness / 2, 15);
     if (tid == 0) {
@@ -241,7 +252,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
             if (!(cls & laneraster::SEG_TRIVIAL)) {
                 // long segments (lane gaps, the connector between the lanes) are drawn by the whole CTA in pass 3
                 if (thickness == 30 && laneraster::stamp_applies(R.vx[i], ya, R.vx[i + 1], yb, W, H) &&
-                    stamps[laneraster::stamp_index(R.vx[i + 1] - R.vx[i], yb - ya)].ok) {
+                    ((R.st.ok >> laneraster::stamp_index(R.vx[i + 1] - R.vx[i], yb - ya)) & 1ull)) {
                     R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (3 << 14));      // precomputed quad + end disc
                     if (i == 0) R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (2 << 14));
                 } else if (max(abs(R.vx[i + 1] - R.vx[i]), abs(yb - ya)) > 24) R.big[atomicAdd(&R.n_big, 1)] = (unsigned short)i;
@@ -263,9 +274,11 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
             const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
             if (type == 0)
                 raster_segment_slow(&red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, lane, y_lo, y_hi);
-            else if (type == 3)
-                laneraster::draw_stamp_part(red, stamps[laneraster::stamp_index(R.vx[i + 1] - R.vx[i], R.vy[i + 1] - R.vy[i])], R.vx[i],
-                                            R.vy[i], lane, 32);
+            else if (type == 3) {                                        // laneraster::draw_stamp_part from the shared-memory copy
+                const int so = laneraster::stamp_index(R.vx[i + 1] - R.vx[i], R.vy[i + 1] - R.vy[i]) * laneraster::STAMP_ROWS;
+                for (int r = lane; r < laneraster::STAMP_ROWS; r += 32)
+                    if (R.st.x1[so + r] <= R.st.x2[so + r]) red.span(R.vy[i] - laneraster::STAMP_HALF + r, R.vx[i] + R.st.x1[so + r], R.vx[i] + R.st.x2[so + r]);
+            }
             else if (type == 1) laneraster::disc_part(red, W, H, R.vx[i + 1], R.vy[i + 1], radius, R.hw, lane, 32);
             else laneraster::disc_part(red, W, H, R.vx[i], R.vy[i], radius, R.hw, lane, 32);
         }
@@ -328,16 +341,13 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
     __syncthreads();
     RPROF(7);
     for (int i = tid; i < (y_hi - y_lo) * CW; i += RASTER_THREADS) {    // green overwrites red
-        // entry e of a row = the 32 pixels [16e - 16, 16e + 16), (red without green, green) interleaved pixel by pixel: the two
+        // entry e of a row = the 32 pixels [16e - 16, 16e + 16) = interleaved words e - 1 and e, zero outside the frame: the two
         // horizontally adjacent taps of any sample (including (-1, 0) and (W - 1, W)) are four consecutive bits of one entry
         const int row = i / CW, e = i - row * CW;
-        const uint32_t* sr = s_red + row * WW;
-        const uint32_t* sg = s_green + row * WW;
-        const int px = 16 * e - 16, w = px >> 5;                        // px = -16, 0, 16, ...; w = -1 for the first entry
-        const uint32_t g_lo = (w >= 0 && w < WW) ? sg[w] : 0u, g_hi = (w + 1 >= 0 && w + 1 < WW) ? sg[w + 1] : 0u;
-        const uint32_t r_lo = (w >= 0 && w < WW) ? sr[w] : 0u, r_hi = (w + 1 >= 0 && w + 1 < WW) ? sr[w + 1] : 0u;
-        const uint32_t g32 = __funnelshift_r(g_lo, g_hi, px & 31), r32 = __funnelshift_r(r_lo, r_hi, px & 31) & ~g32;
-        out_planes[i] = make_uint2(spread16(r32 & 0xFFFFu) | (spread16(g32 & 0xFFFFu) << 1), spread16(r32 >> 16) | (spread16(g32 >> 16) << 1));
+        const uint32_t* sc = s_canvas + row * (2 * WW);
+        const uint32_t a = (e >= 1 && e <= 2 * WW) ? sc[e - 1] : 0u, b = e < 2 * WW ? sc[e] : 0u;
+        const uint32_t ga = a & 0xAAAAAAAAu, gb = b & 0xAAAAAAAAu;       // (red without green, green)
+        out_planes[i] = make_uint2((a & 0x55555555u & ~(ga >> 1)) | ga, (b & 0x55555555u & ~(gb >> 1)) | gb);
     }
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
     RPROF(8);

@@ -110,7 +110,8 @@ typedef struct ld_frame_fit {
     uint32_t rowmap[2][LD_ROWMAP_WORDS]; /* distinct values of Line.fity (bit 720 = bottom anchor) */
     int32_t near_integer;            /* polygon vertices np.int_(fit(y)) (Project.py:139, :160) whose fit(y) lies within 1e-6 of an
                                         integer: the fit agrees with np.polyfit to ~1e-10 relative, so only such a vertex could
-                                        truncate to the neighbouring pixel; 0 = the frame's polygon is provably the reference's */
+                                        truncate to the neighbouring pixel; 0 = the frame's polygon is provably the reference's.
+                                        Filled by ld_process_batch / ld_postpass (after the overlay); -1 from ld_fit alone */
 } ld_frame_fit;
 
 typedef struct ld_plan ld_plan;
