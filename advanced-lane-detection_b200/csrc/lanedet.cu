@@ -55,7 +55,8 @@ struct ld_plan {
     // The shared pass (process_image only): the tiles from row share_y0 down are undistorted ONCE for the mask and the
     // overlay (k_frame_pass_mf<3> -> k_mask_b, k_blend_px); `text` tiles are the overlay tiles above share_y0 (putText).
     const int32_t* share_tiles; const int32_t* text_tiles; const int32_t* plain_top_tiles;   // plain_top = plain tiles above share_y0
-    int n_share, n_text, n_plain_top, shared_ok;
+    const int32_t* mask_tiles;                                          // share tiles with a pixel the bird's-eye warp samples (ld_mask)
+    int n_share, n_text, n_plain_top, n_mask_tiles, shared_ok;
 };
 
 enum { HOST_CHUNK = 32, PIPE_SUB = 8, HALO_MAX = 32 };               // HALO_MAX: look-back records a sharded rank may put in front of its range
@@ -172,10 +173,22 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if (b > ms) ms = b;
     }
     if (ms > 96 * 1024) { ld_plan_destroy(p); return LD_ERR_ARG; }                              // k_mask double-buffers its chunk boxes
+    // the colour pre-decision in the form the kernels read (mask_kernels.cuh: colour_words4): per 32 cells an ON word and a MIXED word
+    static uint32_t cpre2[MASK_PRE_WORDS];
+    for (int w = 0; w < MASK_PRE_WORDS / 2; ++w) {
+        uint32_t on = 0, mixed = 0;
+        for (int i = 0; i < 32; ++i) {
+            const int cell = 32 * w + i;
+            const uint32_t code = (desc->cpre[cell >> 4] >> (2 * (cell & 15))) & 3u;
+            on |= (uint32_t)(code == 1u) << i;
+            mixed |= (uint32_t)(code >= 2u) << i;
+        }
+        cpre2[2 * w] = on; cpre2[2 * w + 1] = mixed;
+    }
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
         (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
-        (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, desc->cpre, (size_t)MASK_PRE_WORDS, &d.cpre)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
+        (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, cpre2, (size_t)MASK_PRE_WORDS, &d.cpre)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
         (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) || (rc = upload(p, desc->inv_pack, ninv ? ninv : 1, &d.inv_pack)) ||
         (rc = upload(p, desc->glyph_bits, (size_t)desc->n_glyphs * LD_GLYPH_ROWS * LD_GLYPH_WORDS, &d.glyph_bits)) ||
         (rc = upload(p, desc->glyph_adv, (size_t)desc->n_glyphs, &d.glyph_adv)) ||
@@ -296,6 +309,20 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
             sg[(size_t)(ny - d.share_y0) * tcols + (nx >> 7)] |= (uint8_t)(1u << ((nx >> 5) & 3));
         }
         rc = upload(p, sg, (size_t)(srows > 0 ? srows : 1) * tcols, &d.share_groups);
+        // the share tiles that hold a sampled pixel at all: the tiles of the mask-only pass (ld_mask: k_frame_pass_mf<4>)
+        int32_t* mt = new (std::nothrow) int32_t[(size_t)desc->n_frame_tiles];
+        int nm = 0;
+        if (!mt) { delete[] sg; ld_plan_destroy(p); return LD_ERR_ARG; }
+        for (int t = 0; t < desc->n_frame_tiles && srows > 0; ++t) {
+            const int x0 = desc->frame_tiles[8 * t], y0 = desc->frame_tiles[8 * t + 1], h = desc->frame_tiles[8 * t + 3];
+            if (y0 < d.share_y0) continue;
+            bool any = false;
+            for (int y = y0; y < y0 + h && y < H; ++y) any = any || sg[(size_t)(y - d.share_y0) * tcols + (x0 >> 7)] != 0;
+            if (any) mt[nm++] = t;
+        }
+        if (!rc) rc = upload(p, mt, (size_t)(nm ? nm : 1), &p->mask_tiles);
+        p->n_mask_tiles = nm;
+        delete[] mt;
         delete[] sg;
         if (rc) { ld_plan_destroy(p); return rc; }
         p->shared_ok = ok ? 1 : 0;
@@ -319,6 +346,8 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
     // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
     // carveout, otherwise an SM has to drain before a kernel with a different carveout can start on it.
     LD_CUDA_OR(cudaFuncSetAttribute(k_mask, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
@@ -484,11 +513,29 @@ static inline int check_launch() {
 }
 #define ARGS_OK(c, a, b, n) ((c) && (a) && (b) && (n) >= 0)
 
+static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted, int which);
+
 // ------------------------------------------------------------------------------------- stages
 extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, void* stream) {
     if (!ARGS_OK(c, frames, mask, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
+    static int fused = -1;                                              // LD_MASK_FUSED=1: always the one-kernel k_mask (A/B measurements, tests)
+    if (fused < 0) { const char* e = getenv("LD_MASK_FUSED"); fused = e ? atoi(e) : 0; }
+    if (c->plan->shared_ok && !fused && !((uintptr_t)frames & 15)) {
+        // 1280x720 plans: the frame pass's multi-frame tile kernel in its mask-only form (per-tile constants in registers, one
+        // tensor-map TMA copy per tile and frame, only the 32-pixel groups the bird's-eye warp samples are gathered) writes the
+        // colour bits of the undistorted pixels; k_mask_b cuts the bird's-eye words out of them
+        for (int done = 0; done < n; done += c->max_frames) {
+            const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
+            int rc;
+            if ((rc = launch_frame_pass(c, frames + (size_t)done * d.W * d.H * 3, m, nullptr, (cudaStream_t)stream, 0, 0, 8))) return rc;
+            k_mask_b<<<dim3(d.n_tiles, m), MASK_THREADS, (size_t)d.max_out_words * 2 + 16, (cudaStream_t)stream>>>(
+                c->und_bits, mask + (size_t)done * d.H * d.WW, d);
+            if ((rc = check_launch())) return rc;
+        }
+        return LD_OK;
+    }
     const int fpc = n >= 256 ? MASK_FPC : (n >= 128 ? 2 : 1);             // small batches: more, shorter CTAs (keep >= 3 waves)
     k_mask<<<dim3(d.n_tiles, (n + fpc - 1) / fpc), MASK_THREADS, c->plan->mask_smem, (cudaStream_t)stream>>>(frames, mask, d, n, fpc);
     return check_launch();
@@ -645,9 +692,10 @@ static int frames_per_cta(int m) {
 }
 // which = 0: every tile with blend + text; 1: the plain tiles as cv2.undistort; 2: the overlay tiles with blend + text;
 // 3: the shared pass over the share tiles (undistorted pixels -> c->und_px, their colour bits -> c->und_bits; fout unused);
-// 4: the text tiles (overlay tiles above share_y0) with blend + text; 5: the plain tiles above share_y0 as cv2.undistort
+// 4: the text tiles (overlay tiles above share_y0) with blend + text; 5: the plain tiles above share_y0 as cv2.undistort;
+// 8: the mask-only pass of ld_mask over the share tiles that hold a sampled pixel (colour bits -> c->und_bits)
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted,
-                             int which = 0) {
+                             int which) {
     const PlanDev& d = c->plan->d;
     const uint32_t* planes = c->planes + (size_t)slot * canvas_words(d);
     const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
@@ -672,6 +720,11 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
             k_frame_pass_mf<3><<<dim3(c->plan->n_share, groups.y), FRAME_MF_THREADS, c->plan->frame_smem + MASK_PRE_WORDS * 4, s>>>(
                 tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->share_tiles,
                 c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, c->und_px + (size_t)slot * c->plan->n_share * 16 * 128);
+        } else if (which == 8) {
+            if (c->plan->n_mask_tiles)
+                k_frame_pass_mf<4><<<dim3(c->plan->n_mask_tiles, groups.y), FRAME_MF_THREADS, c->plan->frame_smem + MASK_PRE_WORDS * 4, s>>>(
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->mask_tiles,
+                    c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, nullptr);
         } else if (which == 5) {
             if (c->plan->n_plain_top)
                 k_frame_pass_mf<0><<<dim3(c->plan->n_plain_top, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
@@ -697,7 +750,7 @@ static int launch_overlay(ld_ctx* c, const uint8_t* frames, const ld_frame_fit* 
         int rc;
         if ((rc = launch_raster(c, fit ? fit + done : nullptr, verts ? verts + (size_t)done * max_verts * 2 : nullptr,
                                 counts ? counts + done : nullptr, max_verts, thickness, m, s, 0))) return rc;
-        if ((rc = launch_frame_pass(c, frames + done * fb, m, out + done * fb, s, 0, already_undistorted))) return rc;
+        if ((rc = launch_frame_pass(c, frames + done * fb, m, out + done * fb, s, 0, already_undistorted, 0))) return rc;
     }
     return LD_OK;
 }
@@ -716,19 +769,20 @@ extern "C" int ld_raster(ld_ctx* c, const ld_frame_fit* fit, int n, void* stream
 extern "C" int ld_frame_pass(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, void* stream) {
     if (!ARGS_OK(c, frames, out, n) || n > c->max_frames) return LD_ERR_ARG;
     if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
-    return n ? launch_frame_pass(c, frames, n, out, (cudaStream_t)stream, 0, 0) : LD_OK;
+    return n ? launch_frame_pass(c, frames, n, out, (cudaStream_t)stream, 0, 0, 0) : LD_OK;
 }
 
 // The launches ld_process_batch is made of, one at a time (measurement / profiling of the real step):
 // which = 3 shared pass (frames -> und_px, und_bits), 7 k_mask_b (und_bits -> the context's mask), 5 plain tiles above
-// share_y0 (frames -> out), 6 k_blend_px (und_px + canvas -> out), 4 text tiles (frames + canvas + text -> out).
+// share_y0 (frames -> out), 6 k_blend_px (und_px + canvas -> out), 4 text tiles (frames + canvas + text -> out),
+// 8 the mask-only pass of ld_mask (frames -> und_bits; followed by 7 it is the whole of ld_mask).
 extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint8_t* out, void* stream) {
     if (!c || n < 0 || n > c->max_frames || !c->plan->shared_ok) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
     cudaStream_t s = (cudaStream_t)stream;
-    if (which == 3 || which == 4 || which == 5) {
-        if (!frames || (which != 3 && !out)) return LD_ERR_ARG;
+    if (which == 3 || which == 4 || which == 5 || which == 8) {
+        if (!frames || (which != 3 && which != 8 && !out)) return LD_ERR_ARG;
         return launch_frame_pass(c, frames, n, out, s, 0, 0, which);
     }
     if (which == 7) {
@@ -746,7 +800,8 @@ extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint
 extern "C" const uint32_t* ld_ctx_mask(ld_ctx* c) { return c ? c->mask : nullptr; }   // the context's packed masks (device), [max_frames][H][W/32]
 extern "C" int ld_stage_tiles(ld_ctx* c, int which) {                   // tiles a stage covers (for byte accounting)
     if (!c) return -1;
-    return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? c->plan->n_text : which == 5 ? c->plan->n_plain_top : -1;
+    return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? c->plan->n_text : which == 5 ? c->plan->n_plain_top :
+           which == 8 ? c->plan->n_mask_tiles : -1;
 }
 
 extern "C" int ld_draw(ld_ctx* c, const uint8_t* undist, const int32_t* verts, const int32_t* counts, int max_verts,
@@ -885,7 +940,7 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
             if ((rc = launch_raster(c, c->fit + off, nullptr, nullptr, 0, 30, m, c->s_lat, off))) return rc;
             LD_CUDA(cudaEventRecord(c->ev_rast[i], c->s_lat));
             LD_CUDA(cudaStreamWaitEvent(c->s_pix, c->ev_rast[i], 0));
-            if ((rc = launch_frame_pass(c, fin + off * fb, m, fout + off * fb, c->s_pix, off, 0))) return rc;
+            if ((rc = launch_frame_pass(c, fin + off * fb, m, fout + off * fb, c->s_pix, off, 0, 0))) return rc;
         }
         if ((rc = join_streams(c, s))) return rc;
     }

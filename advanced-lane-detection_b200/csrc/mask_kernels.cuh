@@ -16,9 +16,9 @@ namespace lanedet {
 //   memory by TMA bulk row copies, DOUBLE BUFFERED over the sequence (frame, chunk): the next chunk -- of this or of the
 //   next frame -- lands while the current one is evaluated.  A warp item is one box row x 128 columns; lane l owns
 //   columns l, l+32, l+64, l+96 (adjacent lanes = adjacent source pixels: conflict-free shared-memory gathers) and
-//   fetches its four map entries with one 16-byte load, one item ahead.  Bilinear on dp2a, then the colour decision:
-//   a 2-bit pre-decision per 8x8x8 RGB cell in shared memory settles every pixel that is not near a threshold;
-//   only the rest gathers from the exact tables.  One bit per box pixel (warp ballot) into shared memory.
+//   fetches its four map entries with one 16-byte load, one item ahead.  Bilinear on dp2a, then the colour decision
+//   (colour_words4): an ON / MIXED bit per 8x8x8 RGB cell in shared memory settles every pixel that is not near a
+//   threshold; only the rest gathers from the exact tables.  One bit per box pixel (warp ballot) into shared memory.
 //   Phase B builds the packed output per OUTPUT WORD: a perspective warp keeps a word's 32 pixels on one
 //   source row, stepping 0/1/2 source pixels per output pixel (plan.bdesc), so a thread cuts a 64-bit
 //   window out of the bit array and expands it with one funnel shift per bit.  Windows that are all
@@ -29,13 +29,33 @@ constexpr int MASK_FPC = 4;                       // frames per CTA
 constexpr int MASK_PRE_WORDS = 2048;
 constexpr uint32_t BDESC_BORDER = 0xFFFFFFFFu, BDESC_FALLBACK = 0xFFFFFFFEu;
 
-// (LUV-L in l_thresh) | (Lab-b in b_thresh): pre-decision from shared memory, exact tables only for mixed cells
-__device__ __forceinline__ bool colour_on_pre(uint32_t rgb, const uint32_t* s_pre, const uint32_t* __restrict__ ctab,
-                                              const uint32_t* __restrict__ cbits) {
-    const uint32_t idx = ((rgb >> 3) & 0x1Fu) | ((rgb >> 6) & 0x3E0u) | ((rgb >> 9) & 0x7C00u);
-    const uint32_t code = (s_pre[idx >> 4] >> ((idx & 15u) * 2u)) & 3u;
-    if (code != 2u) return code != 0u;
-    return colour_on(rgb, ctab, cbits);
+// (LUV-L in l_thresh) | (Lab-b in b_thresh) of the four pixels a lane owns (c[k] = r | g << 8 | b << 16, top byte zero), as one
+// mask word per 32-pixel group.  The pre-decision table in shared memory (ld_plan_create: plan.colour_prefilter re-packed) holds,
+// per 32 cells of 8x8x8 colours (cell = r5 | g5 << 5 | b5 << 10), an ON word and a MIXED word, so a pixel costs one 8-byte load
+// and two wrapping shifts, with no branch: the cell index is two bit-muxes of three shifts, the word address is cell >> 5 and
+// the shifts take the low five bits of the cell by themselves.  Only when some lane of the warp sits in a mixed cell (a colour
+// near a threshold) does the warp visit the exact tables -- ONE vote for the four groups.
+__device__ __forceinline__ uint32_t colour_cell(uint32_t rgb) {
+    const uint32_t rg = ((rgb >> 3) & 0x1Fu) | ((rgb >> 6) & ~0x1Fu);          // r5 | g5 << 5 | junk above bit 9
+    return (rg & 0x3FFu) | ((rgb >> 9) & ~0x3FFu);                              // ... | b5 << 10 (the top byte of rgb is zero)
+}
+__device__ __forceinline__ void colour_words4(const uint32_t (&c)[4], const uint2* s_pre, const uint32_t* __restrict__ ctab,
+                                              const uint32_t* __restrict__ cbits, uint32_t (&words)[4]) {
+    uint32_t on[4], mixed[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t cell = colour_cell(c[k]);
+        const uint2 e = s_pre[cell >> 5];
+        on[k] = __funnelshift_r(e.x, 0u, cell);
+        mixed[k] = __funnelshift_r(e.y, 0u, cell);
+    }
+    if (__any_sync(0xffffffffu, (mixed[0] | mixed[1] | mixed[2] | mixed[3]) & 1u)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (mixed[k] & 1u) on[k] = colour_on(c[k], ctab, cbits) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) words[k] = __ballot_sync(0xffffffffu, on[k] & 1u);
 }
 
 // one pixel from a plan.gather_offsets entry (tap byte offset << 10 | fy << 5 | fx), weights decoded on the fly
@@ -54,8 +74,8 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
     // layout: box bits (+4 zero words) | job list (u16 per output word) | colour pre-decision | two chunk boxes
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem_raw);
     uint16_t* s_job = reinterpret_cast<uint16_t*>(s_bits + P.max_box_words + 4);
-    uint32_t* s_pre = reinterpret_cast<uint32_t*>(smem_raw + (((size_t)(P.max_box_words + 4) * 4 + (size_t)P.max_out_words * 2 + 15) / 16) * 16);
-    uint8_t* s_box = reinterpret_cast<uint8_t*>(s_pre + MASK_PRE_WORDS);
+    uint2* s_pre = reinterpret_cast<uint2*>(smem_raw + (((size_t)(P.max_box_words + 4) * 4 + (size_t)P.max_out_words * 2 + 15) / 16) * 16);
+    uint8_t* s_box = reinterpret_cast<uint8_t*>(s_pre + MASK_PRE_WORDS / 2);
     const uint32_t box_bytes = (uint32_t)P.mask_box_bytes;              // one chunk box (a multiple of 128)
     const uint32_t box0 = smem_u32(s_box), bar0 = smem_u32(&bar[0]);
 
@@ -69,7 +89,7 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
 
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     if (threadIdx.x < 4) s_bits[box_words + threadIdx.x] = 0;
-    for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += MASK_THREADS) s_pre[i] = __ldg(P.cpre + i);
+    for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += MASK_THREADS) reinterpret_cast<uint32_t*>(s_pre)[i] = __ldg(P.cpre + i);
     __syncthreads();
 
     // the sequence of (frame, chunk) items; item `it` is staged into buffer it & 1
@@ -100,23 +120,20 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
             const int ncg = (g.w + 127) >> 7, nitems = g.h * ncg, nwc = (g.w + 31) >> 5, wc0 = (g.x0 - u0) >> 5;
             const uint4* am4 = reinterpret_cast<const uint4*>(P.mask_amap + P.mask_amap_start[c0 + ci]);
             if (!g.slow) {
-                uint4 e = make_uint4(~0u, ~0u, ~0u, ~0u);
+                uint4 e = make_uint4(0u, 0u, 0u, 0u);
                 if (warp < nitems) e = __ldg(am4 + warp * 32 + lane);                        // first item's entries: before the wait
                 mbar_wait_addr(bar0 + 8u * (it & 1), (it & 1) ? phase1 : phase0);
                 if (it & 1) phase1 ^= 1u; else phase0 ^= 1u;
                 const uint32_t box = box0 + (it & 1) * box_bytes;
                 for (int item = warp; item < nitems; item += nwarp) {
-                    uint4 en = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    uint4 en = make_uint4(0u, 0u, 0u, 0u);
                     if (item + nwarp < nitems) en = __ldg(am4 + (item + nwarp) * 32 + lane);   // one item ahead
                     const int r = ncg == 1 ? item : (ncg == 2 ? item >> 1 : item / ncg), cg = item - r * ncg;   // chunks are <= 256 px wide
                     const uint32_t es[4] = {e.x, e.y, e.z, e.w};
-                    uint32_t words[4];
+                    uint32_t c[4], words[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        bool on = false;
-                        if (es[k] != 0xFFFFFFFFu) on = colour_on_pre(bilinear_rgb_smem(box, (uint32_t)g.stride, es[k]), s_pre, P.ctab, P.cbits);
-                        words[k] = __ballot_sync(0xffffffffu, on);
-                    }
+                    for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_smem(box, (uint32_t)g.stride, es[k]);   // columns beyond the chunk: entry 0 (their words are not stored)
+                    colour_words4(c, s_pre, P.ctab, P.cbits, words);
                     if (lane < 4 && cg * 4 + lane < nwc)
                         s_bits[r * rw + wc0 + cg * 4 + lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
                     e = en;

@@ -12,7 +12,7 @@
 #include "fit_math.h"
 #include "gather.cuh"
 #include "raster_math.h"
-#include "mask_kernels.cuh"                        // colour_on_pre (the shared pass decides the mask colours)
+#include "mask_kernels.cuh"                        // colour_words4 (the shared pass decides the mask colours)
 #include <cuda.h>                                // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 
 namespace lanedet {
@@ -539,9 +539,10 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     uint32_t box0 = (smem_u32(s_boxes) + 127u) & ~127u;
     keep_u32(box0);
     // MODE 3: the colour pre-decision table sits behind the ring of boxes
-    const uint32_t* s_pre = reinterpret_cast<const uint32_t*>(s_boxes + (box0 - smem_u32(s_boxes)) + FRAME_STAGES * box_bytes);
-    if (MODE == 3)
-        for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += FRAME_MF_THREADS) const_cast<uint32_t*>(s_pre)[i] = __ldg(P.cpre + i);
+    const uint2* s_pre = reinterpret_cast<const uint2*>(s_boxes + (box0 - smem_u32(s_boxes)) + FRAME_STAGES * box_bytes);
+    if (MODE == 3 || MODE == 4)
+        for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += FRAME_MF_THREADS)
+            reinterpret_cast<uint32_t*>(const_cast<uint2*>(s_pre))[i] = __ldg(P.cpre + i);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < FRAME_STAGES; ++b) { mbar_init(&bar[b], 1); mbar_init(&empty[b], FRAME_MF_THREADS / 32); }
@@ -573,12 +574,12 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
     // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
-    uint32_t gmask = 0;                                                  // MODE 3: which 32-pixel groups of the row hold a pixel the bird's-eye warp samples
-    if (MODE == 3) {
-        if (row_on) gmask = __ldg(P.share_groups + (size_t)(y - P.share_y0) * (W / 128) + (t.x0 >> 7));
+    uint32_t gmask = 0;                                                  // MODE 4: which 32-pixel groups of the row hold a pixel the bird's-eye warp samples
+    if (MODE == 3 || MODE == 4) {
+        if (MODE == 4 && row_on) gmask = __ldg(P.share_groups + (size_t)(y - P.share_y0) * (W / 128) + (t.x0 >> 7));
         // und_px: u32[n][share tiles][16 rows][4][32] (pixel l + 32k of the row at [k][l]); und_bits: u32[n][H - share_y0][WW]
         frame_words = gridDim.x * 16u * 128u;
-        orow = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + r * 128 + lane;
+        if (MODE == 3) orow = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + r * 128 + lane;
         und_bits += (size_t)f0 * (H - P.share_y0) * WW + (size_t)(y - P.share_y0) * WW + (t.x0 >> 5);
     }
     const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f0 * cv_frame;
@@ -616,7 +617,10 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             const uint32_t box = box0 + b * box_bytes;
             if (row_on) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
+                for (int k = 0; k < 4; ++k) {
+                    if (MODE == 4 && !((gmask >> k) & 1u)) { c[k] = 0u; continue; }      // warp-uniform: no sampled pixel in this group
+                    c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
+                }
             }
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");   // this warp is done with buffer b
@@ -627,16 +631,18 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             for (int k = 0; k < 4; ++k)
                 c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
         }
-        if (MODE == 3) {
-            if (row_on) {
+        if (MODE == 3 || MODE == 4) {
+            // the shared pass only runs on 1280-wide plans (ld_plan_create: shared_ok): every tile row is four whole groups and
+            // its four mask words are one aligned 16-byte store.  Groups the bird's-eye warp never samples get a decision too
+            // (MODE 3) or the decision of a black pixel (MODE 4): k_mask_b reads neither.
+            if (row_on && (MODE == 3 || gmask)) {
                 uint32_t words[4];
+                colour_words4(c, s_pre, P.ctab, P.cbits, words);
+                if (MODE == 3) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    words[k] = 0u;
-                    if ((gmask >> k) & 1u) words[k] = __ballot_sync(0xffffffffu, colour_on_pre(c[k], s_pre, P.ctab, P.cbits));   // warp-uniform
-                    if (k < ngroups) orow[32 * k] = c[k];
+                    for (int k = 0; k < 4; ++k) orow[32 * k] = c[k];
                 }
-                if (lane < ngroups) und_bits[lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
+                if (lane == 0) *reinterpret_cast<uint4*>(und_bits) = make_uint4(words[0], words[1], words[2], words[3]);
             }
             und_bits += (size_t)(H - P.share_y0) * WW;
         } else if (row_on)

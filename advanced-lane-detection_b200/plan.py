@@ -327,7 +327,7 @@ def gather_tiles(sx, sy, size, regions, tw=128, fixed_stride=None):
 def gather_offsets_items(sx, sy, fi, gt, size):
     """gather_offsets for the mask chunks, ordered by WARP ITEM: an item is one row of a chunk x one group of 128 columns;
     lane l of the warp owns columns 128 cg + l + 32 k (k = 0..3) and fetches its four entries with one 16-byte load:
-    amap[((row * ncg + cg) * 32 + lane) * 4 + k].  Columns beyond the chunk hold 0xFFFFFFFF (skip).  Slow chunks get no
+    amap[((row * ncg + cg) * 32 + lane) * 4 + k].  Columns beyond the chunk hold 0 (a valid tap; their words are not stored).  Slow chunks get no
     entries.  Returns (amap u32, start int32[T+1] in u32 units)."""
     g = gt.view(np.uint32).astype(np.int64)
     start = np.zeros(len(g) + 1, np.int64)
@@ -341,7 +341,7 @@ def gather_offsets_items(sx, sy, fi, gt, size):
         bx, by, bf = sx[y0:y0 + h, x0:x0 + w], sy[y0:y0 + h, x0:x0 + w], fi[y0:y0 + h, x0:x0 + w]
         off = (by - sy0).astype(np.int64) * stride + bx.astype(np.int64) * 3 - b0
         assert off.min() >= 0 and off.max() < (1 << 22)
-        e = np.full((h, ncg * 128), 0xFFFFFFFF, np.uint32)
+        e = np.zeros((h, ncg * 128), np.uint32)                        # columns beyond the chunk: entry 0 (evaluated, never stored)
         e[:, :w] = ((off << 10) | bf).astype(np.uint32)
         parts.append(e.reshape(h, ncg, 4, 32).transpose(0, 1, 3, 2).reshape(-1))    # [row][cg][lane][k]
         start[i + 1] = start[i] + parts[-1].size

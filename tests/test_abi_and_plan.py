@@ -201,7 +201,7 @@ def test_gather_maps_and_canvas_encoding(pkg, variant):
         ncg = (w + 127) // 128
         e = plan.mask_amap[plan.mask_amap_start[c]:plan.mask_amap_start[c + 1]].astype(np.int64).reshape(h, ncg, 32, 4)
         off = (sy[y0:y0 + h, x0:x0 + w] - sy0) * stride + sx[y0:y0 + h, x0:x0 + w] * 3 - b0
-        want = np.full((h, ncg * 128), 0xFFFFFFFF, np.int64)
+        want = np.zeros((h, ncg * 128), np.int64)                         # columns beyond the chunk: entry 0 (a valid tap, never stored)
         want[:, :w] = (off << 10) | fi[y0:y0 + h, x0:x0 + w]
         assert (e == want.reshape(h, ncg, 4, 32).transpose(0, 1, 3, 2)).all()
     # inverse map: the packed entry addresses the same four taps as (inv_idx, inv_fi) in the padded, interleaved canvas

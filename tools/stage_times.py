@@ -57,6 +57,7 @@ def main():
     if hasattr(L, "ld_stage"):                                            # the launches process_batch is really made of
         t("shared pass k_frame_pass_mf<3>", lambda: L.ld_stage(h, 3, frames.data_ptr(), n, None, s))
         t("k_mask_b", lambda: L.ld_stage(h, 7, None, n, None, s))
+        t("mask-only pass k_frame_pass_mf<4>", lambda: L.ld_stage(h, 8, frames.data_ptr(), n, None, s))
         t("plain tiles k_frame_pass_mf<0>", lambda: L.ld_stage(h, 5, frames.data_ptr(), n, out.data_ptr(), s))
         t("k_blend_px", lambda: L.ld_stage(h, 6, None, n, out.data_ptr(), s))
         t("text tiles k_frame_pass_mf<1>", lambda: L.ld_stage(h, 4, frames.data_ptr(), n, out.data_ptr(), s))
