@@ -71,11 +71,19 @@ __device__ __forceinline__ uint32_t bilinear_taps(uint32_t a, uint32_t stride, u
     uint32_t p0, p1, p2, q0, q1, q2;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p0) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(p1) : "r"(a));
+#ifdef LD_EXP_LDS2                                                   // timing experiment only (wrong pixels when the tap starts at byte 3 of a word)
+    p2 = p1;
+#else
     asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(p2) : "r"(a));
+#endif
     const uint32_t a2 = a + stride;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q0) : "r"(a2));
     asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(q1) : "r"(a2));
+#ifdef LD_EXP_LDS2
+    q2 = q1;
+#else
     asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(q2) : "r"(a2));
+#endif
     const uint32_t lt = __funnelshift_r(p0, p1, sh), ht = __funnelshift_r(p1, p2, sh);   // r0 g0 b0 r1 | g1 b1 . .
     const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
     const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11

@@ -229,7 +229,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if ((rc = upload(p, &table, (size_t)1, &sd))) { ld_plan_destroy(p); return rc; }
         d.stamps = sd;
     }
-    p->frame_smem = FRAME_STAGES * fs + 128;                             // FRAME_STAGES source boxes in flight
+    p->frame_smem = FRAME_STAGES * FRAME_PAIR * fs + 128;                // FRAME_STAGES ring buffers of FRAME_PAIR source boxes each
     p->frame_box_rows = box_rows;
     {
         int32_t* ids = new (std::nothrow) int32_t[2 * (size_t)desc->n_frame_tiles];
@@ -675,7 +675,7 @@ static int frame_tensor_map(const ld_plan* p, const uint8_t* frames, int m, CUte
     const cuuint64_t row = (cuuint64_t)d.W * 3;
     const cuuint64_t gdim[3] = {row / 4, (cuuint64_t)d.H, (cuuint64_t)m};
     const cuuint64_t gstride[2] = {row, row * d.H};
-    const cuuint32_t box[3] = {FRAME_BOX_PITCH / 4, (cuuint32_t)p->frame_box_rows, 1};
+    const cuuint32_t box[3] = {FRAME_BOX_PITCH / 4, (cuuint32_t)p->frame_box_rows, FRAME_PAIR};   // out-of-range frames of the last pair: zero fill
     const cuuint32_t estride[3] = {1, 1, 1};
     const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), gdim, gstride, box, estride,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -687,8 +687,8 @@ static int frame_tensor_map(const ld_plan* p, const uint8_t* frames, int m, CUte
 // frames one CTA of the multi-frame pass walks through: long enough to amortise its per-tile set-up, short enough
 // that a small batch still fills the machine with several waves of CTAs
 static int frames_per_cta(int m) {
-    const int f = m / 8;
-    return f < 1 ? 1 : (f > FRAME_FPC ? FRAME_FPC : f);
+    const int f = (m / 8) & ~(FRAME_PAIR - 1);                          // whole pairs (one TMA copy / mbarrier round trip per pair)
+    return f < 1 ? (m >= 2 * FRAME_PAIR ? FRAME_PAIR : 1) : (f > FRAME_FPC ? FRAME_FPC : f);
 }
 // which = 0: every tile with blend + text; 1: the plain tiles as cv2.undistort; 2: the overlay tiles with blend + text;
 // 3: the shared pass over the share tiles (undistorted pixels -> c->und_px, their colour bits -> c->und_bits; fout unused);

@@ -435,16 +435,21 @@ __device__ __forceinline__ uint32_t blend_canvas_px(uint32_t c, uint32_t e, uint
     return (c & 0xFF0000u) | (g << 8) | r;
 }
 
-// Per-lane constants of the row store.  A 32-pixel group is 96 output bytes = 24 words; lane j < 24 builds word j from
-// the pixels of lanes wp = floor(4j/3) and wp + 1 with two shuffles and ONE byte permute (selector by 4j mod 3).
+// Per-lane constants of the row store.  A 32-pixel group is 96 output bytes = 24 words.  Word j starts inside pixel
+// p = floor(4j/3) at byte 4j mod 3 and ends inside pixel p or p + 1, so lane p builds it from its own pixel and its right
+// neighbour's: ONE shuffle (down by one lane) and one byte permute per group; the lanes with p mod 4 == 3 start no word.
+// (Two indexed shuffles per group -- the word built in lane j -- cost 15 % of the plain-tile pass: the kernels are bound by
+// the shared-memory / shuffle data pipe, one wavefront per instruction.)
 struct RowStore {
-    int wp, wp1;
+    int j;                                                              // the output word this lane stores (lanes with on == false: none)
     uint32_t sel;
+    bool on;
     __device__ __forceinline__ RowStore(int lane) {
-        wp = (4 * lane) / 3; wp1 = min(wp + 1, 31);
-        const int m = (4 * lane) % 3;
+        j = lane - (lane >> 2);
+        on = (lane & 3) != 3;
+        const int m = lane & 3;                                         // 4j mod 3 = (4 lane - 4 floor(lane / 4)) mod 3 = lane mod 4 for the lanes that store
         sel = m == 0 ? 0x4210u : (m == 1 ? 0x5421u : 0x6542u);
-        keep_s32(wp); keep_s32(wp1); keep_u32(sel);
+        keep_s32(j); keep_u32(sel);
     }
 };
 
@@ -469,11 +474,16 @@ __device__ __forceinline__ void finish_row(uint32_t (&c)[4], const uint32_t (&ie
             if (k < ngroups && tw >= 0 && tw < LD_TEXT_WORDS && ((__ldg(trow + tw) >> lane) & 1u)) c[k] = 0xFFFFFFu;
         }
     }
+#ifdef LD_EXP_NOSHFL                                                 // timing experiment only (wrong layout): what the shuffles cost
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < ngroups && rs.on) orow[24 * k] = c[k];
+#else
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t a = __shfl_sync(0xffffffffu, c[k], rs.wp), b = __shfl_sync(0xffffffffu, c[k], rs.wp1);
-        if (k < ngroups && lane < 24) orow[24 * k] = __byte_perm(a, b, rs.sel);
+        const uint32_t nb = __shfl_down_sync(0xffffffffu, c[k], 1);     // the right neighbour's pixel (lane 31 stores nothing)
+        if (k < ngroups && rs.on) orow[24 * k] = __byte_perm(c[k], nb, rs.sel);
     }
+#endif
 }
 
 // inv_pack entries of the four pixels lane i owns in tile row y (~0 = the inverse warp does not touch the pixel)
@@ -512,9 +522,10 @@ __device__ __forceinline__ uint32_t bilinear_rgb_pre(uint32_t box, uint32_t stri
 // shared pass and the read-modify-write chain cost more issue slots than the bytes saved: 4.14 against 4.00 ms per step.)
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
 #ifndef LD_FRAME_STAGES
-#define LD_FRAME_STAGES 4
+#define LD_FRAME_STAGES 3
 #endif
-constexpr int FRAME_STAGES = LD_FRAME_STAGES;   // source boxes in flight (a power of two)
+constexpr int FRAME_STAGES = LD_FRAME_STAGES;   // ring buffers, each holding the source boxes of FRAME_PAIR consecutive frames
+constexpr int FRAME_PAIR = 2;                   // frames per TMA copy / per mbarrier round trip
 constexpr int FRAME_BOX_PITCH = 512;            // bytes per staged source row (plan.FRAME_BOX_PITCH): 128 uint32 = the TMA box width
 
 template <int MODE>
@@ -539,7 +550,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     uint32_t box0 = (smem_u32(s_boxes) + 127u) & ~127u;
     keep_u32(box0);
     // MODE 3: the colour pre-decision table sits behind the ring of boxes
-    const uint2* s_pre = reinterpret_cast<const uint2*>(s_boxes + (box0 - smem_u32(s_boxes)) + FRAME_STAGES * box_bytes);
+    const uint2* s_pre = reinterpret_cast<const uint2*>(s_boxes + (box0 - smem_u32(s_boxes)) + FRAME_STAGES * FRAME_PAIR * box_bytes);
     if (MODE == 3 || MODE == 4)
         for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += FRAME_MF_THREADS)
             reinterpret_cast<uint32_t*>(const_cast<uint2*>(s_pre))[i] = __ldg(P.cpre + i);
@@ -573,7 +584,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop); everything
     // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
     // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
-    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + lane;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + rs.j;
     uint32_t gmask = 0;                                                  // MODE 4: which 32-pixel groups of the row hold a pixel the bird's-eye warp samples
     if (MODE == 3 || MODE == 4) {
         if (MODE == 4 && row_on) gmask = __ldg(P.share_groups + (size_t)(y - P.share_y0) * (W / 128) + (t.x0 >> 7));
@@ -587,69 +598,79 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     keep_u32(full0); keep_u32(empty0);
     __syncthreads();                                                     // barriers initialised
 
-    // Producer = thread 0: ONE tensor-map TMA copy stages the whole 512 B x box_rows source box of frame f0 + j into ring
-    // buffer j % FRAME_STAGES, once all 16 warps have released it (empty[]).  There is no CTA-wide barrier in the frame loop.
+    // Producer = thread 0: ONE tensor-map TMA copy stages the 512 B x box_rows source boxes of the frame PAIR f0 + 2j, f0 + 2j + 1
+    // into ring buffer j % FRAME_STAGES, once all 16 warps have released it (empty[]).  There is no CTA-wide barrier in the frame
+    // loop, and one wait / one release per warp covers two frames (the ring bookkeeping was ~25 % of a row's instructions).
+    const int npairs = (nf + 1) >> 1;
     auto stage = [&](int j) {
         if (threadIdx.x == 0) {
-            const int sb = j & (FRAME_STAGES - 1), su = j / FRAME_STAGES;
+            const int sb = j % FRAME_STAGES, su = j / FRAME_STAGES;
             if (su > 0) mbar_wait_addr(empty0 + 8u * sb, (uint32_t)((su - 1) & 1));   // use su of buffer sb needs release su - 1
             const uint32_t mb = full0 + 8u * sb;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(box_bytes) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(FRAME_PAIR * box_bytes) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(box0 + sb * box_bytes), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(t.b0 >> 2), "r"(t.sy0), "r"(f0 + j), "r"(mb)
+                         ::"r"(box0 + sb * (FRAME_PAIR * box_bytes)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(t.b0 >> 2), "r"(t.sy0),
+                           "r"(f0 + FRAME_PAIR * j), "r"(mb)
                          : "memory");
         }
     };
     if (!t.slow) {
 #pragma unroll
-        for (int j = 0; j < FRAME_STAGES - 1; ++j) if (j < nf) stage(j);
+        for (int j = 0; j < FRAME_STAGES - 1; ++j) if (j < npairs) stage(j);
     }
-    for (int i = 0; i < nf; ++i) {
-        const int b = i & (FRAME_STAGES - 1);
-        if (!t.slow && i + FRAME_STAGES - 1 < nf) stage(i + FRAME_STAGES - 1);
-        uint32_t codes = 0u;
-        if (row_on && inv_row) {
-            codes = canvas_codes(ie, cv, CW);                            // issued before the wait and the gather
-        }
-        uint32_t c[4];
+    uint32_t rb = 0u, rph = 0u;                                          // ring buffer of the current pair and its mbarrier parity
+    for (int p = 0; p < npairs; ++p) {
         if (!t.slow) {
-            mbar_wait_addr(full0 + 8u * b, (uint32_t)((i / FRAME_STAGES) & 1));
-            const uint32_t box = box0 + b * box_bytes;
-            if (row_on) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (MODE == 4 && !((gmask >> k) & 1u)) { c[k] = 0u; continue; }      // warp-uniform: no sampled pixel in this group
-                    c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");   // this warp is done with buffer b
-        } else if (row_on) {
-            const uint8_t* frame = frames + (size_t)(f0 + i) * fbytes;
-            const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
+            if (p + FRAME_STAGES - 1 < npairs) stage(p + FRAME_STAGES - 1);
+            mbar_wait_addr(full0 + 8u * rb, rph);
         }
-        if (MODE == 3 || MODE == 4) {
-            // the shared pass only runs on 1280-wide plans (ld_plan_create: shared_ok): every tile row is four whole groups and
-            // its four mask words are one aligned 16-byte store.  Groups the bird's-eye warp never samples get a decision too
-            // (MODE 3) or the decision of a black pixel (MODE 4): k_mask_b reads neither.
-            if (row_on && (MODE == 3 || gmask)) {
-                uint32_t words[4];
-                colour_words4(c, s_pre, P.ctab, P.cbits, words);
-                if (MODE == 3) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) orow[32 * k] = c[k];
+        for (int h = 0; h < FRAME_PAIR; ++h) {
+            const bool have = h == 0 || FRAME_PAIR * p + h < nf;         // the last pair of an odd range holds one frame (the other box is zero fill)
+            uint32_t codes = 0u;
+            if (have && row_on && inv_row) codes = canvas_codes(ie, cv, CW);   // issued before the gather
+            uint32_t c[4];
+            if (!t.slow) {
+                const uint32_t box = box0 + (rb * FRAME_PAIR + h) * box_bytes;
+                if (have && row_on) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (MODE == 4 && !((gmask >> k) & 1u)) { c[k] = 0u; continue; }      // warp-uniform: no sampled pixel in this group
+                        c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
+                    }
                 }
-                if (lane == 0) *reinterpret_cast<uint4*>(und_bits) = make_uint4(words[0], words[1], words[2], words[3]);
+                if (h == FRAME_PAIR - 1) {
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * rb) : "memory");   // this warp is done with buffer rb
+                }
+            } else if (have && row_on) {
+                const uint8_t* frame = frames + (size_t)(f0 + FRAME_PAIR * p + h) * fbytes;
+                const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
             }
-            und_bits += (size_t)(H - P.share_y0) * WW;
-        } else if (row_on)
-            finish_row<MODE>(c, ie, codes, ngroups, lane, text_row ? text : nullptr,
-                             ((size_t)(f0 + i) * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS, tw0, orow, rs);
-        orow += frame_words;                                             // W % 32 == 0: a frame is a whole number of words
-        cv += cv_frame;
+            if (MODE == 3 || MODE == 4) {
+                // the shared pass only runs on 1280-wide plans (ld_plan_create: shared_ok): every tile row is four whole groups and
+                // its four mask words are one aligned 16-byte store.  Groups the bird's-eye warp never samples get a decision too
+                // (MODE 3) or the decision of a black pixel (MODE 4): k_mask_b reads neither.
+                if (have && row_on && (MODE == 3 || gmask)) {
+                    uint32_t words[4];
+                    colour_words4(c, s_pre, P.ctab, P.cbits, words);
+                    if (MODE == 3) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) orow[32 * k] = c[k];
+                    }
+                    if (lane == 0) *reinterpret_cast<uint4*>(und_bits) = make_uint4(words[0], words[1], words[2], words[3]);
+                }
+                und_bits += (size_t)(H - P.share_y0) * WW;
+            } else if (have && row_on)
+                finish_row<MODE>(c, ie, codes, ngroups, lane, text_row ? text : nullptr,
+                                 ((size_t)(f0 + FRAME_PAIR * p + h) * LD_TEXT_ROWS + (y - LD_TEXT_Y0)) * LD_TEXT_WORDS, tw0, orow, rs);
+            orow += frame_words;                                         // W % 32 == 0: a frame is a whole number of words
+            cv += cv_frame;
+        }
+        if (++rb == FRAME_STAGES) { rb = 0u; rph ^= 1u; }
     }
 }
 
@@ -680,7 +701,7 @@ k_blend_px(const uint32_t* __restrict__ und_px, const uint32_t* __restrict__ pla
     keep_u32(frame_words); keep_u32(cv_frame); keep_u32(px_frame);
     const uint32_t* px = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + warp * 128 + lane;
     const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f0 * cv_frame;
-    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * W * H * 3 + ((size_t)(t.y0 + warp) * W + t.x0) * 3) + lane;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * W * H * 3 + ((size_t)(t.y0 + warp) * W + t.x0) * 3) + rs.j;
     // the pixels of the next frame are fetched while the current one is blended (the kernel is a load -> blend -> store chain
     // with little else to hide the HBM latency behind)
     uint32_t nx[2][4];
@@ -741,7 +762,7 @@ k_blend_pass(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ pl
         }
         load_inv4(ie, ngroups, t.x0, y, lane, P);
         finish_row<2>(c, ie, canvas_codes(ie, cv, CW), ngroups, lane, nullptr, 0, 0,
-                      reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + lane, rs);
+                      reinterpret_cast<uint32_t*>(out_frame + ((size_t)y * W + t.x0) * 3) + rs.j, rs);
     }
 }
 
