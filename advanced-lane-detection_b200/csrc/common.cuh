@@ -16,7 +16,7 @@ struct PlanDev {
     const int32_t* near_map;
     const int4* tiles;               // 2 x int4 per tile: (y0,y1,u0,v0) (row_words,rows,0,0)
     const uint16_t* bmap;
-    const uint32_t* ctab;
+    const uint32_t* ctab;            // [g << 8 | r]: the plan's ctab transposed (colour_entry_on)
     const uint32_t* cbits;
     const uint32_t* cpre;            // 2048 words: 2-bit colour pre-decision per 8x8x8 RGB cell (plan.colour_prefilter)
     int inv_y0, inv_y1;
@@ -40,6 +40,7 @@ struct PlanDev {
     const uint8_t* share_groups;     // [(H - share_y0)][W/128]: bit k = the row's 32-pixel group k of that 128-column tile holds a sampled pixel
     const uint4* bdesc_g;            // bdesc with the first source bit as an index into und_bits ((ny - share_y0) * W + nx)
     int mask_box_bytes;              // shared-memory bytes of the largest mask chunk box, rounded up to 128
+    uint32_t mul24, mul21, mul29;    // 2^24, 2^21, 2^29: right shifts as mul.hi on the FMA pipe (mask_kernels.cuh: colour_lookup)
 };
 
 // ---- cv2.undistort / cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) for one output pixel -----------
@@ -76,16 +77,20 @@ __device__ __forceinline__ uint32_t bilinear_rgb(const uint8_t* __restrict__ fra
 }
 
 // ---- (LUV-L in l_thresh) | (Lab-b in b_thresh) of cv2's 8-bit conversions, as a table decision ----
-__device__ __forceinline__ bool colour_on(uint32_t rgb, const uint32_t* __restrict__ ctab,
-                                          const uint32_t* __restrict__ cbits) {
-    const uint32_t r = rgb & 255, g = (rgb >> 8) & 255, b = (rgb >> 16) & 255;
-    const uint32_t e = __ldg(ctab + ((r << 8) | g));
-    bool on = (b >= (e & 255) && b <= ((e >> 8) & 255)) || (b >= ((e >> 16) & 255) && b <= (e >> 24));
-    if (e == 0x00010001u) {                               // > 2 runs along B for this (R,G): raw bit table
-        const uint32_t idx = (r << 16) | (g << 8) | b;
+// ctab (device form, ld_plan_create): entry [g << 8 | r] = lo1 | hi1 << 8 | lo2 << 16 | hi2 << 24, the <= 2 runs of B values for
+// which the colour is ON, indexed by the low half of the pixel word; 0x00010001 = more than two runs: raw bit table cbits.
+__device__ __forceinline__ bool colour_entry_on(uint32_t e, uint32_t rgb, const uint32_t* __restrict__ cbits) {
+    const uint32_t b = rgb >> 16;
+    bool on = (b >= (e & 255u) && b <= ((e >> 8) & 255u)) || (b >= ((e >> 16) & 255u) && b <= (e >> 24));
+    if (e == 0x00010001u) {
+        const uint32_t idx = ((rgb & 255u) << 16) | (rgb & 0xFF00u) | b;
         on = (__ldg(cbits + (idx >> 5)) >> (idx & 31)) & 1;
     }
     return on;
+}
+__device__ __forceinline__ bool colour_on(uint32_t rgb, const uint32_t* __restrict__ ctab,
+                                          const uint32_t* __restrict__ cbits) {
+    return colour_entry_on(__ldg(ctab + (rgb & 0xFFFFu)), rgb, cbits);
 }
 
 // float32 multiply-add with round-half-even, saturated: cv2.addWeighted(a, 1, b, 0.3, 0) on u8

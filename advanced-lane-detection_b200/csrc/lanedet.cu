@@ -2,6 +2,7 @@
 // launch sequence of the sm_100a kernels.  No CPU fallback anywhere: every entry point either
 // launches kernels on the plan's device or returns an error code.
 #include <cuda_runtime.h>
+#include <memory>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -143,6 +144,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     p->device = device;
     PlanDev& d = p->d;
     d.W = W; d.H = H; d.WW = W / 32;
+    d.mul24 = 1u << 24; d.mul21 = 1u << 21; d.mul29 = 1u << 29;
     d.search_mode = desc->search_mode; d.margin = desc->margin; d.minpix = desc->minpix;
     d.depth = desc->frame_num; d.top_anchor = desc->top_anchor; d.clip_polygon = desc->clip_polygon;
     d.curv_fixed_xm = desc->curv_fixed_xm; d.n_tiles = desc->n_tiles; d.ym_per_pix = desc->ym_per_pix;
@@ -173,8 +175,14 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if (b > ms) ms = b;
     }
     if (ms > 96 * 1024) { ld_plan_destroy(p); return LD_ERR_ARG; }                              // k_mask double-buffers its chunk boxes
+    // the interval table indexed by the low half of a pixel word (g << 8 | r) instead of the plan's r << 8 | g
+    std::unique_ptr<uint32_t[]> tab_mem(new (std::nothrow) uint32_t[65536 + MASK_PRE_WORDS]);
+    if (!tab_mem) { ld_plan_destroy(p); return LD_ERR_ARG; }
+    uint32_t* ctab_gr = tab_mem.get();
+    for (int r = 0; r < 256; ++r)
+        for (int g = 0; g < 256; ++g) ctab_gr[(g << 8) | r] = desc->ctab[(r << 8) | g];
     // the colour pre-decision in the form the kernels read (mask_kernels.cuh: colour_words4): per 32 cells an ON word and a MIXED word
-    static uint32_t cpre2[MASK_PRE_WORDS];
+    uint32_t* cpre2 = tab_mem.get() + 65536;
     for (int w = 0; w < MASK_PRE_WORDS / 2; ++w) {
         uint32_t on = 0, mixed = 0;
         for (int i = 0; i < 32; ++i) {
@@ -187,7 +195,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     }
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
-        (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, desc->ctab, (size_t)65536, &d.ctab)) ||
+        (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, ctab_gr, (size_t)65536, &d.ctab)) ||
         (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, cpre2, (size_t)MASK_PRE_WORDS, &d.cpre)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
         (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) || (rc = upload(p, desc->inv_pack, ninv ? ninv : 1, &d.inv_pack)) ||
         (rc = upload(p, desc->glyph_bits, (size_t)desc->n_glyphs * LD_GLYPH_ROWS * LD_GLYPH_WORDS, &d.glyph_bits)) ||

@@ -32,23 +32,31 @@ constexpr uint32_t BDESC_BORDER = 0xFFFFFFFFu, BDESC_FALLBACK = 0xFFFFFFFEu;
 // (LUV-L in l_thresh) | (Lab-b in b_thresh) of the four pixels a lane owns (c[k] = r | g << 8 | b << 16, top byte zero), as one
 // mask word per 32-pixel group.  The pre-decision table in shared memory (ld_plan_create: plan.colour_prefilter re-packed) holds,
 // per 32 cells of 8x8x8 colours (cell = r5 | g5 << 5 | b5 << 10), an ON word and a MIXED word, so a pixel costs one 8-byte load
-// and two wrapping shifts, with no branch: the cell index is two bit-muxes of three shifts, the word address is cell >> 5 and
-// the shifts take the low five bits of the cell by themselves.  Only when some lane of the warp sits in a mixed cell (a colour
-// near a threshold) does the warp visit the exact tables -- ONE vote for the four groups.
-__device__ __forceinline__ uint32_t colour_cell(uint32_t rgb) {
-    const uint32_t rg = ((rgb >> 3) & 0x1Fu) | ((rgb >> 6) & ~0x1Fu);          // r5 | g5 << 5 | junk above bit 9
-    return (rg & 0x3FFu) | ((rgb >> 9) & ~0x3FFu);                              // ... | b5 << 10 (the top byte of rgb is zero)
+// and two wrapping shifts, with no branch.  Only when some lane of the warp sits in a mixed cell (a colour near a threshold) does
+// the warp visit the exact tables -- ONE vote for the four groups.
+// The ALU pipe (shifts, logic, byte permutes: 16 lanes per cycle and scheduler) is what binds the kernels that decide colours
+// (74 % busy in the shared pass, the FMA pipe 13 %), so the address arithmetic runs on the FMA pipe instead: a right shift by k
+// is mul.hi by 2^(32-k), and mad.hi folds the add.  The multipliers come from kernel parameters (PlanDev::mul24 / mul21 / mul29)
+// so that the compiler does not turn them back into shifts.  Per pixel: 2 logic ops + 3 multiply-adds + one 8-byte load + two
+// wrapping shifts (the shift amount r5 is the low five bits of rgb >> 3; the entry address is base + 8 (g5 + 32 b5)).
+struct ColourPre {
+    uint32_t base;                                                      // shared-window address of the table
+    uint32_t m24, m21, m29;                                             // 2^24, 2^21, 2^29
+};
+__device__ __forceinline__ void colour_lookup(uint32_t rgb, const ColourPre& T, uint32_t& on, uint32_t& mixed) {
+    uint32_t a, sh, ex, ey;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(rgb & 0xF800u), "r"(T.m24), "r"(T.base));      // + 8 g5
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(rgb & 0xF80000u), "r"(T.m21), "r"(a));         // + 256 b5
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(sh) : "r"(rgb), "r"(T.m29));                                // rgb >> 3
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(a));
+    on = __funnelshift_r(ex, 0u, sh);
+    mixed = __funnelshift_r(ey, 0u, sh);
 }
-__device__ __forceinline__ void colour_words4(const uint32_t (&c)[4], const uint2* s_pre, const uint32_t* __restrict__ ctab,
+__device__ __forceinline__ void colour_words4(const uint32_t (&c)[4], const ColourPre& T, const uint32_t* __restrict__ ctab,
                                               const uint32_t* __restrict__ cbits, uint32_t (&words)[4]) {
     uint32_t on[4], mixed[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t cell = colour_cell(c[k]);
-        const uint2 e = s_pre[cell >> 5];
-        on[k] = __funnelshift_r(e.x, 0u, cell);
-        mixed[k] = __funnelshift_r(e.y, 0u, cell);
-    }
+    for (int k = 0; k < 4; ++k) colour_lookup(c[k], T, on[k], mixed[k]);
     if (__any_sync(0xffffffffu, (mixed[0] | mixed[1] | mixed[2] | mixed[3]) & 1u)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -78,6 +86,7 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
     uint8_t* s_box = reinterpret_cast<uint8_t*>(s_pre + MASK_PRE_WORDS / 2);
     const uint32_t box_bytes = (uint32_t)P.mask_box_bytes;              // one chunk box (a multiple of 128)
     const uint32_t box0 = smem_u32(s_box), bar0 = smem_u32(&bar[0]);
+    const ColourPre pre{smem_u32(s_pre), P.mul24, P.mul21, P.mul29};
 
     const int tile = blockIdx.x, f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
     const int4 t0 = P.tiles[2 * tile], t1 = P.tiles[2 * tile + 1];
@@ -133,7 +142,7 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
                     uint32_t c[4], words[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_smem(box, (uint32_t)g.stride, es[k]);   // columns beyond the chunk: entry 0 (their words are not stored)
-                    colour_words4(c, s_pre, P.ctab, P.cbits, words);
+                    colour_words4(c, pre, P.ctab, P.cbits, words);
                     if (lane < 4 && cg * 4 + lane < nwc)
                         s_bits[r * rw + wc0 + cg * 4 + lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
                     e = en;

@@ -558,6 +558,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
 #pragma unroll
         for (int b = 0; b < FRAME_STAGES; ++b) { mbar_init(&bar[b], 1); mbar_init(&empty[b], FRAME_MF_THREADS / 32); }
     }
+    const ColourPre pre{smem_u32(s_pre), P.mul24, P.mul21, P.mul29};
 
     // ---- per-tile constants of this thread's row
     uint32_t po[4], wx[4], wy[4], ie[4];
@@ -656,11 +657,17 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
                 // (MODE 3) or the decision of a black pixel (MODE 4): k_mask_b reads neither.
                 if (have && row_on && (MODE == 3 || gmask)) {
                     uint32_t words[4];
-                    colour_words4(c, s_pre, P.ctab, P.cbits, words);
+#ifdef LD_EXP_NOCOLOUR                                               // timing experiments only
+                    words[0] = c[0]; words[1] = c[1]; words[2] = c[2]; words[3] = c[3];
+#else
+                    colour_words4(c, pre, P.ctab, P.cbits, words);
+#endif
+#ifndef LD_EXP_NOPX
                     if (MODE == 3) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) orow[32 * k] = c[k];
                     }
+#endif
                     if (lane == 0) *reinterpret_cast<uint4*>(und_bits) = make_uint4(words[0], words[1], words[2], words[3]);
                 }
                 und_bits += (size_t)(H - P.share_y0) * WW;
