@@ -40,7 +40,7 @@ struct PlanDev {
     const uint8_t* share_groups;     // [(H - share_y0)][W/128]: bit k = the row's 32-pixel group k of that 128-column tile holds a sampled pixel
     const uint4* bdesc_g;            // bdesc with the first source bit as an index into und_bits ((ny - share_y0) * W + nx)
     int mask_box_bytes;              // shared-memory bytes of the largest mask chunk box, rounded up to 128
-    uint32_t mul24, mul21, mul29;    // 2^24, 2^21, 2^29: right shifts as mul.hi on the FMA pipe (mask_kernels.cuh: colour_lookup)
+    uint32_t mul13;                  // 2^13: a right shift by 19 as mul.hi on the FMA pipe (mask_kernels.cuh: colour_lookup)
 };
 
 // ---- cv2.undistort / cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) for one output pixel -----------

@@ -65,9 +65,11 @@ __device__ __forceinline__ void frame_weights(uint32_t fx, uint32_t fy, uint32_t
     wy = tt * fy64;
 }
 
-// The pixel (r | g << 8 | b << 16) whose first tap starts at shared-window byte address `a` + (sh / 8), sh = 0, 8, 16, 24
-// (the funnel shifts use the low five bits of sh), with the next tap row `stride` bytes further.
-__device__ __forceinline__ uint32_t bilinear_taps(uint32_t a, uint32_t stride, uint32_t sh, uint32_t wx, uint32_t wy) {
+// The bilinear sums of the pixel whose first tap starts at shared-window byte address `a` + (sh / 8), sh = 0, 8, 16, 24 (the
+// funnel shifts use the low five bits of sh), with the next tap row `stride` bytes further: r / g / b = the accumulators
+// sum 2 w p + 2^15 (< 2^24), whose byte 2 is the channel value.
+__device__ __forceinline__ void bilinear_acc(uint32_t a, uint32_t stride, uint32_t sh, uint32_t wx, uint32_t wy,
+                                             uint32_t& r, uint32_t& g, uint32_t& b) {
     uint32_t p0, p1, p2, q0, q1, q2;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(p0) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(p1) : "r"(a));
@@ -88,13 +90,22 @@ __device__ __forceinline__ uint32_t bilinear_taps(uint32_t a, uint32_t stride, u
     const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
     const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11
     const uint32_t GBt = __byte_perm(lt, ht, 0x5241), GBb = __byte_perm(lb, hb, 0x5241);   // g0 g1 b0 b1
-    uint32_t r = __dp2a_lo(wx, R, 32768u);
+    r = __dp2a_lo(wx, R, 32768u);
     r = __dp2a_hi(wy, R, r);
-    uint32_t g = __dp2a_lo(wx, GBt, 32768u);
+    g = __dp2a_lo(wx, GBt, 32768u);
     g = __dp2a_lo(wy, GBb, g);
-    uint32_t b = __dp2a_hi(wx, GBt, 32768u);
+    b = __dp2a_hi(wx, GBt, 32768u);
     b = __dp2a_hi(wy, GBb, b);
-    return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);           // (r >> 16) | (g >> 16) << 8 | (b >> 16) << 16
+}
+// (r >> 16) | (g >> 16) << 8 | (b >> 16) << 16 of three accumulators
+__device__ __forceinline__ uint32_t pack_rgb(uint32_t r, uint32_t g, uint32_t b) {
+    return __byte_perm(__byte_perm(r, g, 0x3362), b, 0x3610);
+}
+// The pixel r | g << 8 | b << 16 (top byte zero)
+__device__ __forceinline__ uint32_t bilinear_taps(uint32_t a, uint32_t stride, uint32_t sh, uint32_t wx, uint32_t wy) {
+    uint32_t r, g, b;
+    bilinear_acc(a, stride, sh, wx, wy, r, g, b);
+    return pack_rgb(r, g, b);
 }
 
 }  // namespace lanedet

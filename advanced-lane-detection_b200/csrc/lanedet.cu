@@ -144,7 +144,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     p->device = device;
     PlanDev& d = p->d;
     d.W = W; d.H = H; d.WW = W / 32;
-    d.mul24 = 1u << 24; d.mul21 = 1u << 21; d.mul29 = 1u << 29;
+    d.mul13 = 1u << 13;
     d.search_mode = desc->search_mode; d.margin = desc->margin; d.minpix = desc->minpix;
     d.depth = desc->frame_num; d.top_anchor = desc->top_anchor; d.clip_polygon = desc->clip_polygon;
     d.curv_fixed_xm = desc->curv_fixed_xm; d.n_tiles = desc->n_tiles; d.ym_per_pix = desc->ym_per_pix;
@@ -188,8 +188,8 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         for (int i = 0; i < 32; ++i) {
             const int cell = 32 * w + i;
             const uint32_t code = (desc->cpre[cell >> 4] >> (2 * (cell & 15))) & 3u;
-            on |= (uint32_t)(code == 1u) << i;
-            mixed |= (uint32_t)(code >= 2u) << i;
+            on |= (uint32_t)(code == 1u) << (31 - i);                    // cell r5 = i sits in bit 31 - i (colour_lookup shifts left)
+            mixed |= (uint32_t)(code >= 2u) << (31 - i);
         }
         cpre2[2 * w] = on; cpre2[2 * w + 1] = mixed;
     }

@@ -35,43 +35,48 @@ constexpr uint32_t BDESC_BORDER = 0xFFFFFFFFu, BDESC_FALLBACK = 0xFFFFFFFEu;
 // and two wrapping shifts, with no branch.  Only when some lane of the warp sits in a mixed cell (a colour near a threshold) does
 // the warp visit the exact tables -- ONE vote for the four groups.
 // The ALU pipe (shifts, logic, byte permutes: 16 lanes per cycle and scheduler) is what binds the kernels that decide colours
-// (74 % busy in the shared pass, the FMA pipe 13 %), so the address arithmetic runs on the FMA pipe instead: a right shift by k
-// is mul.hi by 2^(32-k), and mad.hi folds the add.  The multipliers come from kernel parameters (PlanDev::mul24 / mul21 / mul29)
-// so that the compiler does not turn them back into shifts.  Per pixel: 2 logic ops + 3 multiply-adds + one 8-byte load + two
-// wrapping shifts (the shift amount r5 is the low five bits of rgb >> 3; the entry address is base + 8 (g5 + 32 b5)).
+// (74 % busy in the shared pass, the FMA pipe 13 %), so the lookup works on the three bilinear ACCUMULATORS (channel value in
+// bits 16..23, nothing above) and does its address arithmetic on the FMA pipe: acc >> 19 = the channel's 5-bit cell coordinate
+// = mul.hi by 2^13, the entry address = base + 8 g5 + 256 b5 two multiply-adds.  The multipliers come from kernel parameters
+// (PlanDev::mul13) so that the compiler does not turn them back into shifts.  The table keeps cell r5 in bit 31 - r5, so a
+// wrapping LEFT shift by r5 (the low five bits of the red accumulator >> 19) puts the decision into the sign bit: per pixel one
+// 8-byte load, two shifts, one compare and one vote, and no byte permute (the packed pixel is only built where it is stored).
 struct ColourPre {
     uint32_t base;                                                      // shared-window address of the table
-    uint32_t m24, m21, m29;                                             // 2^24, 2^21, 2^29
+    uint32_t m13;                                                       // 2^13
 };
-__device__ __forceinline__ void colour_lookup(uint32_t rgb, const ColourPre& T, uint32_t& on, uint32_t& mixed) {
-    uint32_t a, sh, ex, ey;
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(rgb & 0xF800u), "r"(T.m24), "r"(T.base));      // + 8 g5
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(rgb & 0xF80000u), "r"(T.m21), "r"(a));         // + 256 b5
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(sh) : "r"(rgb), "r"(T.m29));                                // rgb >> 3
+__device__ __forceinline__ void colour_lookup(uint32_t r, uint32_t g, uint32_t b, const ColourPre& T, uint32_t& on, uint32_t& mixed) {
+    uint32_t g5, b5, sh, a, ex, ey;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(g5) : "r"(g), "r"(T.m13));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(b5) : "r"(b), "r"(T.m13));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(sh) : "r"(r), "r"(T.m13));
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a) : "r"(g5), "r"(T.base));
+    asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(a) : "r"(b5), "r"(a));
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(a));
-    on = __funnelshift_r(ex, 0u, sh);
-    mixed = __funnelshift_r(ey, 0u, sh);
+    on = __funnelshift_l(0u, ex, sh);                                   // ex << r5: the cell's bit in the sign position
+    mixed = __funnelshift_l(0u, ey, sh);
 }
-__device__ __forceinline__ void colour_words4(const uint32_t (&c)[4], const ColourPre& T, const uint32_t* __restrict__ ctab,
-                                              const uint32_t* __restrict__ cbits, uint32_t (&words)[4]) {
+// Mask words of the four pixels a lane owns (accumulators r / g / b [k]) for the four 32-pixel groups of a tile row.
+__device__ __forceinline__ void colour_words4(const uint32_t (&r)[4], const uint32_t (&g)[4], const uint32_t (&b)[4], const ColourPre& T,
+                                              const uint32_t* __restrict__ ctab, const uint32_t* __restrict__ cbits, uint32_t (&words)[4]) {
     uint32_t on[4], mixed[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) colour_lookup(c[k], T, on[k], mixed[k]);
-    if (__any_sync(0xffffffffu, (mixed[0] | mixed[1] | mixed[2] | mixed[3]) & 1u)) {
+    for (int k = 0; k < 4; ++k) colour_lookup(r[k], g[k], b[k], T, on[k], mixed[k]);
+    if (__any_sync(0xffffffffu, (int)(mixed[0] | mixed[1] | mixed[2] | mixed[3]) < 0)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (mixed[k] & 1u) on[k] = colour_on(c[k], ctab, cbits) ? 1u : 0u;
+            if ((int)mixed[k] < 0) on[k] = colour_on(pack_rgb(r[k], g[k], b[k]), ctab, cbits) ? 0x80000000u : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) words[k] = __ballot_sync(0xffffffffu, on[k] & 1u);
+    for (int k = 0; k < 4; ++k) words[k] = __ballot_sync(0xffffffffu, (int)on[k] < 0);
 }
 
-// one pixel from a plan.gather_offsets entry (tap byte offset << 10 | fy << 5 | fx), weights decoded on the fly
-__device__ __forceinline__ uint32_t bilinear_rgb_smem(uint32_t box, uint32_t stride, uint32_t e2) {
+// one pixel from a plan.gather_offsets entry (tap byte offset << 10 | fy << 5 | fx), weights decoded on the fly: accumulators
+__device__ __forceinline__ void bilinear_acc_smem(uint32_t box, uint32_t stride, uint32_t e2, uint32_t& r, uint32_t& g, uint32_t& b) {
     uint32_t wx, wy;
     frame_weights(e2 & 31u, (e2 >> 5) & 31u, wx, wy);
     const uint32_t o = e2 >> 10;
-    return bilinear_taps(box + (o & ~3u), stride, o << 3, wx, wy);
+    bilinear_acc(box + (o & ~3u), stride, o << 3, wx, wy, r, g, b);
 }
 
 __global__ void __launch_bounds__(MASK_THREADS, 3)
@@ -86,7 +91,7 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
     uint8_t* s_box = reinterpret_cast<uint8_t*>(s_pre + MASK_PRE_WORDS / 2);
     const uint32_t box_bytes = (uint32_t)P.mask_box_bytes;              // one chunk box (a multiple of 128)
     const uint32_t box0 = smem_u32(s_box), bar0 = smem_u32(&bar[0]);
-    const ColourPre pre{smem_u32(s_pre), P.mul24, P.mul21, P.mul29};
+    const ColourPre pre{smem_u32(s_pre), P.mul13};
 
     const int tile = blockIdx.x, f0 = blockIdx.y * fpc, nf = min(fpc, n - f0);
     const int4 t0 = P.tiles[2 * tile], t1 = P.tiles[2 * tile + 1];
@@ -139,10 +144,10 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
                     if (item + nwarp < nitems) en = __ldg(am4 + (item + nwarp) * 32 + lane);   // one item ahead
                     const int r = ncg == 1 ? item : (ncg == 2 ? item >> 1 : item / ncg), cg = item - r * ncg;   // chunks are <= 256 px wide
                     const uint32_t es[4] = {e.x, e.y, e.z, e.w};
-                    uint32_t c[4], words[4];
+                    uint32_t acr[4], acg[4], acb[4], words[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) c[k] = bilinear_rgb_smem(box, (uint32_t)g.stride, es[k]);   // columns beyond the chunk: entry 0 (their words are not stored)
-                    colour_words4(c, pre, P.ctab, P.cbits, words);
+                    for (int k = 0; k < 4; ++k) bilinear_acc_smem(box, (uint32_t)g.stride, es[k], acr[k], acg[k], acb[k]);   // columns beyond the chunk: entry 0 (their words are not stored)
+                    colour_words4(acr, acg, acb, pre, P.ctab, P.cbits, words);
                     if (lane < 4 && cg * 4 + lane < nwc)
                         s_bits[r * rw + wc0 + cg * 4 + lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
                     e = en;

@@ -558,7 +558,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
 #pragma unroll
         for (int b = 0; b < FRAME_STAGES; ++b) { mbar_init(&bar[b], 1); mbar_init(&empty[b], FRAME_MF_THREADS / 32); }
     }
-    const ColourPre pre{smem_u32(s_pre), P.mul24, P.mul21, P.mul29};
+    const ColourPre pre{smem_u32(s_pre), P.mul13};
 
     // ---- per-tile constants of this thread's row
     uint32_t po[4], wx[4], wy[4], ie[4];
@@ -630,14 +630,19 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
             const bool have = h == 0 || FRAME_PAIR * p + h < nf;         // the last pair of an odd range holds one frame (the other box is zero fill)
             uint32_t codes = 0u;
             if (have && row_on && inv_row) codes = canvas_codes(ie, cv, CW);   // issued before the gather
-            uint32_t c[4];
+            uint32_t c[4];                                               // the packed pixels (MODE 0 / 1 / 3)
+            uint32_t ar[4], ag[4], ab[4];                                // MODE 3 / 4: their bilinear accumulators (colour_words4 reads those)
             if (!t.slow) {
                 const uint32_t box = box0 + (rb * FRAME_PAIR + h) * box_bytes;
                 if (have && row_on) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (MODE == 4 && !((gmask >> k) & 1u)) { c[k] = 0u; continue; }      // warp-uniform: no sampled pixel in this group
-                        c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
+                        if (MODE == 4 && !((gmask >> k) & 1u)) { ar[k] = ag[k] = ab[k] = 0u; continue; }   // warp-uniform: no sampled pixel in this group
+                        if (MODE == 3 || MODE == 4) {
+                            bilinear_acc(box + (po[k] & 0x3FFFFFFFu), (uint32_t)FRAME_BOX_PITCH, po[k] >> 27, wx[k], wy[k], ar[k], ag[k], ab[k]);
+                            if (MODE == 3) c[k] = pack_rgb(ar[k], ag[k], ab[k]);
+                        } else
+                            c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
                     }
                 }
                 if (h == FRAME_PAIR - 1) {
@@ -648,8 +653,10 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
                 const uint8_t* frame = frames + (size_t)(f0 + FRAME_PAIR * p + h) * fbytes;
                 const uint32_t* um = P.und_map + (size_t)y * W + t.x0 + lane;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < 4; ++k) {
                     c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
+                    if (MODE == 3 || MODE == 4) { ar[k] = (c[k] & 255u) << 16; ag[k] = (c[k] & 0xFF00u) << 8; ab[k] = c[k] & 0xFF0000u; }
+                }
             }
             if (MODE == 3 || MODE == 4) {
                 // the shared pass only runs on 1280-wide plans (ld_plan_create: shared_ok): every tile row is four whole groups and
@@ -658,9 +665,9 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
                 if (have && row_on && (MODE == 3 || gmask)) {
                     uint32_t words[4];
 #ifdef LD_EXP_NOCOLOUR                                               // timing experiments only
-                    words[0] = c[0]; words[1] = c[1]; words[2] = c[2]; words[3] = c[3];
+                    words[0] = ar[0]; words[1] = ag[1]; words[2] = ab[2]; words[3] = ar[3];
 #else
-                    colour_words4(c, pre, P.ctab, P.cbits, words);
+                    colour_words4(ar, ag, ab, pre, P.ctab, P.cbits, words);
 #endif
 #ifndef LD_EXP_NOPX
                     if (MODE == 3) {
