@@ -16,8 +16,7 @@ struct PlanDev {
     const int32_t* near_map;
     const int4* tiles;               // 2 x int4 per tile: (y0,y1,u0,v0) (row_words,rows,0,0)
     const uint16_t* bmap;
-    const uint32_t* ctab;            // [g << 8 | r]: the plan's ctab transposed (colour_entry_on)
-    const uint32_t* cbits;
+    const uint32_t* cbits;           // 2^19 words: the exact decision, bit (c & 31) of word c >> 5 for the pixel word c = r | g << 8 | b << 16
     const uint32_t* cpre;            // 2048 words: 2-bit colour pre-decision per 8x8x8 RGB cell (plan.colour_prefilter)
     int inv_y0, inv_y1;
     const uint32_t* inv_idx;
@@ -77,20 +76,10 @@ __device__ __forceinline__ uint32_t bilinear_rgb(const uint8_t* __restrict__ fra
 }
 
 // ---- (LUV-L in l_thresh) | (Lab-b in b_thresh) of cv2's 8-bit conversions, as a table decision ----
-// ctab (device form, ld_plan_create): entry [g << 8 | r] = lo1 | hi1 << 8 | lo2 << 16 | hi2 << 24, the <= 2 runs of B values for
-// which the colour is ON, indexed by the low half of the pixel word; 0x00010001 = more than two runs: raw bit table cbits.
-__device__ __forceinline__ bool colour_entry_on(uint32_t e, uint32_t rgb, const uint32_t* __restrict__ cbits) {
-    const uint32_t b = rgb >> 16;
-    bool on = (b >= (e & 255u) && b <= ((e >> 8) & 255u)) || (b >= ((e >> 16) & 255u) && b <= (e >> 24));
-    if (e == 0x00010001u) {
-        const uint32_t idx = ((rgb & 255u) << 16) | (rgb & 0xFF00u) | b;
-        on = (__ldg(cbits + (idx >> 5)) >> (idx & 31)) & 1;
-    }
-    return on;
-}
-__device__ __forceinline__ bool colour_on(uint32_t rgb, const uint32_t* __restrict__ ctab,
-                                          const uint32_t* __restrict__ cbits) {
-    return colour_entry_on(__ldg(ctab + (rgb & 0xFFFFu)), rgb, cbits);
+// cbits (device form, ld_plan_create): the plan's raw decision table re-ordered to the pixel word, bit (c & 31) of word c >> 5
+// for c = r | g << 8 | b << 16 -- exact for all 2^24 colours by construction, one shift, one load, one shift.
+__device__ __forceinline__ bool colour_on(uint32_t rgb, const uint32_t* __restrict__ cbits) {
+    return (__funnelshift_r(__ldg(cbits + (rgb >> 5)), 0u, rgb) & 1u) != 0u;
 }
 
 // float32 multiply-add with round-half-even, saturated: cv2.addWeighted(a, 1, b, 0.3, 0) on u8

@@ -175,14 +175,26 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         if (b > ms) ms = b;
     }
     if (ms > 96 * 1024) { ld_plan_destroy(p); return LD_ERR_ARG; }                              // k_mask double-buffers its chunk boxes
-    // the interval table indexed by the low half of a pixel word (g << 8 | r) instead of the plan's r << 8 | g
-    std::unique_ptr<uint32_t[]> tab_mem(new (std::nothrow) uint32_t[65536 + MASK_PRE_WORDS]);
+    // the raw decision table re-ordered from the plan's bit index (r << 16 | g << 8 | b) to the pixel word (r | g << 8 | b << 16):
+    // colour_on is then one shift, one load, one shift (common.cuh)
+    std::unique_ptr<uint32_t[]> tab_mem(new (std::nothrow) uint32_t[((size_t)1 << 19) + MASK_PRE_WORDS]);
     if (!tab_mem) { ld_plan_destroy(p); return LD_ERR_ARG; }
-    uint32_t* ctab_gr = tab_mem.get();
-    for (int r = 0; r < 256; ++r)
-        for (int g = 0; g < 256; ++g) ctab_gr[(g << 8) | r] = desc->ctab[(r << 8) | g];
+    uint32_t* cbits_px = tab_mem.get();
+    memset(cbits_px, 0, sizeof(uint32_t) << 19);
+    for (uint32_t rg = 0; rg < 65536u; ++rg) {
+        const uint32_t r = rg >> 8, g = rg & 255u;
+        const uint32_t* src = desc->cbits + (rg << 3);                  // 256 B values = 8 words
+        for (uint32_t w = 0; w < 8; ++w) {
+            uint32_t bits = src[w];
+            while (bits) {
+                const uint32_t b = 32u * w + (uint32_t)__builtin_ctz(bits);
+                bits &= bits - 1u;
+                cbits_px[(b << 11) | (g << 3) | (r >> 5)] |= 1u << (r & 31u);
+            }
+        }
+    }
     // the colour pre-decision in the form the kernels read (mask_kernels.cuh: colour_words4): per 32 cells an ON word and a MIXED word
-    uint32_t* cpre2 = tab_mem.get() + 65536;
+    uint32_t* cpre2 = tab_mem.get() + ((size_t)1 << 19);
     for (int w = 0; w < MASK_PRE_WORDS / 2; ++w) {
         uint32_t on = 0, mixed = 0;
         for (int i = 0; i < 32; ++i) {
@@ -195,8 +207,8 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     }
     if ((rc = upload(p, desc->und_map, npix, &d.und_map)) || (rc = upload(p, desc->wtab, (size_t)4096, &wt)) ||
         (rc = upload(p, desc->near_map, npix, &d.near_map)) || (rc = upload(p, desc->tiles, (size_t)desc->n_tiles * 8, &tl)) ||
-        (rc = upload(p, desc->bmap, npix, &d.bmap)) || (rc = upload(p, ctab_gr, (size_t)65536, &d.ctab)) ||
-        (rc = upload(p, desc->cbits, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, cpre2, (size_t)MASK_PRE_WORDS, &d.cpre)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
+        (rc = upload(p, desc->bmap, npix, &d.bmap)) ||
+        (rc = upload(p, cbits_px, (size_t)1 << 19, &d.cbits)) || (rc = upload(p, cpre2, (size_t)MASK_PRE_WORDS, &d.cpre)) || (rc = upload(p, desc->inv_idx, ninv ? ninv : 1, &d.inv_idx)) ||
         (rc = upload(p, desc->inv_fi, ninv ? ninv : 1, &d.inv_fi)) || (rc = upload(p, desc->inv_pack, ninv ? ninv : 1, &d.inv_pack)) ||
         (rc = upload(p, desc->glyph_bits, (size_t)desc->n_glyphs * LD_GLYPH_ROWS * LD_GLYPH_WORDS, &d.glyph_bits)) ||
         (rc = upload(p, desc->glyph_adv, (size_t)desc->n_glyphs, &d.glyph_adv)) ||
@@ -356,6 +368,10 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    if (const char* e = getenv("LD_CARVEOUT_COLOUR")) {                 // experiment: leave the colour-deciding passes some L1 for the exact tables
+        LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)), ld_plan_destroy(p));
+        LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)), ld_plan_destroy(p));
+    }
     // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
     // carveout, otherwise an SM has to drain before a kernel with a different carveout can start on it.
     LD_CUDA_OR(cudaFuncSetAttribute(k_mask, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));

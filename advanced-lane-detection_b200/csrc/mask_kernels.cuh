@@ -58,14 +58,21 @@ __device__ __forceinline__ void colour_lookup(uint32_t r, uint32_t g, uint32_t b
 }
 // Mask words of the four pixels a lane owns (accumulators r / g / b [k]) for the four 32-pixel groups of a tile row.
 __device__ __forceinline__ void colour_words4(const uint32_t (&r)[4], const uint32_t (&g)[4], const uint32_t (&b)[4], const ColourPre& T,
-                                              const uint32_t* __restrict__ ctab, const uint32_t* __restrict__ cbits, uint32_t (&words)[4]) {
+                                              const uint32_t* __restrict__ cbits, uint32_t (&words)[4]) {
     uint32_t on[4], mixed[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) colour_lookup(r[k], g[k], b[k], T, on[k], mixed[k]);
+#ifdef LD_EXP_NOSLOW                                                 // timing experiment only: what the exact-table visits cost
+    if (false) {
+#else
     if (__any_sync(0xffffffffu, (int)(mixed[0] | mixed[1] | mixed[2] | mixed[3]) < 0)) {
+#endif
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if ((int)mixed[k] < 0) on[k] = colour_on(pack_rgb(r[k], g[k], b[k]), ctab, cbits) ? 0x80000000u : 0u;
+            if ((int)mixed[k] < 0) {                                     // the exact bit of the colour, moved to the sign position
+                const uint32_t c = pack_rgb(r[k], g[k], b[k]);
+                on[k] = __funnelshift_l(0u, __ldg(cbits + (c >> 5)), ~c);
+            }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) words[k] = __ballot_sync(0xffffffffu, (int)on[k] < 0);
@@ -147,7 +154,7 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
                     uint32_t acr[4], acg[4], acb[4], words[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) bilinear_acc_smem(box, (uint32_t)g.stride, es[k], acr[k], acg[k], acb[k]);   // columns beyond the chunk: entry 0 (their words are not stored)
-                    colour_words4(acr, acg, acb, pre, P.ctab, P.cbits, words);
+                    colour_words4(acr, acg, acb, pre, P.cbits, words);
                     if (lane < 4 && cg * 4 + lane < nwc)
                         s_bits[r * rw + wc0 + cg * 4 + lane] = lane == 0 ? words[0] : (lane == 1 ? words[1] : (lane == 2 ? words[2] : words[3]));
                     e = en;
@@ -160,8 +167,7 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
                         const int col = wc * 32 + lane, v = g.y0 + r;
                         bool on = false;
                         if (col < g.w)
-                            on = colour_on(bilinear_rgb(frame, P.W, P.H, g.x0 + col, v, __ldg(P.und_map + (size_t)v * P.W + g.x0 + col), P.wtab),
-                                           P.ctab, P.cbits);
+                            on = colour_on(bilinear_rgb(frame, P.W, P.H, g.x0 + col, v, __ldg(P.und_map + (size_t)v * P.W + g.x0 + col), P.wtab), P.cbits);
                         const uint32_t word = __ballot_sync(0xffffffffu, on);
                         if (lane == 0) s_bits[r * rw + wc0 + wc] = word;
                     }
@@ -353,7 +359,7 @@ k_colour_mask(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, const 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     const uint8_t* p = img + ((size_t)f * npix + i) * 3;
-    out[(size_t)f * npix + i] = colour_on(p[0] | (p[1] << 8) | (p[2] << 16), P.ctab, P.cbits) ? 1 : 0;
+    out[(size_t)f * npix + i] = colour_on(p[0] | (p[1] << 8) | (p[2] << 16), P.cbits) ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(256)

@@ -667,7 +667,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
 #ifdef LD_EXP_NOCOLOUR                                               // timing experiments only
                     words[0] = ar[0]; words[1] = ag[1]; words[2] = ab[2]; words[3] = ar[3];
 #else
-                    colour_words4(ar, ag, ab, pre, P.ctab, P.cbits, words);
+                    colour_words4(ar, ag, ab, pre, P.cbits, words);
 #endif
 #ifndef LD_EXP_NOPX
                     if (MODE == 3) {
