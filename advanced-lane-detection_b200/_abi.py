@@ -79,6 +79,7 @@ _SIGNATURES = {
     "ld_ctx_create": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     "ld_ctx_destroy": (C.c_int, [_P]),
     "ld_mask": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "ld_mask_fused": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_hist": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_search": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_fit": (C.c_int, [_P, _P, C.c_int, _P, _P]),

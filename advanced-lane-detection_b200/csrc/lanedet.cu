@@ -544,9 +544,7 @@ extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, 
     if (!ARGS_OK(c, frames, mask, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    static int fused = -1;                                              // LD_MASK_FUSED=1: always the one-kernel k_mask (A/B measurements, tests)
-    if (fused < 0) { const char* e = getenv("LD_MASK_FUSED"); fused = e ? atoi(e) : 0; }
-    if (c->plan->shared_ok && !fused && !((uintptr_t)frames & 15)) {
+    if (c->plan->shared_ok && !((uintptr_t)frames & 15)) {
         // 1280x720 plans: the frame pass's multi-frame tile kernel in its mask-only form (per-tile constants in registers, one
         // tensor-map TMA copy per tile and frame, only the 32-pixel groups the bird's-eye warp samples are gathered) writes the
         // colour bits of the undistorted pixels; k_mask_b cuts the bird's-eye words out of them
@@ -560,6 +558,13 @@ extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, 
         }
         return LD_OK;
     }
+    return ld_mask_fused(c, frames, n, mask, stream);
+}
+
+extern "C" int ld_mask_fused(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, void* stream) {
+    if (!ARGS_OK(c, frames, mask, n)) return LD_ERR_ARG;
+    if (n == 0) return LD_OK;
+    const PlanDev& d = c->plan->d;
     const int fpc = n >= 256 ? MASK_FPC : (n >= 128 ? 2 : 1);             // small batches: more, shorter CTAs (keep >= 3 waves)
     k_mask<<<dim3(d.n_tiles, (n + fpc - 1) / fpc), MASK_THREADS, c->plan->mask_smem, (cudaStream_t)stream>>>(frames, mask, d, n, fpc);
     return check_launch();
@@ -904,7 +909,7 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
 // touches the range only.  fin / fout = first frame of the RANGE.
 static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld_frame_fit* fit_out, void* state_out,
                          cudaStream_t s, int frame_offset, int search_first = 0, int skip_plain = 0, int fit_first = 0, int halo = 0,
-                         int look = 0, int look_check = 0) {
+                         int look = 0, int look_check = 0, int lat_continues = 0) {
     const PlanDev& d = c->plan->d;
     const size_t fb = (size_t)d.W * d.H * 3;
     const int nsub = sub_batches(M);
@@ -914,8 +919,10 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         // The latency-bound chain (search ->) fit -> raster (few resident warps, ~1 us/frame) runs on the high-priority stream; the
         // caller's stream meanwhile undistorts the tiles that depend on neither the fit nor the canvas (64 % of them), whose
         // CTAs fill the issue slots the chain leaves idle.  The overlay tiles follow the raster.
-        LD_CUDA(cudaEventRecord(c->ev_fork, s));
-        LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
+        if (!lat_continues) {                                            // (process_impl already runs the prepass on s_lat)
+            LD_CUDA(cudaEventRecord(c->ev_fork, s));
+            LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
+        }
         if (halo && c->halo_wait) {                                      // look-back records still on their way (ld_halo_arrives):
             LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_halo_in, 0));   // only the fit chain waits, the plain tiles start now
             c->halo_wait = 0;
@@ -985,6 +992,22 @@ static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, l
             if ((rc = ld_mask(c, frames + base * fb, M, c->mask, s))) return rc;
             if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
                                     frame_offset + base, 1))) return rc;
+            continue;
+        }
+        static int early = -1;                                          // LD_EARLY_PLAIN=0: the previous schedule (A/B measurements)
+        if (early < 0) { const char* e = getenv("LD_EARLY_PLAIN"); early = e ? atoi(e) : 1; }
+        if (early && c->plan->shared_ok && sub_batches(M) < 2) {
+            // The plain tiles (pure cv2.undistort, 59 % of the frame) depend on nothing: they start FIRST, on the caller's stream,
+            // and the whole dependent chain -- shared pass -> k_mask_b -> k_search -> fit -> raster -> blend -- runs on the
+            // high-priority stream.  The chain's full-machine kernels take the SMs as plain-tile CTAs retire; its latency-bound
+            // ones (k_mask_b, k_search, the fit kernels: 0.4 us/frame with most issue slots idle) leave room for the plain tiles,
+            // which before only overlapped the fit stage and then starved behind the raster and the blend.
+            LD_CUDA(cudaEventRecord(c->ev_fork, s));
+            LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
+            if ((rc = launch_frame_pass(c, frames + base * fb, M, out + base * fb, s, 0, 0, 5))) return rc;
+            if ((rc = prepass_impl(c, frames + base * fb, M, c->s_lat))) return rc;
+            if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
+                                    frame_offset + base, 0, 1, 0, 0, 0, 0, 1))) return rc;
             continue;
         }
         if ((rc = prepass_impl(c, frames + base * fb, M, s))) return rc;

@@ -115,11 +115,13 @@ class LaneEngine:
         _abi.check(self.lib, self.lib.ld_check(self._ctx_h, self._stream(), C.byref(bad)))
 
     # ------------------------------------------------------------------ hot path, stage by stage
-    def mask_dev(self, frames):
-        """undistort + warp + luv_lab_filter -> packed mask int32[n,H,W/32] (bit i of word k = pixel 32k+i)."""
+    def mask_dev(self, frames, fused=False):
+        """undistort + warp + luv_lab_filter -> packed mask int32[n,H,W/32] (bit i of word k = pixel 32k+i).
+        fused=True: the one-kernel route (ld_mask_fused) instead of the plan's default."""
         frames = self._frames(frames)
         out = self._dev((frames.shape[0], self.H, self.WW), self.torch.int32)
-        _abi.check(self.lib, self.lib.ld_mask(self._ctx_h, _ptr(frames), frames.shape[0], _ptr(out), self._stream()))
+        fn = self.lib.ld_mask_fused if fused else self.lib.ld_mask
+        _abi.check(self.lib, fn(self._ctx_h, _ptr(frames), frames.shape[0], _ptr(out), self._stream()))
         return out
 
     def hist_dev(self, mask):

@@ -522,7 +522,10 @@ def single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg):
 
     L, h, st = eng.lib, eng._ctx_h, eng._stream()
     mask_t = eng.mask_dev(frames)
-    time_stage("k_mask", lambda: L.ld_mask(h, frames.data_ptr(), n, mask_t.data_ptr(), st))
+    MK = "ld_mask (k_frame_pass_mf<4> mask-only pass + k_mask_b)"
+    time_stage(MK, lambda: L.ld_mask(h, frames.data_ptr(), n, mask_t.data_ptr(), st))
+    time_stage("k_frame_pass_mf<4> (mask-only pass)", lambda: L.ld_stage(h, 8, frames.data_ptr(), n, None, st))
+    time_stage("k_mask (ld_mask_fused: the one-kernel route)", lambda: L.ld_mask_fused(h, frames.data_ptr(), n, mask_t.data_ptr(), st))
     rec_t = eng.search_dev(mask_t)
     time_stage("k_search", lambda: L.ld_search(h, mask_t.data_ptr(), n, rec_t.data_ptr(), st))
     eng.reset()
@@ -547,7 +550,8 @@ def single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg):
                lambda: eng.grad_binary_dev(frames, eng.gray_dev(frames), s_thresh=(100, 255), sx_thresh=(20, 100), mag_thresh=(50, 255)), reps=3)
     eng.check()
     tile_px = 128 * 16
-    bytes_per_frame = {"k_mask": alg, "k_search": 115200 + 560, "k_raster": 722 * 82 * 8,
+    bytes_per_frame = {MK: alg, "k_mask (ld_mask_fused: the one-kernel route)": alg, "k_frame_pass_mf<4> (mask-only pass)": alg - 115200 + 43520,
+                       "k_search": 115200 + 560, "k_raster": 722 * 82 * 8,
                        "k_frame_pass_mf<1> (whole frame: ld_frame_pass / ld_overlay)": 2 * FRAME_BYTES,
                        SH: n_share * tile_px * (3 + 4) + 43520,          # source pixels read, u32 pixels + decision bits written
                        "k_mask_b": 43520 + 115200, PL: n_plain * tile_px * 6, TX: n_text * tile_px * 6,
@@ -576,9 +580,10 @@ def single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg):
     # the dominant launch of the step: the larger of the two big frame-pass launches
     dom = SH if stage[SH] >= stage[PL] else PL
     roofline = roof(dom, bytes_per_frame[dom], "k_frame_pass_shared_dram_bytes_per_frame" if dom == SH else "k_frame_pass_plain_dram_bytes_per_frame")
-    mask_roofline = roof("k_mask", alg, "k_mask_dram_bytes_per_frame")
-    mask_roofline["note"] = ("the fused mask kernel of ld_mask (north-star kernel 1), timed alone; inside ld_process_batch the mask comes "
-                             "from the shared pass + k_mask_b")
+    mask_roofline = roof(MK, alg, "ld_mask_dram_bytes_per_frame")
+    mask_roofline["note"] = ("the mask stage ld_mask (north-star kernel 1: undistort + warp + colour threshold -> packed mask), both of its "
+                             "launches timed together; algorithmic bytes = the source rows the warp samples + the packed mask; inside "
+                             "ld_process_batch the mask comes from the shared pass + k_mask_b")
     step_bytes = 6650880                                    # end-to-end device-resident algorithmic bytes per frame
     step_roofline = {"bound": "hbm", "achieved": step_bytes * n / (ms / a.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "algorithmic_bytes_per_frame": step_bytes}

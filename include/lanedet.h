@@ -133,6 +133,9 @@ int ld_ctx_destroy(ld_ctx* ctx);
 /* cv2.undistort + warp + luv_lab_filter (Project.py:294-295, 222-248) -> packed mask
  * u32[n][H][W/32], bit i of word k = pixel 32k+i. */
 int ld_mask(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint32_t* mask_dev, void* stream);
+/* The same stage as ONE kernel (k_mask: band boxes, bits in shared memory) whatever the plan; ld_mask uses it for plans the
+ * tile kernels do not serve (sizes other than 1280x720, general homographies).  Identical results. */
+int ld_mask_fused(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint32_t* mask_dev, void* stream);
 /* np.sum(image[top:bottom,:], axis=0) for the eight 90-row bands (Project.py:83) ->
  * u16[n][8][W], band k = rows [H-90(k+1), H-90k). */
 int ld_hist(ld_ctx* ctx, const uint32_t* mask_dev, int n, uint16_t* hist_dev, void* stream);

@@ -87,10 +87,12 @@ def test_mask_noise_and_extremes(engines):
     yellow[..., 0], yellow[..., 1] = 255, 220
     frames.append(yellow)
     frames = np.stack(frames)
-    masks = unpack(eng.mask_dev(eng.to_device(frames)))
+    dev = eng.to_device(frames)
+    masks = unpack(eng.mask_dev(dev))
     for i in range(len(frames)):
         want = O.binary_birdseye(O.undistort(frames[i], orc.mtx, orc.dist), orc.v)
         assert (masks[i] == want).all(), "frame %d differs in %d px" % (i, (masks[i] != want).sum())
+    assert (unpack(eng.mask_dev(dev, fused=True)) == masks).all()         # the one-kernel route (k_mask)
 
 
 def test_colour_decision_all_colours(engines):
@@ -304,7 +306,8 @@ def test_config5_independent_streams(engines, stills, golden):
 
 def test_shared_pass_equals_fused_kernels(engines, stills):
     """ld_process_batch takes the mask from the shared pass (k_frame_pass_mf<3> -> k_mask_b) and blends onto its pixels
-    (k_blend_px); ld_mask (fused k_mask) and ld_overlay (whole-frame k_frame_pass_mf<1>) must give the same bytes."""
+    (k_blend_px); ld_mask (mask-only tile pass k_frame_pass_mf<4> -> k_mask_b), ld_mask_fused (the one-kernel k_mask) and
+    ld_overlay (whole-frame k_frame_pass_mf<1>) must give the same bytes."""
     eng = engines("project")
     rng = np.random.default_rng(11)
     frames = np.stack([stills("test1"), stills("test5"), rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8),
@@ -316,7 +319,9 @@ def test_shared_pass_equals_fused_kernels(engines, stills):
         eng.check()
     except TypeError:
         pass                                                    # the noise / white frames have no lanes; masks and pixels still compare
-    assert (eng.context_masks(len(frames)) == eng.mask_dev(dev)).all()
+    ctx_masks = eng.context_masks(len(frames)).clone()
+    assert (ctx_masks == eng.mask_dev(dev)).all()
+    assert (ctx_masks == eng.mask_dev(dev, fused=True)).all()
     ok = eng.fits_to_numpy(fit_t)["status"] == 0
     assert ok.sum() >= 3
     assert (out_t[torch_idx(ok, out_t)] == eng.overlay_dev(dev, fit_t)[torch_idx(ok, out_t)]).all()
