@@ -552,8 +552,8 @@ extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, 
             const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
             int rc;
             if ((rc = launch_frame_pass(c, frames + (size_t)done * d.W * d.H * 3, m, nullptr, (cudaStream_t)stream, 0, 0, 8))) return rc;
-            k_mask_b<<<dim3(d.n_tiles, m), MASK_THREADS, (size_t)d.max_out_words * 2 + 16, (cudaStream_t)stream>>>(
-                c->und_bits, mask + (size_t)done * d.H * d.WW, d);
+            k_mask_b<<<dim3(d.n_tiles, (m + MASKB_FPC - 1) / MASKB_FPC), MASK_THREADS, 0, (cudaStream_t)stream>>>(
+                c->und_bits, mask + (size_t)done * d.H * d.WW, d, m);
             if ((rc = check_launch())) return rc;
         }
         return LD_OK;
@@ -815,7 +815,7 @@ extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint
         return launch_frame_pass(c, frames, n, out, s, 0, 0, which);
     }
     if (which == 7) {
-        k_mask_b<<<dim3(d.n_tiles, n), MASK_THREADS, (size_t)d.max_out_words * 2 + 16, s>>>(c->und_bits, c->mask, d);
+        k_mask_b<<<dim3(d.n_tiles, (n + MASKB_FPC - 1) / MASKB_FPC), MASK_THREADS, 0, s>>>(c->und_bits, c->mask, d, n);
         return check_launch();
     }
     if (which == 6) {
@@ -881,7 +881,7 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
             // mask out of the bit plane; the overlay later blends the canvas onto und_px instead of gathering again
             if ((rc = launch_frame_pass(c, fin, M, nullptr, s, 0, 0, 3))) return rc;
             tl_mark("shared pass", s);
-            k_mask_b<<<dim3(d.n_tiles, M), MASK_THREADS, (size_t)d.max_out_words * 2 + 16, s>>>(c->und_bits, c->mask, d);
+            k_mask_b<<<dim3(d.n_tiles, (M + MASKB_FPC - 1) / MASKB_FPC), MASK_THREADS, 0, s>>>(c->und_bits, c->mask, d, M);
             if ((rc = check_launch())) return rc;
             tl_mark("mask_b", s);
         } else if ((rc = ld_mask(c, fin, M, c->mask, s))) return rc;

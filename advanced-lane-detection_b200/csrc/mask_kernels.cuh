@@ -246,69 +246,88 @@ k_mask(const uint8_t* __restrict__ frames, uint32_t* __restrict__ mask, const Pl
 // Inside process_image the undistorted pixels under plan.share_y0 are computed ONCE (k_frame_pass_mf<3>,
 // overlay_kernels.cuh) for both the mask and the overlay; their colour decisions land in und_bits
 // (u32[n][H - share_y0][W/32]).  This kernel is k_mask's phase B over that plane: per OUTPUT WORD a 64-bit window
-// (plan.bdesc_g: first source bit as a global index) is cut out and expanded.  One CTA = one band of one frame.
+// (plan.bdesc_g: first source bit as a global index) is cut out and expanded.  One CTA = one band of MASKB_FPC frames: the
+// 16-byte descriptor of a word (460 KB for the whole frame, four times the mask itself) is fetched once for all of them and
+// their windows are loaded together.
+constexpr int MASKB_FPC = 4;                      // frames per CTA: a word's descriptor is fetched once for all of them
+constexpr int MASKB_JOBS = 4096;                  // job list entries (frame << 16 | word); beyond that a mixed word is expanded on the spot
+
+// one bird's-eye word from its 64-bit source window (lo, hi) by the descriptor's step bits
+__device__ __forceinline__ uint32_t expand_word(uint32_t lo, uint32_t hi, const uint4& d) {
+    uint32_t o = 0;
+    if (d.z == 0u) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            o = __funnelshift_r(o, lo, 1);                 // append source bit 0 at the top; after 32 steps bit i = pixel i
+            const uint32_t st = (d.y >> i) & 1u;
+            lo = __funnelshift_r(lo, hi, st);
+            hi >>= st;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            o = __funnelshift_r(o, lo, 1);
+            const uint32_t st = ((d.y >> i) & 1u) + ((d.z >> i) & 1u);
+            lo = __funnelshift_r(lo, hi, st);
+            hi >>= st;
+        }
+    }
+    return o & d.w;
+}
+
 __global__ void __launch_bounds__(MASK_THREADS)
-k_mask_b(const uint32_t* __restrict__ und_bits, uint32_t* __restrict__ mask, const PlanDev P) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+k_mask_b(const uint32_t* __restrict__ und_bits, uint32_t* __restrict__ mask, const PlanDev P, int n) {
+    __shared__ uint32_t s_job[MASKB_JOBS];
     __shared__ int n_jobs;
-    uint16_t* s_job = reinterpret_cast<uint16_t*>(smem_raw);
-    const int tile = blockIdx.x, f = blockIdx.y;
+    const int tile = blockIdx.x, f0 = blockIdx.y * MASKB_FPC, nf = min(MASKB_FPC, n - f0);
     const int4 t0 = P.tiles[2 * tile];
     const int y0 = t0.x, y1 = t0.y;
-    const uint32_t* bits = und_bits + (size_t)f * (P.H - P.share_y0) * P.WW;
+    const size_t bits_frame = (size_t)(P.H - P.share_y0) * P.WW, mask_frame = (size_t)P.H * P.WW;
+    const uint32_t* bits = und_bits + (size_t)f0 * bits_frame;
     if (threadIdx.x == 0) n_jobs = 0;
     __syncthreads();
     const int out_words = (y1 - y0) * P.WW;
-    uint32_t* out = mask + ((size_t)f * P.H + y0) * P.WW;
+    uint32_t* out = mask + (size_t)f0 * mask_frame + (size_t)y0 * P.WW;
     const uint4* bd = P.bdesc_g + (size_t)y0 * P.WW;
-#pragma unroll 2
     for (int wi = threadIdx.x; wi < out_words; wi += MASK_THREADS) {
         const uint4 d = __ldg(bd + wi);
-        uint32_t o = 0;
-        bool job = false;
-        if (d.x != BDESC_BORDER) {
-            const uint32_t* p = bits + (d.x >> 5);
-            const uint32_t sh = d.x & 31;
-            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-            uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-            const int span = __popc(d.y) + __popc(d.z) + 1;                          // source bits the word reads (<= 63)
-            const uint32_t mlo = span >= 32 ? 0xFFFFFFFFu : (1u << span) - 1u;
-            const uint32_t mhi = span <= 32 ? 0u : (1u << (span - 32)) - 1u;
-            lo &= mlo; hi &= mhi;
-            if ((lo | hi) == 0u) o = 0u;
-            else if (lo == mlo && hi == mhi) o = d.w;
-            else job = true;
+        if (d.x == BDESC_BORDER) {
+            for (int f = 0; f < nf; ++f) out[(size_t)f * mask_frame + wi] = 0u;
+            continue;
         }
-        if (job) s_job[atomicAdd(&n_jobs, 1)] = (uint16_t)wi;
-        else out[wi] = o;
-    }
-    __syncthreads();
-    const int nj = n_jobs;
-    for (int k = threadIdx.x; k < nj; k += MASK_THREADS) {
-        const int wi = s_job[k];
-        const uint4 d = __ldg(bd + wi);
         const uint32_t* p = bits + (d.x >> 5);
         const uint32_t sh = d.x & 31;
-        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh), o = 0;
-        if (d.z == 0u) {
+        const int span = __popc(d.y) + __popc(d.z) + 1;                              // source bits the word reads (<= 63)
+        const uint32_t mlo = span >= 32 ? 0xFFFFFFFFu : (1u << span) - 1u;
+        const uint32_t mhi = span <= 32 ? 0u : (1u << (span - 32)) - 1u;
+        uint32_t w0[MASKB_FPC], w1[MASKB_FPC], w2[MASKB_FPC];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                o = __funnelshift_r(o, lo, 1);             // append source bit 0 at the top; after 32 steps bit i = pixel i
-                const uint32_t st = (d.y >> i) & 1u;
-                lo = __funnelshift_r(lo, hi, st);
-                hi >>= st;
-            }
-        } else {
+        for (int f = 0; f < MASKB_FPC; ++f) {                                         // all frames' windows in flight together
+            const bool in = f < nf;
+            w0[f] = in ? __ldg(p + f * bits_frame) : 0u; w1[f] = in ? __ldg(p + f * bits_frame + 1) : 0u; w2[f] = in ? __ldg(p + f * bits_frame + 2) : 0u;
+        }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                o = __funnelshift_r(o, lo, 1);
-                const uint32_t st = ((d.y >> i) & 1u) + ((d.z >> i) & 1u);
-                lo = __funnelshift_r(lo, hi, st);
-                hi >>= st;
+        for (int f = 0; f < MASKB_FPC; ++f) {
+            if (f >= nf) break;
+            const uint32_t lo = __funnelshift_r(w0[f], w1[f], sh) & mlo, hi = __funnelshift_r(w1[f], w2[f], sh) & mhi;
+            if ((lo | hi) == 0u) out[(size_t)f * mask_frame + wi] = 0u;
+            else if (lo == mlo && hi == mhi) out[(size_t)f * mask_frame + wi] = d.w;
+            else {                                                                    // mixed window: bit-serial expansion, compacted
+                const int slot = atomicAdd(&n_jobs, 1);
+                if (slot < MASKB_JOBS) s_job[slot] = ((uint32_t)f << 16) | (uint32_t)wi;
+                else out[(size_t)f * mask_frame + wi] = expand_word(lo, hi, d);
             }
         }
-        out[wi] = o & d.w;
+    }
+    __syncthreads();
+    const int nj = min(n_jobs, (int)MASKB_JOBS);
+    for (int k = threadIdx.x; k < nj; k += MASK_THREADS) {
+        const int wi = s_job[k] & 0xFFFF, f = s_job[k] >> 16;
+        const uint4 d = __ldg(bd + wi);
+        const uint32_t* p = bits + (size_t)f * bits_frame + (d.x >> 5);
+        const uint32_t sh = d.x & 31;
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        out[(size_t)f * mask_frame + wi] = expand_word(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), d);
     }
 }
 

@@ -18,6 +18,9 @@
 namespace lanedet {
 
 constexpr int RASTER_THREADS = 256;
+#ifndef LD_RASTER_OCC
+#define LD_RASTER_OCC 4                          // CTAs per SM k_raster is compiled for (register cap 64)
+#endif
 constexpr int RASTER_BAND = 90;                 // canvas rows per CTA (8 bands of a 720-row frame)
 constexpr int MAX_VERTS = 2 * 724;
 constexpr int RASTER_CW = 2 * (1280 / 32) + 2;  // canvas entries per row; the raster is hard-wired to 1280x720 like the reference's windows
@@ -202,7 +205,7 @@ k_raster_prep(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ 
 // red = red without green; rows 0 and H+1 stay zero);
 // text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  The vertices and the prepared long segments come from
 // k_raster_prep; every CTA draws only the primitives whose rows can touch its band, expensive ones one per warp.
-__global__ void __launch_bounds__(RASTER_THREADS, 4)
+__global__ void __launch_bounds__(RASTER_THREADS, LD_RASTER_OCC)
 k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ prep, int thickness, uint32_t* __restrict__ planes,
          uint32_t* __restrict__ text, const PlanDev P, int* __restrict__ poly_error) {
     extern __shared__ uint32_t smem[];
