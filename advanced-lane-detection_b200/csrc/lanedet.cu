@@ -58,6 +58,7 @@ struct ld_plan {
     const int32_t* share_tiles; const int32_t* text_tiles; const int32_t* plain_top_tiles;   // plain_top = plain tiles above share_y0
     const int32_t* mask_tiles;                                          // share tiles with a pixel the bird's-eye warp samples (ld_mask)
     int n_share, n_text, n_plain_top, n_mask_tiles, shared_ok;
+    int mask_ok;               // ld_mask can take its tile route (k_frame_pass_mf<4> + k_mask_b): any size with W % 128 == 0
 };
 
 enum { HOST_CHUNK = 32, PIPE_SUB = 8, HALO_MAX = 32 };               // HALO_MAX: look-back records a sharded rank may put in front of its range
@@ -298,7 +299,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         uint32_t* g = new (std::nothrow) uint32_t[nw * 4];
         if (!g) { ld_plan_destroy(p); return LD_ERR_ARG; }
         memcpy(g, desc->bdesc, nw * 16);
-        bool ok = W == 1280 && H == 720 && p->n_share > 0;
+        bool ok = W % 128 == 0 && p->n_share > 0;                        // (the shared pass itself also needs 1280x720: the raster is hard-wired)
         for (int t = 0; t < desc->n_tiles; ++t) {
             const int y0 = desc->tiles[8 * t], y1 = desc->tiles[8 * t + 1], u0 = desc->tiles[8 * t + 2], v0 = desc->tiles[8 * t + 3];
             const int pitch = desc->tiles[8 * t + 4] * 32;
@@ -345,7 +346,8 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
         delete[] mt;
         delete[] sg;
         if (rc) { ld_plan_destroy(p); return rc; }
-        p->shared_ok = ok ? 1 : 0;
+        p->mask_ok = ok ? 1 : 0;
+        p->shared_ok = (ok && W == 1280 && H == 720) ? 1 : 0;
     }
     int mow = 0;
     for (int t = 0; t < desc->n_tiles; ++t) {
@@ -429,10 +431,8 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     CTX_ALLOC(c->planes, canvas_words(d) * 4 * max_frames);
     CTX_ALLOC(c->text, (size_t)LD_TEXT_ROWS * LD_TEXT_WORDS * 4 * max_frames);
     CTX_ALLOC(c->prep, sizeof(RasterPrep) * (size_t)max_frames);
-    if (plan->shared_ok) {
-        CTX_ALLOC(c->und_bits, (size_t)(d.H - d.share_y0) * d.WW * 4 * max_frames + 64);
-        CTX_ALLOC(c->und_px, (size_t)plan->n_share * 16 * 128 * 4 * max_frames);
-    }
+    if (plan->mask_ok) CTX_ALLOC(c->und_bits, (size_t)(d.H - d.share_y0) * d.WW * 4 * max_frames + 64);
+    if (plan->shared_ok) CTX_ALLOC(c->und_px, (size_t)plan->n_share * 16 * 128 * 4 * max_frames);
     CTX_ALLOC(c->state, sizeof(TrackState));
     CTX_ALLOC(c->fb_state, (size_t)2 * (max_frames + HALO_MAX));
     CTX_ALLOC(c->fb_list, sizeof(int) * 2 * (max_frames + HALO_MAX));
@@ -544,8 +544,8 @@ extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, 
     if (!ARGS_OK(c, frames, mask, n)) return LD_ERR_ARG;
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
-    if (c->plan->shared_ok && !((uintptr_t)frames & 15)) {
-        // 1280x720 plans: the frame pass's multi-frame tile kernel in its mask-only form (per-tile constants in registers, one
+    if (c->plan->mask_ok && !((uintptr_t)frames & 15)) {
+        // plans whose width is a multiple of the 128-pixel tiles (1280x720, 4K): the frame pass's multi-frame tile kernel in its mask-only form (per-tile constants in registers, one
         // tensor-map TMA copy per tile and frame, only the 32-pixel groups the bird's-eye warp samples are gathered) writes the
         // colour bits of the undistorted pixels; k_mask_b cuts the bird's-eye words out of them
         for (int done = 0; done < n; done += c->max_frames) {
@@ -575,7 +575,9 @@ extern "C" int ld_hist(ld_ctx* c, const uint32_t* mask, int n, uint16_t* hist, v
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
     const int band_h = d.H / 8;                                 // 90 rows at H = 720 (Project.py:78-79)
-    k_hist<<<dim3(8, n), HIST_THREADS, 0, (cudaStream_t)stream>>>(mask, hist, d.W, d.H, d.WW, band_h, 8);
+    if (band_h > HIST_MAX_BAND || ((uintptr_t)hist & 15)) return LD_ERR_ARG;
+    const long long tasks = (long long)n * 8 * d.WW;
+    k_hist<<<(unsigned)((tasks + HIST_THREADS - 1) / HIST_THREADS), HIST_THREADS, 0, (cudaStream_t)stream>>>(mask, hist, d.W, d.H, d.WW, band_h, 8, n);
     return check_launch();
 }
 

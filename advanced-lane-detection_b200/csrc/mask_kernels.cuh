@@ -332,29 +332,49 @@ k_mask_b(const uint32_t* __restrict__ und_bits, uint32_t* __restrict__ mask, con
 }
 
 // ============================ K2: column histogram of the eight 90-row bands ========================
-// np.sum(image[win_top:win_bottom, :], axis=0) (Project.py:83).  A warp owns a 32-column word
-// column of one band: lane r holds the mask word of row r, bit b of all 32 rows is gathered with
-// one __ballot_sync and counted with __popc; lane b keeps column b's count.
-constexpr int HIST_THREADS = 320;   // 10 warps x 4 word-columns = 40 words (W = 1280); loops otherwise
+// np.sum(image[win_top:win_bottom, :], axis=0) (Project.py:83).  ONE thread owns a 32-column word column of one band and
+// adds its rows bit-parallel into nine bit planes (a ripple-carry counter per column, 32 columns per integer operation:
+// the scheme of k_search's histograms, search_math.h, with two more planes so that the 270-row bands of a 4K frame fit);
+// the 32 counts are then read out of the planes and stored as 64 contiguous bytes.  (The warp-ballot transpose this replaced
+// spent 3 instructions per row AND column: 0.48 us/frame, 4 % of the HBM roofline.)
+constexpr int HIST_THREADS = 128;
+constexpr int HIST_MAX_BAND = 511;  // rows per band the nine planes can count
 
 __global__ void __launch_bounds__(HIST_THREADS)
-k_hist(const uint32_t* __restrict__ mask, uint16_t* __restrict__ hist, int W, int H, int WW, int band_h, int n_bands) {
-    const int band = blockIdx.x, f = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = HIST_THREADS / 32;
+k_hist(const uint32_t* __restrict__ mask, uint16_t* __restrict__ hist, int W, int H, int WW, int band_h, int n_bands, int n) {
+    const int task = blockIdx.x * HIST_THREADS + threadIdx.x;           // (frame, band, word column)
+    if (task >= n * n_bands * WW) return;
+    const int wc = task % WW, fb = task / WW, band = fb % n_bands, f = fb / n_bands;
     const int top = H - band_h * (band + 1);
-    const uint32_t* m = mask + (size_t)f * H * WW;
-    for (int wc = warp; wc < WW; wc += nwarp) {
-        uint32_t count = 0;
-        for (int r0 = 0; r0 < band_h; r0 += 32) {
-            const int r = r0 + lane;
-            const uint32_t word = (r < band_h) ? __ldg(m + (size_t)(top + r) * WW + wc) : 0u;
+    const uint32_t* m = mask + ((size_t)f * H + top) * WW + wc;
+    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, p8 = 0;
+#pragma unroll 6
+    for (int r = 0; r < band_h; ++r) {
+        uint32_t c = __ldg(m + (size_t)r * WW), t;
+        t = p0 & c; p0 ^= c; c = t;
+        t = p1 & c; p1 ^= c; c = t;
+        t = p2 & c; p2 ^= c; c = t;
+        t = p3 & c; p3 ^= c; c = t;
+        t = p4 & c; p4 ^= c; c = t;
+        t = p5 & c; p5 ^= c; c = t;
+        t = p6 & c; p6 ^= c; c = t;
+        t = p7 & c; p7 ^= c; c = t;
+        p8 ^= c;
+    }
+    uint4* out = reinterpret_cast<uint4*>(hist + ((size_t)f * n_bands + band) * W + wc * 32);   // W % 32 == 0: 64-byte aligned
 #pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                const uint32_t col = __ballot_sync(0xffffffffu, (word >> b) & 1u);
-                if (lane == b) count += __popc(col);
-            }
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int b = 8 * q + 2 * jj;                               // columns 32 wc + b, + b + 1
+            uint32_t lo = 0, hi = 0;
+            const uint32_t pl[9] = {p0, p1, p2, p3, p4, p5, p6, p7, p8};
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { lo |= ((pl[k] >> b) & 1u) << k; hi |= ((pl[k] >> (b + 1)) & 1u) << k; }
+            w[jj] = lo | (hi << 16);
         }
-        hist[((size_t)f * n_bands + band) * W + wc * 32 + lane] = (uint16_t)count;
+        out[q] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 

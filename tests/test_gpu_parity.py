@@ -266,7 +266,9 @@ def test_config4_4k_mask_and_histogram():
     from conftest import read_still
     up = np.repeat(np.repeat(read_still("test1"), k, axis=0), k, axis=1)          # nearest-upscaled still
     frames = np.stack([noise, up])
-    mask_t = eng.mask_dev(eng.to_device(frames))
+    dev = eng.to_device(frames)
+    mask_t = eng.mask_dev(dev)                                                     # tile route (3840 = 30 x 128)
+    assert (eng.mask_dev(dev, fused=True) == mask_t).all()                         # the one-kernel route
     masks = unpack(mask_t)
     hist = eng.hist_dev(mask_t).cpu().numpy().astype(np.int64)
     M = cv2.getPerspectiveTransform(np.float32(v.src), np.float32(v.dst))
