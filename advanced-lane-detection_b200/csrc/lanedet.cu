@@ -359,7 +359,7 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     d.mask_box_bytes = (int)((ms + 127) / 128 * 128);
     p->mask_smem = (((size_t)mb + 4) * 4 + (size_t)mow * 2 + 15) / 16 * 16 + MASK_PRE_WORDS * 4 + 2 * (size_t)d.mask_box_bytes + 32;
     p->search_smem = (size_t)H * d.WW * 4 + (size_t)9 * W * 2;
-    p->raster_smem = (size_t)2 * RASTER_BAND * d.WW * 4 + sizeof(RasterShared);   // interleaved band canvas (the text plane, 6.7 KB, aliases it) + lists
+    p->raster_smem = (size_t)RASTER_CANVAS_WORDS * 4 + sizeof(RasterShared);   // interleaved band canvas (the text plane, 6.7 KB, aliases it) + lists
     // The opt-in limit is a per-function, per-device attribute shared by every plan: always raise it to
     // the fixed upper bound of the kernel, never to this plan's own (possibly smaller) need.
     if (p->mask_smem > 220 * 1024 || mow > 65535) { ld_plan_destroy(p); return LD_ERR_ARG; }

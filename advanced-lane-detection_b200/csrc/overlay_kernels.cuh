@@ -24,6 +24,11 @@ constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_BAND = 90;                 // canvas rows per CTA (8 bands of a 720-row frame)
 constexpr int MAX_VERTS = 2 * 724;
 constexpr int RASTER_CW = 2 * (1280 / 32) + 2;  // canvas entries per row; the raster is hard-wired to 1280x720 like the reference's windows
+// Shared-memory row pitch of the band canvas in words: 2 WW + 1, ODD.  The primitives are drawn with lanes = rows, so a warp's
+// atomicOr's hit the same word column of up to 32 different rows; with the natural pitch of 80 words those fall on two banks
+// (16-way conflicts: 64 % of the kernel's shared-memory wavefronts were conflicts), with an odd pitch on 32.
+constexpr int RASTER_ROW_WORDS = 2 * (1280 / 32) + 1;
+constexpr int RASTER_CANVAS_WORDS = (RASTER_BAND * RASTER_ROW_WORDS + 3) & ~3;   // the lists behind it stay 16-byte aligned
 constexpr int RASTER_BIG_ROUND = 4;             // long segments set up per round (one thread each)
 
 #ifdef LD_RASTER_PROF
@@ -210,14 +215,14 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
          uint32_t* __restrict__ text, const PlanDev P, int* __restrict__ poly_error) {
     extern __shared__ uint32_t smem[];
     const int W = P.W, H = P.H, WW = P.WW;
-    uint32_t* s_canvas = smem;                                          // [RASTER_BAND][2 WW] interleaved (BandPlotter)
+    uint32_t* s_canvas = smem;                                          // [RASTER_BAND][RASTER_ROW_WORDS] interleaved (BandPlotter)
     uint32_t* s_text = smem;                                            // TEXT_ROWS*TEXT_WORDS: band 0, after the canvas is stored
-    RasterShared& R = *reinterpret_cast<RasterShared*>(smem + 2 * RASTER_BAND * WW);
+    RasterShared& R = *reinterpret_cast<RasterShared*>(smem + RASTER_CANVAS_WORDS);
     const int f = blockIdx.y, band = blockIdx.x;
     const int y_lo = band * RASTER_BAND, y_hi = min(H, y_lo + RASTER_BAND);
     constexpr int CW = RASTER_CW;                                       // padded, interleaved canvas: 64-bit entries per row (canvas_codes)
     uint2* out_planes = reinterpret_cast<uint2*>(planes) + ((size_t)f * (H + 2) + y_lo + 1) * CW;
-    BandPlotter red{s_canvas, 0x55555555u, 2 * WW, W, y_lo, y_hi}, green{s_canvas, 0xAAAAAAAAu, 2 * WW, W, y_lo, y_hi};
+    BandPlotter red{s_canvas, 0x55555555u, RASTER_ROW_WORDS, W, y_lo, y_hi}, green{s_canvas, 0xAAAAAAAAu, RASTER_ROW_WORDS, W, y_lo, y_hi};
     const int tid = threadIdx.x;
     const RasterPrep& Q = prep[f];
 
@@ -227,7 +232,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
     for (int i = tid; i < nv; i += RASTER_THREADS) { R.vx[i] = Q.vx[i]; R.vy[i] = Q.vy[i]; }     // issued first: their latency hides behind the clear
     for (int i = tid; i < (int)(sizeof(StampTable) / 8); i += RASTER_THREADS)
         reinterpret_cast<unsigned long long*>(&R.st)[i] = __ldg(static_cast<const unsigned long long*>(P.stamps) + i);
-    for (int i = tid; i < 2 * RASTER_BAND * WW; i += RASTER_THREADS) s_canvas[i] = 0;
+    for (int i = tid; i < RASTER_BAND * RASTER_ROW_WORDS; i += RASTER_THREADS) s_canvas[i] = 0;
     for (int i = tid; i < RASTER_BAND; i += RASTER_THREADS) R.cnt[i] = 0;
     const int radius = min(thickness / 2, 15);
     if (tid == 0) {
@@ -347,7 +352,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
         // entry e of a row = the 32 pixels [16e - 16, 16e + 16) = interleaved words e - 1 and e, zero outside the frame: the two
         // horizontally adjacent taps of any sample (including (-1, 0) and (W - 1, W)) are four consecutive bits of one entry
         const int row = i / CW, e = i - row * CW;
-        const uint32_t* sc = s_canvas + row * (2 * WW);
+        const uint32_t* sc = s_canvas + row * RASTER_ROW_WORDS;
         const uint32_t a = (e >= 1 && e <= 2 * WW) ? sc[e - 1] : 0u, b = e < 2 * WW ? sc[e] : 0u;
         const uint32_t ga = a & 0xAAAAAAAAu, gb = b & 0xAAAAAAAAu;       // (red without green, green)
         out_planes[i] = make_uint2((a & 0x55555555u & ~(ga >> 1)) | ga, (b & 0x55555555u & ~(gb >> 1)) | gb);
