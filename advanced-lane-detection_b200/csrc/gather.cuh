@@ -86,8 +86,12 @@ __device__ __forceinline__ void bilinear_acc(uint32_t a, uint32_t stride, uint32
 #else
     asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(q2) : "r"(a2));
 #endif
+#ifdef LD_EXP_NOSHF                                                  // timing experiment only (wrong pixels): the funnel shifts off the ALU pipe
+    const uint32_t lt = p0 * sh + p1, ht = p1 * sh + p2, lb = q0 * sh + q1, hb = q1 * sh + q2;
+#else
     const uint32_t lt = __funnelshift_r(p0, p1, sh), ht = __funnelshift_r(p1, p2, sh);   // r0 g0 b0 r1 | g1 b1 . .
     const uint32_t lb = __funnelshift_r(q0, q1, sh), hb = __funnelshift_r(q1, q2, sh);
+#endif
     const uint32_t R = __byte_perm(lt, lb, 0x7430);                     // r00 r01 r10 r11
     const uint32_t GBt = __byte_perm(lt, ht, 0x5241), GBb = __byte_perm(lb, hb, 0x5241);   // g0 g1 b0 b1
     r = __dp2a_lo(wx, R, 32768u);

@@ -734,7 +734,12 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
         k_blend_pass<<<dim3(d.n_frame_tiles, m), FRAME_THREADS, 0, s>>>(fin, planes, fout, d);
     else
     {
-        const int fpc = frames_per_cta(m);
+        int fpc = frames_per_cta(m);
+        if (which == 5) {                                                // LD_FPC_PLAIN: frames per CTA of the plain-tile launch (tuning knob)
+            static int plain_fpc = -1;
+            if (plain_fpc < 0) { const char* e = getenv("LD_FPC_PLAIN"); plain_fpc = e ? atoi(e) : 0; }
+            if (plain_fpc > 0 && plain_fpc < fpc) fpc = plain_fpc;
+        }
         CUtensorMap tm;
         int rc;
         if ((rc = frame_tensor_map(c->plan, fin, m, &tm))) return rc;
