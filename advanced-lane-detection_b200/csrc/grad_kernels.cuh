@@ -9,7 +9,8 @@
 //     IEEE round-to-nearest like numpy's, then truncation; the two maxima are per IMAGE -> a reduction pass first;
 //   * dir_bin is identically 1 (arctan2 of two absolute values lies in [0, pi/2], the thresholds of helper.py:86);
 //   * `(s) | ((mag & dir) | abs_bin == 1)` parses as s | ((mag | abs_bin) == 1)  (helper.py:103) = s | mag | abs;
-//   * the HLS S channel of cv2's 8-bit RGB2HLS is a function of the colour only: a 16 MiB table built once from cv2.
+//   * the HLS S channel of cv2's 8-bit RGB2HLS is a function of the colour's largest and smallest channel only: a 64 KB table
+//     (max << 8 | min) collapsed from cv2's output for all 2^24 colours (plan.hls_s_minmax_table).
 #pragma once
 #include "common.cuh"
 
@@ -77,14 +78,15 @@ k_sobel_max(const uint8_t* __restrict__ gray, uint32_t* __restrict__ mx, int W, 
     const uint8_t* g = gray + (size_t)f * npix;
     uint32_t ma = 0, mm = 0;
     const int qw = W / 4;                                               // W % 4 == 0 (plans require W % 32 == 0)
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npix / 4; q += gridDim.x * blockDim.x) {
-        const Sobel4 sb = sobel4_at(g, W, H, (q % qw) * 4, q / qw);
+    for (int y = blockIdx.x; y < H; y += gridDim.x)                     // rows dealt to the CTAs, quads of a row to the threads: no index division
+        for (int xq = threadIdx.x; xq < qw; xq += blockDim.x) {
+            const Sobel4 sb = sobel4_at(g, W, H, xq * 4, y);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            ma = max(ma, (uint32_t)abs(sb.sx[k]));
-            mm = max(mm, (uint32_t)(sb.sx[k] * sb.sx[k] + sb.sy[k] * sb.sy[k]));
+            for (int k = 0; k < 4; ++k) {
+                ma = max(ma, (uint32_t)abs(sb.sx[k]));
+                mm = max(mm, (uint32_t)(sb.sx[k] * sb.sx[k] + sb.sy[k] * sb.sy[k]));
+            }
         }
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ma = max(ma, __shfl_xor_sync(0xffffffffu, ma, o));
@@ -99,19 +101,26 @@ __global__ void __launch_bounds__(256)
 k_grad_binary(const uint8_t* __restrict__ img, const uint8_t* __restrict__ gray, const uint32_t* __restrict__ mx,
               const uint8_t* __restrict__ s_table, int s_lo, int s_hi, int sx_lo, int sx_hi, int use_mag, int mag_lo, int mag_hi,
               uint8_t* __restrict__ out, int W, int H) {
-    const int f = blockIdx.y, npix = W * H, qw = W / 4;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;                // four pixels per thread
-    if (q >= npix / 4) return;
-    const Sobel4 sb = sobel4_at(gray + (size_t)f * npix, W, H, (q % qw) * 4, q / qw);
+    const int f = blockIdx.z, y = blockIdx.y, npix = W * H, qw = W / 4;
+    const int xq = blockIdx.x * blockDim.x + threadIdx.x;               // four pixels per thread; grid = (quads of a row, rows, frames)
+    if (xq >= qw) return;
+    const int q = y * qw + xq;
+    const Sobel4 sb = sobel4_at(gray + (size_t)f * npix, W, H, xq * 4, y);
     const uint32_t max_abs = __ldg(mx + 2 * f), max_m2 = __ldg(mx + 2 * f + 1);
-    uint32_t rgb[4] = {0u, 0u, 0u, 0u};
+    // np.uint8(255 * abs_sobelx / np.max(abs_sobelx)) in [sx_lo, sx_hi] without the division: floor(255 a / M) >= lo  <=>
+    // 255 a >= lo M, and floor(255 a / M) <= hi  <=>  255 a < (hi + 1) M  (integers; 255 a <= 260,100)
+    const int lo_c = max(sx_lo, 0), hi_c = min(sx_hi, 255);
+    const uint32_t abs_lo = (uint32_t)lo_c * max_abs, abs_hi = (uint32_t)(hi_c + 1) * max_abs;
+    const bool abs_any = sx_lo <= sx_hi && hi_c >= lo_c;
+    uint32_t mm[4] = {0u, 0u, 0u, 0u};                                  // max << 8 | min of the pixel's channels: the S table's index
     if (s_table) {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(img + ((size_t)f * npix + 4 * (size_t)q) * 3);
         const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);   // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
-        rgb[0] = ((a & 255u) << 16) | (a & 0xFF00u) | ((a >> 16) & 255u);                                  // r << 16 | g << 8 | b
-        rgb[1] = ((a >> 24) << 16) | ((b & 255u) << 8) | ((b >> 8) & 255u);
-        rgb[2] = (((b >> 16) & 255u) << 16) | ((b >> 24) << 8) | (c & 255u);
-        rgb[3] = (((c >> 8) & 255u) << 16) | (((c >> 16) & 255u) << 8) | (c >> 24);
+        const uint32_t ch[4][3] = {{a & 255u, (a >> 8) & 255u, (a >> 16) & 255u}, {a >> 24, b & 255u, (b >> 8) & 255u},
+                                   {(b >> 16) & 255u, b >> 24, c & 255u}, {(c >> 8) & 255u, (c >> 16) & 255u, c >> 24}};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            mm[k] = (max(max(ch[k][0], ch[k][1]), ch[k][2]) << 8) | min(min(ch[k][0], ch[k][1]), ch[k][2]);
     }
     uint32_t packed = 0;
 #pragma unroll
@@ -120,8 +129,8 @@ k_grad_binary(const uint8_t* __restrict__ img, const uint8_t* __restrict__ gray,
         // np.uint8(255 * abs_sobelx / np.max(abs_sobelx))   (helper.py:68).  The exact quotient 255 a / max is a fraction with a
         // denominator <= 1020: when it is not an integer it is at least 1/1020 away from one, far more than float64 rounding can
         // bridge, so truncating the float64 quotient equals the integer division.  A flat image (0/0 = nan) casts to 0.
-        const int scaled = max_abs ? (int)((255u * (uint32_t)abs(sx)) / max_abs) : 0;
-        bool on = scaled >= sx_lo && scaled <= sx_hi;
+        const uint32_t a255 = 255u * (uint32_t)abs(sx);
+        bool on = max_abs ? (abs_any && a255 >= abs_lo && a255 < abs_hi) : (0 >= sx_lo && 0 <= sx_hi);
         if (use_mag) {
             // gradmag = np.sqrt(sobelx**2 + sobely**2); (gradmag / (np.max(gradmag) / 255)).astype(np.uint8)   (helper.py:76-80).
             // v = 255 sqrt(m2 / M2): gm >= k  <=>  65025 m2 >= k^2 M2 unless the two sides are EQUAL (v is exactly the integer k;
@@ -138,7 +147,7 @@ k_grad_binary(const uint8_t* __restrict__ img, const uint8_t* __restrict__ gray,
             on = on || mag_on;
         }
         if (s_table) {
-            const int sv = __ldg(s_table + rgb[k]);
+            const int sv = __ldg(s_table + mm[k]);
             on = on || (sv >= s_lo && sv <= s_hi);
         }
         packed |= (on ? 1u : 0u) << (8 * k);

@@ -1308,7 +1308,7 @@ extern "C" int ld_grad_binary(ld_ctx* c, const uint8_t* img, const uint8_t* gray
     if (n == 0) return LD_OK;
     const PlanDev& d = c->plan->d;
     if (((uintptr_t)gray | (uintptr_t)out | (uintptr_t)img) & 3) return LD_ERR_ARG;   // word loads / stores
-    k_grad_binary<<<dim3((d.W * d.H / 4 + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(img, gray, maxima, s_table, s_lo, s_hi, sx_lo, sx_hi,
+    k_grad_binary<<<dim3((d.W / 4 + 127) / 128, d.H, n), 128, 0, (cudaStream_t)stream>>>(img, gray, maxima, s_table, s_lo, s_hi, sx_lo, sx_hi,
                                                                                      use_mag ? 1 : 0, mag_lo, mag_hi, out, d.W, d.H);
     return check_launch();
 }

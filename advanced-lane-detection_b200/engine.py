@@ -452,8 +452,8 @@ class LaneEngine:
     # ------------------------------------------------------------------ helper.py gradient / HLS / RGB thresholds
     def _s_table_dev(self):
         if getattr(self, "_s_table", None) is None:
-            from .plan import hls_s_table
-            self._s_table = self.torch.from_numpy(hls_s_table()).to("cuda:%d" % self.device)
+            from .plan import hls_s_minmax_table
+            self._s_table = self.torch.from_numpy(hls_s_minmax_table()).to("cuda:%d" % self.device)
         return self._s_table
 
     def gray_dev(self, img, warped=False):

@@ -227,6 +227,17 @@ def hls_s_table() -> np.ndarray:
     return np.ascontiguousarray(cv2.cvtColor(img, cv2.COLOR_RGB2HLS)[..., 2].reshape(-1))
 
 
+@functools.lru_cache(maxsize=1)
+def hls_s_minmax_table() -> np.ndarray:
+    """u8[65536]: the same S channel indexed by (max << 8 | min) of the colour's three channels.  cv2's 8-bit RGB2HLS computes
+    S from vmax and vmin alone (s = diff / (vmax + vmin) or diff / (2 - vmax - vmin), float32), so the 16 MiB table collapses
+    to 64 KB that stays in L1; tests/test_grad_thresholds.py checks the collapse against all 2^24 colours."""
+    tab = hls_s_table().reshape(256, 256, 256)
+    mx, mn = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    out = tab[mx, np.minimum(mx, mn), np.minimum(mx, mn)]                          # the colour (max, min, min); entries with min > max are unused
+    return np.ascontiguousarray(out.reshape(-1))
+
+
 @functools.lru_cache(maxsize=8)
 def colour_prefilter(l_thresh: Tuple[int, int], b_thresh: Tuple[int, int]) -> np.ndarray:
     """Coarse form of the same decision: RGB space cut into 32^3 cells of 8x8x8 colours, two bits per cell

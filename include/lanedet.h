@@ -277,8 +277,9 @@ int ld_draw(ld_ctx* ctx, const uint8_t* undist_dev, const int32_t* verts_dev, co
 int ld_gray(ld_ctx* ctx, const uint8_t* img_dev, int n, int warped, uint8_t* gray_dev, void* stream);
 /* per image: max |Sobel_x| and max (Sobel_x^2 + Sobel_y^2) of a gray image (helper.py:64-68, :76-78) -> u32[n][2] */
 int ld_sobel_max(ld_ctx* ctx, const uint8_t* gray_dev, int n, uint32_t* maxima_dev, void* stream);
-/* img2binary's combined binary (helper.py:50-105: use_mag = 1, s_table_dev = cv2's 8-bit HLS S channel of every colour,
- * u8[1<<24] indexed r<<16|g<<8|b) or sobelx_filter's abs_bin (helper.py:108-122: use_mag = 0, s_table_dev = NULL)
+/* img2binary's combined binary (helper.py:50-105: use_mag = 1, s_table_dev = cv2's 8-bit HLS S channel as a function of the
+ * colour's largest and smallest channel, u8[1<<16] indexed max<<8|min) or sobelx_filter's abs_bin (helper.py:108-122:
+ * use_mag = 0, s_table_dev = NULL)
  * -> u8[n][H][W] in {0,1}.  img_dev = the RGB frames (only read for the S channel). */
 int ld_grad_binary(ld_ctx* ctx, const uint8_t* img_dev, const uint8_t* gray_dev, const uint32_t* maxima_dev, int n,
                    const uint8_t* s_table_dev, int s_lo, int s_hi, int sx_lo, int sx_hi, int use_mag, int mag_lo, int mag_hi,

@@ -63,6 +63,12 @@ def test_kernel_arithmetic_against_cv2(stills):
     tab = plan.hls_s_table()
     idx = (und[..., 0].astype(np.int64) << 16) | (und[..., 1].astype(np.int64) << 8) | und[..., 2]
     assert (tab[idx] == cv2.cvtColor(und, cv2.COLOR_RGB2HLS)[..., 2]).all()
+    # ... and of its largest and smallest channel alone: the 64 KB table the kernel reads reproduces all 2^24 entries
+    mm = plan.hls_s_minmax_table()
+    c = np.arange(1 << 24, dtype=np.uint32)
+    r, g, b = (c >> 16) & 255, (c >> 8) & 255, c & 255
+    key = (np.maximum(np.maximum(r, g), b) << 8) | np.minimum(np.minimum(r, g), b)
+    assert (mm[key] == tab).all()
 
 
 @pytest.mark.gpu
