@@ -57,8 +57,9 @@ typedef struct ld_plan_desc {
     const int32_t* near_map;         /* [H*W]   INTER_NEAREST source index of warp(), -1 = border */
     const int32_t* tiles;            /* [n_tiles*8] mask-kernel bands */
     const uint16_t* bmap;            /* [H*W]   bird's-eye pixel -> bit of its band's box */
-    const uint32_t* ctab;            /* [65536] colour decision, <=2 B-intervals per (R,G) */
-    const uint32_t* cbits;           /* [1<<19] colour decision, raw bit per colour */
+    const uint32_t* ctab;            /* [65536] colour decision, <=2 B-intervals per (R,G); must be non-NULL, no longer uploaded
+                                      * (since round 2 the exact test reads cbits, re-ordered to the pixel word by ld_plan_create) */
+    const uint32_t* cbits;           /* [1<<19] colour decision, raw bit per colour, bit index r<<16|g<<8|b */
     int32_t inv_y0, inv_y1;          /* output rows the inverse warp can touch */
     const uint32_t* inv_idx;         /* [(inv_y1-inv_y0)*W] */
     const uint16_t* inv_fi;          /* [(inv_y1-inv_y0)*W] */
@@ -77,7 +78,8 @@ typedef struct ld_plan_desc {
     const uint32_t* bdesc;           /* [H*(W/32)*4] per output word of the mask: first source bit, step masks, valid pixels */
     int32_t n_mask_chunks;
     int32_t reserved;
-    const uint32_t* cpre;            /* [2048] colour pre-decision per 8x8x8 cell of RGB space, 2 bits: 0 off, 1 on, 2 mixed */
+    const uint32_t* cpre;            /* [2048] colour pre-decision per 8x8x8 cell of RGB space, 2 bits: 0 off, 1 on, 2 mixed
+                                      * (cell r5|g5<<5|b5<<10; re-packed into ON / MIXED bit planes by ld_plan_create) */
 } ld_plan_desc;
 
 /* One lane of one frame as the window search leaves it (Line.blind_search, Project.py:73-101):
