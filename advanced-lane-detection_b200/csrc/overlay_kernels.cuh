@@ -33,7 +33,11 @@ constexpr int RASTER_BIG_ROUND = 4;             // long segments set up per roun
 
 #ifdef LD_RASTER_PROF
 __device__ long long g_raster_prof[64][16];
-#define RPROF(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.y < 8) g_raster_prof[blockIdx.y * 8 + blockIdx.x][i] = clock64(); } while (0)
+#ifndef LD_RASTER_PROF_F0
+#define LD_RASTER_PROF_F0 640                    // the eight frames whose CTAs are timed: mid-batch, steady state (warm caches, full machine)
+#endif
+#define RPROF_ON (blockIdx.y >= LD_RASTER_PROF_F0 && blockIdx.y < LD_RASTER_PROF_F0 + 8)
+#define RPROF(i) do { __syncthreads(); if (threadIdx.x == 0 && RPROF_ON) g_raster_prof[(blockIdx.y - LD_RASTER_PROF_F0) * 8 + blockIdx.x][i] = clock64(); } while (0)
 #else
 #define RPROF(i) do {} while (0)
 #endif
@@ -66,35 +70,38 @@ struct StampTable {
 };
 static_assert(sizeof(StampTable) % 8 == 0, "StampTable is copied as 64-bit words");
 
-constexpr int RASTER_MAX_BIG = 16;             // long segments per frame whose set-up k_raster_prep does ahead of the band CTAs
+constexpr int RASTER_MAX_REC = 64;             // general segments per frame whose set-up k_raster_prep does ahead of the band CTAs
 
 // Per frame, written once by k_raster_prep and read by the eight band CTAs of k_raster: the polygon's vertices and the
-// ThickSetup records of its long red segments (lane gaps, the connector between the lanes).
+// ThickSetup records of its GENERAL red segments -- everything that is neither a unit vertical step nor a stamp: lane gaps,
+// the connector between the lanes, steps next to the frame border.  Their set-up (clipping, the quad's corners, four outline
+// DDAs, the scan edges: some thirty 64-bit and double divisions) is the expensive, serial part of cv2's thick line; it is done
+// here once per frame by one thread per segment, and the band CTAs only draw from the records.
 struct RasterPrep {
-    int n_verts, n_big, bad, pad;
-    int big_idx[RASTER_MAX_BIG];                // segment i = vertex i -> i + 1
-    laneraster::ThickSetup big[RASTER_MAX_BIG];
+    int n_verts, n_rec, bad, pad;
+    unsigned char seg_rec[MAX_VERTS];           // segment i = vertex i -> i + 1: index of its record, 0xFF = none
+    laneraster::ThickSetup rec[RASTER_MAX_REC];
     int vx[MAX_VERTS], vy[MAX_VERTS];
 };
+static_assert(MAX_VERTS % 8 == 0 && MAX_VERTS <= 2048, "seg_rec keeps the records 8-byte aligned; a job entry holds a segment index in 11 bits");
 
 struct RasterShared {
-    int n_verts, overflow, n_jobs, n_big, n_bigedge, pad;
+    int n_verts, overflow, n_jobs, n_bigedge, n_long, pad;
     int hw[16];
     int vx[MAX_VERTS], vy[MAX_VERTS];
     int cnt[RASTER_BAND];
-    // the red phase's job list is consumed before the long segments' ThickSetup records and then the green phase's crossing lists
-    // take its place; the list of long red segments is consumed before the list of long polygon edges is written
+    // the red phase's job list is consumed before the green phase's crossing lists take its place
     union {
-        unsigned short job[2 * MAX_VERTS];   // segment index | type << 14
+        unsigned short job[2 * MAX_VERTS + 64]; // segment index | part << 11 | type << 14
         alignas(8) int cross[RASTER_BAND * LD_MAX_CROSSINGS];
     };
-    union { unsigned short big[MAX_VERTS], bigedge[MAX_VERTS]; };
+    unsigned short bigedge[MAX_VERTS];
     // the thick-line stamps (plan: 49 x 40 rows of x1, x2; they fit a byte) next to the code that draws dozens of them per band
     alignas(16) StampTable st;
 };
-
-static_assert(sizeof(laneraster::ThickSetup) * RASTER_BIG_ROUND <= sizeof(int) * RASTER_BAND * LD_MAX_CROSSINGS,
-              "ThickSetup records must fit the crossing lists they alias");
+constexpr int RASTER_LONG_PARTS = 4;           // warps that share the drawing of one long segment ...
+constexpr int RASTER_MAX_LONG = 16;            // ... for the first few of a band (the job list holds 2 entries per segment + 64)
+static_assert(RASTER_MAX_LONG * (RASTER_LONG_PARTS - 1) <= 64, "job list capacity");
 
 __device__ __forceinline__ void add_crossing(RasterShared& R, const laneraster::PolyEdge& e, int y, int y_lo) {
     long long x = e.x + (long long)(y - e.y0) * e.dx;
@@ -112,32 +119,29 @@ __device__ __forceinline__ int vertex_x(const double* c, int y) {
     return (int)v;                                              // truncation toward zero
 }
 
-// The rare general paths of k_raster, kept out of line so that their register appetite (64-bit divisions, the quad's corners)
-// does not spill the common path: a long segment k_raster_prep had no room for, and a short segment no stamp covers.
-__device__ __noinline__ void raster_setup_slow(int W, int H, int x0, int y0, int x1, int y1, int thickness, laneraster::ThickSetup* T) {
-    laneraster::thick_segment_setup(W, H, x0, y0, x1, y1, thickness, *T);
-}
+// The rare path of k_raster, kept out of line so that its register appetite (64-bit divisions, the quad's corners) does not
+// spill the common path: a general segment k_raster_prep had no record left for (more than RASTER_MAX_REC per frame).
 __device__ __noinline__ void raster_segment_slow(BandPlotter* red, int W, int H, int x0, int y0, int x1, int y1, int thickness, const int* hw,
-                                                 bool first, int lane, int y_lo, int y_hi) {
-    laneraster::thick_segment_part(*red, W, H, x0, y0, x1, y1, thickness, hw, first, lane, 32, y_lo, y_hi);
+                                                 bool first, int tid, int nt, int y_lo, int y_hi) {
+    laneraster::thick_segment_part(*red, W, H, x0, y0, x1, y1, thickness, hw, first, tid, nt, y_lo, y_hi);
 }
 
-// Set-up half of the raster, once per frame (the band CTAs of k_raster used to repeat all of it eight times, and the long
-// segments' set-up -- clipping, the quad's corners, four outline DDAs, the scan edges: some thirty 64-bit and double divisions
-// -- ran on ONE thread while 255 waited: 46 % of k_raster's time).  Lists the polygon's vertices -- left lane descending y,
-// then right lane ascending y (Project.py:153-157), x = np.int_(fit(y)) -- from the frame's fit and row maps (verts == nullptr)
-// or copies the caller's (ld_draw), finds the long red segments and prepares them, one warp each.
+// Set-up half of the raster, once per frame (the band CTAs of k_raster used to repeat all of it eight times, and the general
+// segments' set-up ran on ONE thread per segment while the rest of the CTA waited).  Lists the polygon's vertices -- left lane
+// descending y, then right lane ascending y (Project.py:153-157), x = np.int_(fit(y)) -- from the frame's fit and row maps
+// (verts == nullptr) or copies the caller's (ld_draw), finds the general red segments and prepares their records.
 __global__ void __launch_bounds__(RASTER_THREADS)
 k_raster_prep(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ verts, const int32_t* __restrict__ counts,
               int max_verts, int thickness, RasterPrep* __restrict__ prep, const PlanDev P) {
     __shared__ uint32_t rowmask[2][LD_ROWMAP_WORDS];
-    __shared__ int prefix[2][LD_ROWMAP_WORDS], count[2], s_cut, s_nbig;
+    __shared__ int prefix[2][LD_ROWMAP_WORDS], count[2], s_cut, s_nrec;
+    __shared__ unsigned short s_rec_seg[RASTER_MAX_REC];
     const int W = P.W, H = P.H;
     const int f = blockIdx.x, tid = threadIdx.x;
     RasterPrep& R = prep[f];
     const bool bad = fit && fit[f].status != LD_OK;
     if (tid == 0) {
-        s_nbig = 0;
+        s_nrec = 0;
         int cut = -1;                                                   // harder:192-197 drops y <= max(min lefty, min righty)
         if (fit && !bad && P.clip_polygon) {
             int mn[2];
@@ -189,21 +193,30 @@ k_raster_prep(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ 
         nv = count[0] + count[1];
     }
     __syncthreads();                                                     // the vertices are in global memory, visible to the CTA
-    // long red segments: everything k_raster's pass 1 sends to its `big` list, whatever band it touches
-    if (thickness >= 2)
-        for (int i = tid; i + 1 < nv; i += RASTER_THREADS)
-            if (max(abs(R.vx[i + 1] - R.vx[i]), abs(R.vy[i + 1] - R.vy[i])) > 24) {
-                const int k = atomicAdd(&s_nbig, 1);
-                if (k < RASTER_MAX_BIG) R.big_idx[k] = i;
+    // general red segments: everything k_raster's pass 1 neither draws as a unit step nor as a stamp, whatever band it touches
+    const unsigned long long stamp_ok = static_cast<const StampTable*>(P.stamps)->ok;
+    for (int i = tid; i + 1 < nv; i += RASTER_THREADS) {
+        unsigned char r = 0xFF;
+        if (thickness >= 2) {
+            const int ax = R.vx[i], ay = R.vy[i], bx = R.vx[i + 1], by = R.vy[i + 1];
+            const bool general = !laneraster::trivial_step(ax, ay, bx, by, W, H, thickness) &&
+                                 !(thickness == 30 && laneraster::stamp_applies(ax, ay, bx, by, W, H) &&
+                                   ((stamp_ok >> laneraster::stamp_index(bx - ax, by - ay)) & 1ull));
+            if (general) {
+                const int k = atomicAdd(&s_nrec, 1);
+                if (k < RASTER_MAX_REC) { s_rec_seg[k] = (unsigned short)i; r = (unsigned char)k; }
             }
-    __syncthreads();
-    const int nb = min(s_nbig, (int)RASTER_MAX_BIG);
-    for (int k = tid >> 5; k < nb; k += RASTER_THREADS / 32)
-        if ((tid & 31) == 0) {
-            const int i = R.big_idx[k];
-            laneraster::thick_segment_setup(W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.big[k]);
         }
-    if (tid == 0) { R.n_verts = nv; R.n_big = nb; R.bad = bad ? 1 : 0; R.pad = 0; }
+        R.seg_rec[i] = r;
+    }
+    __syncthreads();
+    const int nb = min(s_nrec, (int)RASTER_MAX_REC);
+    if ((tid & 15) == 0)                                                 // two set-ups per warp: their paths diverge, more would serialise
+        for (int k = tid >> 4; k < nb; k += RASTER_THREADS / 16) {
+            const int i = s_rec_seg[k];
+            laneraster::thick_segment_setup(W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.rec[k]);
+        }
+    if (tid == 0) { R.n_verts = nv; R.n_rec = nb; R.bad = bad ? 1 : 0; R.pad = 0; }
 }
 
 // One CTA = one 90-row band of one frame's canvas.  planes: padded, interleaved canvas u64[n][H+2][2 WW + 2] (plan.py: inv_pack;
@@ -239,7 +252,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
         R.overflow = 0;
         R.n_verts = nv;
         R.n_jobs = 0;
-        R.n_big = 0;
+        R.n_long = 0;
         R.n_bigedge = 0;
         laneraster::circle_half_widths(radius, R.hw);
     }
@@ -258,13 +271,16 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
             const int cls = laneraster::classify_segment(W, H, R.vx[i], ya, R.vx[i + 1], yb, nx, nx ? R.vx[i + 2] : 0,
                                                          nx ? R.vy[i + 2] : 0, thickness, i == 0);
             if (!(cls & laneraster::SEG_TRIVIAL)) {
-                // long segments (lane gaps, the connector between the lanes) are drawn by the whole CTA in pass 3
                 if (thickness == 30 && laneraster::stamp_applies(R.vx[i], ya, R.vx[i + 1], yb, W, H) &&
                     ((R.st.ok >> laneraster::stamp_index(R.vx[i + 1] - R.vx[i], yb - ya)) & 1ull)) {
                     R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (3 << 14));      // precomputed quad + end disc
                     if (i == 0) R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (2 << 14));
-                } else if (max(abs(R.vx[i + 1] - R.vx[i]), abs(yb - ya)) > 24) R.big[atomicAdd(&R.n_big, 1)] = (unsigned short)i;
-                else R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)i;
+                } else if (max(abs(R.vx[i + 1] - R.vx[i]), abs(yb - ya)) > 24 && atomicAdd(&R.n_long, 1) < RASTER_MAX_LONG) {
+                    // long (lane gaps, the connector between the lanes): several warps share the drawing
+                    const int k = atomicAdd(&R.n_jobs, RASTER_LONG_PARTS);
+                    for (int q = 0; q < RASTER_LONG_PARTS; ++q) R.job[k + q] = (unsigned short)(i | (q << 11));
+                } else
+                    R.job[atomicAdd(&R.n_jobs, 1)] = (unsigned short)(i | (RASTER_LONG_PARTS << 11));   // general, one warp
                 continue;
             }
             red.span(ya, R.vx[i] - radius, R.vx[i] + radius);
@@ -279,9 +295,13 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
     {
         const int lane = tid & 31, warp = tid >> 5;
         for (int k = warp; k < R.n_jobs; k += RASTER_THREADS / 32) {
-            const int i = R.job[k] & 0x3FFF, type = R.job[k] >> 14;
-            if (type == 0)
-                raster_segment_slow(&red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, lane, y_lo, y_hi);
+            const int i = R.job[k] & 0x7FF, part = (R.job[k] >> 11) & 7, type = R.job[k] >> 14;
+            if (type == 0) {                                             // a general segment from the record k_raster_prep made
+                const int wt = part == RASTER_LONG_PARTS ? lane : lane + 32 * part, nt = part == RASTER_LONG_PARTS ? 32 : 32 * RASTER_LONG_PARTS;
+                const unsigned rec = Q.seg_rec[i];
+                if (rec != 0xFFu) laneraster::thick_segment_draw(red, W, H, Q.rec[rec], thickness, R.hw, i == 0, wt, nt, y_lo, y_hi);
+                else raster_segment_slow(&red, W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, R.hw, i == 0, wt, nt, y_lo, y_hi);
+            }
             else if (type == 3) {                                        // laneraster::draw_stamp_part from the shared-memory copy
                 const int so = laneraster::stamp_index(R.vx[i + 1] - R.vx[i], R.vy[i + 1] - R.vy[i]) * laneraster::STAMP_ROWS;
                 for (int r = lane; r < laneraster::STAMP_ROWS; r += 32)
@@ -292,30 +312,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
         }
     }
     RPROF(3);
-    // long segments (lane gaps, the connector between the lanes): their set-up (a chain of 64-bit divisions) is done by
-    // ONE thread per segment into shared memory, four segments per round; then the whole CTA draws them
-    {
-        laneraster::ThickSetup* ts = reinterpret_cast<laneraster::ThickSetup*>(R.cross);     // the crossing lists are not in use yet
-        for (int k0 = 0; k0 < R.n_big; k0 += RASTER_BIG_ROUND) {
-            const int nb = min(RASTER_BIG_ROUND, R.n_big - k0);
-            __syncthreads();
-            if ((tid >> 5) < nb) {                                       // one warp per segment: copy the record k_raster_prep made
-                const int i = R.big[k0 + (tid >> 5)];
-                int found = -1;
-                for (int q = 0; q < Q.n_big; ++q) if (Q.big_idx[q] == i) found = q;
-                if (found >= 0) {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.big[found]);
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(&ts[tid >> 5]);
-                    for (int w = tid & 31; w < (int)(sizeof(laneraster::ThickSetup) / 4); w += 32) dst[w] = src[w];
-                } else if ((tid & 31) == 0)                              // more long segments than the prep kernel holds: set up here
-                    raster_setup_slow(W, H, R.vx[i], R.vy[i], R.vx[i + 1], R.vy[i + 1], thickness, &ts[tid >> 5]);
-            }
-            __syncthreads();
-            for (int k = 0; k < nb; ++k)
-                laneraster::thick_segment_draw(red, W, H, ts[k], thickness, R.hw, R.big[k0 + k] == 0, tid, RASTER_THREADS, y_lo, y_hi);
-        }
-        __syncthreads();                                                // ts aliases the crossing lists of the green phase
-    }
+    __syncthreads();                                                    // the job list aliases the crossing lists of the green phase
     RPROF(4);
     // ---- green: cv2.fillPoly(canvas, pts, (0,255,0)) (Project.py:164): outline + scanline crossings of this band
     for (int i = tid; i < nv && nv >= 2; i += RASTER_THREADS) {
@@ -360,8 +357,8 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
     RPROF(8);
 #ifdef LD_RASTER_PROF
-    if (tid == 0 && blockIdx.y < 8) { g_raster_prof[blockIdx.y * 8 + blockIdx.x][10] = R.n_jobs; g_raster_prof[blockIdx.y * 8 + blockIdx.x][11] = R.n_big;
-        g_raster_prof[blockIdx.y * 8 + blockIdx.x][12] = R.n_bigedge; g_raster_prof[blockIdx.y * 8 + blockIdx.x][13] = nv; }
+    if (tid == 0 && RPROF_ON) { long long* g = g_raster_prof[(blockIdx.y - LD_RASTER_PROF_F0) * 8 + blockIdx.x];
+        g[10] = R.n_jobs; g[11] = Q.n_rec; g[12] = R.n_bigedge; g[13] = nv; }
 #endif
 
     // ---- text plane: glyph bitmaps OR-ed at integer pen positions (Project.py:326-332); band 0 only

@@ -159,3 +159,57 @@ void hs_row_count_sx(const uint32_t* mask, int W, int row, int x0, int x1, uint3
     lanesearch::row_count_sx(mask, W / 32, W, row, x0, x1, *cnt, *sx);
 }
 }
+
+// How k_raster's red pass 1 classifies the segments that can touch the band [y_lo, y_hi): counts of
+// {trivial steps, stamp jobs, general short segments, long segments, disc jobs} (tuning aid for the band raster)
+extern "C" void hs_band_classify(const int32_t* pts, int n, int w, int h, int y_lo, int y_hi, int thickness, int* out5) {
+    using namespace laneraster;
+    const int radius = thickness / 2;
+    std::vector<int> hw(radius + 1);
+    circle_half_widths(radius, hw.data());
+    for (int k = 0; k < 5; ++k) out5[k] = 0;
+    for (int i = 0; i + 1 < n; ++i) {
+        const int ax = pts[2 * i], ay = pts[2 * i + 1], bx = pts[2 * i + 2], by = pts[2 * i + 3];
+        if (std::max(ay, by) + radius + 1 < y_lo || std::min(ay, by) - radius - 1 >= y_hi) continue;
+        const bool nx = i + 2 < n;
+        const int cls = classify_segment(w, h, ax, ay, bx, by, nx, nx ? pts[2 * i + 4] : 0, nx ? pts[2 * i + 5] : 0, thickness, i == 0);
+        if (!(cls & SEG_TRIVIAL)) {
+            if (thickness == 30 && stamp_applies(ax, ay, bx, by, w, h) && hs_stamp_ok(bx - ax, by - ay, thickness)) out5[1]++;
+            else if (std::max(std::abs(bx - ax), std::abs(by - ay)) > 24) out5[3]++;
+            else out5[2]++;
+            continue;
+        }
+        out5[0]++;
+        if (cls & SEG_END_DISC) out5[4]++;
+        if (cls & SEG_START_DISC) out5[4]++;
+    }
+}
+
+namespace {
+struct CountPlotter {                      // counts what BandPlotter::span would do: calls and words touched inside the band
+    int y_lo, y_hi, w; long calls, words;
+    void span(int y, int x1, int x2) {
+        if (y < y_lo || y >= y_hi) return;
+        if (x1 < 0) x1 = 0;
+        if (x2 >= w) x2 = w - 1;
+        if (x1 > x2) return;
+        ++calls; words += (x2 >> 4) - (x1 >> 4) + 1;
+    }
+};
+}
+// per-thread cost of drawing segment i of the polyline as a long segment in the band: out[2 * tid] = span calls, out[2 * tid + 1] = words
+extern "C" int hs_big_segment_cost(const int32_t* pts, int i, int w, int h, int y_lo, int y_hi, int thickness, int nt, long* out) {
+    using namespace laneraster;
+    std::vector<int> hw(thickness / 2 + 1);
+    circle_half_widths(thickness / 2, hw.data());
+    ThickSetup T;
+    thick_segment_setup(w, h, pts[2 * i], pts[2 * i + 1], pts[2 * i + 2], pts[2 * i + 3], thickness, T);
+    for (int t = 0; t < nt; ++t) {
+        CountPlotter P{y_lo, y_hi, w, 0, 0};
+        thick_segment_draw(P, w, h, T, thickness, hw.data(), i == 0, t, nt, y_lo, y_hi);
+        out[2 * t] = P.calls; out[2 * t + 1] = P.words;
+    }
+    int ec = 0;
+    for (int e = 0; e < 4; ++e) if (T.L[e].valid && T.L[e].ecount > ec) ec = T.L[e].ecount;
+    return T.valid ? (T.quad ? T.S.n * 10000 + ec : -2) : -1;
+}

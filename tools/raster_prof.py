@@ -14,7 +14,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "build":
 os.environ["LANEDET_LIB"] = PROF
 import bench, torch
 pkg = importlib.import_module(bench.PKG)
-n = 64
+n = 1260                                            # the timed CTAs are frames 640..647 (LD_RASTER_PROF_F0): steady state
 eng = pkg.LaneEngine("project", device=0, max_frames=n)
 frames = torch.from_numpy(bench.synth_frames(n, 0)).cuda()
 out, fits = eng.process_dev(frames)
@@ -31,5 +31,10 @@ print("phase cycles per CTA (frame, band) -- mean / max over 64 CTAs")
 for i in range(8):
     print("%-22s mean %8.0f  max %8.0f" % (names[i + 0] if i < len(names) else i, d[:, i].mean(), d[:, i].max()))
 print("total mean %.0f max %.0f cycles" % ((a[:, 8] - a[:, 0]).mean(), (a[:, 8] - a[:, 0]).max()))
+print("per band (mean over 8 frames): " + " ".join(n.split()[0] for n in names))
+for b in range(8):
+    print("band %d " % b + " ".join("%7.0f" % d[b::8, i].mean() for i in range(8)))
+print("long segments: cycles until the records are in shared memory (last round), per band; not-found set-ups per band")
+print(np.array([(a[b::8, 14] - a[b::8, 3]).mean() for b in range(8)]).round(0), [int(a[b::8, 15].sum()) for b in range(8)])
 print("n_jobs / n_big / n_bigedge / nv per CTA (first 16):")
 print(a[:16, 10:14])
