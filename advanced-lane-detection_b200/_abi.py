@@ -88,6 +88,7 @@ _SIGNATURES = {
     "ld_frame_pass": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_stage": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "ld_stage_tiles": (C.c_int, [_P, C.c_int]),
+    "ld_debug_knob": (C.c_int, [C.c_int, C.c_int]),
     "ld_ctx_mask": (_P, [_P]),
     "ld_process_batch": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "ld_process_batch_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),

@@ -66,6 +66,7 @@ enum { HOST_CHUNK = 32, PIPE_SUB = 8, HALO_MAX = 32 };               // HALO_MAX
 struct ld_ctx {
     ld_plan* plan;
     int max_frames;
+    int n_sm;                  // SMs of the device (sizes the persistent grids)
     uint32_t* mask;            // [max][H][WW]
     // [max][2] / [max][2] / [max]; each has HALO_MAX more slots IN FRONT (rec[-2h..0), ...) for the look-back halo of ld_halo_set
     ld_lane_record* rec;
@@ -97,6 +98,21 @@ struct ld_ctx {
     uint8_t* stage_out[2];
     int chunk;
 };
+
+// Tuning knobs of the step schedule, settable at run time so that one process can sweep them (tools/knob_sweep.py);
+// -1 = take the default / the environment variable of the same purpose.
+enum { KNOB_RASTER_PERSIST = 0, KNOB_EARLY_PLAIN = 1, KNOB_PLAIN_FPC = 2, KNOB_SPLIT_PLAIN = 4, N_KNOBS = 8 };
+static int g_knob[N_KNOBS] = {-1, -1, -1, -1, -1, -1, -1, -1};
+extern "C" int ld_debug_knob(int id, int value) {
+    if (id < 0 || id >= N_KNOBS) return LD_ERR_ARG;
+    g_knob[id] = value;
+    return LD_OK;
+}
+static int knob(int id, const char* env, int dflt) {
+    if (g_knob[id] >= 0) return g_knob[id];
+    const char* e = getenv(env);
+    return e ? atoi(e) : dflt;
+}
 
 // u32 words of one frame's padded canvas (overlay_kernels.cuh: canvas_codes)
 static inline size_t canvas_words(const PlanDev& d) { return (size_t)(d.H + 2) * (2 * d.WW + 2) * 2; }
@@ -409,6 +425,7 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
     memset(c, 0, sizeof(*c));
     c->plan = plan;
     c->max_frames = max_frames;
+    LD_CUDA_OR(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, plan->device), ld_ctx_destroy(c));
     const PlanDev& d = plan->d;
     const size_t mw = (size_t)d.H * d.WW, fb = (size_t)d.W * d.H * 3;
     c->chunk = max_frames < HOST_CHUNK ? max_frames : HOST_CHUNK;
@@ -537,7 +554,8 @@ static inline int check_launch() {
 }
 #define ARGS_OK(c, a, b, n) ((c) && (a) && (b) && (n) >= 0)
 
-static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted, int which);
+static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted, int which,
+                             int tile_lo = 0, int tile_cnt = -1);
 
 // ------------------------------------------------------------------------------------- stages
 extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, void* stream) {
@@ -548,6 +566,9 @@ extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, 
         // plans whose width is a multiple of the 128-pixel tiles (1280x720, 4K): the frame pass's multi-frame tile kernel in its mask-only form (per-tile constants in registers, one
         // tensor-map TMA copy per tile and frame, only the 32-pixel groups the bird's-eye warp samples are gathered) writes the
         // colour bits of the undistorted pixels; k_mask_b cuts the bird's-eye words out of them
+        // (Pipelining the two launches over sub-batches -- k_mask_b of sub-batch i on a side stream beside the pass of sub-batch
+        // i + 1 -- was measured in round 2: 1 / 2 / 4 / 8 sub-batches = 0.536 / 0.552 / 0.587 / 0.663 us/frame; the tails cost more
+        // than the overlap gives.)
         for (int done = 0; done < n; done += c->max_frames) {
             const int m = (n - done) < c->max_frames ? (n - done) : c->max_frames;
             int rc;
@@ -677,14 +698,17 @@ extern "C" int ld_fit(ld_ctx* c, const ld_lane_record* rec, int n, ld_frame_fit*
 
 // raster + frame pass for m frames whose workspace slots start at `slot` (frame index inside the context buffers)
 static int launch_raster(ld_ctx* c, const ld_frame_fit* fit, const int32_t* verts, const int32_t* counts, int max_verts,
-                         int thickness, int m, cudaStream_t s, int slot) {
+                         int thickness, int m, cudaStream_t s, int slot, int persist_per_sm = 0) {
     const PlanDev& d = c->plan->d;
     if (d.W != 1280 || d.H != 720) return LD_ERR_ARG;                    // RASTER_CW
     // once per frame: vertices + the set-up of the long segments; then one CTA per 90-row band draws
     k_raster_prep<<<m, RASTER_THREADS, 0, s>>>(fit, verts, counts, max_verts, thickness, c->prep + slot, d);
-    k_raster<<<dim3((d.H + RASTER_BAND - 1) / RASTER_BAND, m), RASTER_THREADS, c->plan->raster_smem, s>>>(
+    const int items = ((d.H + RASTER_BAND - 1) / RASTER_BAND) * m;
+    int grid = items;
+    if (persist_per_sm > 0 && c->n_sm * persist_per_sm < grid) grid = c->n_sm * persist_per_sm;
+    k_raster<<<grid, RASTER_THREADS, c->plan->raster_smem, s>>>(
         fit, c->prep + slot, thickness, c->planes + (size_t)slot * canvas_words(d),
-        c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3);
+        c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS, d, c->flags + 3, items);
     return check_launch();
 }
 // Tensor map of m frames at `frames` seen as uint32[m][H][W*3/4], box = 128 words x box_rows rows x 1 frame: the source
@@ -726,7 +750,7 @@ static int frames_per_cta(int m) {
 // 4: the text tiles (overlay tiles above share_y0) with blend + text; 5: the plain tiles above share_y0 as cv2.undistort;
 // 8: the mask-only pass of ld_mask over the share tiles that hold a sampled pixel (colour bits -> c->und_bits)
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted,
-                             int which) {
+                             int which, int tile_lo, int tile_cnt) {
     const PlanDev& d = c->plan->d;
     const uint32_t* planes = c->planes + (size_t)slot * canvas_words(d);
     const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
@@ -736,8 +760,7 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
     {
         int fpc = frames_per_cta(m);
         if (which == 5) {                                                // LD_FPC_PLAIN: frames per CTA of the plain-tile launch (tuning knob)
-            static int plain_fpc = -1;
-            if (plain_fpc < 0) { const char* e = getenv("LD_FPC_PLAIN"); plain_fpc = e ? atoi(e) : 0; }
+            const int plain_fpc = knob(KNOB_PLAIN_FPC, "LD_FPC_PLAIN", 0);
             if (plain_fpc > 0 && plain_fpc < fpc) fpc = plain_fpc;
         }
         CUtensorMap tm;
@@ -761,10 +784,11 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
                 k_frame_pass_mf<4><<<dim3(c->plan->n_mask_tiles, groups.y), FRAME_MF_THREADS, c->plan->frame_smem + MASK_PRE_WORDS * 4, s>>>(
                     tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->mask_tiles,
                     c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, nullptr);
-        } else if (which == 5) {
-            if (c->plan->n_plain_top)
-                k_frame_pass_mf<0><<<dim3(c->plan->n_plain_top, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_top_tiles, nullptr, nullptr);
+        } else if (which == 5) {                                         // [tile_lo, tile_lo + tile_cnt) of the list (the step may launch it in two parts)
+            const int cnt = tile_cnt < 0 ? c->plan->n_plain_top - tile_lo : tile_cnt;
+            if (cnt > 0)
+                k_frame_pass_mf<0><<<dim3(cnt, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_top_tiles + tile_lo, nullptr, nullptr);
         } else if (which == 4) {
             if (c->plan->n_text)
                 k_frame_pass_mf<1><<<dim3(c->plan->n_text, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
@@ -916,7 +940,7 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
 // touches the range only.  fin / fout = first frame of the RANGE.
 static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld_frame_fit* fit_out, void* state_out,
                          cudaStream_t s, int frame_offset, int search_first = 0, int skip_plain = 0, int fit_first = 0, int halo = 0,
-                         int look = 0, int look_check = 0, int lat_continues = 0) {
+                         int look = 0, int look_check = 0, int lat_continues = 0, int plain_done_tiles = -1) {
     const PlanDev& d = c->plan->d;
     const size_t fb = (size_t)d.W * d.H * 3;
     const int nsub = sub_batches(M);
@@ -941,13 +965,19 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         if (state_out) LD_CUDA(cudaMemcpyAsync(state_out, c->state, sizeof(TrackState), cudaMemcpyDefault, c->s_lat));
         LD_CUDA(cudaEventRecord(c->ev_state, c->s_lat));
         tl_mark("fit (s_lat)", c->s_lat);
-        if ((rc = launch_raster(c, c->fit + look, nullptr, nullptr, 0, 30, M, c->s_lat, look))) return rc;
+        // inside the step the raster is a persistent grid of a few CTAs per SM (k_raster): the plain tiles keep the rest of the SM
+        if ((rc = launch_raster(c, c->fit + look, nullptr, nullptr, 0, 30, M, c->s_lat, look, knob(KNOB_RASTER_PERSIST, "LD_RASTER_PERSIST", 0)))) return rc;
         LD_CUDA(cudaEventRecord(c->ev_rast[0], c->s_lat));
         tl_mark("raster (s_lat)", c->s_lat);
         // LD_POST_FIT_FIRST (sharded runs): the plain tiles start when the fit stage is done -- run beside them the tiny fit
         // kernels take 2.8x longer, and every successor rank waits for exactly that stage.  (On one GPU the overlap wins: 4.18
         // vs 4.39 ms per 1260 frames.)
         if (fit_first) LD_CUDA(cudaStreamWaitEvent(s, c->ev_state, 0));
+        if (skip_plain && plain_done_tiles >= 0 && plain_done_tiles < c->plan->n_plain_top) {
+            // the caller launched only the first plain tiles early: the rest starts with the raster (they share the SMs with it)
+            LD_CUDA(cudaStreamWaitEvent(s, c->ev_state, 0));
+            if ((rc = launch_frame_pass(c, fin, M, fout, s, look, 0, 5, plain_done_tiles, -1))) return rc;
+        }
         if (!(skip_plain && c->plan->shared_ok && !search_first) &&
             (rc = launch_frame_pass(c, fin, M, fout, s, look, 0, (c->plan->shared_ok && !search_first) ? 5 : 1))) return rc;
         tl_mark("plain tiles (s)", s);
@@ -1001,8 +1031,7 @@ static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, l
                                     frame_offset + base, 1))) return rc;
             continue;
         }
-        static int early = -1;                                          // LD_EARLY_PLAIN=0: the previous schedule (A/B measurements)
-        if (early < 0) { const char* e = getenv("LD_EARLY_PLAIN"); early = e ? atoi(e) : 1; }
+        const int early = knob(KNOB_EARLY_PLAIN, "LD_EARLY_PLAIN", 1);  // 0: the previous schedule (A/B measurements)
         if (early && c->plan->shared_ok && sub_batches(M) < 2) {
             // The plain tiles (pure cv2.undistort, 59 % of the frame) depend on nothing: they start FIRST, on the caller's stream,
             // and the whole dependent chain -- shared pass -> k_mask_b -> k_search -> fit -> raster -> blend -- runs on the
@@ -1011,10 +1040,11 @@ static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, l
             // which before only overlapped the fit stage and then starved behind the raster and the blend.
             LD_CUDA(cudaEventRecord(c->ev_fork, s));
             LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
-            if ((rc = launch_frame_pass(c, frames + base * fb, M, out + base * fb, s, 0, 0, 5))) return rc;
+            const int early_tiles = c->plan->n_plain_top * knob(KNOB_SPLIT_PLAIN, "LD_SPLIT_PLAIN", 100) / 100;
+            if ((rc = launch_frame_pass(c, frames + base * fb, M, out + base * fb, s, 0, 0, 5, 0, early_tiles))) return rc;
             if ((rc = prepass_impl(c, frames + base * fb, M, c->s_lat))) return rc;
             if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
-                                    frame_offset + base, 0, 1, 0, 0, 0, 0, 1))) return rc;
+                                    frame_offset + base, 0, 1, 0, 0, 0, 0, 1, early_tiles))) return rc;
             continue;
         }
         if ((rc = prepass_impl(c, frames + base * fb, M, s))) return rc;

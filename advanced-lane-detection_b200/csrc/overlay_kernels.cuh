@@ -36,8 +36,8 @@ __device__ long long g_raster_prof[64][16];
 #ifndef LD_RASTER_PROF_F0
 #define LD_RASTER_PROF_F0 640                    // the eight frames whose CTAs are timed: mid-batch, steady state (warm caches, full machine)
 #endif
-#define RPROF_ON (blockIdx.y >= LD_RASTER_PROF_F0 && blockIdx.y < LD_RASTER_PROF_F0 + 8)
-#define RPROF(i) do { __syncthreads(); if (threadIdx.x == 0 && RPROF_ON) g_raster_prof[(blockIdx.y - LD_RASTER_PROF_F0) * 8 + blockIdx.x][i] = clock64(); } while (0)
+#define RPROF_ON (f >= LD_RASTER_PROF_F0 && f < LD_RASTER_PROF_F0 + 8)
+#define RPROF(i) do { __syncthreads(); if (threadIdx.x == 0 && RPROF_ON) g_raster_prof[(f - LD_RASTER_PROF_F0) * 8 + band][i] = clock64(); } while (0)
 #else
 #define RPROF(i) do {} while (0)
 #endif
@@ -223,15 +223,14 @@ k_raster_prep(const ld_frame_fit* __restrict__ fit, const int32_t* __restrict__ 
 // red = red without green; rows 0 and H+1 stay zero);
 // text: u32[n][TEXT_ROWS][TEXT_WORDS] (written by band 0).  The vertices and the prepared long segments come from
 // k_raster_prep; every CTA draws only the primitives whose rows can touch its band, expensive ones one per warp.
-__global__ void __launch_bounds__(RASTER_THREADS, LD_RASTER_OCC)
-k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ prep, int thickness, uint32_t* __restrict__ planes,
-         uint32_t* __restrict__ text, const PlanDev P, int* __restrict__ poly_error) {
+__device__ __forceinline__ void
+raster_band(const int f, const int band, const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ prep, int thickness,
+            uint32_t* __restrict__ planes, uint32_t* __restrict__ text, const PlanDev& P, int* __restrict__ poly_error) {
     extern __shared__ uint32_t smem[];
     const int W = P.W, H = P.H, WW = P.WW;
     uint32_t* s_canvas = smem;                                          // [RASTER_BAND][RASTER_ROW_WORDS] interleaved (BandPlotter)
     uint32_t* s_text = smem;                                            // TEXT_ROWS*TEXT_WORDS: band 0, after the canvas is stored
     RasterShared& R = *reinterpret_cast<RasterShared*>(smem + RASTER_CANVAS_WORDS);
-    const int f = blockIdx.y, band = blockIdx.x;
     const int y_lo = band * RASTER_BAND, y_hi = min(H, y_lo + RASTER_BAND);
     constexpr int CW = RASTER_CW;                                       // padded, interleaved canvas: 64-bit entries per row (canvas_codes)
     uint2* out_planes = reinterpret_cast<uint2*>(planes) + ((size_t)f * (H + 2) + y_lo + 1) * CW;
@@ -357,7 +356,7 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
     if (tid == 0 && R.overflow && poly_error) atomicOr(poly_error, 1);
     RPROF(8);
 #ifdef LD_RASTER_PROF
-    if (tid == 0 && RPROF_ON) { long long* g = g_raster_prof[(blockIdx.y - LD_RASTER_PROF_F0) * 8 + blockIdx.x];
+    if (tid == 0 && RPROF_ON) { long long* g = g_raster_prof[(f - LD_RASTER_PROF_F0) * 8 + band];
         g[10] = R.n_jobs; g[11] = Q.n_rec; g[12] = R.n_bigedge; g[13] = nv; }
 #endif
 
@@ -393,6 +392,19 @@ k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ pr
     }
     __syncthreads();
     for (int i = tid; i < LD_TEXT_ROWS * LD_TEXT_WORDS; i += RASTER_THREADS) out_text[i] = s_text[i];
+}
+
+// The band items of a batch, (frame, band) = (item / bands, item % bands).  Launched with one CTA per item, or -- inside the
+// step -- as a PERSISTENT grid of a few CTAs per SM that walks the items: a grid whose CTAs are all resident has no pending
+// high-priority CTAs, so the plain-tile CTAs of the caller's stream keep the rest of each SM instead of starving behind it.
+__global__ void __launch_bounds__(RASTER_THREADS, LD_RASTER_OCC)
+k_raster(const ld_frame_fit* __restrict__ fit, const RasterPrep* __restrict__ prep, int thickness, uint32_t* __restrict__ planes,
+         uint32_t* __restrict__ text, const PlanDev P, int* __restrict__ poly_error, int n_items) {
+    const int bands = (P.H + RASTER_BAND - 1) / RASTER_BAND;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        raster_band(item / bands, item % bands, fit, prep, thickness, planes, text, P, poly_error);
+        __syncthreads();                                                // the next item reuses the shared memory
+    }
 }
 
 // + 0.3 * warpPerspective(canvas, Minv) (Project.py:167-170).  cv = this frame's PADDED, INTERLEAVED canvas (plan.py:

@@ -163,6 +163,10 @@ int ld_frame_pass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_de
  * ld_stage_tiles: how many 128x16 tiles stage `which` covers. */
 int ld_stage(ld_ctx* ctx, int which, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
 int ld_stage_tiles(ld_ctx* ctx, int which);
+/* Tuning aid (process-wide): knob 0 = CTAs per SM of the persistent raster grid inside ld_process_batch (0 = one CTA per band),
+ * 1 = plain tiles first (1, default) or after the window search (0), 2 = frames per CTA of the plain-tile launch (0 = default),
+ * 4 = percentage of the plain tiles launched first (the rest starts with the raster); value -1 = back to the default. */
+int ld_debug_knob(int id, int value);
 /* the packed masks ld_prepass / ld_process_batch / ld_stage(7) leave in the context: device u32[max_frames][H][W/32] */
 const uint32_t* ld_ctx_mask(ld_ctx* ctx);
 /* process_image for n consecutive frames (Project.py:289-334).  fit_dev may be NULL. */
