@@ -93,6 +93,7 @@ _SIGNATURES = {
     "ld_process_batch": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "ld_process_batch_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_prepass": (C.c_int, [_P, _P, C.c_int, _P]),
+    "ld_prepass_out": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ld_postpass": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "ld_postpass_flags": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int]),
     "ld_wait_state": (C.c_int, [_P, _P]),

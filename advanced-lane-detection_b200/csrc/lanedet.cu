@@ -58,6 +58,11 @@ struct ld_plan {
     const int32_t* share_tiles; const int32_t* text_tiles; const int32_t* plain_top_tiles;   // plain_top = plain tiles above share_y0
     const int32_t* mask_tiles;                                          // share tiles with a pixel the bird's-eye warp samples (ld_mask)
     int n_share, n_text, n_plain_top, n_mask_tiles, shared_ok;
+    // the share tiles split by the inverse warp's static footprint: it can touch `blend` tiles (their pixels wait in und_px for
+    // k_blend_px) and cannot touch `final` tiles (their pixels are final after the undistortion: k_frame_pass_mf<5>)
+    int n_blend, n_final;
+    const int32_t* blend_tiles;
+    const int32_t* final_tiles;
     int mask_ok;               // ld_mask can take its tile route (k_frame_pass_mf<4> + k_mask_b): any size with W % 128 == 0
 };
 
@@ -94,6 +99,7 @@ struct ld_ctx {
     // ev_valid[0/1] = the pinned copies of flags[4] (halo invalid) / flags[5] (tail invalid) are readable
     cudaEvent_t ev_halo_in, ev_valid[2];
     int halo_wait;             // ev_halo_in was recorded for the next ld_postpass_flags(LD_POST_USE_HALO)
+    int px_split;              // the last shared pass had the output frames: the groups the inverse warp cannot touch are already there
     uint8_t* stage_in[2];
     uint8_t* stage_out[2];
     int chunk;
@@ -346,6 +352,25 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
             sg[(size_t)(ny - d.share_y0) * tcols + (nx >> 7)] |= (uint8_t)(1u << ((nx >> 5) & 3));
         }
         rc = upload(p, sg, (size_t)(srows > 0 ? srows : 1) * tcols, &d.share_groups);
+        {   // the share tiles the inverse warp can / cannot touch
+            int32_t* bt = new (std::nothrow) int32_t[2 * (size_t)(p->n_share > 0 ? p->n_share : 1)];
+            if (!bt) { delete[] sg; ld_plan_destroy(p); return LD_ERR_ARG; }
+            int32_t* ft = bt + (p->n_share > 0 ? p->n_share : 1);
+            int nbl = 0, nfi = 0;
+            for (int t = 0; t < desc->n_frame_tiles; ++t) {              // same order as share_tiles
+                const int x0 = desc->frame_tiles[8 * t], y0 = desc->frame_tiles[8 * t + 1], w = desc->frame_tiles[8 * t + 2], h = desc->frame_tiles[8 * t + 3];
+                if (y0 < d.share_y0) continue;
+                bool any = false;
+                for (int y = (y0 > desc->inv_y0 ? y0 : desc->inv_y0); !any && y < y0 + h && y < desc->inv_y1; ++y)
+                    for (int x = x0; x < x0 + w; ++x)
+                        if (desc->inv_pack[(size_t)(y - desc->inv_y0) * W + x] != 0xFFFFFFFFu) { any = true; break; }
+                if (any) bt[nbl++] = t; else ft[nfi++] = t;
+            }
+            if (!rc) rc = upload(p, bt, (size_t)(nbl ? nbl : 1), &p->blend_tiles);
+            if (!rc) rc = upload(p, ft, (size_t)(nfi ? nfi : 1), &p->final_tiles);
+            p->n_blend = nbl; p->n_final = nfi;
+            delete[] bt;
+        }
         // the share tiles that hold a sampled pixel at all: the tiles of the mask-only pass (ld_mask: k_frame_pass_mf<4>)
         int32_t* mt = new (std::nothrow) int32_t[(size_t)desc->n_frame_tiles];
         int nm = 0;
@@ -386,9 +411,12 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
     LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), ld_plan_destroy(p));
+    LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), ld_plan_destroy(p));
     if (const char* e = getenv("LD_CARVEOUT_COLOUR")) {                 // experiment: leave the colour-deciding passes some L1 for the exact tables
         LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<3>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)), ld_plan_destroy(p));
         LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<4>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)), ld_plan_destroy(p));
+        LD_CUDA_OR(cudaFuncSetAttribute(k_frame_pass_mf<5>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)), ld_plan_destroy(p));
     }
     // Kernels of the two pipeline streams must be able to share an SM: give them all the same (maximum) shared-memory
     // carveout, otherwise an SM has to drain before a kernel with a different carveout can start on it.
@@ -555,7 +583,7 @@ static inline int check_launch() {
 #define ARGS_OK(c, a, b, n) ((c) && (a) && (b) && (n) >= 0)
 
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted, int which,
-                             int tile_lo = 0, int tile_cnt = -1);
+                             int tile_lo = 0, int tile_cnt = -1, int px_look = 0);
 
 // ------------------------------------------------------------------------------------- stages
 extern "C" int ld_mask(ld_ctx* c, const uint8_t* frames, int n, uint32_t* mask, void* stream) {
@@ -750,7 +778,7 @@ static int frames_per_cta(int m) {
 // 4: the text tiles (overlay tiles above share_y0) with blend + text; 5: the plain tiles above share_y0 as cv2.undistort;
 // 8: the mask-only pass of ld_mask over the share tiles that hold a sampled pixel (colour bits -> c->und_bits)
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted,
-                             int which, int tile_lo, int tile_cnt) {
+                             int which, int tile_lo, int tile_cnt, int px_look) {
     const PlanDev& d = c->plan->d;
     const uint32_t* planes = c->planes + (size_t)slot * canvas_words(d);
     const uint32_t* text = c->text + (size_t)slot * LD_TEXT_ROWS * LD_TEXT_WORDS;
@@ -770,32 +798,42 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
         if (which == 1) {
             if (c->plan->n_plain)
                 k_frame_pass_mf<0><<<dim3(c->plan->n_plain, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_tiles, nullptr, nullptr);
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_tiles, nullptr, nullptr, 0);
         } else if (which == 2) {
             if (c->plan->n_overlay)
                 k_frame_pass_mf<1><<<dim3(c->plan->n_overlay, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->overlay_tiles, nullptr, nullptr);
+                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->overlay_tiles, nullptr, nullptr, 0);
         } else if (which == 3) {
-            k_frame_pass_mf<3><<<dim3(c->plan->n_share, groups.y), FRAME_MF_THREADS, c->plan->frame_smem + MASK_PRE_WORDS * 4, s>>>(
-                tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->share_tiles,
-                c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, c->und_px + (size_t)slot * c->plan->n_share * 16 * 128);
+            // with the output frames at hand the share tiles the inverse warp cannot touch are finished here (MODE 5: packed RGB
+            // out, colour bits to und_bits); only the others park their pixels in und_px for k_blend_px
+            uint32_t* bits = c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW;
+            const size_t smem = c->plan->frame_smem + MASK_PRE_WORDS * 4;
+            c->px_split = fout != nullptr;
+            const int nb = c->px_split ? c->plan->n_blend : c->plan->n_share;
+            if (nb)
+                k_frame_pass_mf<3><<<dim3(nb, groups.y), FRAME_MF_THREADS, smem, s>>>(
+                    tm, fin, nullptr, nullptr, nullptr, d, m, fpc, c->plan->frame_box_rows, c->px_split ? c->plan->blend_tiles : c->plan->share_tiles,
+                    bits, c->und_px + (size_t)slot * nb * 16 * 128, px_look);
+            if (c->px_split && c->plan->n_final)
+                k_frame_pass_mf<5><<<dim3(c->plan->n_final, groups.y), FRAME_MF_THREADS, smem, s>>>(
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->final_tiles, bits, nullptr, px_look);
         } else if (which == 8) {
             if (c->plan->n_mask_tiles)
                 k_frame_pass_mf<4><<<dim3(c->plan->n_mask_tiles, groups.y), FRAME_MF_THREADS, c->plan->frame_smem + MASK_PRE_WORDS * 4, s>>>(
                     tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->mask_tiles,
-                    c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, nullptr);
+                    c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, nullptr, 0);
         } else if (which == 5) {                                         // [tile_lo, tile_lo + tile_cnt) of the list (the step may launch it in two parts)
             const int cnt = tile_cnt < 0 ? c->plan->n_plain_top - tile_lo : tile_cnt;
             if (cnt > 0)
                 k_frame_pass_mf<0><<<dim3(cnt, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_top_tiles + tile_lo, nullptr, nullptr);
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_top_tiles + tile_lo, nullptr, nullptr, 0);
         } else if (which == 4) {
             if (c->plan->n_text)
                 k_frame_pass_mf<1><<<dim3(c->plan->n_text, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->text_tiles, nullptr, nullptr);
+                    tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->text_tiles, nullptr, nullptr, 0);
         } else
             k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, nullptr, nullptr, nullptr);
+                tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, nullptr, nullptr, nullptr, 0);
     }
     return check_launch();
 }
@@ -842,7 +880,7 @@ extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint
     const PlanDev& d = c->plan->d;
     cudaStream_t s = (cudaStream_t)stream;
     if (which == 3 || which == 4 || which == 5 || which == 8) {
-        if (!frames || (which != 3 && which != 8 && !out)) return LD_ERR_ARG;
+        if (!frames || (which != 3 && which != 8 && !out)) return LD_ERR_ARG;  // which == 3: out optional (see ld_prepass_out)
         return launch_frame_pass(c, frames, n, out, s, 0, 0, which);
     }
     if (which == 7) {
@@ -852,7 +890,10 @@ extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint
     if (which == 6) {
         if (!out) return LD_ERR_ARG;
         const int bf = frames_per_cta(n);
-        k_blend_px<<<dim3(c->plan->n_share, (n + bf - 1) / bf), FRAME_THREADS, 0, s>>>(c->und_px, c->planes, out, d, c->plan->share_tiles, n, bf);
+        const int nbt = c->px_split ? c->plan->n_blend : c->plan->n_share;
+        if (nbt)
+            k_blend_px<<<dim3(nbt, (n + bf - 1) / bf), FRAME_THREADS, 0, s>>>(c->und_px, c->planes, out, d,
+                                                                              c->px_split ? c->plan->blend_tiles : c->plan->share_tiles, n, bf);
         return check_launch();
     }
     return LD_ERR_ARG;
@@ -860,6 +901,7 @@ extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint
 extern "C" const uint32_t* ld_ctx_mask(ld_ctx* c) { return c ? c->mask : nullptr; }   // the context's packed masks (device), [max_frames][H][W/32]
 extern "C" int ld_stage_tiles(ld_ctx* c, int which) {                   // tiles a stage covers (for byte accounting)
     if (!c) return -1;
+    if (which == 9) return c->plan->n_blend;                            // share tiles the inverse warp can touch (und_px -> k_blend_px)
     return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? c->plan->n_text : which == 5 ? c->plan->n_plain_top :
            which == 8 ? c->plan->n_mask_tiles : -1;
 }
@@ -900,7 +942,10 @@ static int join_streams(ld_ctx* c, cudaStream_t s) {
     return LD_OK;
 }
 
-static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
+// fout != nullptr (shared-pass plans): the output frames of fin's frames [look, M) start at fout -- the shared pass then stores
+// the pixels the inverse warp cannot touch straight into them (launch_frame_pass(3)); the frames below `look` only feed the
+// mask (the look-back of a sharded range, a warm-up): none of their pixels is stored.  look = M: no pixels at all.
+static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s, uint8_t* fout = nullptr, int look = 0) {
     const PlanDev& d = c->plan->d;
     const size_t fb = (size_t)d.W * d.H * 3, mw = (size_t)d.H * d.WW;
     const int nsub = sub_batches(M);
@@ -910,7 +955,7 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s) {
         if (c->plan->shared_ok) {
             // shared pass: undistort the tiles under share_y0 once (pixels -> und_px, colour bits -> und_bits), then pick the
             // mask out of the bit plane; the overlay later blends the canvas onto und_px instead of gathering again
-            if ((rc = launch_frame_pass(c, fin, M, nullptr, s, 0, 0, 3))) return rc;
+            if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, 3, 0, -1, look))) return rc;
             tl_mark("shared pass", s);
             k_mask_b<<<dim3(d.n_tiles, (M + MASKB_FPC - 1) / MASKB_FPC), MASK_THREADS, 0, s>>>(c->und_bits, c->mask, d, M);
             if ((rc = check_launch())) return rc;
@@ -984,8 +1029,11 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         if (c->plan->shared_ok && !search_first) {
             // the shared pass of ld_prepass left the undistorted pixels of the share tiles in und_px: blend, do not gather again
             const int bf = frames_per_cta(M);
-            k_blend_px<<<dim3(c->plan->n_share, (M + bf - 1) / bf), FRAME_THREADS, 0, c->s_lat>>>(
-                c->und_px + (size_t)look * c->plan->n_share * 16 * 128, c->planes + (size_t)look * canvas_words(d), fout, d, c->plan->share_tiles, M, bf);
+            const int nbt = c->px_split ? c->plan->n_blend : c->plan->n_share;   // the tiles the shared pass parked in und_px
+            if (nbt)
+                k_blend_px<<<dim3(nbt, (M + bf - 1) / bf), FRAME_THREADS, 0, c->s_lat>>>(
+                    c->und_px + (size_t)look * nbt * 16 * 128, c->planes + (size_t)look * canvas_words(d), fout, d,
+                    c->px_split ? c->plan->blend_tiles : c->plan->share_tiles, M, bf);
             if ((rc = check_launch())) return rc;
             tl_mark("blend_px (s_lat)", c->s_lat);
             // the putText tiles only need the raster's text plane: they follow the plain tiles on the caller's stream
@@ -1042,12 +1090,12 @@ static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, l
             LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
             const int early_tiles = c->plan->n_plain_top * knob(KNOB_SPLIT_PLAIN, "LD_SPLIT_PLAIN", 100) / 100;
             if ((rc = launch_frame_pass(c, frames + base * fb, M, out + base * fb, s, 0, 0, 5, 0, early_tiles))) return rc;
-            if ((rc = prepass_impl(c, frames + base * fb, M, c->s_lat))) return rc;
+            if ((rc = prepass_impl(c, frames + base * fb, M, c->s_lat, out + base * fb))) return rc;
             if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
                                     frame_offset + base, 0, 1, 0, 0, 0, 0, 1, early_tiles))) return rc;
             continue;
         }
-        if ((rc = prepass_impl(c, frames + base * fb, M, s))) return rc;
+        if ((rc = prepass_impl(c, frames + base * fb, M, s, out + base * fb))) return rc;
         if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,
                                 frame_offset + base))) return rc;
     }
@@ -1057,6 +1105,13 @@ extern "C" int ld_prepass(ld_ctx* c, const uint8_t* frames, int n, void* stream)
     if (!c || !frames || n < 0 || n > c->max_frames) return LD_ERR_ARG;
     if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
     return n ? prepass_impl(c, frames, n, (cudaStream_t)stream) : LD_OK;
+}
+// ld_prepass for a caller that already knows where the output frames go (the same `out` it will hand to ld_postpass*): the
+// shared pass stores the pixels the inverse warp cannot touch straight into them.
+extern "C" int ld_prepass_out(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, void* stream) {
+    if (!ARGS_OK(c, frames, out, n) || n > c->max_frames) return LD_ERR_ARG;
+    if (c->plan->d.H != 720 || c->plan->d.W != 1280) return LD_ERR_ARG;
+    return n ? prepass_impl(c, frames, n, (cudaStream_t)stream, out) : LD_OK;
 }
 extern "C" int ld_postpass(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, ld_frame_fit* fit_out, void* state_out,
                            void* stream) {
@@ -1121,7 +1176,7 @@ extern "C" int ld_halo_status(ld_ctx* c, int* halo_invalid, int* tail_invalid) {
 // lane the trackers are exactly what a single GPU would carry into the range (k_halo_valid).  Follow with ld_process_batch.
 static int warmup_impl(ld_ctx* c, const uint8_t* frames, int n, int n_total, int check, cudaStream_t s) {
     int rc;
-    if ((rc = prepass_impl(c, frames, n, s))) return rc;
+    if ((rc = prepass_impl(c, frames, n, s, nullptr, n))) return rc;  // mask only: no pixel of a look-back frame is stored
     // an empty lane on a fresh tracker inside a look-back that does NOT start the video is not the reference's TypeError (the
     // real tracker had points there): it only makes the halo invalid, so its frame index goes to a scratch slot
     return fit_core(c, c->rec, c->work, n, c->fit, s, 0, 1, n, n_total, check, check ? c->flags + 6 : nullptr);
@@ -1140,7 +1195,7 @@ extern "C" int ld_process_range(ld_ctx* c, const uint8_t* frames, int n_lookback
         return process_impl(c, frames + (size_t)n_lookback * c->plan->d.W * c->plan->d.H * 3, n, out, fit_out, (cudaStream_t)stream, 0);
     }
     int rc;
-    if ((rc = prepass_impl(c, frames, n_lookback + n, (cudaStream_t)stream))) return rc;
+    if ((rc = prepass_impl(c, frames, n_lookback + n, (cudaStream_t)stream, out, n_lookback))) return rc;
     return postpass_impl(c, frames + (size_t)n_lookback * c->plan->d.W * c->plan->d.H * 3, n, out, fit_out, nullptr, (cudaStream_t)stream, 0,
                          0, 0, 0, 0, n_lookback, check_frames ? 1 : 0);
 }
@@ -1202,7 +1257,7 @@ static int process_host_impl(ld_ctx* c, const uint8_t* lookback, int n_lookback,
         if (ce != cudaSuccess) break;
         if (warm) {
             if (pos == 0) rc = warmup_impl(c, c->stage_in[b], m, n_lookback, check_frames ? 1 : 0, c->s_comp);
-            else if (!(rc = prepass_impl(c, c->stage_in[b], m, c->s_comp)))
+            else if (!(rc = prepass_impl(c, c->stage_in[b], m, c->s_comp, nullptr, m)))
                 rc = fit_core(c, c->rec, c->work, m, c->fit, c->s_comp, 0, 0, 0, 0, 0, check_frames ? c->flags + 6 : nullptr);
             HOST_TRY(cudaEventRecord(c->ev_comp[b], c->s_comp));
         } else {
@@ -1277,7 +1332,7 @@ extern "C" int ld_undistort(ld_ctx* c, const uint8_t* frames, int n, uint8_t* ou
     int rc;
     if ((rc = frame_tensor_map(c->plan, frames, n, &tm))) return rc;
     k_frame_pass_mf<0><<<dim3(d.n_frame_tiles, (n + fpc - 1) / fpc), FRAME_MF_THREADS, c->plan->frame_smem, (cudaStream_t)stream>>>(
-        tm, frames, nullptr, nullptr, out, d, n, fpc, c->plan->frame_box_rows, nullptr, nullptr, nullptr);
+        tm, frames, nullptr, nullptr, out, d, n, fpc, c->plan->frame_box_rows, nullptr, nullptr, nullptr, 0);
     return check_launch();
 }
 extern "C" int ld_warp(ld_ctx* c, const uint8_t* img, int n, int channels, uint8_t* out, void* stream) {

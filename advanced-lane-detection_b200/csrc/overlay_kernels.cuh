@@ -536,7 +536,13 @@ __device__ __forceinline__ uint32_t bilinear_rgb_pre(uint32_t box, uint32_t stri
 // k_mask_b picks the mask out of it) and the pixels themselves to a scratch buffer in lane order (und_px, k_blend_px adds
 // the canvas later).  (Writing the share tiles' pixels straight into the output frames and blending only the 32-pixel groups
 // the canvas touches in place was tried in round 2: 2.99 instead of 4.81 MB of traffic per frame, but the packed store in the
-// shared pass and the read-modify-write chain cost more issue slots than the bytes saved: 4.14 against 4.00 ms per step.)
+// shared pass and the read-modify-write chain cost more issue slots than the bytes saved: 4.14 against 4.00 ms per step.
+// Deciding it per 32-pixel group from the inverse warp's static footprint inside MODE 3 -- und_px for the groups it can touch,
+// packed RGB for the others -- put two running pointers into the 64-register loop: shared pass 0.62 -> 0.89 us/frame.)
+// MODE 5: the share tiles the inverse warp cannot touch at all (a quarter of them): their pixels are final after the
+// undistortion, so they leave as packed RGB like MODE 0, next to the colour bits of MODE 3 -- they never pass through
+// und_px and k_blend_px.  Used when the caller of the shared pass already has the output frames (`out`); frames below
+// `look` (the look-back of a sharded range) only feed the mask: MODE 3 / 5 store none of their pixels.
 constexpr int FRAME_MF_THREADS = 512;           // 16 warps = the 16 rows of a tile
 #ifndef LD_FRAME_STAGES
 #define LD_FRAME_STAGES 3
@@ -549,7 +555,8 @@ template <int MODE>
 __global__ void __launch_bounds__(FRAME_MF_THREADS, 2)
 k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames, const uint32_t* __restrict__ planes,
                 const uint32_t* __restrict__ text, uint8_t* __restrict__ out, const PlanDev P, int n, int fpc, int box_rows,
-                const int32_t* __restrict__ tile_ids, uint32_t* __restrict__ und_bits, uint32_t* __restrict__ und_px) {
+                const int32_t* __restrict__ tile_ids, uint32_t* __restrict__ und_bits, uint32_t* __restrict__ und_px, int look) {
+    constexpr bool COLOUR = MODE == 3 || MODE == 4 || MODE == 5;        // the pass decides the mask colours (und_bits)
     extern __shared__ __align__(128) uint8_t s_boxes[];
     __shared__ __align__(8) uint64_t bar[FRAME_STAGES], empty[FRAME_STAGES];     // box landed / box released by all warps
     const int W = P.W, H = P.H, WW = P.WW;
@@ -568,7 +575,7 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     keep_u32(box0);
     // MODE 3: the colour pre-decision table sits behind the ring of boxes
     const uint2* s_pre = reinterpret_cast<const uint2*>(s_boxes + (box0 - smem_u32(s_boxes)) + FRAME_STAGES * FRAME_PAIR * box_bytes);
-    if (MODE == 3 || MODE == 4)
+    if (COLOUR)
         for (int i = threadIdx.x; i < MASK_PRE_WORDS; i += FRAME_MF_THREADS)
             reinterpret_cast<uint32_t*>(const_cast<uint2*>(s_pre))[i] = __ldg(P.cpre + i);
     if (threadIdx.x == 0) {
@@ -602,13 +609,16 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
     // running per-frame pointers (advanced by one frame per iteration: no 64-bit multiplies in the loop); everything
     // that only a few rows need (text plane, the slow path's frame pointer) is recomputed where it is used, and all ring
     // indices derive from the frame counter (FRAME_STAGES is a power of two): the loop has to fit 64 registers
-    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)f0 * fbytes + ((size_t)y * W + t.x0) * 3) + rs.j;
+    // (MODE 3 / 5: `out` is the frame of index `look`)
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + ((long long)f0 - (COLOUR ? look : 0)) * (long long)fbytes + ((size_t)y * W + t.x0) * 3) + rs.j;
     uint32_t gmask = 0;                                                  // MODE 4: which 32-pixel groups of the row hold a pixel the bird's-eye warp samples
-    if (MODE == 3 || MODE == 4) {
+    if (COLOUR) {
         if (MODE == 4 && row_on) gmask = __ldg(P.share_groups + (size_t)(y - P.share_y0) * (W / 128) + (t.x0 >> 7));
-        // und_px: u32[n][share tiles][16 rows][4][32] (pixel l + 32k of the row at [k][l]); und_bits: u32[n][H - share_y0][WW]
-        frame_words = gridDim.x * 16u * 128u;
-        if (MODE == 3) orow = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + r * 128 + lane;
+        // und_px: u32[n][tiles of this launch][16 rows][4][32] (pixel l + 32k of the row at [k][l]); und_bits: u32[n][H - share_y0][WW]
+        if (MODE == 3) {
+            frame_words = gridDim.x * 16u * 128u;
+            orow = und_px + ((size_t)f0 * gridDim.x + blockIdx.x) * (16u * 128u) + r * 128 + lane;
+        }
         und_bits += (size_t)f0 * (H - P.share_y0) * WW + (size_t)(y - P.share_y0) * WW + (t.x0 >> 5);
     }
     const uint2* cv = reinterpret_cast<const uint2*>(planes) + (size_t)f0 * cv_frame;
@@ -655,9 +665,9 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (MODE == 4 && !((gmask >> k) & 1u)) { ar[k] = ag[k] = ab[k] = 0u; continue; }   // warp-uniform: no sampled pixel in this group
-                        if (MODE == 3 || MODE == 4) {
+                        if (COLOUR) {
                             bilinear_acc(box + (po[k] & 0x3FFFFFFFu), (uint32_t)FRAME_BOX_PITCH, po[k] >> 27, wx[k], wy[k], ar[k], ag[k], ab[k]);
-                            if (MODE == 3) c[k] = pack_rgb(ar[k], ag[k], ab[k]);
+                            if (MODE == 3 || MODE == 5) c[k] = pack_rgb(ar[k], ag[k], ab[k]);
                         } else
                             c[k] = bilinear_rgb_pre(box, (uint32_t)FRAME_BOX_PITCH, po[k], wx[k], wy[k]);
                     }
@@ -672,14 +682,14 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     c[k] = k < ngroups ? bilinear_rgb(frame, W, H, t.x0 + lane + 32 * k, y, __ldg(um + 32 * k), P.wtab) : 0u;
-                    if (MODE == 3 || MODE == 4) { ar[k] = (c[k] & 255u) << 16; ag[k] = (c[k] & 0xFF00u) << 8; ab[k] = c[k] & 0xFF0000u; }
+                    if (COLOUR) { ar[k] = (c[k] & 255u) << 16; ag[k] = (c[k] & 0xFF00u) << 8; ab[k] = c[k] & 0xFF0000u; }
                 }
             }
-            if (MODE == 3 || MODE == 4) {
+            if (COLOUR) {
                 // the shared pass only runs on 1280-wide plans (ld_plan_create: shared_ok): every tile row is four whole groups and
                 // its four mask words are one aligned 16-byte store.  Groups the bird's-eye warp never samples get a decision too
                 // (MODE 3) or the decision of a black pixel (MODE 4): k_mask_b reads neither.
-                if (have && row_on && (MODE == 3 || gmask)) {
+                if (have && row_on && (MODE != 4 || gmask)) {
                     uint32_t words[4];
 #ifdef LD_EXP_NOCOLOUR                                               // timing experiments only
                     words[0] = ar[0]; words[1] = ag[1]; words[2] = ab[2]; words[3] = ar[3];
@@ -687,9 +697,17 @@ k_frame_pass_mf(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restr
                     colour_words4(ar, ag, ab, pre, P.cbits, words);
 #endif
 #ifndef LD_EXP_NOPX
-                    if (MODE == 3) {
+                    if ((MODE == 3 || MODE == 5) && f0 + FRAME_PAIR * p + h >= look) {   // (a look-back frame: mask only)
+                        if (MODE == 3) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) orow[32 * k] = c[k];
+                            for (int k = 0; k < 4; ++k) orow[32 * k] = c[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {                // the row store of finish_row (every share tile row is four whole groups)
+                                const uint32_t nb = __shfl_down_sync(0xffffffffu, c[k], 1);
+                                if (rs.on) orow[24 * k] = __byte_perm(c[k], nb, rs.sel);
+                            }
+                        }
                     }
 #endif
                     if (lane == 0) *reinterpret_cast<uint4*>(und_bits) = make_uint4(words[0], words[1], words[2], words[3]);

@@ -160,7 +160,8 @@ int ld_frame_pass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_de
  * which = 3 shared pass: the tiles from plan row share_y0 down are undistorted once for the mask AND the overlay (pixels and
  * their colour decisions stay in the context); 7: the packed mask out of those decisions (context mask); 5: the plain tiles
  * above share_y0 (pure cv2.undistort) -> out; 6: canvas blend onto the shared pixels -> out; 4: the putText tiles -> out.
- * ld_stage_tiles: how many 128x16 tiles stage `which` covers. */
+ * ld_stage_tiles: how many 128x16 tiles stage `which` covers (which = 9: how many tiles of the shared rows the inverse
+ * warp can touch -- the only ones that pass through k_blend_px when the shared pass had the output frames). */
 int ld_stage(ld_ctx* ctx, int which, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
 int ld_stage_tiles(ld_ctx* ctx, int which);
 /* Tuning aid (process-wide): knob 0 = CTAs per SM of the persistent raster grid inside ld_process_batch (0 = one CTA per band),
@@ -178,6 +179,10 @@ int ld_process_batch(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out
  * (ld_state_import).  If state_out_dev is not NULL the updated blob is copied there right after the fit stage and
  * ld_wait_state makes `stream` wait for exactly that copy, so it can be sent on while the overlay still runs. */
 int ld_prepass(ld_ctx* ctx, const uint8_t* frames_dev, int n, void* stream);
+/* ld_prepass for a caller that already knows where the output frames will go (the same `out_dev` it later hands to
+ * ld_postpass / ld_postpass_flags): the pixels under the horizon that the inverse warp cannot touch are final after the
+ * undistortion and are stored straight into out_dev; only the rest waits in the context for the overlay. */
+int ld_prepass_out(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
 /* ld_postpass_flags: LD_POST_SKIP_PLAIN = the caller has already written the plain tiles of this range with
  * ld_stage(ctx, 5, ...) -- what a sharded rank does while it waits for its predecessor's tracker state. */
 enum { LD_POST_USE_HALO = 4,        /* fit the look-back records of ld_halo_set first, from empty trackers (see ld_halo_set) */

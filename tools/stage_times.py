@@ -55,7 +55,7 @@ def main():
         t("k_raster", lambda: L.ld_raster(h, fits.data_ptr(), n, s))
         t("k_frame_pass", lambda: L.ld_frame_pass(h, frames.data_ptr(), n, out.data_ptr(), s))
     if hasattr(L, "ld_stage"):                                            # the launches process_batch is really made of
-        t("shared pass k_frame_pass_mf<3>", lambda: L.ld_stage(h, 3, frames.data_ptr(), n, None, s))
+        t("shared pass k_frame_pass_mf<3>", lambda: L.ld_stage(h, 3, frames.data_ptr(), n, out.data_ptr(), s))   # out: the pixels the inverse warp cannot touch go straight there
         t("k_mask_b", lambda: L.ld_stage(h, 7, None, n, None, s))
         t("mask-only pass k_frame_pass_mf<4>", lambda: L.ld_stage(h, 8, frames.data_ptr(), n, None, s))
         t("plain tiles k_frame_pass_mf<0>", lambda: L.ld_stage(h, 5, frames.data_ptr(), n, out.data_ptr(), s))
