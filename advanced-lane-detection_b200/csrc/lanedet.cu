@@ -54,8 +54,9 @@ struct ld_plan {
     const int32_t* plain_tiles; const int32_t* overlay_tiles;
     int n_plain, n_overlay;
     // The shared pass (process_image only): the tiles from row share_y0 down are undistorted ONCE for the mask and the
-    // overlay (k_frame_pass_mf<3> -> k_mask_b, k_blend_px); `text` tiles are the overlay tiles above share_y0 (putText).
-    const int32_t* share_tiles; const int32_t* text_tiles; const int32_t* plain_top_tiles;   // plain_top = plain tiles above share_y0
+    // overlay (k_frame_pass_mf<3> / <5> -> k_mask_b, k_blend_px); plain_top = all tiles above share_y0 (pure cv2.undistort, the
+    // putText pixels go on top afterwards: k_text_px); `text` tiles = those of them under the putText window.
+    const int32_t* share_tiles; const int32_t* text_tiles; const int32_t* plain_top_tiles;
     const int32_t* mask_tiles;                                          // share tiles with a pixel the bird's-eye warp samples (ld_mask)
     int n_share, n_text, n_plain_top, n_mask_tiles, shared_ok;
     // the share tiles split by the inverse warp's static footprint: it can touch `blend` tiles (their pixels wait in und_px for
@@ -107,7 +108,7 @@ struct ld_ctx {
 
 // Tuning knobs of the step schedule, settable at run time so that one process can sweep them (tools/knob_sweep.py);
 // -1 = take the default / the environment variable of the same purpose.
-enum { KNOB_RASTER_PERSIST = 0, KNOB_EARLY_PLAIN = 1, KNOB_PLAIN_FPC = 2, KNOB_SPLIT_PLAIN = 4, N_KNOBS = 8 };
+enum { KNOB_RASTER_PERSIST = 0, KNOB_EARLY_PLAIN = 1, KNOB_PLAIN_FPC = 2, KNOB_SPLIT_PLAIN = 4, KNOB_TEXT_TILES = 5, KNOB_NO_PX_SPLIT = 6, N_KNOBS = 8 };
 static int g_knob[N_KNOBS] = {-1, -1, -1, -1, -1, -1, -1, -1};
 extern "C" int ld_debug_knob(int id, int value) {
     if (id < 0 || id >= N_KNOBS) return LD_ERR_ARG;
@@ -301,16 +302,19 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
             if (desc->frame_tiles[8 * t + 1] >= d.share_y0) plain[ns++] = t;          // (re-using the scratch arrays)
         if (!rc) rc = upload(p, plain, (size_t)(ns ? ns : 1), &p->share_tiles);
         for (int k = 0; k < no; ++k)
-            if (desc->frame_tiles[8 * over[k] + 1] < d.share_y0) plain[nt++] = over[k];
+            if (desc->frame_tiles[8 * over[k] + 1] < d.share_y0) plain[nt++] = over[k];   // the tiles under the putText window
         if (!rc) rc = upload(p, plain, (size_t)(nt ? nt : 1), &p->text_tiles);
         p->n_share = ns; p->n_text = nt;
         int npt = 0;
-        for (int t = 0; t < desc->n_frame_tiles; ++t) {                  // everything above share_y0 that is not a text tile
-            if (desc->frame_tiles[8 * t + 1] >= d.share_y0) continue;
-            bool is_text = false;
-            for (int k = 0; k < no; ++k) is_text = is_text || over[k] == t;
-            if (!is_text) plain[npt++] = t;
-        }
+        // everything above share_y0 is a plain tile of the step: the inverse warp cannot reach it (share_y0 <= inv_y0) and the
+        // text goes on top afterwards (k_text_px)
+        for (int pass = 0; pass < 2; ++pass)                             // (the tiles under the text window last)
+            for (int t = 0; t < desc->n_frame_tiles; ++t) {
+                if (desc->frame_tiles[8 * t + 1] >= d.share_y0) continue;
+                bool is_text = false;
+                for (int k = 0; k < no; ++k) is_text = is_text || over[k] == t;
+                if (is_text == (pass == 1)) plain[npt++] = t;
+            }
         if (!rc) rc = upload(p, plain, (size_t)(npt ? npt : 1), &p->plain_top_tiles);
         p->n_plain_top = npt;
         delete[] ids;
@@ -775,7 +779,7 @@ static int frames_per_cta(int m) {
 }
 // which = 0: every tile with blend + text; 1: the plain tiles as cv2.undistort; 2: the overlay tiles with blend + text;
 // 3: the shared pass over the share tiles (undistorted pixels -> c->und_px, their colour bits -> c->und_bits; fout unused);
-// 4: the text tiles (overlay tiles above share_y0) with blend + text; 5: the plain tiles above share_y0 as cv2.undistort;
+// 4: the putText pixels on top of finished frames (k_text_px); 5: the tiles above share_y0 as cv2.undistort;
 // 8: the mask-only pass of ld_mask over the share tiles that hold a sampled pixel (colour bits -> c->und_bits)
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted,
                              int which, int tile_lo, int tile_cnt, int px_look) {
@@ -808,7 +812,7 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
             // out, colour bits to und_bits); only the others park their pixels in und_px for k_blend_px
             uint32_t* bits = c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW;
             const size_t smem = c->plan->frame_smem + MASK_PRE_WORDS * 4;
-            c->px_split = fout != nullptr;
+            c->px_split = fout != nullptr && !knob(KNOB_NO_PX_SPLIT, "LD_NO_PX_SPLIT", 0);
             const int nb = c->px_split ? c->plan->n_blend : c->plan->n_share;
             if (nb)
                 k_frame_pass_mf<3><<<dim3(nb, groups.y), FRAME_MF_THREADS, smem, s>>>(
@@ -823,14 +827,22 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
                     tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->mask_tiles,
                     c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, nullptr, 0);
         } else if (which == 5) {                                         // [tile_lo, tile_lo + tile_cnt) of the list (the step may launch it in two parts)
-            const int cnt = tile_cnt < 0 ? c->plan->n_plain_top - tile_lo : tile_cnt;
+            int cnt = tile_cnt < 0 ? c->plan->n_plain_top - tile_lo : tile_cnt;
+            if (knob(KNOB_TEXT_TILES, "LD_TEXT_TILES", 0) && tile_lo + cnt > c->plan->n_plain_top - c->plan->n_text)
+                cnt = c->plan->n_plain_top - c->plan->n_text - tile_lo;  // A/B: the text window's tiles (last in the list) stay out
             if (cnt > 0)
                 k_frame_pass_mf<0><<<dim3(cnt, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
                     tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_top_tiles + tile_lo, nullptr, nullptr, 0);
-        } else if (which == 4) {
+        } else if (which == 4) {                                         // the text on top of the (plain) tiles under its window
+            k_text_px<<<dim3((LD_TEXT_ROWS * LD_TEXT_WORDS + 255) / 256, m), 256, 0, s>>>(text, fout, d.W, d.H);
+        } else if (which == 11) {                                        // A/B (knob 5): the window's tiles as undistort + text in one launch after the raster
             if (c->plan->n_text)
                 k_frame_pass_mf<1><<<dim3(c->plan->n_text, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
                     tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->text_tiles, nullptr, nullptr, 0);
+        } else if (which == 10) {                                        // the tiles under the putText window as cv2.undistort (wipes an earlier text)
+            if (c->plan->n_text)
+                k_frame_pass_mf<0><<<dim3(c->plan->n_text, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->text_tiles, nullptr, nullptr, 0);
         } else
             k_frame_pass_mf<1><<<dim3(d.n_frame_tiles, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
                 tm, fin, planes, text, fout, d, m, fpc, c->plan->frame_box_rows, nullptr, nullptr, nullptr, 0);
@@ -872,7 +884,7 @@ extern "C" int ld_frame_pass(ld_ctx* c, const uint8_t* frames, int n, uint8_t* o
 
 // The launches ld_process_batch is made of, one at a time (measurement / profiling of the real step):
 // which = 3 shared pass (frames -> und_px, und_bits), 7 k_mask_b (und_bits -> the context's mask), 5 plain tiles above
-// share_y0 (frames -> out), 6 k_blend_px (und_px + canvas -> out), 4 text tiles (frames + canvas + text -> out),
+// share_y0 (frames -> out), 6 k_blend_px (und_px + canvas -> out), 4 the putText pixels (text plane -> out),
 // 8 the mask-only pass of ld_mask (frames -> und_bits; followed by 7 it is the whole of ld_mask).
 extern "C" int ld_stage(ld_ctx* c, int which, const uint8_t* frames, int n, uint8_t* out, void* stream) {
     if (!c || n < 0 || n > c->max_frames || !c->plan->shared_ok) return LD_ERR_ARG;
@@ -902,7 +914,7 @@ extern "C" const uint32_t* ld_ctx_mask(ld_ctx* c) { return c ? c->mask : nullptr
 extern "C" int ld_stage_tiles(ld_ctx* c, int which) {                   // tiles a stage covers (for byte accounting)
     if (!c) return -1;
     if (which == 9) return c->plan->n_blend;                            // share tiles the inverse warp can touch (und_px -> k_blend_px)
-    return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? c->plan->n_text : which == 5 ? c->plan->n_plain_top :
+    return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? 0 : which == 5 ? c->plan->n_plain_top :
            which == 8 ? c->plan->n_mask_tiles : -1;
 }
 
@@ -1036,10 +1048,14 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
                     c->px_split ? c->plan->blend_tiles : c->plan->share_tiles, M, bf);
             if ((rc = check_launch())) return rc;
             tl_mark("blend_px (s_lat)", c->s_lat);
-            // the putText tiles only need the raster's text plane: they follow the plain tiles on the caller's stream
+            // putText: white pixels on top of the plain tiles under the text window, once the raster has made the frame's text plane.
+            // A caller that ran the plain tiles itself (LD_POST_SKIP_PLAIN) may be fitting this range a second time over the same
+            // output (a sharded rank repairing its boundary): the window's tiles are undistorted again so that no earlier text stays.
+            const int text_tiles = knob(KNOB_TEXT_TILES, "LD_TEXT_TILES", 0);
+            if (!text_tiles && skip_plain && !lat_continues && (rc = launch_frame_pass(c, fin, M, fout, s, look, 0, 10))) return rc;
             LD_CUDA(cudaStreamWaitEvent(s, c->ev_rast[0], 0));
-            if ((rc = launch_frame_pass(c, fin, M, fout, s, look, 0, 4))) return rc;
-            tl_mark("text tiles (s)", s);
+            if ((rc = launch_frame_pass(c, fin, M, fout, s, look, 0, text_tiles ? 11 : 4))) return rc;
+            tl_mark("text (s)", s);
         } else if ((rc = launch_frame_pass(c, fin, M, fout, c->s_lat, 0, 0, 2))) return rc;
         k_near_integer<<<M, 128, 0, c->s_lat>>>(c->fit + look, M);      // the vertex guard of ld_frame_fit, off the critical chain
         LD_CUDA(cudaEventRecord(c->ev_join[1], c->s_lat));

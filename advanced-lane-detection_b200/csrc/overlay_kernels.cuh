@@ -782,6 +782,35 @@ k_blend_px(const uint32_t* __restrict__ und_px, const uint32_t* __restrict__ pla
     }
 }
 
+// cv2.putText (Project.py:326-332) inside the step: the tiles under the text window are undistorted with the plain tiles (they
+// depend on nothing), and once the raster has written the frame's text plane every set bit of it becomes a white pixel.  One
+// thread per plane word.  (The window used to be a launch of its own -- MODE 1 over its 35 tiles after the raster, 0.175
+// us/frame at 37 % of the HBM roofline; as plain tiles the same pixels cost 0.10 and start with everything else.)
+__global__ void __launch_bounds__(256)
+k_text_px(const uint32_t* __restrict__ text, uint8_t* __restrict__ out, int W, int H) {
+    // a warp takes 32 plane words (one per lane); for every non-empty one the 32 pixels are 96 contiguous output bytes = 24
+    // words, one per lane: white is all ones, so a word is stored whole or OR-ed (nobody else writes these tiles any more)
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < LD_TEXT_ROWS * LD_TEXT_WORDS;
+    const uint32_t mine = in ? __ldg(text + (size_t)f * LD_TEXT_ROWS * LD_TEXT_WORDS + i) : 0u;
+    uint32_t todo = __ballot_sync(0xffffffffu, mine != 0u);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t m = __shfl_sync(0xffffffffu, mine, src);
+        const int wi = i - lane + src, row = wi / LD_TEXT_WORDS, w = wi - row * LD_TEXT_WORDS;
+        const int y = LD_TEXT_Y0 + row, x0 = LD_TEXT_X0 + 32 * w;
+        if (y >= H || x0 + 32 > W || lane >= 24) continue;
+        uint32_t bytes = 0;                                             // byte b of the 96 belongs to pixel b / 3
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bytes |= ((m >> ((4 * lane + j) / 3)) & 1u) ? (0xFFu << (8 * j)) : 0u;
+        if (!bytes) continue;
+        uint32_t* p = reinterpret_cast<uint32_t*>(out + (size_t)f * W * H * 3 + ((size_t)y * W + x0) * 3) + lane;
+        if (bytes == 0xFFFFFFFFu) *p = bytes; else *p |= bytes;
+    }
+}
+
 // ld_draw: the input is ALREADY undistorted -> canvas blend only (helper.py:758-779, Project.py:144-170 with explicit
 // vertices).  One CTA per 128x16 tile and frame; pixels are fetched as words by lanes < 24 and dealt to their owners
 // with two shuffles (the mirror image of the store in finish_row).

@@ -160,10 +160,15 @@ class LaneEngine:
         _abi.check(self.lib, self.lib.ld_process_batch(self._ctx_h, _ptr(frames), n, _ptr(out), _ptr(fits), self._stream()))
         return out, fits
 
-    def prepass_dev(self, frames):
-        """mask + search of a frame range into the context workspace (no tracker access)"""
+    def prepass_dev(self, frames, out=None):
+        """mask + search of a frame range into the context workspace (no tracker access).  out = the buffer the following
+        postpass_dev will fill, if it is already known: the pixels under the horizon that the inverse warp cannot touch are
+        final after the undistortion and go straight there (ld_prepass_out)."""
         frames = self._frames(frames)
-        _abi.check(self.lib, self.lib.ld_prepass(self._ctx_h, _ptr(frames), frames.shape[0], self._stream()))
+        if out is None:
+            _abi.check(self.lib, self.lib.ld_prepass(self._ctx_h, _ptr(frames), frames.shape[0], self._stream()))
+        else:
+            _abi.check(self.lib, self.lib.ld_prepass_out(self._ctx_h, _ptr(frames), frames.shape[0], _ptr(out), self._stream()))
 
     def context_masks(self, n):
         """copy of the packed masks the last prepass / process call left in the context: int32[n, H, W/32] (device)"""

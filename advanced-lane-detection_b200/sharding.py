@@ -303,7 +303,7 @@ class ShardedRun:
         main = self.S.current()
         if rank == 0:
             eng.reset()                                     # the other ranks rebuild their trackers from the halo
-        eng.prepass_dev(frames_dev)                         # mask + search of the range: no tracker access
+        eng.prepass_dev(frames_dev, out=out)                # mask + search of the range: no tracker access
         send_t = eng.context_records(n)[n - h:] if rank + 1 < world else None
         recv_t = eng.halo_slots(h) if rank > 0 else None
         self.side.wait_stream(main)
@@ -332,7 +332,7 @@ class ShardedRun:
         eng, rank, world = self.engine, self.rank, self.world
         if rank == 0:
             eng.reset()
-        eng.prepass_dev(frames_dev)
+        eng.prepass_dev(frames_dev, out=out)
         plain_done = rank > 0 and eng.plain_pass_dev(frames_dev, out)   # while the predecessors fit
         if rank > 0:
             self.transport.recv(self.blob_in, rank - 1)

@@ -395,10 +395,10 @@ def main():
     ms = reduce_max(ev0.elapsed_time(ev1))
     value = world * n * a.steps / (ms / 1e3)
     repairs = run.repairs
-    # kernels of one step (profiles/r02_launches.csv): state reset; plain tiles; shared pass, k_mask_b, k_search; 5 fit kernels;
-    # k_raster_prep, k_raster; k_blend_px, text tiles; k_near_integer (rank 0 prints: its range starts the video, so it has no
-    # look-back; the other ranks of a 'lookback' run add k_halo_start)
-    launches_per_step = (1 + 1 + 3 + 5 + 2 + 2 + 1) if (world == 1 or mode != "records") else 16
+    # kernels of one step (profiles/r02_launches.csv): state reset; plain tiles; shared pass (two launches: the tiles the inverse
+    # warp can / cannot touch), k_mask_b, k_search; 5 fit kernels; k_raster_prep, k_raster; k_blend_px, k_text_px; k_near_integer
+    # (rank 0 prints: its range starts the video, so it has no look-back; the other ranks of a 'lookback' run add k_halo_start)
+    launches_per_step = (1 + 1 + 4 + 5 + 2 + 2 + 1) if (world == 1 or mode != "records") else 17
 
     # ---- sharded results against the serial protocol and against each other, then the other protocols' rates
     shard = None
@@ -532,8 +532,8 @@ def single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg):
     eng.reset()
     time_stage("k_fit*", lambda: L.ld_fit(h, rec_t.data_ptr(), n, fits.data_ptr(), st))
     time_stage("k_raster", lambda: L.ld_raster(h, fits.data_ptr(), n, st))
-    # the launches the step is really made of (ld_stage): shared pass -> k_mask_b -> ... plain tiles, k_blend_px, text tiles
-    SH, PL, BL, TX = "k_frame_pass_mf<3> (shared pass)", "k_frame_pass_mf<0> (plain tiles)", "k_blend_px", "k_frame_pass_mf<1> (text tiles)"
+    # the launches the step is really made of (ld_stage): shared pass -> k_mask_b -> ... plain tiles, k_blend_px, k_text_px
+    SH, PL, BL, TX = "k_frame_pass_mf<3> + <5> (shared pass)", "k_frame_pass_mf<0> (plain tiles)", "k_blend_px", "k_text_px (putText pixels)"
     time_stage(SH, lambda: L.ld_stage(h, 3, frames.data_ptr(), n, out.data_ptr(), st))   # with the output frames, as the step runs it
     time_stage("k_mask_b", lambda: L.ld_stage(h, 7, None, n, None, st))
     time_stage(PL, lambda: L.ld_stage(h, 5, frames.data_ptr(), n, out.data_ptr(), st))
@@ -557,7 +557,7 @@ def single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg):
                        "k_search": 115200 + 560, "k_raster": 722 * 82 * 8,
                        "k_frame_pass_mf<1> (whole frame: ld_frame_pass / ld_overlay)": 2 * FRAME_BYTES,
                        SH: n_share * tile_px * 3 + blend_px * 4 + final_px * 3 + 43520,   # source pixels read; u32 pixels / RGB + decision bits written
-                       "k_mask_b": 43520 + 115200, PL: n_plain * tile_px * 6, TX: n_text * tile_px * 6,
+                       "k_mask_b": 43520 + 115200, PL: n_plain * tile_px * 6,
                        BL: blend_px * (4 + 3) + 722 * 82 * 8,            # u32 pixels + canvas read, RGB written
                        "k_hist": 115200 + 20480, "k_frame_pass_mf<0> (cv2.undistort alone)": 2 * FRAME_BYTES,
                        # RGB read twice (gray, S channel), gray written once and read twice, binary written once

@@ -159,14 +159,16 @@ int ld_frame_pass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_de
 /* The individual launches ld_process_batch is made of, for measurement and profiling (n <= max_frames, 1280x720 plans):
  * which = 3 shared pass: the tiles from plan row share_y0 down are undistorted once for the mask AND the overlay (pixels and
  * their colour decisions stay in the context); 7: the packed mask out of those decisions (context mask); 5: the plain tiles
- * above share_y0 (pure cv2.undistort) -> out; 6: canvas blend onto the shared pixels -> out; 4: the putText tiles -> out.
+ * above share_y0 (pure cv2.undistort) -> out; 6: canvas blend onto the shared pixels -> out; 4: the putText pixels -> out.
  * ld_stage_tiles: how many 128x16 tiles stage `which` covers (which = 9: how many tiles of the shared rows the inverse
  * warp can touch -- the only ones that pass through k_blend_px when the shared pass had the output frames). */
 int ld_stage(ld_ctx* ctx, int which, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
 int ld_stage_tiles(ld_ctx* ctx, int which);
 /* Tuning aid (process-wide): knob 0 = CTAs per SM of the persistent raster grid inside ld_process_batch (0 = one CTA per band),
  * 1 = plain tiles first (1, default) or after the window search (0), 2 = frames per CTA of the plain-tile launch (0 = default),
- * 4 = percentage of the plain tiles launched first (the rest starts with the raster); value -1 = back to the default. */
+ * 4 = percentage of the plain tiles launched first (the rest starts with the raster), 5 = 1: the tiles under the putText
+ * window as one undistort + text launch after the raster instead of plain tiles + k_text_px, 6 = 1: every share tile through
+ * und_px and k_blend_px; value -1 = back to the default. */
 int ld_debug_knob(int id, int value);
 /* the packed masks ld_prepass / ld_process_batch / ld_stage(7) leave in the context: device u32[max_frames][H][W/32] */
 const uint32_t* ld_ctx_mask(ld_ctx* ctx);

@@ -249,6 +249,36 @@ def test_prepass_postpass_equals_process(engines, stills, golden):
     assert bytes(blob.cpu().numpy().tobytes()) == want_state
 
 
+def test_prepass_out_and_second_postpass_over_the_same_output(engines, stills, golden):
+    """ld_prepass_out (the share tiles the inverse warp cannot touch are written by the prepass already) followed by the
+    post-pass gives ld_process_batch's bytes; and a SECOND post-pass over the same output with other trackers -- what a sharded
+    rank does when it repairs its boundary (skip_plain: the plain tiles are in place) -- leaves no pixel of the first one's text"""
+    g = golden["sequences"]["project_seed0_40"]
+    frames = np.stack(list(O.synth_sequence([stills(s) for s in g["stills"]], 40, seed=g["seed"])))
+    eng = engines("project")
+    dev = eng.to_device(frames)
+    eng.reset()
+    want, want_fit = eng.process_dev(dev[20:40])            # trackers start empty at frame 20: other medians, other text
+    eng.check()
+    eng.reset()
+    full, _ = eng.process_dev(dev)
+    eng.check()
+    assert not (full[20:40] == want).all()                  # the two histories really print different numbers
+    out = eng.new_like(dev[20:40])
+    eng.reset()
+    eng.process_dev(dev[:20])                               # trackers as after frame 19
+    eng.prepass_dev(dev[20:40], out=out)
+    out_b, fit_b = eng.postpass_dev(dev[20:40], out=out)
+    eng.check()
+    assert (out_b == full[20:40]).all()
+    eng.reset()                                             # the "repair": empty trackers, same context records, same output buffer
+    out[:, 74:139, 62:538] = 255                            # (whatever the first pass printed: the whole putText window white)
+    out_c, fit_c = eng.postpass_dev(dev[20:40], out=out, skip_plain=True)
+    eng.check()
+    assert (fit_c == want_fit).all()
+    assert (out_c == want).all()
+
+
 def test_config4_4k_mask_and_histogram():
     """BASELINE.json configs[3]: 3840x2160 frames through the fused mask + histogram kernels (maps from the
     calibration scaled x3), against cv2 run directly at that size."""

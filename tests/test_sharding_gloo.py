@@ -166,7 +166,7 @@ class ModelEngine:
     def new_state_blob(self):
         return torch.zeros(4 + 2 * F_MODEL + 2, dtype=torch.float64)
 
-    def prepass_dev(self, frames):
+    def prepass_dev(self, frames, out=None):
         self.rec = frames.clone()
 
     def context_records(self, n):

@@ -60,7 +60,7 @@ def main():
         t("mask-only pass k_frame_pass_mf<4>", lambda: L.ld_stage(h, 8, frames.data_ptr(), n, None, s))
         t("plain tiles k_frame_pass_mf<0>", lambda: L.ld_stage(h, 5, frames.data_ptr(), n, out.data_ptr(), s))
         t("k_blend_px", lambda: L.ld_stage(h, 6, None, n, out.data_ptr(), s))
-        t("text tiles k_frame_pass_mf<1>", lambda: L.ld_stage(h, 4, frames.data_ptr(), n, out.data_ptr(), s))
+        t("k_text_px", lambda: L.ld_stage(h, 4, frames.data_ptr(), n, out.data_ptr(), s))
     und = torch.empty_like(frames)
     t("k_undistort", lambda: L.ld_undistort(h, frames.data_ptr(), n, und.data_ptr(), s))
     eng.reset()
