@@ -57,6 +57,10 @@ struct ld_plan {
     // overlay (k_frame_pass_mf<3> / <5> -> k_mask_b, k_blend_px); plain_top = all tiles above share_y0 (pure cv2.undistort, the
     // putText pixels go on top afterwards: k_text_px); `text` tiles = those of them under the putText window.
     const int32_t* share_tiles; const int32_t* text_tiles; const int32_t* plain_top_tiles;
+    // plain_split = the plain tiles of a step whose shared pass has the output frames: plain_top plus the share tiles that hold
+    // neither a pixel the inverse warp can touch nor one the bird's-eye warp samples (pure cv2.undistort as well)
+    const int32_t* plain_split_tiles;
+    int n_plain_split;
     const int32_t* mask_tiles;                                          // share tiles with a pixel the bird's-eye warp samples (ld_mask)
     int n_share, n_text, n_plain_top, n_mask_tiles, shared_ok;
     // the share tiles split by the inverse warp's static footprint: it can touch `blend` tiles (their pixels wait in und_px for
@@ -368,12 +372,38 @@ extern "C" int ld_plan_create(const ld_plan_desc* desc, int device, ld_plan** ou
                 for (int y = (y0 > desc->inv_y0 ? y0 : desc->inv_y0); !any && y < y0 + h && y < desc->inv_y1; ++y)
                     for (int x = x0; x < x0 + w; ++x)
                         if (desc->inv_pack[(size_t)(y - desc->inv_y0) * W + x] != 0xFFFFFFFFu) { any = true; break; }
-                if (any) bt[nbl++] = t; else ft[nfi++] = t;
+                bool sampled = false;
+                for (int y = y0; y < y0 + h && y < H; ++y) sampled = sampled || sg[(size_t)(y - d.share_y0) * tcols + (x0 >> 7)] != 0;
+                if (any) bt[nbl++] = t; else if (sampled) ft[nfi++] = t;   // (untouched and unsampled: a plain tile, below)
             }
             if (!rc) rc = upload(p, bt, (size_t)(nbl ? nbl : 1), &p->blend_tiles);
             if (!rc) rc = upload(p, ft, (size_t)(nfi ? nfi : 1), &p->final_tiles);
             p->n_blend = nbl; p->n_final = nfi;
             delete[] bt;
+            // plain_split: those share tiles first, then plain_top in its own order (the text window's tiles stay last)
+            int32_t* ps = new (std::nothrow) int32_t[(size_t)desc->n_frame_tiles + 1];
+            if (!ps) { delete[] sg; ld_plan_destroy(p); return LD_ERR_ARG; }
+            int nps = 0;
+            auto text_tile = [&](int t) {
+                const int x0 = desc->frame_tiles[8 * t], y0 = desc->frame_tiles[8 * t + 1], w = desc->frame_tiles[8 * t + 2], h = desc->frame_tiles[8 * t + 3];
+                return y0 < LD_TEXT_Y0 + LD_TEXT_ROWS && y0 + h > LD_TEXT_Y0 && x0 < LD_TEXT_X0 + 32 * LD_TEXT_WORDS && x0 + w > LD_TEXT_X0;
+            };
+            for (int t = 0; t < desc->n_frame_tiles; ++t) {
+                const int x0 = desc->frame_tiles[8 * t], y0 = desc->frame_tiles[8 * t + 1], w = desc->frame_tiles[8 * t + 2], h = desc->frame_tiles[8 * t + 3];
+                if (y0 < d.share_y0) continue;
+                bool any = false;
+                for (int y = (y0 > desc->inv_y0 ? y0 : desc->inv_y0); !any && y < y0 + h && y < desc->inv_y1; ++y)
+                    for (int x = x0; x < x0 + w; ++x)
+                        if (desc->inv_pack[(size_t)(y - desc->inv_y0) * W + x] != 0xFFFFFFFFu) { any = true; break; }
+                for (int y = y0; y < y0 + h && y < H; ++y) any = any || sg[(size_t)(y - d.share_y0) * tcols + (x0 >> 7)] != 0;
+                if (!any) ps[nps++] = t;
+            }
+            for (int pass = 0; pass < 2; ++pass)
+                for (int t = 0; t < desc->n_frame_tiles; ++t)
+                    if (desc->frame_tiles[8 * t + 1] < d.share_y0 && text_tile(t) == (pass == 1)) ps[nps++] = t;
+            if (!rc) rc = upload(p, ps, (size_t)(nps ? nps : 1), &p->plain_split_tiles);
+            p->n_plain_split = nps;
+            delete[] ps;
         }
         // the share tiles that hold a sampled pixel at all: the tiles of the mask-only pass (ld_mask: k_frame_pass_mf<4>)
         int32_t* mt = new (std::nothrow) int32_t[(size_t)desc->n_frame_tiles];
@@ -781,6 +811,10 @@ static int frames_per_cta(int m) {
 // 3: the shared pass over the share tiles (undistorted pixels -> c->und_px, their colour bits -> c->und_bits; fout unused);
 // 4: the putText pixels on top of finished frames (k_text_px); 5: the tiles above share_y0 as cv2.undistort;
 // 8: the mask-only pass of ld_mask over the share tiles that hold a sampled pixel (colour bits -> c->und_bits)
+// the plain tiles of the step (launch_frame_pass(5)): with the shared pass split by the inverse warp's footprint (px_split)
+// the share tiles nobody else needs are plain tiles too
+static int plain_count(const ld_ctx* c) { return c->px_split ? c->plan->n_plain_split : c->plan->n_plain_top; }
+static bool split_wanted(const ld_ctx* c) { return c->plan->shared_ok && !knob(KNOB_NO_PX_SPLIT, "LD_NO_PX_SPLIT", 0); }
 static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout, cudaStream_t s, int slot, int already_undistorted,
                              int which, int tile_lo, int tile_cnt, int px_look) {
     const PlanDev& d = c->plan->d;
@@ -812,7 +846,7 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
             // out, colour bits to und_bits); only the others park their pixels in und_px for k_blend_px
             uint32_t* bits = c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW;
             const size_t smem = c->plan->frame_smem + MASK_PRE_WORDS * 4;
-            c->px_split = fout != nullptr && !knob(KNOB_NO_PX_SPLIT, "LD_NO_PX_SPLIT", 0);
+            c->px_split = fout != nullptr && split_wanted(c);
             const int nb = c->px_split ? c->plan->n_blend : c->plan->n_share;
             if (nb)
                 k_frame_pass_mf<3><<<dim3(nb, groups.y), FRAME_MF_THREADS, smem, s>>>(
@@ -827,12 +861,14 @@ static int launch_frame_pass(ld_ctx* c, const uint8_t* fin, int m, uint8_t* fout
                     tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->mask_tiles,
                     c->und_bits + (size_t)slot * (d.H - d.share_y0) * d.WW, nullptr, 0);
         } else if (which == 5) {                                         // [tile_lo, tile_lo + tile_cnt) of the list (the step may launch it in two parts)
-            int cnt = tile_cnt < 0 ? c->plan->n_plain_top - tile_lo : tile_cnt;
-            if (knob(KNOB_TEXT_TILES, "LD_TEXT_TILES", 0) && tile_lo + cnt > c->plan->n_plain_top - c->plan->n_text)
-                cnt = c->plan->n_plain_top - c->plan->n_text - tile_lo;  // A/B: the text window's tiles (last in the list) stay out
+            const int n_list = plain_count(c);
+            const int32_t* list = c->px_split ? c->plan->plain_split_tiles : c->plan->plain_top_tiles;
+            int cnt = tile_cnt < 0 ? n_list - tile_lo : tile_cnt;
+            if (knob(KNOB_TEXT_TILES, "LD_TEXT_TILES", 0) && tile_lo + cnt > n_list - c->plan->n_text)
+                cnt = n_list - c->plan->n_text - tile_lo;                // A/B: the text window's tiles (last in the list) stay out
             if (cnt > 0)
                 k_frame_pass_mf<0><<<dim3(cnt, groups.y), FRAME_MF_THREADS, c->plan->frame_smem, s>>>(
-                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, c->plan->plain_top_tiles + tile_lo, nullptr, nullptr, 0);
+                    tm, fin, nullptr, nullptr, fout, d, m, fpc, c->plan->frame_box_rows, list + tile_lo, nullptr, nullptr, 0);
         } else if (which == 4) {                                         // the text on top of the (plain) tiles under its window
             k_text_px<<<dim3((LD_TEXT_ROWS * LD_TEXT_WORDS + 255) / 256, m), 256, 0, s>>>(text, fout, d.W, d.H);
         } else if (which == 11) {                                        // A/B (knob 5): the window's tiles as undistort + text in one launch after the raster
@@ -914,7 +950,8 @@ extern "C" const uint32_t* ld_ctx_mask(ld_ctx* c) { return c ? c->mask : nullptr
 extern "C" int ld_stage_tiles(ld_ctx* c, int which) {                   // tiles a stage covers (for byte accounting)
     if (!c) return -1;
     if (which == 9) return c->plan->n_blend;                            // share tiles the inverse warp can touch (und_px -> k_blend_px)
-    return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? 0 : which == 5 ? c->plan->n_plain_top :
+    if (which == 12) return c->plan->n_final;                           // share tiles it cannot touch but the bird's-eye warp samples (k_frame_pass_mf<5>)
+    return which == 3 || which == 6 ? c->plan->n_share : which == 4 ? 0 : which == 5 ? plain_count(c) :
            which == 8 ? c->plan->n_mask_tiles : -1;
 }
 
@@ -1030,7 +1067,7 @@ static int postpass_impl(ld_ctx* c, const uint8_t* fin, int M, uint8_t* fout, ld
         // kernels take 2.8x longer, and every successor rank waits for exactly that stage.  (On one GPU the overlap wins: 4.18
         // vs 4.39 ms per 1260 frames.)
         if (fit_first) LD_CUDA(cudaStreamWaitEvent(s, c->ev_state, 0));
-        if (skip_plain && plain_done_tiles >= 0 && plain_done_tiles < c->plan->n_plain_top) {
+        if (skip_plain && plain_done_tiles >= 0 && plain_done_tiles < plain_count(c)) {
             // the caller launched only the first plain tiles early: the rest starts with the raster (they share the SMs with it)
             LD_CUDA(cudaStreamWaitEvent(s, c->ev_state, 0));
             if ((rc = launch_frame_pass(c, fin, M, fout, s, look, 0, 5, plain_done_tiles, -1))) return rc;
@@ -1104,7 +1141,8 @@ static int process_impl(ld_ctx* c, const uint8_t* frames, int n, uint8_t* out, l
             // which before only overlapped the fit stage and then starved behind the raster and the blend.
             LD_CUDA(cudaEventRecord(c->ev_fork, s));
             LD_CUDA(cudaStreamWaitEvent(c->s_lat, c->ev_fork, 0));
-            const int early_tiles = c->plan->n_plain_top * knob(KNOB_SPLIT_PLAIN, "LD_SPLIT_PLAIN", 100) / 100;
+            c->px_split = split_wanted(c);                               // (the shared pass below gets the output frames: same decision)
+            const int early_tiles = plain_count(c) * knob(KNOB_SPLIT_PLAIN, "LD_SPLIT_PLAIN", 100) / 100;
             if ((rc = launch_frame_pass(c, frames + base * fb, M, out + base * fb, s, 0, 0, 5, 0, early_tiles))) return rc;
             if ((rc = prepass_impl(c, frames + base * fb, M, c->s_lat, out + base * fb))) return rc;
             if ((rc = postpass_impl(c, frames + base * fb, M, out + base * fb, fit_out ? fit_out + base : nullptr, nullptr, s,

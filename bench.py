@@ -541,7 +541,8 @@ def single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg):
     time_stage(TX, lambda: L.ld_stage(h, 4, frames.data_ptr(), n, out.data_ptr(), st))
     n_share, n_plain, n_text = L.ld_stage_tiles(h, 3), L.ld_stage_tiles(h, 5), L.ld_stage_tiles(h, 4)
     blend_px = 128 * 16 * L.ld_stage_tiles(h, 9)           # pixels of the share tiles the inverse warp can touch (und_px -> k_blend_px)
-    final_px = n_share * 128 * 16 - blend_px               # the other share tiles are final after the undistortion: shared pass -> output frame
+    final_px = 128 * 16 * L.ld_stage_tiles(h, 12)          # share tiles it cannot touch but the mask samples: shared pass -> output frame
+    # (the share tiles neither of them needs are plain tiles of this step: counted in n_plain)
     time_stage("k_frame_pass_mf<1> (whole frame: ld_frame_pass / ld_overlay)", lambda: L.ld_frame_pass(h, frames.data_ptr(), n, out.data_ptr(), st))
     hist_t = eng.hist_dev(mask_t)
     time_stage("k_hist", lambda: L.ld_hist(h, mask_t.data_ptr(), n, hist_t.data_ptr(), st))
@@ -556,7 +557,7 @@ def single_gpu_extras(a, eng, pkg, torch, frames, out, fits, ms, n, cfg):
     bytes_per_frame = {MK: alg, "k_mask (ld_mask_fused: the one-kernel route)": alg, "k_frame_pass_mf<4> (mask-only pass)": alg - 115200 + 43520,
                        "k_search": 115200 + 560, "k_raster": 722 * 82 * 8,
                        "k_frame_pass_mf<1> (whole frame: ld_frame_pass / ld_overlay)": 2 * FRAME_BYTES,
-                       SH: n_share * tile_px * 3 + blend_px * 4 + final_px * 3 + 43520,   # source pixels read; u32 pixels / RGB + decision bits written
+                       SH: blend_px * (3 + 4) + final_px * (3 + 3) + 43520,   # source pixels read; u32 pixels / RGB + decision bits written
                        "k_mask_b": 43520 + 115200, PL: n_plain * tile_px * 6,
                        BL: blend_px * (4 + 3) + 722 * 82 * 8,            # u32 pixels + canvas read, RGB written
                        "k_hist": 115200 + 20480, "k_frame_pass_mf<0> (cv2.undistort alone)": 2 * FRAME_BYTES,

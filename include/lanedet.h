@@ -161,7 +161,9 @@ int ld_frame_pass(ld_ctx* ctx, const uint8_t* frames_dev, int n, uint8_t* out_de
  * their colour decisions stay in the context); 7: the packed mask out of those decisions (context mask); 5: the plain tiles
  * above share_y0 (pure cv2.undistort) -> out; 6: canvas blend onto the shared pixels -> out; 4: the putText pixels -> out.
  * ld_stage_tiles: how many 128x16 tiles stage `which` covers (which = 9: how many tiles of the shared rows the inverse
- * warp can touch -- the only ones that pass through k_blend_px when the shared pass had the output frames). */
+ * warp can touch -- the only ones that pass through k_blend_px when the shared pass had the output frames; which = 12: the
+ * tiles it cannot touch although the bird's-eye warp samples them: k_frame_pass_mf<5>; the remaining tiles of the shared
+ * rows are then plain tiles and counted under which = 5). */
 int ld_stage(ld_ctx* ctx, int which, const uint8_t* frames_dev, int n, uint8_t* out_dev, void* stream);
 int ld_stage_tiles(ld_ctx* ctx, int which);
 /* Tuning aid (process-wide): knob 0 = CTAs per SM of the persistent raster grid inside ld_process_batch (0 = one CTA per band),
