@@ -784,12 +784,13 @@ k_blend_px(const uint32_t* __restrict__ und_px, const uint32_t* __restrict__ pla
 
 // cv2.putText (Project.py:326-332) inside the step: the tiles under the text window are undistorted with the plain tiles (they
 // depend on nothing), and once the raster has written the frame's text plane every set bit of it becomes a white pixel.  One
-// thread per plane word.  (The window used to be a launch of its own -- MODE 1 over its 35 tiles after the raster, 0.175
-// us/frame at 37 % of the HBM roofline; as plain tiles the same pixels cost 0.10 and start with everything else.)
+// warp per 32 plane words.  (The window used to be a launch of its own -- MODE 1 over its 35 tiles after the raster, 0.175
+// us/frame at 37 % of the HBM roofline; as plain tiles the same pixels cost 0.10 and start with everything else, and this
+// kernel 0.06: some 1,000 non-empty plane words = 24,000 output words per frame.  The step time is the same either way.)
 __global__ void __launch_bounds__(256)
 k_text_px(const uint32_t* __restrict__ text, uint8_t* __restrict__ out, int W, int H) {
     // a warp takes 32 plane words (one per lane); for every non-empty one the 32 pixels are 96 contiguous output bytes = 24
-    // words, one per lane: white is all ones, so a word is stored whole or OR-ed (nobody else writes these tiles any more)
+    // words, one per lane, stored whole or byte by byte
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < LD_TEXT_ROWS * LD_TEXT_WORDS;
@@ -806,8 +807,14 @@ k_text_px(const uint32_t* __restrict__ text, uint8_t* __restrict__ out, int W, i
 #pragma unroll
         for (int j = 0; j < 4; ++j) bytes |= ((m >> ((4 * lane + j) / 3)) & 1u) ? (0xFFu << (8 * j)) : 0u;
         if (!bytes) continue;
-        uint32_t* p = reinterpret_cast<uint32_t*>(out + (size_t)f * W * H * 3 + ((size_t)y * W + x0) * 3) + lane;
-        if (bytes == 0xFFFFFFFFu) *p = bytes; else *p |= bytes;
+        uint8_t* p = out + (size_t)f * W * H * 3 + ((size_t)y * W + x0) * 3 + 4 * lane;
+        if (bytes == 0xFFFFFFFFu) *reinterpret_cast<uint32_t*>(p) = bytes;
+        else {
+            // a stroke edge inside the word: byte stores, no read-modify-write
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((bytes >> (8 * j)) & 0xFFu) p[j] = 255;
+        }
     }
 }
 
