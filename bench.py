@@ -395,10 +395,11 @@ def main():
     ms = reduce_max(ev0.elapsed_time(ev1))
     value = world * n * a.steps / (ms / 1e3)
     repairs = run.repairs
-    # kernels of one step (profiles/r02_launches.csv): state reset; plain tiles; shared pass (two launches: the tiles the inverse
-    # warp can / cannot touch), k_mask_b, k_search; 5 fit kernels; k_raster_prep, k_raster; k_blend_px, k_text_px; k_near_integer
+    # kernels of one step (profiles/r02_launches.csv): state reset; plain tiles; shared pass (on these plans one launch: no share
+    # tile is sampled by the mask without being touched by the inverse warp), k_mask_b, k_search; 5 fit kernels; k_raster_prep,
+    # k_raster; k_blend_px, k_text_px; k_near_integer
     # (rank 0 prints: its range starts the video, so it has no look-back; the other ranks of a 'lookback' run add k_halo_start)
-    launches_per_step = (1 + 1 + 4 + 5 + 2 + 2 + 1) if (world == 1 or mode != "records") else 17
+    launches_per_step = (1 + 1 + 3 + 5 + 2 + 2 + 1) if (world == 1 or mode != "records") else 16
 
     # ---- sharded results against the serial protocol and against each other, then the other protocols' rates
     shard = None
