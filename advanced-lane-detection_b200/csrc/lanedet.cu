@@ -99,6 +99,7 @@ struct ld_ctx {
     cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
     // intra-batch pipeline: pixel-heavy kernels on s_pix, the latency-bound search/fit/raster chain on s_lat
     cudaStream_t s_pix, s_lat;
+    cudaStream_t s_lat2;       // a second high-priority stream: k_mask_b / k_search of alternate frame pieces (prepass_impl)
     cudaEvent_t ev_fork, ev_state, ev_join[2], ev_mask[PIPE_SUB], ev_rast[PIPE_SUB];
     // sharding: ev_halo_in = the look-back records have landed in front of rec (the next fit stage waits for it, nothing else does);
     // ev_valid[0/1] = the pinned copies of flags[4] (halo invalid) / flags[5] (tail invalid) are readable
@@ -112,7 +113,7 @@ struct ld_ctx {
 
 // Tuning knobs of the step schedule, settable at run time so that one process can sweep them (tools/knob_sweep.py);
 // -1 = take the default / the environment variable of the same purpose.
-enum { KNOB_RASTER_PERSIST = 0, KNOB_EARLY_PLAIN = 1, KNOB_PLAIN_FPC = 2, KNOB_SPLIT_PLAIN = 4, KNOB_TEXT_TILES = 5, KNOB_NO_PX_SPLIT = 6, N_KNOBS = 8 };
+enum { KNOB_RASTER_PERSIST = 0, KNOB_EARLY_PLAIN = 1, KNOB_PLAIN_FPC = 2, KNOB_SPLIT_PLAIN = 4, KNOB_TEXT_TILES = 5, KNOB_NO_PX_SPLIT = 6, KNOB_PRE_PIECES = 7, N_KNOBS = 8 };
 static int g_knob[N_KNOBS] = {-1, -1, -1, -1, -1, -1, -1, -1};
 extern "C" int ld_debug_knob(int id, int value) {
     if (id < 0 || id >= N_KNOBS) return LD_ERR_ARG;
@@ -535,6 +536,7 @@ extern "C" int ld_ctx_create(ld_plan* plan, int max_frames, ld_ctx** out) {
         int lo = 0, hi = 0;
         LD_CUDA_OR(cudaDeviceGetStreamPriorityRange(&lo, &hi), ld_ctx_destroy(c));
         LD_CUDA_OR(cudaStreamCreateWithPriority(&c->s_lat, cudaStreamNonBlocking, hi), ld_ctx_destroy(c));
+        LD_CUDA_OR(cudaStreamCreateWithPriority(&c->s_lat2, cudaStreamNonBlocking, hi), ld_ctx_destroy(c));
     }
     LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), ld_ctx_destroy(c));
     LD_CUDA_OR(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming), ld_ctx_destroy(c));
@@ -575,6 +577,7 @@ extern "C" int ld_ctx_destroy(ld_ctx* c) {
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->s_pix) cudaStreamDestroy(c->s_pix);
+    if (c->s_lat2) cudaStreamDestroy(c->s_lat2);
     if (c->s_lat) cudaStreamDestroy(c->s_lat);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_state) cudaEventDestroy(c->ev_state);
@@ -1006,6 +1009,28 @@ static int prepass_impl(ld_ctx* c, const uint8_t* fin, int M, cudaStream_t s, ui
             // mask out of the bit plane; the overlay later blends the canvas onto und_px instead of gathering again
             if ((rc = launch_frame_pass(c, fin, M, fout, s, 0, 0, 3, 0, -1, look))) return rc;
             tl_mark("shared pass", s);
+            // k_mask_b and k_search are both latency-bound (L2 round trips; one 115 KB CTA per SM): in `pieces` frame pieces on two
+            // high-priority streams k_mask_b of one piece runs beside k_search of the piece before
+            int pieces = knob(KNOB_PRE_PIECES, "LD_PRE_PIECES", 1);
+            if (pieces > PIPE_SUB) pieces = PIPE_SUB;
+            if (pieces > 1 && M >= 128 * pieces) {
+                const size_t bw = (size_t)(d.H - d.share_y0) * d.WW;
+                const int S = ((M + pieces - 1) / pieces + MASKB_FPC - 1) / MASKB_FPC * MASKB_FPC;
+                LD_CUDA(cudaEventRecord(c->ev_mask[0], s));
+                LD_CUDA(cudaStreamWaitEvent(c->s_lat2, c->ev_mask[0], 0));
+                int i = 0;
+                for (int off = 0; off < M; off += S, ++i) {
+                    const int m = (M - off) < S ? (M - off) : S;
+                    cudaStream_t st = (i & 1) ? c->s_lat2 : s;
+                    k_mask_b<<<dim3(d.n_tiles, (m + MASKB_FPC - 1) / MASKB_FPC), MASK_THREADS, 0, st>>>(c->und_bits + off * bw, c->mask + off * mw, d, m);
+                    if ((rc = check_launch())) return rc;
+                    if ((rc = ld_search(c, c->mask + off * mw, m, c->rec + 2 * off, st))) return rc;
+                }
+                LD_CUDA(cudaEventRecord(c->ev_mask[1], c->s_lat2));
+                LD_CUDA(cudaStreamWaitEvent(s, c->ev_mask[1], 0));
+                tl_mark("mask_b + search", s);
+                return LD_OK;
+            }
             k_mask_b<<<dim3(d.n_tiles, (M + MASKB_FPC - 1) / MASKB_FPC), MASK_THREADS, 0, s>>>(c->und_bits, c->mask, d, M);
             if ((rc = check_launch())) return rc;
             tl_mark("mask_b", s);

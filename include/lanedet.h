@@ -170,7 +170,8 @@ int ld_stage_tiles(ld_ctx* ctx, int which);
  * 1 = plain tiles first (1, default) or after the window search (0), 2 = frames per CTA of the plain-tile launch (0 = default),
  * 4 = percentage of the plain tiles launched first (the rest starts with the raster), 5 = 1: the tiles under the putText
  * window as one undistort + text launch after the raster instead of plain tiles + k_text_px, 6 = 1: every share tile through
- * und_px and k_blend_px; value -1 = back to the default. */
+ * und_px and k_blend_px, 7 = frame pieces k_mask_b / k_search are pipelined over on two streams (default 1); value -1 =
+ * back to the default. */
 int ld_debug_knob(int id, int value);
 /* the packed masks ld_prepass / ld_process_batch / ld_stage(7) leave in the context: device u32[max_frames][H][W/32] */
 const uint32_t* ld_ctx_mask(ld_ctx* ctx);
