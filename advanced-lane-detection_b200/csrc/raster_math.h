@@ -6,7 +6,7 @@
 // what follows restates the published behaviour of its non-antialiased 8-connected primitives
 // (imgproc drawing: thick line = filled convex quad in 16.16 fixed point + filled end discs;
 // polygon fill = 1-px outline + even-odd scanline spans) and is pinned by fuzzing against the
-// cv2 build in this image (tests/test_raster_hostsim.py).
+// cv2 build in this image (tests/test_hostsim_math.py; its hs_band_raster also runs k_raster's band algorithm on the host).
 //
 // Everything writes through a Plotter:  void span(int y, int x1, int x2)  -- inclusive, the
 // callee clips to the image -- so the same code sets bits with atomicOr on the device and

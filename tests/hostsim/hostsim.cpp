@@ -213,3 +213,89 @@ extern "C" int hs_big_segment_cost(const int32_t* pts, int i, int w, int h, int 
     for (int e = 0; e < 4; ++e) if (T.L[e].valid && T.L[e].ecount > ec) ec = T.L[e].ecount;
     return T.valid ? (T.quad ? T.S.n * 10000 + ec : -2) : -1;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_raster's band algorithm on the host (overlay_kernels.cuh: raster_band), one band [y_lo, y_hi) of the canvas:
+// red = the segments that can touch the band, classified as in pass 1 -- unit vertical steps drawn as two spans, stamps,
+// end / start discs, and every GENERAL segment from the ThickSetup record k_raster_prep would have made, drawn by `nt`
+// cooperating workers (a long segment: 4 warps = 128) -- and green = outline + scanline crossings of the band.
+// img: u8[h][w], bit 0 = red, bit 1 = green (green overwrites red when the kernel stores the band).
+namespace {
+struct BandPlot {
+    uint8_t* img; int w, h, y_lo, y_hi; uint8_t bit;
+    void span(int y, int x1, int x2) {
+        if (y < y_lo || y >= y_hi) return;
+        if (x1 < 0) x1 = 0;
+        if (x2 >= w) x2 = w - 1;
+        for (int x = x1; x <= x2; ++x) img[(size_t)y * w + x] |= bit;
+    }
+};
+}
+extern "C" int hs_band_raster(uint8_t* img, int w, int h, const int32_t* pts, int nv, int thickness, int y_lo, int y_hi) {
+    using namespace laneraster;
+    const int radius = thickness / 2 < 15 ? thickness / 2 : 15;
+    int hw[16];
+    circle_half_widths(radius, hw);
+    static std::vector<Stamp> stamps;
+    if (stamps.empty()) {
+        stamps.assign(STAMP_N, Stamp());
+        StampCanvas cv;
+        int hw30[16];
+        circle_half_widths(15, hw30);
+        for (int dy = -STAMP_K; dy <= STAMP_K; ++dy)
+            for (int dx = -STAMP_K; dx <= STAMP_K; ++dx) build_stamp(dx, dy, 30, hw30, stamps[stamp_index(dx, dy)], cv);
+    }
+    BandPlot red{img, w, h, y_lo, y_hi, 1}, green{img, w, h, y_lo, y_hi, 2};
+    auto X = [&](int i) { return pts[2 * i]; };
+    auto Y = [&](int i) { return pts[2 * i + 1]; };
+    int general = 0;
+    if (thickness >= 2)
+        for (int i = 0; i + 1 < nv; ++i) {
+            const int ya = Y(i), yb = Y(i + 1);
+            if (std::max(ya, yb) + radius + 1 < y_lo || std::min(ya, yb) - radius - 1 >= y_hi) continue;
+            const bool nx = i + 2 < nv;
+            const int cls = classify_segment(w, h, X(i), ya, X(i + 1), yb, nx, nx ? X(i + 2) : 0, nx ? Y(i + 2) : 0, thickness, i == 0);
+            if (!(cls & SEG_TRIVIAL)) {
+                if (thickness == 30 && stamp_applies(X(i), ya, X(i + 1), yb, w, h) && stamps[stamp_index(X(i + 1) - X(i), yb - ya)].ok) {
+                    draw_stamp(red, stamps[stamp_index(X(i + 1) - X(i), yb - ya)], X(i), ya);
+                    if (i == 0) disc(red, w, h, X(i), ya, radius, hw);
+                } else {
+                    ThickSetup T;                                       // k_raster_prep's record
+                    thick_segment_setup(w, h, X(i), ya, X(i + 1), yb, thickness, T);
+                    const int nt = std::max(std::abs(X(i + 1) - X(i)), std::abs(yb - ya)) > 24 ? 128 : 32;
+                    for (int t = 0; t < nt; ++t) thick_segment_draw(red, w, h, T, thickness, hw, i == 0, t, nt, y_lo, y_hi);
+                    ++general;
+                }
+                continue;
+            }
+            red.span(ya, X(i) - radius, X(i) + radius);
+            red.span(yb, X(i) - radius, X(i) + radius);
+            if (cls & SEG_END_DISC) for (int t = 0; t < 32; ++t) disc_part(red, w, h, X(i + 1), yb, radius, hw, t, 32);
+            if (cls & SEG_START_DISC) for (int t = 0; t < 32; ++t) disc_part(red, w, h, X(i), ya, radius, hw, t, 32);
+        }
+    // green: cv2.fillPoly -- short edges by one worker, long ones cooperatively, crossings per band row
+    std::vector<std::vector<int64_t>> cross(y_hi - y_lo);
+    for (int i = 0; i < nv && nv >= 2; ++i) {
+        const int j = i == 0 ? nv - 1 : i - 1;
+        const int ya = Y(j), yb = Y(i);
+        if (std::max(ya, yb) < y_lo || std::min(ya, yb) >= y_hi) continue;
+        PolyEdge e;
+        if (std::max(std::abs(X(i) - X(j)), std::abs(yb - ya)) > 32) {
+            Pt a{X(j), Y(j)}, b{X(i), Y(i)};
+            for (int t = 0; t < 256; ++t) line8_part(green, w, h, a, b, t, 256);
+            e = poly_edge_scan(w, h, X(j), ya, X(i), yb);
+        } else
+            e = poly_edge(green, w, h, X(j), ya, X(i), yb);
+        if (!e.valid) continue;
+        for (int y = std::max(e.y0, y_lo); y < std::min(e.y1, y_hi); ++y) {
+            int64_t x = e.x + (int64_t)(y - e.y0) * e.dx;
+            x = x < -(1ll << 30) ? -(1ll << 30) : x > (1ll << 30) ? (1ll << 30) : x;     // add_crossing's order-preserving clamp
+            cross[y - y_lo].push_back((int)x);
+        }
+    }
+    for (int r = 0; r < y_hi - y_lo; ++r) {
+        std::sort(cross[r].begin(), cross[r].end());
+        for (size_t k = 0; k + 1 < cross[r].size(); k += 2) poly_span(green, w, y_lo + r, cross[r][k], cross[r][k + 1]);
+    }
+    return general;
+}

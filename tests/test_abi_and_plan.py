@@ -240,3 +240,57 @@ def test_bilinear_weights_closed_form_and_doubling(pkg):
     want = (np.einsum("fk,fnk->fn", closed, taps) + 16384) >> 15
     got = (np.einsum("fk,fnk->fn", dbl, taps) + 32768) >> 16
     assert (want == got).all() and got.max() <= 255
+
+
+@pytest.mark.parametrize("variant", ["project", "harder"])
+def test_share_tile_split_invariants(pkg, variant):
+    """what ld_plan_create's split of the share tiles rests on (lanedet.cu: blend / final / plain_split lists): the inverse warp
+    touches nothing above share_y0; on both reference geometries the 128x16 tiles it can touch are exactly the tiles the
+    bird's-eye warp samples (so the others need neither a colour decision nor the canvas: plain tiles, no MODE 5 tile); and the
+    putText window lies above share_y0, inside the text plane"""
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    plan = P.build_plan(P.VARIANTS[variant])
+    W, H = 1280, 720
+    touched = np.zeros((H, W), bool)
+    touched[plan.inv_y0:plan.inv_y1] = plan.inv_pack != 0xFFFFFFFF
+    near = np.asarray(plan.near).reshape(-1)
+    sampled = np.zeros(H * W, bool)
+    sampled[near[near >= 0]] = True
+    sampled = sampled.reshape(H, W)
+    first_row = min(int(np.nonzero(sampled.any(1))[0][0]), plan.inv_y0)
+    share_y0 = first_row // 16 * 16                                     # ld_plan_create: d.share_y0
+    assert share_y0 == 480
+    assert not touched[:share_y0].any() and not sampled[:share_y0].any()
+    rows = (H - share_y0) // 16
+    inv_t = touched[share_y0:].reshape(rows, 16, W // 128, 128).any(axis=(1, 3))
+    smp_t = sampled[share_y0:].reshape(rows, 16, W // 128, 128).any(axis=(1, 3))
+    assert (inv_t == smp_t).all()
+    assert int(inv_t.sum()) == {"project": 113, "harder": 88}[variant] and inv_t.size == 150
+    assert P.TEXT_Y0 + P.TEXT_ROWS <= share_y0
+
+
+def test_text_pixel_kernel_arithmetic(pkg):
+    """k_text_px (overlay_kernels.cuh) in numpy: plane word w of row r covers pixels x0 = TEXT_X0 + 32 w .. x0 + 31 of image row
+    TEXT_Y0 + r = 96 output bytes = 24 words; byte b of them belongs to pixel b // 3.  Composing a putText plane that way must
+    give cv2.putText's white pixels on an RGB frame"""
+    import cv2
+    P = importlib.import_module("advanced-lane-detection_b200.plan")
+    font = cv2.FONT_HERSHEY_SIMPLEX
+    want = np.full((720, 1280, 3), 37, np.uint8)
+    cv2.putText(want, "Radius of Curvature: 1266(m)", (60, 100), font, 1.0, (255, 255, 255), thickness=2)
+    cv2.putText(want, "Offset from center: -0.33(m)", (60, 130), font, 1.0, (255, 255, 255), thickness=2)
+    ink = (want == 255).all(2)
+    plane = np.zeros((P.TEXT_ROWS, P.TEXT_WORDS), np.uint32)             # what k_raster writes: bit i of word w = pixel 32 w + i
+    win = ink[P.TEXT_Y0:P.TEXT_Y0 + P.TEXT_ROWS, P.TEXT_X0:P.TEXT_X0 + 32 * P.TEXT_WORDS]
+    assert ink.sum() == win.sum()
+    plane[:] = np.packbits(win, axis=1, bitorder="little").view("<u4")
+    out = np.full((720, 1280, 3), 37, np.uint8)
+    flat = out.reshape(720, 1280 * 3)
+    for r, w in zip(*np.nonzero(plane)):
+        m = int(plane[r, w])
+        y, x0 = P.TEXT_Y0 + r, P.TEXT_X0 + 32 * w
+        for lane in range(24):                                          # one output word per lane
+            for j in range(4):
+                if (m >> ((4 * lane + j) // 3)) & 1:
+                    flat[y, 3 * x0 + 4 * lane + j] = 255
+    assert (out == want).all()

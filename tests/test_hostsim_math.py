@@ -180,3 +180,69 @@ def test_bitsliced_histogram_and_row_sums(hs):
             hs.hs_row_count_sx(packed.ctypes.data_as(ctypes.c_void_p), W, row, x0, x1, ctypes.byref(cnt), ctypes.byref(sx))
             xs = np.nonzero(mask[row, max(x0, 0):max(min(x1, W - 1) + 1, 0)])[0] + max(x0, 0)
             assert cnt.value == xs.size and sx.value == int(xs.sum()), (row, x0, x1)
+
+
+def _lane_polygon(rng):
+    """draw_area's vertex list (Project.py:153-157): left chain descending y, right chain ascending y, sparse rows, anchors"""
+    def chain(right):
+        A, B = rng.normal(0, 3e-4), rng.normal(0, 0.3)
+        C = rng.uniform(600, 1400) if right else rng.uniform(-150, 650)
+        rows = np.nonzero(rng.random(720) < rng.choice([0.02, 0.3, 0.9]))[0]
+        ys = np.concatenate([[0], rows, [720]]) if rng.random() < 0.7 else np.concatenate([rows, [720]])
+        ys = np.unique(ys).astype(np.float64)
+        return A * ys ** 2 + B * ys + C, ys
+    lx, ly = chain(False)
+    rx, ry = chain(True)
+    left = np.array([np.flipud(np.transpose(np.vstack([lx, ly])))])
+    right = np.array([np.transpose(np.vstack([rx, ry]))])
+    return np.int_([np.hstack((left, right))])
+
+
+def test_cooperative_forms_match_cv2(hs):
+    """the worker-shared forms the kernels run (thick_segment_setup + thick_segment_draw, line8_part, poly_edge_scan) with the
+    worker counts k_raster uses: a warp, four warps, the CTA"""
+    import cv2
+    ci, vp = ctypes.c_int, ctypes.c_void_p
+    hs.hs_polyline_coop.argtypes = [vp, ci, ci, vp, ci, ci, ci]
+    hs.hs_fillpoly_coop.argtypes = [vp, ci, ci, vp, ci, ci]
+    rng = np.random.default_rng(21)
+    for it in range(24):
+        pts = _lane_polygon(rng)
+        p = np.ascontiguousarray(pts[0][0], dtype=np.int32)
+        ref = np.zeros((H, W), np.uint8)
+        cv2.polylines(ref, pts, False, 1, 30)
+        for nt in ((32, 128) if it % 2 else (256,)):
+            got = np.zeros((H, W), np.uint8)
+            hs.hs_polyline_coop(got.ctypes.data, W, H, p.ctypes.data, len(p), 30, nt)
+            assert (got == ref).all(), (it, nt)
+        ref = np.zeros((H, W), np.uint8)
+        cv2.fillPoly(ref, pts, 1)
+        got = np.zeros((H, W), np.uint8)
+        hs.hs_fillpoly_coop(got.ctypes.data, W, H, p.ctypes.data, len(p), 256)
+        assert (got == ref).all(), it
+
+
+def test_band_raster_matches_cv2(hs):
+    """k_raster's band algorithm (hostsim.cpp: hs_band_raster mirrors raster_band): eight 90-row bands, each drawing only what
+    can touch it -- unit steps, stamps, discs, general segments from their set-up records -- give cv2's canvas"""
+    import cv2
+    ci, vp = ctypes.c_int, ctypes.c_void_p
+    hs.hs_band_raster.argtypes = [vp, ci, ci, vp, ci, ci, ci, ci]
+    rng = np.random.default_rng(22)
+    n_general = 0
+    for it in range(40):
+        pts = _lane_polygon(rng)
+        p = pts[0][0]
+        keep = np.ones(len(p), bool)
+        keep[1:] = (p[1:] != p[:-1]).any(1)                             # consecutive duplicates are removable (same raster)
+        p = np.ascontiguousarray(p[keep], dtype=np.int32)
+        red = np.zeros((H, W), np.uint8)
+        cv2.polylines(red, pts, False, 1, 30)
+        green = np.zeros((H, W), np.uint8)
+        cv2.fillPoly(green, pts, 1)
+        got = np.zeros((H, W), np.uint8)
+        for band in range(8):
+            n_general += hs.hs_band_raster(got.ctypes.data, W, H, p.ctypes.data, len(p), 30, band * 90, band * 90 + 90)
+        assert ((got & 1) == red).all(), it
+        assert ((got >> 1) == green).all(), it
+    assert n_general > 100                                              # the record path is exercised (gaps, connector, border steps)
