@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call C (8 GPUs): bench at N = 8 and 4, per-rank timelines of the protocols, PCIe probe
+# one gpurun --gpus 8 call: bench at N = 8 and 4, per-rank timelines of the protocols, PCIe probe
 set -x
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
